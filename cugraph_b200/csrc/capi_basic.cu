@@ -1,0 +1,321 @@
+// C-ABI entry points that carry no graph logic: errors, resource handle, type-erased arrays.
+// Boundary being replaced: cpp/src/c_api/{error,resource_handle,array}.cpp of the reference.
+#include "graph.cuh"
+
+#include <cstdlib>
+
+using namespace b200;
+
+extern "C" {
+
+// ----------------------------------------------------------------------------- error.h:28-29
+const char* cugraph_error_message(const cugraph_error_t* error)
+{
+  if (error == nullptr) return nullptr;
+  return reinterpret_cast<error_impl const*>(error)->message.c_str();
+}
+
+void cugraph_error_free(cugraph_error_t* error)
+{
+  if (error != nullptr) delete reinterpret_cast<error_impl*>(error);
+}
+
+// ------------------------------------------------------------------- resource_handle.h:25-31
+// NULL -> single-GPU handle on the current device.  Non-NULL -> a cugraph_b200_comm_t* (b200_ext.h).
+cugraph_resource_handle_t* cugraph_create_resource_handle(void* raft_handle)
+{
+  try {
+    auto* h = new handle_impl{};
+    CUDA_TRY(cudaGetDevice(&h->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    h->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
+    CUDA_TRY(cudaMallocHost(&h->pinned, 4096));
+    // keep freed blocks in the pool: algorithm calls allocate/free V- and E-sized scratch
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, h->device));
+    uint64_t threshold = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    if (raft_handle != nullptr) {
+      attach_comm(h, raft_handle);
+    }
+    return reinterpret_cast<cugraph_resource_handle_t*>(h);
+  } catch (std::exception const& e) {
+    std::fprintf(stderr, "cugraph_create_resource_handle: %s\n", e.what());
+    return nullptr;
+  }
+}
+
+int cugraph_resource_handle_get_comm_size(const cugraph_resource_handle_t* handle)
+{
+  return handle ? reinterpret_cast<handle_impl const*>(handle)->size : 1;
+}
+
+int cugraph_resource_handle_get_rank(const cugraph_resource_handle_t* handle)
+{
+  return handle ? reinterpret_cast<handle_impl const*>(handle)->rank : 0;
+}
+
+void cugraph_free_resource_handle(cugraph_resource_handle_t* handle)
+{
+  if (!handle) return;
+  auto* h = reinterpret_cast<handle_impl*>(handle);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->aux_stream);
+  cudaEventDestroy(h->ev_a);
+  cudaEventDestroy(h->ev_b);
+  cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->aux_stream);
+  cudaFreeHost(h->pinned);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------ b200_ext.h
+const char* cugraph_b200_version(void) { return "cugraph_b200 0.1 (sm_100a)"; }
+
+void* cugraph_b200_handle_stream(const cugraph_resource_handle_t* handle)
+{
+  return handle ? reinterpret_cast<void*>(reinterpret_cast<handle_impl const*>(handle)->stream) : nullptr;
+}
+
+size_t cugraph_b200_handle_launch_count(const cugraph_resource_handle_t* handle)
+{
+  return handle ? reinterpret_cast<handle_impl const*>(handle)->launches : 0;
+}
+
+// -------------------------------------------------------------------------- array.h:43-121
+cugraph_error_code_t cugraph_type_erased_device_array_create(const cugraph_resource_handle_t* handle,
+                                                             size_t n_elems,
+                                                             cugraph_data_type_id_t dtype,
+                                                             cugraph_type_erased_device_array_t** array,
+                                                             cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(array != nullptr, CUGRAPH_INVALID_INPUT, "array out-pointer is NULL");
+    size_t es = dtype_size(dtype);
+    B200_EXPECTS(es > 0, CUGRAPH_UNSUPPORTED_TYPE_COMBINATION, "invalid dtype");
+    dbuf b(n_elems * es, h.stream);
+    *array = wrap_array(std::move(b), n_elems, dtype);
+  });
+}
+
+cugraph_error_code_t cugraph_type_erased_device_array_create_from_view(
+  const cugraph_resource_handle_t* handle,
+  const cugraph_type_erased_device_array_view_t* view,
+  cugraph_type_erased_device_array_t** array,
+  cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(view != nullptr && array != nullptr, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto const* v = V(view);
+    dbuf b(v->nbytes(), h.stream);
+    if (v->nbytes() > 0)
+      CUDA_TRY(cudaMemcpyAsync(b.data(), v->data, v->nbytes(), cudaMemcpyDeviceToDevice, h.stream));
+    sync(h);
+    *array = wrap_array(std::move(b), v->size, v->type);
+  });
+}
+
+void cugraph_type_erased_device_array_free(cugraph_type_erased_device_array_t* p)
+{
+  if (p) delete reinterpret_cast<device_array_impl*>(p);
+}
+
+cugraph_type_erased_device_array_view_t* cugraph_type_erased_device_array_view(
+  cugraph_type_erased_device_array_t* array)
+{
+  if (!array) return nullptr;
+  return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(
+    reinterpret_cast<device_array_impl*>(array)->new_view());
+}
+
+cugraph_error_code_t cugraph_type_erased_device_array_view_as_type(
+  cugraph_type_erased_device_array_t* array,
+  cugraph_data_type_id_t dtype,
+  cugraph_type_erased_device_array_view_t** result_view,
+  cugraph_error_t** error)
+{
+  // reinterpretation is only allowed between types of equal width (reference array.cpp)
+  return guarded(error, [&] {
+    B200_EXPECTS(array != nullptr && result_view != nullptr, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto* a = reinterpret_cast<device_array_impl*>(array);
+    B200_EXPECTS(dtype_size(dtype) == dtype_size(a->type) && dtype_size(dtype) > 0,
+                 CUGRAPH_INVALID_INPUT,
+                 "Could not treat type_erased_device_array_t as requested type");
+    *result_view = reinterpret_cast<cugraph_type_erased_device_array_view_t*>(
+      new device_array_view_impl{a->buf.data(), a->size, dtype});
+  });
+}
+
+// ------------------------------------------------------------------------- array.h:123-170
+cugraph_type_erased_device_array_view_t* cugraph_type_erased_device_array_view_create(
+  void* pointer, size_t n_elems, cugraph_data_type_id_t dtype)
+{
+  return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(
+    new device_array_view_impl{pointer, n_elems, dtype});
+}
+
+void cugraph_type_erased_device_array_view_free(cugraph_type_erased_device_array_view_t* p)
+{
+  if (p) delete reinterpret_cast<device_array_view_impl*>(p);
+}
+
+size_t cugraph_type_erased_device_array_view_size(const cugraph_type_erased_device_array_view_t* p)
+{
+  return p ? V(p)->size : 0;
+}
+
+cugraph_data_type_id_t cugraph_type_erased_device_array_view_type(
+  const cugraph_type_erased_device_array_view_t* p)
+{
+  return p ? V(p)->type : NTYPES;
+}
+
+const void* cugraph_type_erased_device_array_view_pointer(const cugraph_type_erased_device_array_view_t* p)
+{
+  return p ? V(p)->data : nullptr;
+}
+
+// ------------------------------------------------------------------------- array.h:172-262
+cugraph_error_code_t cugraph_type_erased_host_array_create(const cugraph_resource_handle_t* handle,
+                                                           size_t n_elems,
+                                                           cugraph_data_type_id_t dtype,
+                                                           cugraph_type_erased_host_array_t** array,
+                                                           cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    (void)H(handle);
+    B200_EXPECTS(array != nullptr, CUGRAPH_INVALID_INPUT, "array out-pointer is NULL");
+    size_t es = dtype_size(dtype);
+    B200_EXPECTS(es > 0, CUGRAPH_UNSUPPORTED_TYPE_COMBINATION, "invalid dtype");
+    void* p = std::malloc(n_elems * es > 0 ? n_elems * es : 1);
+    B200_EXPECTS(p != nullptr, CUGRAPH_ALLOC_ERROR, "host allocation failed");
+    *array = reinterpret_cast<cugraph_type_erased_host_array_t*>(new host_array_impl{p, n_elems, dtype});
+  });
+}
+
+void cugraph_type_erased_host_array_free(cugraph_type_erased_host_array_t* p)
+{
+  if (!p) return;
+  auto* a = reinterpret_cast<host_array_impl*>(p);
+  std::free(a->data);
+  delete a;
+}
+
+cugraph_type_erased_host_array_view_t* cugraph_type_erased_host_array_view(
+  cugraph_type_erased_host_array_t* array)
+{
+  if (!array) return nullptr;
+  auto* a = reinterpret_cast<host_array_impl*>(array);
+  return reinterpret_cast<cugraph_type_erased_host_array_view_t*>(
+    new host_array_view_impl{a->data, a->size, a->type});
+}
+
+cugraph_type_erased_host_array_view_t* cugraph_type_erased_host_array_view_create(
+  void* pointer, size_t n_elems, cugraph_data_type_id_t dtype)
+{
+  return reinterpret_cast<cugraph_type_erased_host_array_view_t*>(
+    new host_array_view_impl{pointer, n_elems, dtype});
+}
+
+void cugraph_type_erased_host_array_view_free(cugraph_type_erased_host_array_view_t* p)
+{
+  if (p) delete reinterpret_cast<host_array_view_impl*>(p);
+}
+
+size_t cugraph_type_erased_host_array_size(const cugraph_type_erased_host_array_view_t* p)
+{
+  return p ? reinterpret_cast<host_array_view_impl const*>(p)->size : 0;
+}
+
+cugraph_data_type_id_t cugraph_type_erased_host_array_type(const cugraph_type_erased_host_array_view_t* p)
+{
+  return p ? reinterpret_cast<host_array_view_impl const*>(p)->type : NTYPES;
+}
+
+void* cugraph_type_erased_host_array_pointer(const cugraph_type_erased_host_array_view_t* p)
+{
+  return p ? reinterpret_cast<host_array_view_impl const*>(p)->data : nullptr;
+}
+
+// ------------------------------------------------------------------------- array.h:264-326
+cugraph_error_code_t cugraph_type_erased_host_array_view_copy(
+  const cugraph_resource_handle_t* handle,
+  cugraph_type_erased_host_array_view_t* dst,
+  const cugraph_type_erased_host_array_view_t* src,
+  cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    (void)H(handle);
+    B200_EXPECTS(dst && src, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto* d       = reinterpret_cast<host_array_view_impl*>(dst);
+    auto const* s = reinterpret_cast<host_array_view_impl const*>(src);
+    B200_EXPECTS(d->nbytes() == s->nbytes(), CUGRAPH_INVALID_INPUT,
+                 "source and destination arrays are different sizes");
+    std::memcpy(d->data, s->data, s->nbytes());
+  });
+}
+
+cugraph_error_code_t cugraph_type_erased_device_array_view_copy_from_host(
+  const cugraph_resource_handle_t* handle,
+  cugraph_type_erased_device_array_view_t* dst,
+  const byte_t* h_src,
+  cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(dst != nullptr, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto* d = reinterpret_cast<device_array_view_impl*>(dst);
+    if (d->nbytes() > 0) {
+      B200_EXPECTS(h_src != nullptr, CUGRAPH_INVALID_INPUT, "host source is NULL");
+      CUDA_TRY(cudaMemcpyAsync(d->data, h_src, d->nbytes(), cudaMemcpyHostToDevice, h.stream));
+    }
+    sync(h);
+  });
+}
+
+cugraph_error_code_t cugraph_type_erased_device_array_view_copy_to_host(
+  const cugraph_resource_handle_t* handle,
+  byte_t* h_dst,
+  const cugraph_type_erased_device_array_view_t* src,
+  cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(src != nullptr, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto const* s = V(src);
+    if (s->nbytes() > 0) {
+      B200_EXPECTS(h_dst != nullptr, CUGRAPH_INVALID_INPUT, "host destination is NULL");
+      CUDA_TRY(cudaMemcpyAsync(h_dst, s->data, s->nbytes(), cudaMemcpyDeviceToHost, h.stream));
+    }
+    sync(h);
+  });
+}
+
+cugraph_error_code_t cugraph_type_erased_device_array_view_copy(
+  const cugraph_resource_handle_t* handle,
+  cugraph_type_erased_device_array_view_t* dst,
+  const cugraph_type_erased_device_array_view_t* src,
+  cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(dst && src, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto* d       = reinterpret_cast<device_array_view_impl*>(dst);
+    auto const* s = V(src);
+    B200_EXPECTS(d->nbytes() == s->nbytes(), CUGRAPH_INVALID_INPUT,
+                 "source and destination arrays are different sizes");
+    if (s->nbytes() > 0)
+      CUDA_TRY(cudaMemcpyAsync(d->data, s->data, s->nbytes(), cudaMemcpyDeviceToDevice, h.stream));
+    sync(h);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// Internal vocabulary of the B200-native libcugraph_c: error plumbing, the resource handle,
+// type-erased arrays, stream-ordered device buffers.  Nothing here is exported.
+#pragma once
+
+#include <cugraph_c/b200_ext.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside, cugraph_error_code_t + heap message at the C boundary
+// (same contract as the reference's run_algorithm wrapper, cpp/src/c_api/utils.hpp:13-47).
+// ---------------------------------------------------------------------------------------------
+struct error_impl {
+  std::string message;
+};
+
+struct capi_exception : public std::runtime_error {
+  cugraph_error_code_t code;
+  capi_exception(cugraph_error_code_t c, std::string const& m) : std::runtime_error(m), code(c) {}
+};
+
+#define B200_EXPECTS(cond, code, msg)                                  \
+  do {                                                                 \
+    if (!(cond)) throw ::b200::capi_exception((code), std::string(msg)); \
+  } while (0)
+
+#define CUDA_TRY(call)                                                                           \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      cudaGetLastError();                                                                        \
+      throw ::b200::capi_exception(                                                              \
+        e__ == cudaErrorMemoryAllocation ? CUGRAPH_ALLOC_ERROR : CUGRAPH_UNKNOWN_ERROR,          \
+        std::string("CUDA error ") + cudaGetErrorName(e__) + " at " + __FILE__ + ":" +           \
+          std::to_string(__LINE__) + ": " + cudaGetErrorString(e__));                            \
+    }                                                                                            \
+  } while (0)
+
+template <typename F>
+cugraph_error_code_t guarded(cugraph_error_t** error, F&& f)
+{
+  if (error) *error = nullptr;
+  try {
+    f();
+    return CUGRAPH_SUCCESS;
+  } catch (capi_exception const& e) {
+    if (error) *error = reinterpret_cast<cugraph_error_t*>(new error_impl{e.what()});
+    return e.code;
+  } catch (std::bad_alloc const&) {
+    if (error) *error = reinterpret_cast<cugraph_error_t*>(new error_impl{"host allocation failed"});
+    return CUGRAPH_ALLOC_ERROR;
+  } catch (std::exception const& e) {
+    if (error) *error = reinterpret_cast<cugraph_error_t*>(new error_impl{e.what()});
+    return CUGRAPH_UNKNOWN_ERROR;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------------
+inline size_t dtype_size(cugraph_data_type_id_t t)
+{
+  switch (t) {
+    case INT8:
+    case UINT8:
+    case BOOL: return 1;
+    case INT16:
+    case UINT16: return 2;
+    case INT32:
+    case UINT32:
+    case FLOAT32: return 4;
+    case INT64:
+    case UINT64:
+    case FLOAT64:
+    case SIZE_T: return 8;
+    default: return 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// communicator (multi-GPU; defined in comm.cu)
+// ---------------------------------------------------------------------------------------------
+struct comm_impl;
+
+// ---------------------------------------------------------------------------------------------
+// resource handle: one device, one stream, the device's default stream-ordered pool.
+// ---------------------------------------------------------------------------------------------
+struct handle_impl {
+  int device{0};
+  cudaStream_t stream{nullptr};
+  cudaStream_t aux_stream{nullptr};  // overlap of independent kernels / collectives
+  cudaEvent_t ev_a{nullptr}, ev_b{nullptr};
+  int sm_count{148};
+  size_t l2_bytes{0};
+  comm_impl* comm{nullptr};  // not owned
+  int rank{0};
+  int size{1};
+  mutable size_t launches{0};
+  void* pinned{nullptr};  // 4 KiB pinned host scratch for scalar read-backs
+};
+
+inline handle_impl const& H(const cugraph_resource_handle_t* h)
+{
+  B200_EXPECTS(h != nullptr, CUGRAPH_INVALID_HANDLE, "resource handle is NULL");
+  return *reinterpret_cast<handle_impl const*>(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream-ordered owning device buffer (the rmm::device_buffer role)
+// ---------------------------------------------------------------------------------------------
+class dbuf {
+ public:
+  dbuf() = default;
+  dbuf(size_t bytes, cudaStream_t s) : bytes_(bytes), stream_(s)
+  {
+    if (bytes_ > 0) { CUDA_TRY(cudaMallocAsync(&p_, bytes_, s)); }
+  }
+  dbuf(dbuf const&)            = delete;
+  dbuf& operator=(dbuf const&) = delete;
+  dbuf(dbuf&& o) noexcept { swap(o); }
+  dbuf& operator=(dbuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      swap(o);
+    }
+    return *this;
+  }
+  ~dbuf() { release(); }
+  void release()
+  {
+    if (p_) cudaFreeAsync(p_, stream_);
+    p_     = nullptr;
+    bytes_ = 0;
+  }
+  void* detach()
+  {
+    void* p = p_;
+    p_      = nullptr;
+    bytes_  = 0;
+    return p;
+  }
+  void* data() const { return p_; }
+  template <typename T>
+  T* as() const
+  {
+    return reinterpret_cast<T*>(p_);
+  }
+  size_t bytes() const { return bytes_; }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  void swap(dbuf& o)
+  {
+    std::swap(p_, o.p_);
+    std::swap(bytes_, o.bytes_);
+    std::swap(stream_, o.stream_);
+  }
+  void* p_{nullptr};
+  size_t bytes_{0};
+  cudaStream_t stream_{nullptr};
+};
+
+template <typename T>
+inline dbuf make_dbuf(size_t n, cudaStream_t s)
+{
+  return dbuf(n * sizeof(T), s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// type-erased arrays (reference cpp/src/c_api/array.hpp:17-97)
+// ---------------------------------------------------------------------------------------------
+struct device_array_view_impl {
+  void* data{nullptr};
+  size_t size{0};
+  cugraph_data_type_id_t type{INT32};
+  size_t nbytes() const { return size * dtype_size(type); }
+};
+
+struct device_array_impl {
+  dbuf buf;
+  size_t size{0};
+  cugraph_data_type_id_t type{INT32};
+  device_array_view_impl* new_view() const { return new device_array_view_impl{buf.data(), size, type}; }
+};
+
+struct host_array_view_impl {
+  void* data{nullptr};
+  size_t size{0};
+  cugraph_data_type_id_t type{INT32};
+  size_t nbytes() const { return size * dtype_size(type); }
+};
+
+struct host_array_impl {
+  void* data{nullptr};
+  size_t size{0};
+  cugraph_data_type_id_t type{INT32};
+};
+
+inline device_array_view_impl const* V(const cugraph_type_erased_device_array_view_t* v)
+{
+  return reinterpret_cast<device_array_view_impl const*>(v);
+}
+
+inline cugraph_type_erased_device_array_t* wrap_array(dbuf&& b, size_t n, cugraph_data_type_id_t t)
+{
+  auto* a = new device_array_impl{std::move(b), n, t};
+  return reinterpret_cast<cugraph_type_erased_device_array_t*>(a);
+}
+
+// result objects (reference cpp/src/c_api/centrality_result.hpp:14-19, paths_result.hpp:12-16)
+struct centrality_result_impl {
+  device_array_impl* vertices{nullptr};
+  device_array_impl* values{nullptr};
+  size_t iterations{0};
+  bool converged{false};
+};
+
+struct paths_result_impl {
+  device_array_impl* vertices{nullptr};
+  device_array_impl* distances{nullptr};
+  device_array_impl* predecessors{nullptr};
+};
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+#define B200_LAUNCH(h, kernel, grid, block, smem, ...)                           \
+  do {                                                                           \
+    if ((grid) > 0) {                                                            \
+      kernel<<<(grid), (block), (smem), (h).stream>>>(__VA_ARGS__);              \
+      (h).launches++;                                                            \
+    }                                                                            \
+  } while (0)
+
+inline void check_last(const char* what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw capi_exception(CUGRAPH_UNKNOWN_ERROR,
+                         std::string("kernel launch failed (") + what + "): " + cudaGetErrorString(e));
+}
+
+inline void sync(handle_impl const& h) { CUDA_TRY(cudaStreamSynchronize(h.stream)); }
+
+}  // namespace b200

@@ -1,0 +1,113 @@
+// Graph data model on one B200: the graph_view_t / edge_partition_device_view_t role
+// (reference cpp/include/cugraph/graph_view.hpp:840-1122, edge_partition_device_view.cuh:912-1215),
+// laid out for the kernels in spmv.cu / traverse.cu.
+//
+// Three id spaces:
+//   external : whatever the caller passed (int32 or int64)
+//   rank     : dense 0..V-1 in ascending external-id order (or == external when renumber=false)
+//   internal : 0..V-1 in DESCENDING degree of the primary orientation's rows, ties by rank.
+// Kernels only see internal ids (always int32: V < 2^31).  The ordering *is* the degree binning:
+// rows with degree >= 32 form a prefix whose edges form a prefix of `indices`
+// (the role of the reference's segment offsets, graph_view.hpp:242-254 / renumber_edgelist_impl.cuh:740-828).
+#pragma once
+#include "common.cuh"
+
+#include <memory>
+
+namespace b200 {
+
+// degree thresholds that delimit the row bins (descending); bin k holds rows with
+// kSegThreshold[k] <= degree < kSegThreshold[k-1].
+constexpr int kNumSeg                = 7;
+constexpr int kSegThreshold[kNumSeg] = {32, 16, 8, 4, 2, 1, 0};
+
+// edges per warp / per CTA in the edge-balanced kernel for the degree>=32 prefix
+constexpr int kWarpChunk  = 1024;
+constexpr int kWarpsPerCta = 8;
+
+// One orientation: compressed rows over `n_rows` physical rows.
+// row_vertex == nullptr  -> physical row r is vertex r (rows are degree-descending by construction)
+// row_vertex != nullptr  -> physical row r is vertex row_vertex[r] (a lazily built transpose whose
+//                           rows were re-sorted by ITS degree so that the same kernels apply)
+struct csx_t {
+  int32_t n_rows{0};
+  int64_t nnz{0};
+  bool offs64{false};
+  dbuf offsets;     // (n_rows+1) x int32|int64
+  dbuf indices;     // nnz x int32, ascending within a row
+  dbuf weights;     // nnz x float|double, or empty
+  dbuf row_vertex;  // n_rows x int32, or empty
+  bool degree_sorted{true};  // rows in descending degree (binning valid)
+  int32_t seg[kNumSeg + 1]{};  // seg[k] = #rows with degree >= kSegThreshold[k]; seg[kNumSeg]=n_rows
+  int64_t nnz_hi{0};           // edges in rows with degree >= 32 (= offsets[seg[0]])
+  // per-warp-chunk metadata for the edge-balanced kernel over [0, nnz_hi)
+  int32_t n_chunks{0};
+  dbuf chunk_first_row;  // n_chunks+1 x int32 : row that contains edge c*kWarpChunk
+  int32_t n_split{0};
+  dbuf split_rows;  // n_split x int32 : rows that straddle a chunk boundary (each listed once)
+};
+
+struct graph_impl {
+  cugraph_data_type_id_t vertex_type{INT32};
+  cugraph_data_type_id_t edge_type{INT32};
+  cugraph_data_type_id_t weight_type{FLOAT32};
+  bool weighted{false};
+  bool is_symmetric{false};
+  bool is_multigraph{false};
+  bool store_transposed{false};
+  bool renumbered{true};
+  int32_t n_vertices{0};
+  int64_t n_edges{0};
+  int device{0};
+
+  // id maps
+  dbuf ext_of_int;    // V x vertex_type : external id of internal vertex i   (the "number_map")
+  dbuf sorted_ext;    // V x vertex_type : external ids ascending (renumber=true only)
+  dbuf int_of_rank;   // V x int32       : internal id of rank r
+  // renumber=false: reported order is external order; results are permuted through int_of_rank.
+
+  std::unique_ptr<csx_t> primary;    // orientation requested at creation (degree-sorted, identity rows)
+  std::unique_ptr<csx_t> pull_alt;   // lazily built CSC with re-sorted rows (PageRank on a CSR graph)
+  std::unique_ptr<csx_t> push_alt;   // lazily built CSR in vertex order (BFS/SSSP on a CSC graph)
+
+  // multi-GPU (mg.cu): this rank's blocks of the 2D partition
+  void* mg{nullptr};
+};
+
+inline graph_impl* G(cugraph_graph_t* g)
+{
+  B200_EXPECTS(g != nullptr, CUGRAPH_INVALID_INPUT, "graph is NULL");
+  return reinterpret_cast<graph_impl*>(g);
+}
+
+// Accessors that build the missing orientation on demand (graph_build.cu).
+csx_t const& pull_view(handle_impl const& h, graph_impl& g);  // rows = destinations, indices = sources
+csx_t const& push_view(handle_impl const& h, graph_impl& g);  // rows = sources, vertex-indexed offsets
+
+// external <-> internal id helpers (graph_build.cu)
+// out[i] = internal id of ext[i], or -1 if ext[i] is not a vertex.
+void ext_to_int(handle_impl const& h, graph_impl const& g, void const* ext, size_t n, int32_t* out);
+// in-place/out-of-place: ext_out[i] = external id of internal id in[i] (in[i] < 0 stays -1)
+void int_to_ext(handle_impl const& h, graph_impl const& g, int32_t const* in, size_t n, void* ext_out);
+// vertices array (external ids) in reported order
+dbuf reported_vertices(handle_impl const& h, graph_impl const& g);
+// permute a per-vertex result from internal order into reported order (no-op copy when renumbered)
+dbuf to_reported_order(handle_impl const& h, graph_impl const& g, void const* internal_vals, size_t elem_size);
+
+// (vertex, value) pairs with external ids -> dense internal-order vector, missing = fill
+template <typename T>
+dbuf collect_vertex_values(handle_impl const& h, graph_impl const& g,
+                           device_array_view_impl const* verts, device_array_view_impl const* vals,
+                           T fill);
+
+// ---- multi-GPU hooks (mg.cu) ----
+struct mg_pr_args {
+  double alpha;
+  double epsilon;
+  size_t max_iterations;
+};
+void attach_comm(handle_impl* h, void* comm);
+void free_mg_graph(graph_impl* g);
+void mg_pagerank(handle_impl const& h, graph_impl& g, mg_pr_args const& a, centrality_result_impl& res);
+
+}  // namespace b200

@@ -1,0 +1,110 @@
+"""pagerank / personalized_pagerank / bfs / sssp with the reference's Python signatures
+(python/pylibcugraph/pylibcugraph/{pagerank.pyx:49-59, personalized_pagerank.pyx:49-61,
+bfs.pyx:50-52, sssp.pyx:48-53})."""
+import ctypes as C
+
+from cugraph_b200 import _capi
+from cugraph_b200.pylibcugraph.exceptions import FailedToConvergeError
+from cugraph_b200.pylibcugraph.utils import View, assert_CAI_type, copy_to_torch
+
+INT32_MAX = 2**31 - 1
+
+
+def _centrality_result(handle, res):
+    L = _capi.lib()
+    verts = copy_to_torch(handle, L.cugraph_centrality_result_get_vertices(res))
+    vals = copy_to_torch(handle, L.cugraph_centrality_result_get_values(res))
+    conv = bool(L.cugraph_centrality_result_converged(res))
+    iters = int(L.cugraph_centrality_result_get_num_iterations(res))
+    L.cugraph_centrality_result_free(res)
+    return verts, vals, conv, iters
+
+
+def pagerank(resource_handle, graph, precomputed_vertex_out_weight_vertices, precomputed_vertex_out_weight_sums,
+             initial_guess_vertices, initial_guess_values, alpha, epsilon, max_iterations, do_expensive_check,
+             fail_on_nonconvergence=True):
+    """Returns (vertices, pageranks), or (vertices, pageranks, converged) when
+    fail_on_nonconvergence is False — pagerank.pyx:150-245."""
+    for a, nm in ((precomputed_vertex_out_weight_vertices, "precomputed_vertex_out_weight_vertices"),
+                  (precomputed_vertex_out_weight_sums, "precomputed_vertex_out_weight_sums"),
+                  (initial_guess_vertices, "initial_guess_vertices"), (initial_guess_values, "initial_guess_values")):
+        assert_CAI_type(a, nm, True)
+    views = [View(a) for a in (precomputed_vertex_out_weight_vertices, precomputed_vertex_out_weight_sums,
+                               initial_guess_vertices, initial_guess_values)]
+    res = C.c_void_p()
+    err = C.c_void_p()
+    code = _capi.lib().cugraph_pagerank_allow_nonconvergence(
+        resource_handle.ptr, graph.ptr, views[0].ptr, views[1].ptr, views[2].ptr, views[3].ptr,
+        float(alpha), float(epsilon), int(max_iterations), int(bool(do_expensive_check)), C.byref(res), C.byref(err))
+    for v in views:
+        v.free()
+    _capi.check(code, err, "cugraph_pagerank_allow_nonconvergence")
+    verts, vals, conv, _ = _centrality_result(resource_handle, res)
+    if fail_on_nonconvergence:
+        if not conv:
+            raise FailedToConvergeError
+        return (verts, vals)
+    return (verts, vals, conv)
+
+
+def personalized_pagerank(resource_handle, graph, precomputed_vertex_out_weight_vertices,
+                          precomputed_vertex_out_weight_sums, initial_guess_vertices, initial_guess_values,
+                          personalization_vertices, personalization_values, alpha, epsilon, max_iterations,
+                          do_expensive_check, fail_on_nonconvergence=True):
+    assert_CAI_type(personalization_vertices, "personalization_vertices", True)
+    assert_CAI_type(personalization_values, "personalization_values", True)
+    views = [View(a) for a in (precomputed_vertex_out_weight_vertices, precomputed_vertex_out_weight_sums,
+                               initial_guess_vertices, initial_guess_values, personalization_vertices,
+                               personalization_values)]
+    res = C.c_void_p()
+    err = C.c_void_p()
+    code = _capi.lib().cugraph_personalized_pagerank_allow_nonconvergence(
+        resource_handle.ptr, graph.ptr, *[v.ptr for v in views], float(alpha), float(epsilon),
+        int(max_iterations), int(bool(do_expensive_check)), C.byref(res), C.byref(err))
+    for v in views:
+        v.free()
+    _capi.check(code, err, "cugraph_personalized_pagerank_allow_nonconvergence")
+    verts, vals, conv, _ = _centrality_result(resource_handle, res)
+    if fail_on_nonconvergence:
+        if not conv:
+            raise FailedToConvergeError
+        return (verts, vals)
+    return (verts, vals, conv)
+
+
+def _paths_result(handle, res, want_pred=True):
+    L = _capi.lib()
+    verts = copy_to_torch(handle, L.cugraph_paths_result_get_vertices(res))
+    dist = copy_to_torch(handle, L.cugraph_paths_result_get_distances(res))
+    pred = copy_to_torch(handle, L.cugraph_paths_result_get_predecessors(res))
+    L.cugraph_paths_result_free(res)
+    return verts, dist, pred
+
+
+def bfs(handle, graph, sources, direction_optimizing, depth_limit, compute_predecessors, do_expensive_check):
+    """Returns (distances, predecessors, vertices) — bfs.pyx:140-200 (note the order)."""
+    assert_CAI_type(sources, "sources")
+    if depth_limit <= 0:
+        depth_limit = INT32_MAX - 1  # bfs.pyx:144-145
+    sv = View(sources)
+    res = C.c_void_p()
+    err = C.c_void_p()
+    code = _capi.lib().cugraph_bfs(handle.ptr, graph.ptr, sv.ptr, int(bool(direction_optimizing)), int(depth_limit),
+                                   int(bool(compute_predecessors)), int(bool(do_expensive_check)),
+                                   C.byref(res), C.byref(err))
+    sv.free()
+    _capi.check(code, err, "cugraph_bfs")
+    verts, dist, pred = _paths_result(handle, res)
+    return (dist, pred, verts)
+
+
+def sssp(resource_handle, graph, source, cutoff, compute_predecessors, do_expensive_check):
+    """Returns (vertices, distances, predecessors) — sssp.pyx:120-170."""
+    res = C.c_void_p()
+    err = C.c_void_p()
+    code = _capi.lib().cugraph_sssp(resource_handle.ptr, graph.ptr, int(source), float(cutoff),
+                                    int(bool(compute_predecessors)), int(bool(do_expensive_check)),
+                                    C.byref(res), C.byref(err))
+    _capi.check(code, err, "cugraph_sssp")
+    verts, dist, pred = _paths_result(resource_handle, res)
+    return (verts, dist, pred)

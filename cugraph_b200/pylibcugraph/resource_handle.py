@@ -1,0 +1,34 @@
+"""ResourceHandle (reference python/pylibcugraph/pylibcugraph/resource_handle.pyx)."""
+from cugraph_b200 import _capi
+
+
+class ResourceHandle:
+    """Owns a cugraph_resource_handle_t.  `handle_ptr` None -> single-GPU handle on the current
+    device; otherwise the integer address of a cugraph_b200_comm_t (see comms.py)."""
+
+    def __init__(self, handle_ptr=None):
+        self._lib = _capi.lib()
+        self._ptr = self._lib.cugraph_create_resource_handle(handle_ptr)
+        if not self._ptr:
+            raise RuntimeError("cugraph_create_resource_handle failed (is a CUDA device available?)")
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    def get_rank(self):
+        return self._lib.cugraph_resource_handle_get_rank(self._ptr)
+
+    def get_comm_size(self):
+        return self._lib.cugraph_resource_handle_get_comm_size(self._ptr)
+
+    def launch_count(self):
+        return int(self._lib.cugraph_b200_handle_launch_count(self._ptr))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None):
+                self._lib.cugraph_free_resource_handle(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass

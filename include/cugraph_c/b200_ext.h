@@ -1,0 +1,47 @@
+/*
+ * Extensions that have no counterpart in the reference ABI (prefixed cugraph_b200_).
+ *
+ *  - comm bootstrap: the reference receives NCCL communicators inside a raft::handle_t built by
+ *    raft-dask / MPI (python/pylibcugraph/pylibcugraph/comms/comms_wrapper.pyx:10-32,
+ *    cpp/tests/utilities/mg_utilities.cpp:37-55).  Here one process per GPU calls
+ *    cugraph_b200_comm_create() with an ncclUniqueId obtained from rank 0
+ *    (cugraph_b200_get_nccl_unique_id) and distributed by the launcher (torch.distributed).
+ *  - profiling hooks used by bench.py to time the dominant kernel on the handle's stream.
+ */
+#pragma once
+#include <cugraph_c/algorithms.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { int32_t align_; } cugraph_b200_comm_t;
+
+#define CUGRAPH_B200_NCCL_UNIQUE_ID_BYTES 128
+
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_get_nccl_unique_id(byte_t* id_out /* 128 bytes */,
+                                                                    cugraph_error_t** error);
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_comm_create(const byte_t* nccl_unique_id, int rank,
+                                                             int size, cugraph_b200_comm_t** comm,
+                                                             cugraph_error_t** error);
+CUGRAPH_EXPORT void cugraph_b200_comm_free(cugraph_b200_comm_t* comm);
+
+/* Library version string and the CUDA stream of a handle (as an integer, for event timing). */
+CUGRAPH_EXPORT const char* cugraph_b200_version(void);
+CUGRAPH_EXPORT void* cugraph_b200_handle_stream(const cugraph_resource_handle_t* handle);
+
+/* Number of kernels this library launched through the handle since it was created. */
+CUGRAPH_EXPORT size_t cugraph_b200_handle_launch_count(const cugraph_resource_handle_t* handle);
+
+/*
+ * Benchmark hook: run `iterations` pull-SpMV sweeps (the PageRank inner kernel set, no vertex pass)
+ * on the graph's pull orientation and return the average time of ONE sweep in milliseconds,
+ * measured with CUDA events on the handle's stream.  x is refreshed from a fixed vector; results
+ * are written to an internal buffer.  Used for roofline.achieved in bench.py.
+ */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_time_pull_spmv(
+  const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, size_t iterations,
+  double* ms_per_sweep, double* algorithmic_bytes_per_sweep, cugraph_error_t** error);
+
+#ifdef __cplusplus
+}
+#endif

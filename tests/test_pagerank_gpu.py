@@ -1,0 +1,184 @@
+"""PageRank parity: CUDA path (through the C-ABI / pylibcugraph mirror) vs the CPU oracle and the
+reference's golden vectors.  Tolerance: 1e-6 relative per vertex against the fp64 oracle at equal
+iteration count (north-star bar; the reference's own bar is 1e-3, pagerank_test.cpp:328-334)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle.rmat import rmat_edgelist
+from tests.gpu_util import by_vertex, make_graph
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def _run(h, g, alpha, eps, iters, **kw):
+    from cugraph_b200 import pylibcugraph as plc
+    return plc.pagerank(h, g, None, None, None, None, alpha, eps, iters, False, fail_on_nonconvergence=False, **kw)
+
+
+@pytest.mark.parametrize("store_transposed", [True, False])
+@pytest.mark.parametrize("renumber", [True, False])
+@pytest.mark.parametrize("case", ["pagerank_6", "pagerank_6_nonconverged", "pagerank_4"])
+def test_c_api_golden(golden, case, store_transposed, renumber):
+    g6 = golden["c_api"][case]
+    h, g = make_graph(g6["src"], g6["dst"], g6["weights"], store_transposed=store_transposed, renumber=renumber)
+    verts, vals, conv = _run(h, g, g6["alpha"], g6["epsilon"], g6["max_iterations"])
+    got = by_vertex(verts, vals, g6["num_vertices"])
+    assert vals.dtype.is_floating_point and vals.element_size() == 4
+    np.testing.assert_allclose(got, g6["values"], rtol=g6["rel_tol"])
+    assert conv == ("nonconverged" not in case)
+    ref, it, _ = oracle.pagerank(g6["src"], g6["dst"], g6["num_vertices"], np.float32(g6["weights"]),
+                                 alpha=g6["alpha"], epsilon=g6["epsilon"], max_iterations=g6["max_iterations"])
+    np.testing.assert_allclose(got, ref, rtol=5e-6)
+
+
+@pytest.mark.parametrize("case", ["personalized_pagerank_4", "personalized_pagerank_4_nonconverged"])
+def test_personalized_golden(golden, case):
+    import torch
+    from cugraph_b200 import pylibcugraph as plc
+    c = golden["c_api"][case]
+    h, g = make_graph(c["src"], c["dst"], c["weights"], store_transposed=False, renumber=False)
+    pv = torch.tensor(c["personalization_vertices"], dtype=torch.int32).cuda()
+    pw = torch.tensor(c["personalization_values"], dtype=torch.float32).cuda()
+    verts, vals, conv = plc.personalized_pagerank(h, g, None, None, None, None, pv, pw, c["alpha"], c["epsilon"],
+                                                  c["max_iterations"], False, fail_on_nonconvergence=False)
+    np.testing.assert_allclose(by_vertex(verts, vals, 4), c["values"], rtol=c["rel_tol"])
+    assert conv == ("nonconverged" not in case)
+
+
+@pytest.mark.parametrize("name", ["karate.csv", "dolphins.csv", "Simple_1", "Simple_2"])
+def test_pylibcugraph_golden(golden, name):
+    """test_pagerank.py:165-208 of the reference, same call, same tolerance."""
+    from cugraph_b200 import pylibcugraph as plc
+    d = golden["pylibcugraph"][name]
+    p = d["pagerank"]
+    h, g = make_graph(d["src"], d["dst"], d["weights"], store_transposed=True, renumber=False)
+    verts, vals = plc.pagerank(h, g, None, None, None, None, p["alpha"], p["epsilon"], p["max_iterations"], False)
+    assert str(verts.dtype) == "torch.int32" and str(vals.dtype) == "torch.float32"
+    av = verts.tolist()
+    ap = vals.tolist()
+    for i in range(len(p["vertices"])):
+        assert ap[i] == pytest.approx(p["values"][av[i]], 1e-4)
+
+
+def test_nonconvergence_raises(golden):
+    from cugraph_b200 import pylibcugraph as plc
+    d = golden["pylibcugraph"]["karate.csv"]
+    h, g = make_graph(d["src"], d["dst"], d["weights"], store_transposed=True)
+    with pytest.raises(plc.FailedToConvergeError):
+        plc.pagerank(h, g, None, None, None, None, 0.85, 1e-12, 2, False)
+
+
+def _random_graph(rng, V, E, weighted):
+    s = rng.integers(0, V, E).astype(np.int32)
+    d = rng.integers(0, V, E).astype(np.int32)
+    w = (rng.random(E).astype(np.float32) + 0.1) if weighted else None
+    return s, d, w
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("store_transposed", [True, False])
+@pytest.mark.parametrize("V,E", [(1, 1), (17, 40), (1000, 20000), (5000, 400000)])
+def test_random_vs_oracle(V, E, weighted, store_transposed):
+    rng = np.random.default_rng(V * 7 + E)
+    s, d, w = _random_graph(rng, V, E, weighted)
+    verts_all = np.arange(V, dtype=np.int32)
+    h, g = make_graph(s, d, w, store_transposed=store_transposed, vertices=verts_all)
+    verts, vals, conv = _run(h, g, 0.85, 0.0, 30)
+    ref, it, _ = oracle.pagerank(s, d, V, w, alpha=0.85, epsilon=0.0, max_iterations=30)
+    assert it == 30 and not conv
+    np.testing.assert_allclose(by_vertex(verts, vals, V), ref, rtol=REL, atol=1e-12)
+
+
+def test_int64_ids_and_double_weights():
+    rng = np.random.default_rng(5)
+    V, E = 300, 5000
+    ids = rng.choice(np.arange(10**12, 10**12 + 10**6), size=V, replace=False).astype(np.int64)
+    s = rng.integers(0, V, E)
+    d = rng.integers(0, V, E)
+    w = rng.random(E) + 0.5
+    h, g = make_graph(ids[s], ids[d], w, store_transposed=True, vertex_dtype=np.int64, weight_dtype=np.float64)
+    verts, vals, conv = _run(h, g, 0.85, 1e-10, 200)
+    assert str(verts.dtype) == "torch.int64" and str(vals.dtype) == "torch.float64"
+    present = np.unique(np.concatenate([s, d]))
+    remap = -np.ones(V, dtype=np.int64)
+    remap[present] = np.arange(present.size)
+    ref, it, rc = oracle.pagerank(remap[s], remap[d], present.size, w, alpha=0.85, epsilon=1e-10, max_iterations=200)
+    got = dict(zip(verts.tolist(), vals.tolist()))
+    for k, v in enumerate(present):
+        assert got[int(ids[v])] == pytest.approx(ref[k], rel=1e-9)
+    assert conv == rc
+
+
+def test_converged_iteration_count_matches_oracle():
+    rng = np.random.default_rng(11)
+    s, d, w = _random_graph(rng, 2000, 30000, False)
+    h, g = make_graph(s, d, None, store_transposed=True, vertices=np.arange(2000, dtype=np.int32))
+    from cugraph_b200 import _capi
+    import ctypes as C
+    res, err = C.c_void_p(), C.c_void_p()
+    code = _capi.lib().cugraph_pagerank_allow_nonconvergence(h.ptr, g.ptr, None, None, None, None, 0.85, 1e-7, 500, 0,
+                                                             C.byref(res), C.byref(err))
+    assert code == 0
+    iters = _capi.lib().cugraph_centrality_result_get_num_iterations(res)
+    _capi.lib().cugraph_centrality_result_free(res)
+    _, it, conv = oracle.pagerank(s, d, 2000, None, alpha=0.85, epsilon=1e-7, max_iterations=500)
+    assert conv and abs(int(iters) - it) <= 1  # fp32 state vs fp64 oracle may cross epsilon one step apart
+
+
+def test_initial_guess_and_precomputed_out_weights():
+    import torch
+    from cugraph_b200 import pylibcugraph as plc
+    rng = np.random.default_rng(3)
+    V, E = 500, 6000
+    s, d, w = _random_graph(rng, V, E, True)
+    h, g = make_graph(s, d, w, store_transposed=True, vertices=np.arange(V, dtype=np.int32))
+    guess = rng.random(V).astype(np.float32)
+    guess /= guess.sum()
+    outw = np.zeros(V, dtype=np.float64)
+    np.add.at(outw, s, w.astype(np.float64))
+    vt = torch.arange(V, dtype=torch.int32).cuda()
+    verts, vals, conv = plc.pagerank(h, g, vt, torch.as_tensor(outw.astype(np.float32)).cuda(), vt,
+                                     torch.as_tensor(guess).cuda(), 0.85, 0.0, 5, False, fail_on_nonconvergence=False)
+    ref, _, _ = oracle.pagerank(s, d, V, w, alpha=0.85, epsilon=0.0, max_iterations=5, initial_guess=guess,
+                                precomputed_out_w=outw.astype(np.float32))
+    np.testing.assert_allclose(by_vertex(verts, vals, V), ref, rtol=2e-6)
+
+
+@pytest.mark.parametrize("scale,weighted", [(14, False), (16, False), (16, True)])
+def test_rmat_vs_oracle(scale, weighted):
+    """RMAT keeps multi-edges and self-loops (reference pagerank_test.cpp:146-162)."""
+    s, d = rmat_edgelist(scale, 16 << scale, seed=scale)
+    w = None
+    if weighted:
+        w = np.random.default_rng(2).random(s.shape[0]).astype(np.float32)
+    V = 1 << scale
+    h, g = make_graph(s, d, w, store_transposed=True, vertices=np.arange(V, dtype=np.int32))
+    verts, vals, conv = _run(h, g, 0.85, 0.0, 50)
+    ref, _, _ = oracle.pagerank(s, d, V, w, alpha=0.85, epsilon=0.0, max_iterations=50)
+    got = by_vertex(verts, vals, V)
+    np.testing.assert_allclose(got, ref, rtol=REL, atol=1e-12)
+    assert abs(got.sum() - 1.0) < 1e-4
+
+
+def test_error_paths():
+    import torch
+    from cugraph_b200 import _capi
+    from cugraph_b200 import pylibcugraph as plc
+    h = plc.ResourceHandle()
+    s = torch.tensor([0, 1], dtype=torch.int32).cuda()
+    d = torch.tensor([1, 2, 3], dtype=torch.int32).cuda()
+    with pytest.raises(_capi.CugraphError) as e:
+        plc.SGGraph(h, plc.GraphProperties(), s, d)
+    assert e.value.code == _capi.INVALID_INPUT
+    d2 = torch.tensor([1, 2], dtype=torch.int32).cuda()
+    w4 = torch.ones(4, dtype=torch.float32).cuda()
+    with pytest.raises(_capi.CugraphError):
+        plc.SGGraph(h, plc.GraphProperties(), s, d2, weight_array=w4)
+    g = plc.SGGraph(h, plc.GraphProperties(), s, d2, store_transposed=True)
+    with pytest.raises(_capi.CugraphError):
+        plc.pagerank(h, g, None, None, None, None, 1.5, 1e-5, 10, False)
+    with pytest.raises(TypeError):
+        plc.SGGraph(h, plc.GraphProperties(), [0, 1], d2)
