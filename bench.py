@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract for the PageRank hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): PageRank on RMAT scale-24 edge-factor-16 (Graph500 a,b,c,
+multi-edges and self-loops kept, scrambled ids, unweighted, int32 ids / float32 scores), alpha 0.85,
+epsilon 0 (never converges), 100 iterations, graph stored transposed.  N>1: scale-27, 2D edge partition.
+
+A STEP is one call of `cugraph_pagerank_allow_nonconvergence` (100 iterations) through the C-ABI.
+  value  = MTEPS = E * iterations * steps / time, graph already resident in HBM (graph creation is
+           staging, excluded exactly as the reference's own harness does, pagerank_test.cpp:221-236)
+  e2e    = the same metric for the whole reference-facing call sequence with HOST buffers inside the
+           timed region: pinned edge list -> H2D -> cugraph_graph_create_with_times_sg -> pagerank ->
+           D2H of (vertices, scores)
+  roofline = the pull-SpMV sweep (kernels k_spmv_hi + k_spmv_hi_finish + k_spmv_low = one
+           per_v_transform_reduce_incoming_e) timed alone with CUDA events on the handle's stream;
+           algorithmic bytes per sweep = 4E + 4(V+1) + 4V + 4V
+  cpu_baseline = oracle port (oracle/oracle.c, OpenMP) on a bounded sample, host cores stated
+Synthetic data, random seed 0.  Inputs (1.2 GB per sweep) exceed the 126 MB L2, so no explicit L2 flush
+is needed between timed iterations (stated in config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALPHA, ITERS = 0.85, 100
+METRIC = "MTEPS (million traversed edges/sec) PageRank RMAT-24 ef-16, 100 iterations"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _cpu_baseline(sample_scale=21, target_s=12.0):
+    """Oracle port on the host cores: float32 pull-SpMV sweeps over a smaller RMAT CSC."""
+    import numpy as np
+    import oracle
+    from oracle.rmat import rmat_edgelist
+    src, dst = rmat_edgelist(sample_scale, 16 << sample_scale, seed=0)
+    V = 1 << sample_scale
+    csc = oracle.coo_to_csx(dst, src, V)
+    x = np.full(V, 1.0 / V, dtype=np.float32)
+    E = src.shape[0]
+    t0 = time.perf_counter()
+    oracle.spmv_f32(csc, x, ALPHA, 0.0)
+    one = time.perf_counter() - t0
+    n = max(1, min(50, int(target_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        x = oracle.spmv_f32(csc, x, ALPHA, 0.15 / V)
+    dt = time.perf_counter() - t0
+    return {"value": E * n / dt / 1e6, "unit": "MTEPS", "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"{n} float32 pull-SpMV sweeps (oracle_spmv_f32, OpenMP) over RMAT scale-{sample_scale} ef-16 CSC"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port
+    (libcugraph itself is not buildable here).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    import oracle
+    from oracle.rmat import rmat_edgelist
+    scale = 20
+    src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
+    V, E = 1 << scale, src.shape[0]
+    csc = oracle.coo_to_csx(dst, src, V)
+
+    def step():
+        oracle.pagerank(src, dst, V, None, alpha=ALPHA, epsilon=0.0, max_iterations=ITERS, csc=csc)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = E * ITERS * args.steps / dt / 1e6
+    sample = f"PageRank {ITERS} iterations on RMAT scale-{scale} ef-16 per step (oracle_pagerank, fp64, OpenMP)"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MTEPS", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "pagerank_rmat24_ef16_100it", "sample_scale": scale},
+           "cpu_baseline": {"value": val, "unit": "MTEPS", "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "MTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_single(args):
+    import torch
+    from cugraph_b200 import _capi
+    from cugraph_b200 import pylibcugraph as plc
+    from cugraph_b200.generators import rmat_edgelist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(0)
+    scale = args.scale
+    L = _capi.lib()
+    src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
+    E = src.numel()
+    h = plc.ResourceHandle()
+    props = plc.GraphProperties(is_symmetric=False, is_multigraph=True)
+    G = plc.SGGraph(h, props, src, dst, store_transposed=True, renumber=True)
+    # pinned host copy of the edge list for the e2e arm
+    h_src = torch.empty(E, dtype=torch.int32).pin_memory()
+    h_dst = torch.empty(E, dtype=torch.int32).pin_memory()
+    h_src.copy_(src)
+    h_dst.copy_(dst)
+    del src, dst
+
+    def step():
+        return plc.pagerank(h, G, None, None, None, None, ALPHA, 0.0, ITERS, False, fail_on_nonconvergence=False)
+
+    for _ in range(args.warmup):
+        v, p, _ = step()
+    nv = v.numel()
+    sampler = ClockSampler(0)
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()  # synchronous on return (the C-ABI syncs the handle's stream)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = h.launch_count() - l0
+    clocks = sampler.stop()
+    ms_step = wall / args.steps * 1e3
+    value = E * ITERS * args.steps / wall / 1e6
+
+    # roofline: the pull sweep alone, CUDA events on the handle's stream inside the library
+    ms, by, err = C.c_double(), C.c_double(), C.c_void_p()
+    code = L.cugraph_b200_time_pull_spmv(h.ptr, G.ptr, 50, C.byref(ms), C.byref(by), C.byref(err))
+    _capi.check(code, err, "cugraph_b200_time_pull_spmv")
+    peak, peak_src = _peaks()
+    achieved = by.value / (ms.value * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_sweep")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "pull sweep: k_spmv_hi+k_spmv_hi_finish+k_spmv_low",
+                "ms_per_sweep": ms.value, "algorithmic_bytes_per_sweep": by.value,
+                "sweep_mteps": E / (ms.value * 1e-3) / 1e6}
+
+    # e2e: host edge list -> H2D -> graph create -> pagerank -> D2H
+    del G
+    torch.cuda.empty_cache()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        s = h_src.cuda(non_blocking=True)
+        d = h_dst.cuda(non_blocking=True)
+        g = plc.SGGraph(h, props, s, d, store_transposed=True, renumber=True)
+        vv, pp, _ = plc.pagerank(h, g, None, None, None, None, ALPHA, 0.0, ITERS, False, fail_on_nonconvergence=False)
+        return vv.cpu(), pp.cpu()
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    e2e = {"value": E * ITERS * e2e_steps / e2e_wall / 1e6, "unit": "MTEPS", "h2d_bytes_per_step": 2 * E * 4,
+           "d2h_bytes_per_step": nv * 8, "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
+           "includes": "pinned H2D of edge list, graph staging, 100 iterations, D2H of vertices+scores"}
+
+    cpu = _cpu_baseline()
+    out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": f"pagerank_rmat{scale}_ef16_100it", "scale": scale, "edge_factor": 16,
+                      "num_vertices": nv, "num_edges": E, "alpha": ALPHA, "iterations": ITERS, "vertex_type": "int32",
+                      "l2": "inputs (1.2 GB/sweep) exceed the 126 MB L2; no explicit flush"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(out), flush=True)
+
+
+def run_multi(args):
+    from cugraph_b200.mg_bench import run_mg_pagerank
+    run_mg_pagerank(args, METRIC, ALPHA, ITERS, ClockSampler, _peaks)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scale", type=int, default=None, help="override RMAT scale (development only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        if args.scale is None:
+            args.scale = 27
+        return run_multi(args)
+    if args.scale is None:
+        args.scale = 24
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,34 @@
 #include "graph.cuh"
 
 #include <cstdlib>
+#include <mutex>
+#include <unordered_set>
+
+namespace b200 {
+namespace {
+std::mutex g_stream_mutex;
+std::unordered_set<cudaStream_t>& live_streams()
+{
+  static auto* s = new std::unordered_set<cudaStream_t>();  // leaked on purpose: used during exit
+  return *s;
+}
+}  // namespace
+bool stream_is_live(cudaStream_t s)
+{
+  std::lock_guard<std::mutex> lk(g_stream_mutex);
+  return live_streams().count(s) != 0;
+}
+void register_stream(cudaStream_t s)
+{
+  std::lock_guard<std::mutex> lk(g_stream_mutex);
+  live_streams().insert(s);
+}
+void unregister_stream(cudaStream_t s)
+{
+  std::lock_guard<std::mutex> lk(g_stream_mutex);
+  live_streams().erase(s);
+}
+}  // namespace b200
 
 using namespace b200;
 
@@ -29,6 +57,8 @@ cugraph_resource_handle_t* cugraph_create_resource_handle(void* raft_handle)
     CUDA_TRY(cudaGetDevice(&h->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    register_stream(h->stream);
+    register_stream(h->aux_stream);
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     cudaDeviceProp prop{};
@@ -67,6 +97,8 @@ void cugraph_free_resource_handle(cugraph_resource_handle_t* handle)
   auto* h = reinterpret_cast<handle_impl*>(handle);
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->aux_stream);
+  unregister_stream(h->stream);
+  unregister_stream(h->aux_stream);
   cudaEventDestroy(h->ev_a);
   cudaEventDestroy(h->ev_b);
   cudaStreamDestroy(h->stream);

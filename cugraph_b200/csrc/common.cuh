@@ -113,6 +113,12 @@ inline handle_impl const& H(const cugraph_resource_handle_t* h)
   return *reinterpret_cast<handle_impl const*>(h);
 }
 
+// streams of live handles: buffers that outlive their handle (graphs, results) are freed
+// synchronously instead of on a destroyed stream (capi_basic.cu)
+bool stream_is_live(cudaStream_t s);
+void register_stream(cudaStream_t s);
+void unregister_stream(cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // stream-ordered owning device buffer (the rmm::device_buffer role)
 // ---------------------------------------------------------------------------------------------
@@ -137,7 +143,10 @@ class dbuf {
   ~dbuf() { release(); }
   void release()
   {
-    if (p_) cudaFreeAsync(p_, stream_);
+    if (p_) {
+      if (stream_is_live(stream_)) cudaFreeAsync(p_, stream_);
+      else cudaFree(p_);
+    }
     p_     = nullptr;
     bytes_ = 0;
   }

@@ -1,23 +1,725 @@
-// BFS / SSSP (placeholder entry points; the frontier engine lands here).
+// Frontier engine + BFS + SSSP on one B200, and their C-ABI entry points.
+// Replaces: transform_reduce_if_v_frontier_outgoing_e_by_dst / extract_transform_if_v_frontier_e
+// (cpp/include/cugraph/prims/transform_reduce_if_v_frontier_outgoing_e_by_dst.cuh:604-1128,
+//  detail/extract_transform_if_v_frontier_e.cuh:127-518), the BFS driver
+// (cpp/src/traversal/bfs_impl.cuh:133-869), the SSSP driver (sssp_impl.cuh:169-566) and
+// cpp/src/c_api/{bfs,sssp}.cpp.
+//
+// Design differences from the reference (same results, see traversal_algorithms.h):
+//  * the advance writes straight into per-vertex slots guarded by a visited bitmap (BFS) or an
+//    atomicMin on the distance word (SSSP); there is no emit-buffer + per-level radix sort/unique
+//    (transform_reduce_if_v_frontier_outgoing_e_by_dst.cuh:225-600).
+//  * load balance: a CTA scans the degrees of 256 frontier vertices and strides over the summed
+//    edge range (owner found by binary search in shared memory); vertices above kLargeDegree go to
+//    a second queue that the whole grid expands edge-parallel.
+//  * bottom-up BFS steps process 32 consecutive vertices per warp: one visited-word load, early
+//    exit on the first parent in the frontier bitmap (neighbours are sorted by internal id, i.e.
+//    hubs first), the next-frontier word is assembled with a ballot — no atomics.
 #include "graph.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <vector>
+
+namespace b200 {
+namespace {
+
+constexpr int kBlock       = 256;
+constexpr int kLargeDegree = 8192;
+
+inline int grid_for(int64_t n) { return (int)std::min<int64_t>(std::max<int64_t>((n + kBlock - 1) / kBlock, 1), 1 << 22); }
+
+struct frontier_counters_t {
+  int n_small;              // entries appended to the next small-degree queue
+  int n_large;              // entries appended to the next large-degree queue
+  int n_far;                // SSSP: entries appended to the far pile
+  int n_conv;               // bitmap -> queue conversion cursor
+  unsigned long long m_f;   // sum of degrees of the vertices appended (direction-optimising heuristic)
+};
+
+// ------------------------------------------------------------------------------------------
+// warp-aggregated append: the active lanes of a diverged warp claim consecutive queue slots
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_append(int* counter)
+{
+  unsigned mask = __activemask();
+  int leader    = __ffs(mask) - 1;
+  int lane      = threadIdx.x & 31;
+  int base      = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void warp_add_u64(unsigned long long* target, unsigned v)
+{
+  unsigned mask = __activemask();
+  unsigned sum  = __reduce_add_sync(mask, v);
+  if ((threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(target, (unsigned long long)sum);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic load-balanced advance over a queue of frontier vertices
+// Op: __device__ void edge(int src, long long e, int nbr)
+// ------------------------------------------------------------------------------------------
+template <typename O, typename Op, bool SKIP_LARGE>
+__global__ void __launch_bounds__(kBlock)
+k_advance(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ frontier,
+          int n_frontier, Op op)
+{
+  __shared__ int s_scan[kBlock + 1];
+  __shared__ long long s_beg[kBlock];
+  __shared__ int s_src[kBlock];
+  __shared__ int s_warp[kBlock / 32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  for (int base = blockIdx.x * kBlock; base < n_frontier; base += gridDim.x * kBlock) {
+    int v = -1, deg = 0;
+    long long beg = 0;
+    if (base + t < n_frontier) {
+      v   = frontier[base + t];
+      beg = (long long)off[v];
+      deg = (int)((long long)off[v + 1] - beg);
+      if (SKIP_LARGE && deg >= kLargeDegree) deg = 0;  // such vertices sit in the large queue
+    }
+    // block exclusive scan of deg
+    int incl = deg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = (lane < kBlock / 32) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < kBlock / 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      if (lane < kBlock / 32) s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int warp_off = wid > 0 ? s_warp[wid - 1] : 0;
+    s_scan[t]    = warp_off + incl - deg;
+    s_beg[t]     = beg;
+    s_src[t]     = v;
+    if (t == kBlock - 1) s_scan[kBlock] = warp_off + incl;
+    __syncthreads();
+    const int total = s_scan[kBlock];
+    for (int i = t; i < total; i += kBlock) {
+      int lo = 0, hi = kBlock;  // last k with s_scan[k] <= i
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (s_scan[mid] <= i) lo = mid; else hi = mid;
+      }
+      long long e = s_beg[lo] + (i - s_scan[lo]);
+      op.edge(s_src[lo], e, idx[e]);
+    }
+    __syncthreads();
+  }
+}
+
+// hubs: every vertex of the large queue is expanded edge-parallel by the whole grid
+template <typename O, typename Op>
+__global__ void __launch_bounds__(kBlock)
+k_advance_large(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ frontier,
+                int n_frontier, Op op)
+{
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nt  = (long long)gridDim.x * blockDim.x;
+  for (int j = 0; j < n_frontier; ++j) {
+    int v         = frontier[j];
+    long long beg = (long long)off[v], end = (long long)off[v + 1];
+    for (long long e = beg + tid; e < end; e += nt) op.edge(v, e, idx[e]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BFS
+// ------------------------------------------------------------------------------------------
+// append v to the small or the large queue according to its degree; returns the degree
+template <typename O>
+__device__ __forceinline__ unsigned enqueue_by_degree(O const* off, int v, int32_t* q_small, int32_t* q_large,
+                                                      frontier_counters_t* cnt)
+{
+  const unsigned d = (unsigned)((long long)off[v + 1] - (long long)off[v]);
+  if (d >= (unsigned)kLargeDegree) q_large[warp_append(&cnt->n_large)] = v;
+  else q_small[warp_append(&cnt->n_small)] = v;
+  return d;
+}
+
+template <typename O>
+struct bfs_topdown_op {
+  O const* off;
+  uint32_t* visited;
+  int32_t* dist;
+  int32_t* pred;  // may be null
+  int32_t* next_q;
+  int32_t* next_q_large;
+  frontier_counters_t* cnt;
+  int level;
+  __device__ __forceinline__ void edge(int src, long long, int nbr) const
+  {
+    const uint32_t bit = 1u << (nbr & 31);
+    if (visited[nbr >> 5] & bit) return;
+    const uint32_t old = atomicOr(visited + (nbr >> 5), bit);
+    if (old & bit) return;
+    dist[nbr] = level + 1;
+    if (pred) pred[nbr] = src;
+    const unsigned d = enqueue_by_degree(off, nbr, next_q, next_q_large, cnt);
+    warp_add_u64(&cnt->m_f, d);
+  }
+};
+
+// 32 consecutive vertices per warp; parents looked up in the frontier bitmap
+template <typename O>
+__global__ void __launch_bounds__(kBlock)
+k_bfs_bottomup(O const* __restrict__ off, int32_t const* __restrict__ idx, uint32_t const* __restrict__ visited,
+               uint32_t const* __restrict__ frontier_bm, uint32_t* __restrict__ next_bm, int32_t* __restrict__ dist,
+               int32_t* __restrict__ pred, int level, int n_vertices, frontier_counters_t* cnt)
+{
+  const int lane     = threadIdx.x & 31;
+  const int n_words  = (n_vertices + 31) >> 5;
+  unsigned my_count  = 0;
+  unsigned my_deg    = 0;
+  for (int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); w < n_words;
+       w += (int)(((long long)gridDim.x * blockDim.x) >> 5)) {
+    const uint32_t vis = visited[w];
+    const int v        = (w << 5) + lane;
+    bool found         = false;
+    if (v < n_vertices && !((vis >> lane) & 1u)) {
+      const long long beg = (long long)off[v], end = (long long)off[v + 1];
+      for (long long e = beg; e < end; ++e) {
+        const int u = idx[e];
+        if ((frontier_bm[u >> 5] >> (u & 31)) & 1u) {
+          dist[v] = level + 1;
+          if (pred) pred[v] = u;
+          found = true;
+          my_count += 1;
+          my_deg += (unsigned)(end - beg);
+          break;
+        }
+      }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, found);
+    if (lane == 0) next_bm[w] = word;
+  }
+  my_count = __reduce_add_sync(0xffffffffu, my_count);
+  my_deg   = __reduce_add_sync(0xffffffffu, my_deg);
+  if (lane == 0 && my_count) {
+    atomicAdd(&cnt->n_small, (int)my_count);
+    atomicAdd(&cnt->m_f, (unsigned long long)my_deg);
+  }
+}
+
+__global__ void k_or_words(uint32_t* __restrict__ a, uint32_t const* __restrict__ b, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] |= b[i];
+}
+
+__global__ void k_queue_to_bitmap(int32_t const* __restrict__ q, int n, uint32_t* __restrict__ bm)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicOr(bm + (q[i] >> 5), 1u << (q[i] & 31));
+}
+
+__global__ void k_bitmap_to_queue(uint32_t const* __restrict__ bm, int n_words, int32_t* __restrict__ q, int* counter)
+{
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t word = (w < n_words) ? bm[w] : 0u;
+  int c         = __popc(word);
+  // warp-level exclusive scan of counts, one atomic per warp
+  int lane = threadIdx.x & 31;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base  = 0;
+  if (lane == 31 && total) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xffffffffu, base, 31) + incl - c;
+  while (word) {
+    int b     = __ffs(word) - 1;
+    q[base++] = (w << 5) + b;
+    word &= word - 1;
+  }
+}
+
+template <typename T>
+__global__ void k_fill(T* a, int64_t n, T v)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = v;
+}
+
+template <typename O>
+__global__ void k_bfs_seed(int32_t const* __restrict__ src, int n, uint32_t* visited, int32_t* dist, int32_t* q,
+                           frontier_counters_t* cnt, O const* __restrict__ off)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v        = src[i];
+  uint32_t bit = 1u << (v & 31);
+  uint32_t old = atomicOr(visited + (v >> 5), bit);
+  if (old & bit) return;  // duplicate source
+  dist[v]     = 0;
+  int pos     = atomicAdd(&cnt->n_small, 1);
+  q[pos]      = v;
+  unsigned d  = (unsigned)((long long)off[v + 1] - (long long)off[v]);
+  atomicAdd(&cnt->m_f, (unsigned long long)d);
+}
+
+__global__ void k_widen_dist(int32_t const* in, int32_t n, int64_t* out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] == INT_MAX ? LLONG_MAX : (int64_t)in[i];
+}
+
+template <typename O>
+void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* sources, int n_sources,
+             bool direction_optimizing, int depth_limit, int32_t* dist, int32_t* pred)
+{
+  O const* off       = c.offsets.as<O>();
+  int32_t const* idx = c.indices.as<int32_t>();
+  const int n_words  = (nv + 31) / 32;
+  dbuf visited = make_dbuf<uint32_t>(n_words, h.stream), fbm = make_dbuf<uint32_t>(n_words, h.stream),
+       nbm = make_dbuf<uint32_t>(n_words, h.stream);
+  dbuf qa = make_dbuf<int32_t>(nv, h.stream), qb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf la = make_dbuf<int32_t>(nv, h.stream), lb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf cnt = make_dbuf<frontier_counters_t>(1, h.stream);
+  frontier_counters_t* dc = cnt.as<frontier_counters_t>();
+  CUDA_TRY(cudaMemsetAsync(visited.data(), 0, sizeof(uint32_t) * n_words, h.stream));
+  CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
+  B200_LAUNCH(h, (k_fill<int32_t>), std::min(grid_for(nv), 148 * 32), kBlock, 0, dist, (int64_t)nv, INT_MAX);
+  if (pred) B200_LAUNCH(h, (k_fill<int32_t>), std::min(grid_for(nv), 148 * 32), kBlock, 0, pred, (int64_t)nv, -1);
+  B200_LAUNCH(h, (k_bfs_seed<O>), grid_for(n_sources), kBlock, 0, sources, n_sources, visited.as<uint32_t>(), dist,
+              qa.as<int32_t>(), dc, off);
+  frontier_counters_t* hc = reinterpret_cast<frontier_counters_t*>(h.pinned);
+  CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  // the current frontier is either (small queue, large queue) or a bitmap
+  int n_small = hc->n_small, n_large = 0;
+  bool mixed_queue         = true;  // small queue may still hold hubs (seed / bitmap conversion)
+  int n_f                  = n_small;
+  unsigned long long m_f   = hc->m_f;
+  unsigned long long m_vis = m_f;  // edges incident to visited vertices
+  long long n_vis          = n_f;
+  const unsigned long long m_total = (unsigned long long)c.nnz;
+  int32_t *cur = qa.as<int32_t>(), *nxt = qb.as<int32_t>();
+  int32_t *cur_l = la.as<int32_t>(), *nxt_l = lb.as<int32_t>();
+  bool bottom_up = false, frontier_is_bitmap = false;
+  int level = 0, prev_n_f = 0;
+  // Beamer's switch points (the reference: bfs_impl.cuh:291-297, alpha ~ E/V*0.267, beta = 24)
+  const double alpha = 14.0, beta = 24.0;
+  const int full_grid = h.sm_count * 8;
+  while (n_f > 0 && level < depth_limit) {
+    if (direction_optimizing) {
+      unsigned long long m_u = m_total - std::min(m_vis, m_total);
+      if (!bottom_up && (double)m_f * alpha > (double)m_u && n_f >= prev_n_f) bottom_up = true;
+      else if (bottom_up && (double)n_f * beta < (double)(nv - n_vis) && n_f < prev_n_f) bottom_up = false;
+    }
+    CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
+    if (!bottom_up) {
+      if (frontier_is_bitmap) {
+        B200_LAUNCH(h, k_bitmap_to_queue, grid_for(n_words), kBlock, 0, fbm.as<uint32_t>(), n_words, cur, &dc->n_conv);
+        frontier_is_bitmap = false;
+        n_small            = n_f;
+        n_large            = 0;
+        mixed_queue        = true;
+      }
+      bfs_topdown_op<O> op{off, visited.as<uint32_t>(), dist, pred, nxt, nxt_l, dc, level};
+      if (n_small > 0) {
+        int grid = std::min((n_small + kBlock - 1) / kBlock, full_grid);
+        if (mixed_queue) B200_LAUNCH(h, (k_advance<O, bfs_topdown_op<O>, false>), grid, kBlock, 0, off, idx, cur, n_small, op);
+        else B200_LAUNCH(h, (k_advance<O, bfs_topdown_op<O>, true>), grid, kBlock, 0, off, idx, cur, n_small, op);
+      }
+      if (n_large > 0) B200_LAUNCH(h, (k_advance_large<O, bfs_topdown_op<O>>), full_grid, kBlock, 0, off, idx, cur_l, n_large, op);
+      std::swap(cur, nxt);
+      std::swap(cur_l, nxt_l);
+      mixed_queue = false;
+    } else {
+      if (!frontier_is_bitmap) {
+        CUDA_TRY(cudaMemsetAsync(fbm.data(), 0, sizeof(uint32_t) * n_words, h.stream));
+        if (n_small > 0) B200_LAUNCH(h, k_queue_to_bitmap, grid_for(n_small), kBlock, 0, cur, n_small, fbm.as<uint32_t>());
+        if (n_large > 0) B200_LAUNCH(h, k_queue_to_bitmap, grid_for(n_large), kBlock, 0, cur_l, n_large, fbm.as<uint32_t>());
+        frontier_is_bitmap = true;
+      }
+      int grid = std::min(grid_for((int64_t)n_words * 32), h.sm_count * 16);
+      B200_LAUNCH(h, (k_bfs_bottomup<O>), grid, kBlock, 0, off, idx, visited.as<uint32_t>(), fbm.as<uint32_t>(),
+                  nbm.as<uint32_t>(), dist, pred, level, nv, dc);
+      B200_LAUNCH(h, k_or_words, grid_for(n_words), kBlock, 0, visited.as<uint32_t>(), nbm.as<uint32_t>(), n_words);
+      std::swap(fbm, nbm);
+    }
+    CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    prev_n_f = n_f;
+    n_small  = hc->n_small;
+    n_large  = hc->n_large;
+    n_f      = n_small + n_large;
+    m_f      = hc->m_f;
+    m_vis += m_f;
+    n_vis += n_f;
+    ++level;
+  }
+  check_last("bfs");
+}
+
+// ------------------------------------------------------------------------------------------
+// SSSP: near/far piles with threshold stepping (sssp_impl.cuh:246-265, 373-566)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atomic_min_nonneg(float* addr, float v)
+{
+  return __int_as_float(atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v)));
+}
+__device__ __forceinline__ double atomic_min_nonneg(double* addr, double v)
+{
+  return __longlong_as_double(atomicMin(reinterpret_cast<long long*>(addr), __double_as_longlong(v)));
+}
+
+template <typename O, typename T>
+struct sssp_relax_op {
+  O const* off;
+  T const* w;
+  T* dist;
+  int32_t* stamp;      // round in which the vertex was last put on a near queue
+  int32_t* far_stamp;  // window in which the vertex was last put on the far pile
+  int32_t* next_near;
+  int32_t* next_near_large;
+  int32_t* far;
+  frontier_counters_t* cnt;
+  T threshold;
+  T cutoff;
+  int round;
+  int window;
+  __device__ __forceinline__ void edge(int src, long long e, int nbr) const
+  {
+    const T nd = dist[src] + w[e];
+    if (!(nd < dist[nbr]) || !(nd < cutoff)) return;
+    const T old = atomic_min_nonneg(dist + nbr, nd);
+    if (!(nd < old)) return;
+    if (nd < threshold) {
+      if (atomicExch(stamp + nbr, round) != round) enqueue_by_degree(off, nbr, next_near, next_near_large, cnt);
+    } else {
+      if (atomicExch(far_stamp + nbr, window) != window) far[warp_append(&cnt->n_far)] = nbr;
+    }
+  }
+};
+
+// split the far pile against the new threshold window [lo, hi)
+template <typename O, typename T>
+__global__ void k_split_far(O const* __restrict__ off, int32_t const* __restrict__ far_in, int n,
+                            T const* __restrict__ dist, T lo, T hi, int32_t* stamp, int32_t* far_stamp, int round,
+                            int window, int32_t* near_out, int32_t* near_large_out, int32_t* far_out,
+                            frontier_counters_t* cnt)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = far_in[i];
+  T d   = dist[v];
+  if (d < lo) return;  // settled through the near pile meanwhile
+  if (d < hi) {
+    if (atomicExch(stamp + v, round) != round) enqueue_by_degree(off, v, near_out, near_large_out, cnt);
+  } else {
+    if (atomicExch(far_stamp + v, window) != window) far_out[warp_append(&cnt->n_far)] = v;
+  }
+}
+
+template <typename T>
+__global__ void k_min_far(int32_t const* __restrict__ far, int n, T const* __restrict__ dist, T lo, T* out_min)
+{
+  T m = (T)INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    T d = dist[far[i]];
+    if (d >= lo && d < m) m = d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T t = __shfl_xor_sync(0xffffffffu, m, o);
+    m   = t < m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m < (T)INFINITY) atomic_min_nonneg(out_min, m);
+}
+
+// predecessors from the distance fixpoint: dist[v] == fl(dist[u] + w(u,v)) for a tree parent u
+template <typename O, typename T>
+__global__ void k_sssp_pred(O const* __restrict__ off, int32_t const* __restrict__ idx, T const* __restrict__ w,
+                            T const* __restrict__ dist, int32_t n_vertices, int32_t source, T unreached,
+                            int32_t* __restrict__ pred)
+{
+  const int lane = threadIdx.x & 31;
+  for (long long u = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; u < n_vertices;
+       u += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const T du = dist[u];
+    if (du == unreached) continue;
+    for (long long e = (long long)off[u] + lane; e < (long long)off[u + 1]; e += 32) {
+      const int v = idx[e];
+      if (v != source && v != (int)u && du + w[e] == dist[v]) pred[v] = (int32_t)u;
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_sum_weights(T const* __restrict__ w, long long n, double* out)
+{
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += (double)w[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+template <typename T>
+__global__ void k_sssp_seed(T* dist, int32_t* stamp, int32_t* q, int32_t source)
+{
+  dist[source]  = (T)0;
+  stamp[source] = 1;
+  q[0]          = source;
+}
+
+template <typename O, typename T>
+void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, double cutoff_d, T* dist, int32_t* pred)
+{
+  O const* off       = c.offsets.as<O>();
+  int32_t const* idx = c.indices.as<int32_t>();
+  T const* w         = c.weights.as<T>();
+  const T unreached  = std::numeric_limits<T>::max();
+  const T cutoff     = cutoff_d >= (double)unreached ? unreached : (T)cutoff_d;
+  B200_LAUNCH(h, (k_fill<T>), std::min(grid_for(nv), 148 * 32), kBlock, 0, dist, (int64_t)nv, unreached);
+  if (pred) B200_LAUNCH(h, (k_fill<int32_t>), std::min(grid_for(nv), 148 * 32), kBlock, 0, pred, (int64_t)nv, -1);
+  if (c.nnz == 0) {
+    B200_LAUNCH(h, (k_fill<T>), 1, 1, 0, dist + source, (int64_t)1, (T)0);
+    return;
+  }
+  // delta = warp_size * average weight / average degree  (sssp_impl.cuh:233-247)
+  dbuf wsum = make_dbuf<double>(2, h.stream);
+  CUDA_TRY(cudaMemsetAsync(wsum.data(), 0, 2 * sizeof(double), h.stream));
+  B200_LAUNCH(h, (k_sum_weights<T>), h.sm_count * 8, kBlock, 0, w, (long long)c.nnz, wsum.as<double>());
+  double hsum = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(&hsum, wsum.data(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  const double avg_w   = hsum / (double)c.nnz;
+  const double avg_deg = (double)c.nnz / (double)nv;
+  T delta              = (T)(32.0 * avg_w / std::max(avg_deg, 1e-30));
+  if (!(delta > (T)0)) delta = (T)1;
+
+  dbuf stamp = make_dbuf<int32_t>(nv, h.stream), far_stamp = make_dbuf<int32_t>(nv, h.stream);
+  CUDA_TRY(cudaMemsetAsync(stamp.data(), 0, sizeof(int32_t) * nv, h.stream));
+  CUDA_TRY(cudaMemsetAsync(far_stamp.data(), 0, sizeof(int32_t) * nv, h.stream));
+  // every queue holds a vertex at most once per round / window (stamps), so V entries suffice
+  dbuf qa = make_dbuf<int32_t>(nv, h.stream), qb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf la = make_dbuf<int32_t>(nv, h.stream), lb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf fa = make_dbuf<int32_t>(nv, h.stream), fb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf cnt = make_dbuf<frontier_counters_t>(1, h.stream);
+  frontier_counters_t* dc = cnt.as<frontier_counters_t>();
+  CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
+  dbuf dmin = make_dbuf<T>(1, h.stream);
+  B200_LAUNCH(h, (k_sssp_seed<T>), 1, 1, 0, dist, stamp.as<int32_t>(), qa.as<int32_t>(), source);
+  frontier_counters_t* hc = reinterpret_cast<frontier_counters_t*>(h.pinned);
+  int32_t *near = qa.as<int32_t>(), *next_near = qb.as<int32_t>();
+  int32_t *near_l = la.as<int32_t>(), *next_near_l = lb.as<int32_t>();
+  int32_t *far = fa.as<int32_t>(), *far2 = fb.as<int32_t>();
+  int n_near = 1, n_near_l = 0, n_far = 0, round = 1, window = 1;
+  bool mixed = true;  // the seed may be a hub sitting in the small queue
+  T lo = (T)0, hi = delta;
+  const int full_grid = h.sm_count * 8;
+  while (true) {
+    while (n_near + n_near_l > 0) {
+      ++round;
+      CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_small, n_large; n_far keeps running
+      sssp_relax_op<O, T> op{off, w, dist, stamp.as<int32_t>(), far_stamp.as<int32_t>(), next_near, next_near_l, far,
+                             dc, hi, cutoff, round, window};
+      if (n_near > 0) {
+        int grid = std::min((n_near + kBlock - 1) / kBlock, full_grid);
+        if (mixed) B200_LAUNCH(h, (k_advance<O, sssp_relax_op<O, T>, false>), grid, kBlock, 0, off, idx, near, n_near, op);
+        else B200_LAUNCH(h, (k_advance<O, sssp_relax_op<O, T>, true>), grid, kBlock, 0, off, idx, near, n_near, op);
+      }
+      if (n_near_l > 0) B200_LAUNCH(h, (k_advance_large<O, sssp_relax_op<O, T>>), full_grid, kBlock, 0, off, idx, near_l, n_near_l, op);
+      CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
+      sync(h);
+      n_near   = hc->n_small;
+      n_near_l = hc->n_large;
+      n_far    = hc->n_far;
+      mixed    = false;
+      std::swap(near, next_near);
+      std::swap(near_l, next_near_l);
+    }
+    if (n_far == 0) break;
+    // advance the window to the smallest pending distance, then split the far pile
+    T inf = (T)INFINITY;
+    CUDA_TRY(cudaMemcpyAsync(dmin.data(), &inf, sizeof(T), cudaMemcpyHostToDevice, h.stream));
+    B200_LAUNCH(h, (k_min_far<T>), std::min(grid_for(n_far), full_grid), kBlock, 0, far, n_far, dist, hi, dmin.as<T>());
+    T hmin;
+    CUDA_TRY(cudaMemcpyAsync(&hmin, dmin.data(), sizeof(T), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    if (!(hmin < inf)) break;  // everything left in the pile was settled earlier
+    lo      = hi;
+    T steps = std::floor((hmin - hi) / delta);
+    hi      = hi + (steps > (T)0 ? steps : (T)0) * delta + delta;
+    ++round;
+    ++window;
+    CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
+    B200_LAUNCH(h, (k_split_far<O, T>), grid_for(n_far), kBlock, 0, off, far, n_far, dist, lo, hi, stamp.as<int32_t>(),
+                far_stamp.as<int32_t>(), round, window, near, near_l, far2, dc);
+    CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    n_near   = hc->n_small;
+    n_near_l = hc->n_large;
+    n_far    = hc->n_far;
+    std::swap(far, far2);
+  }
+  if (pred) {
+    B200_LAUNCH(h, (k_sssp_pred<O, T>), h.sm_count * 16, kBlock, 0, off, idx, w, dist, nv, source, unreached, pred);
+  }
+  check_last("sssp");
+}
+
+device_array_impl* make_array(dbuf&& b, size_t n, cugraph_data_type_id_t t) { return new device_array_impl{std::move(b), n, t}; }
+
+// internal predecessors (int32, internal ids) -> reported order, external ids, graph's vertex dtype
+device_array_impl* finish_predecessors(handle_impl const& h, graph_impl const& g, int32_t const* pred_int)
+{
+  dbuf ordered = to_reported_order(h, g, pred_int, sizeof(int32_t));
+  dbuf ext((size_t)g.n_vertices * dtype_size(g.vertex_type), h.stream);
+  int_to_ext(h, g, ordered.as<int32_t>(), (size_t)g.n_vertices, ext.data());
+  return make_array(std::move(ext), (size_t)g.n_vertices, g.vertex_type);
+}
+
+}  // namespace
+}  // namespace b200
+
 using namespace b200;
+
 extern "C" {
+
 cugraph_type_erased_device_array_view_t* cugraph_paths_result_get_vertices(cugraph_paths_result_t* r)
-{ return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<paths_result_impl*>(r)->vertices->new_view()); }
+{
+  return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<paths_result_impl*>(r)->vertices->new_view());
+}
 cugraph_type_erased_device_array_view_t* cugraph_paths_result_get_distances(cugraph_paths_result_t* r)
-{ return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<paths_result_impl*>(r)->distances->new_view()); }
+{
+  return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<paths_result_impl*>(r)->distances->new_view());
+}
 cugraph_type_erased_device_array_view_t* cugraph_paths_result_get_predecessors(cugraph_paths_result_t* r)
-{ return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<paths_result_impl*>(r)->predecessors->new_view()); }
+{
+  return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<paths_result_impl*>(r)->predecessors->new_view());
+}
 void cugraph_paths_result_free(cugraph_paths_result_t* r)
 {
   if (!r) return;
   auto* p = reinterpret_cast<paths_result_impl*>(r);
-  delete p->vertices; delete p->distances; delete p->predecessors; delete p;
+  delete p->vertices;
+  delete p->distances;
+  delete p->predecessors;
+  delete p;
 }
-cugraph_error_code_t cugraph_bfs(const cugraph_resource_handle_t*, cugraph_graph_t*, cugraph_type_erased_device_array_view_t*,
-                                 bool_t, size_t, bool_t, bool_t, cugraph_paths_result_t**, cugraph_error_t** error)
-{ return guarded(error, [&] { throw capi_exception(CUGRAPH_NOT_IMPLEMENTED, "bfs"); }); }
-cugraph_error_code_t cugraph_sssp(const cugraph_resource_handle_t*, cugraph_graph_t*, size_t, double, bool_t, bool_t,
-                                  cugraph_paths_result_t**, cugraph_error_t** error)
-{ return guarded(error, [&] { throw capi_exception(CUGRAPH_NOT_IMPLEMENTED, "sssp"); }); }
+
+cugraph_error_code_t cugraph_bfs(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph,
+                                 cugraph_type_erased_device_array_view_t* sources, bool_t direction_optimizing,
+                                 size_t depth_limit, bool_t compute_predecessors, bool_t do_expensive_check,
+                                 cugraph_paths_result_t** result, cugraph_error_t** error)
+{
+  (void)do_expensive_check;
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    auto* g       = G(graph);
+    B200_EXPECTS(result != nullptr, CUGRAPH_INVALID_INPUT, "result out-pointer is NULL");
+    *result = nullptr;
+    B200_EXPECTS(sources != nullptr, CUGRAPH_INVALID_INPUT, "sources is NULL");
+    auto const* s = V(sources);
+    B200_EXPECTS(s->type == g->vertex_type, CUGRAPH_INVALID_INPUT, "vertex type of graph and sources must match");
+    B200_EXPECTS(g->mg == nullptr, CUGRAPH_NOT_IMPLEMENTED, "multi-GPU BFS is not implemented");
+    B200_EXPECTS(g->is_symmetric || direction_optimizing == FALSE, CUGRAPH_UNKNOWN_ERROR,
+                 "Invalid input argument: input graph should be symmetric for direction optimizing BFS.");
+    const int32_t nv = g->n_vertices;
+    dbuf src_int     = make_dbuf<int32_t>(std::max<size_t>(s->size, 1), h.stream);
+    ext_to_int(h, *g, s->data, s->size, src_int.as<int32_t>());
+    if (s->size > 0) {
+      std::vector<int32_t> hs(s->size);
+      CUDA_TRY(cudaMemcpyAsync(hs.data(), src_int.data(), sizeof(int32_t) * s->size, cudaMemcpyDeviceToHost, h.stream));
+      sync(h);
+      for (auto v : hs) B200_EXPECTS(v >= 0, CUGRAPH_INVALID_INPUT, "Found invalid vertex in the input sources");
+    }
+    dbuf dist = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+    dbuf pred;
+    if (compute_predecessors) pred = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+    const int dl = (int)std::min<size_t>(depth_limit, (size_t)INT_MAX);
+    if (nv > 0) {
+      csx_t const& c = push_view(h, *g);
+      if (c.offs64)
+        run_bfs<int64_t>(h, c, nv, src_int.as<int32_t>(), (int)s->size, direction_optimizing == TRUE, dl,
+                         dist.as<int32_t>(), pred.as<int32_t>());
+      else
+        run_bfs<int32_t>(h, c, nv, src_int.as<int32_t>(), (int)s->size, direction_optimizing == TRUE, dl,
+                         dist.as<int32_t>(), pred.as<int32_t>());
+    }
+    auto res      = std::make_unique<paths_result_impl>();
+    res->vertices = make_array(reported_vertices(h, *g), (size_t)nv, g->vertex_type);
+    dbuf dord     = to_reported_order(h, *g, dist.data(), sizeof(int32_t));
+    if (g->vertex_type == INT64) {
+      dbuf wide = make_dbuf<int64_t>(std::max(nv, 1), h.stream);
+      B200_LAUNCH(h, k_widen_dist, grid_for(nv), kBlock, 0, dord.as<int32_t>(), nv, wide.as<int64_t>());
+      res->distances = make_array(std::move(wide), (size_t)nv, INT64);
+    } else {
+      res->distances = make_array(std::move(dord), (size_t)nv, INT32);
+    }
+    if (compute_predecessors) res->predecessors = finish_predecessors(h, *g, pred.as<int32_t>());
+    else res->predecessors = make_array(dbuf(0, h.stream), 0, g->vertex_type);
+    sync(h);
+    *result = reinterpret_cast<cugraph_paths_result_t*>(res.release());
+  });
 }
+
+cugraph_error_code_t cugraph_sssp(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, size_t source,
+                                  double cutoff, bool_t compute_predecessors, bool_t do_expensive_check,
+                                  cugraph_paths_result_t** result, cugraph_error_t** error)
+{
+  (void)do_expensive_check;
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    auto* g       = G(graph);
+    B200_EXPECTS(result != nullptr, CUGRAPH_INVALID_INPUT, "result out-pointer is NULL");
+    *result = nullptr;
+    B200_EXPECTS(g->mg == nullptr, CUGRAPH_NOT_IMPLEMENTED, "multi-GPU SSSP is not implemented");
+    B200_EXPECTS(g->weighted, CUGRAPH_INVALID_INPUT, "SSSP requires a weighted graph");
+    const int32_t nv = g->n_vertices;
+    // external source id -> internal
+    dbuf src_ext(8, h.stream), src_int = make_dbuf<int32_t>(1, h.stream);
+    int64_t s64 = (int64_t)source;
+    int32_t s32 = (int32_t)source;
+    if (g->vertex_type == INT64) CUDA_TRY(cudaMemcpyAsync(src_ext.data(), &s64, 8, cudaMemcpyHostToDevice, h.stream));
+    else CUDA_TRY(cudaMemcpyAsync(src_ext.data(), &s32, 4, cudaMemcpyHostToDevice, h.stream));
+    ext_to_int(h, *g, src_ext.data(), 1, src_int.as<int32_t>());
+    int32_t src = -1;
+    CUDA_TRY(cudaMemcpyAsync(&src, src_int.data(), sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    B200_EXPECTS(src >= 0 && (g->vertex_type == INT64 || source <= (size_t)INT_MAX), CUGRAPH_INVALID_INPUT,
+                 "Invalid input argument: source vertex is invalid.");
+    csx_t const& c = push_view(h, *g);
+    auto res       = std::make_unique<paths_result_impl>();
+    res->vertices  = make_array(reported_vertices(h, *g), (size_t)nv, g->vertex_type);
+    dbuf pred;
+    if (compute_predecessors) pred = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+    if (g->weight_type == FLOAT32) {
+      dbuf dist = make_dbuf<float>(std::max(nv, 1), h.stream);
+      if (c.offs64) run_sssp<int64_t, float>(h, c, nv, src, cutoff, dist.as<float>(), pred.as<int32_t>());
+      else run_sssp<int32_t, float>(h, c, nv, src, cutoff, dist.as<float>(), pred.as<int32_t>());
+      res->distances = make_array(to_reported_order(h, *g, dist.data(), sizeof(float)), (size_t)nv, FLOAT32);
+    } else {
+      dbuf dist = make_dbuf<double>(std::max(nv, 1), h.stream);
+      if (c.offs64) run_sssp<int64_t, double>(h, c, nv, src, cutoff, dist.as<double>(), pred.as<int32_t>());
+      else run_sssp<int32_t, double>(h, c, nv, src, cutoff, dist.as<double>(), pred.as<int32_t>());
+      res->distances = make_array(to_reported_order(h, *g, dist.data(), sizeof(double)), (size_t)nv, FLOAT64);
+    }
+    if (compute_predecessors) res->predecessors = finish_predecessors(h, *g, pred.as<int32_t>());
+    else res->predecessors = make_array(dbuf(0, h.stream), 0, g->vertex_type);
+    sync(h);
+    *result = reinterpret_cast<cugraph_paths_result_t*>(res.release());
+  });
+}
+
+}  // extern "C"
