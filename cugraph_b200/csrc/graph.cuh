@@ -25,6 +25,36 @@ constexpr int kSegThreshold[kNumSeg] = {32, 16, 8, 4, 2, 1, 0};
 constexpr int kWarpChunk  = 1024;
 constexpr int kWarpsPerCta = 8;
 
+// ---------------------------------------------------------------------------------------------
+// Column-blocked copy of the degree>=32 prefix for the shared-memory gather kernel (spmv_hot.cuh).
+// The source (column) space is cut into B "hot" blocks of W vertices (W * sizeof(T) = 192 KiB, the
+// slice of x one CTA keeps in shared memory) plus one cold block (everything >= B*W).  Because rows
+// keep their neighbours sorted by source id, a row's adjacency is already partitioned by block; the
+// copy stores the segments block-major: all (row, block 0) segments, then block 1, ...
+// Hot blocks store 16-bit local column ids (halves the index stream), the cold block 32-bit ids.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHotSliceBytes = 192 * 1024;  // x slice a CTA keeps in shared memory
+
+struct hot_layout_t {
+  int W{0};
+  int B{0};
+  int32_t n_hi{0};
+  int64_t nnz_hi{0};
+  int64_t nnz_hot{0};
+  dbuf idx16;        // nnz_hot x uint16 : column id - block*W, block-major permuted order
+  dbuf idx32;        // (nnz_hi - nnz_hot) x int32 : column ids of the cold block
+  dbuf w;            // nnz_hi x T in permuted order, or empty
+  dbuf block_start;  // (B+2) x int32 : first permuted position of each block (cold = block B), 8-aligned
+  dbuf seg_row;      // row of every non-empty segment, block-major
+  dbuf seg_start;    // (n_segments+1) x int32 : permuted position where each non-empty segment starts
+  dbuf chunks;       // (n_chunks+1) x int32 : index of the segment that contains the chunk's first edge
+  int32_t n_chunks{0};
+  dbuf units;        // n_units x hot_unit_t (spmv_hot.cuh): <= 128 consecutive chunks of one block
+  int32_t n_units{0};
+  dbuf unit_counter; // 1 x int : dynamic work distribution cursor (reset by the finish kernel)
+  int n_cta{0};
+};
+
 // One orientation: compressed rows over `n_rows` physical rows.
 // row_vertex == nullptr  -> physical row r is vertex r (rows are degree-descending by construction)
 // row_vertex != nullptr  -> physical row r is vertex row_vertex[r] (a lazily built transpose whose
@@ -45,6 +75,10 @@ struct csx_t {
   dbuf chunk_first_row;  // n_chunks+1 x int32 : row that contains edge c*kWarpChunk
   int32_t n_split{0};
   dbuf split_rows;  // n_split x int32 : rows that straddle a chunk boundary (each listed once)
+  // lazily built column-blocked copies (float / double element width) and cached out-weight sums
+  mutable std::unique_ptr<hot_layout_t> hot4, hot8;
+  mutable bool hot4_tried{false}, hot8_tried{false};
+  mutable dbuf out_w;  // n_vertices x T : per-source sum of edge weights (or out-degree), T = weight type
 };
 
 struct graph_impl {
@@ -82,6 +116,8 @@ inline graph_impl* G(cugraph_graph_t* g)
 
 // Accessors that build the missing orientation on demand (graph_build.cu).
 csx_t const& pull_view(handle_impl const& h, graph_impl& g);  // rows = destinations, indices = sources
+// column-blocked copy for elements of `elem_size` bytes, or nullptr when the graph is too small for it
+hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size);
 csx_t const& push_view(handle_impl const& h, graph_impl& g);  // rows = sources, vertex-indexed offsets
 
 // external <-> internal id helpers (graph_build.cu)

@@ -7,7 +7,7 @@
 // advances the device-resident loop state.  The host enqueues iterations in batches and only reads the
 // `done` flag between batches; kernels of iterations past convergence are no-ops, so the iteration
 // count and result are exactly those of a check-every-iteration loop.
-#include "spmv.cuh"
+#include "spmv_hot.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -157,29 +157,35 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
   B200_EXPECTS(c.degree_sorted, CUGRAPH_UNKNOWN_ERROR, "internal: pull view is not binned");
   const bool weighted = g.weighted;
 
-  // out-weight sums (pagerank_impl.cuh:180-198)
-  dbuf out_w;
+  // out-weight sums (pagerank_impl.cuh:180-198).  A property of the graph: computed once per graph
+  // (the reference recomputes it on every call with a push-model prim, one atomic per edge).
+  dbuf out_w_user;
+  T const* out_w = nullptr;
   if (a.pre_w) {
-    out_w = collect_vertex_values<T>(h, g, a.pre_v, a.pre_w, (T)0);
+    out_w_user = collect_vertex_values<T>(h, g, a.pre_v, a.pre_w, (T)0);
+    out_w      = out_w_user.as<T>();
   } else {
-    out_w = make_dbuf<T>(nv, h.stream);
-    if (weighted) {
-      dbuf sums = make_dbuf<double>(nv, h.stream);
-      CUDA_TRY(cudaMemsetAsync(sums.data(), 0, sizeof(double) * nv, h.stream));
-      if (c.nnz > 0)
-        B200_LAUNCH(h, (k_out_weight<T>), std::min(grid_for(c.nnz), 148 * 16), kBlock, 0, c.indices.as<int32_t>(),
-                    c.weights.as<T>(), (long long)c.nnz, sums.as<double>());
-      B200_LAUNCH(h, (k_cast<double, T>), grid_for(nv), kBlock, 0, sums.as<double>(), nv, out_w.as<T>());
+    if (c.out_w.data() == nullptr) {
+      dbuf ow = make_dbuf<T>(nv, h.stream);
+      if (weighted) {
+        dbuf sums = make_dbuf<double>(nv, h.stream);
+        CUDA_TRY(cudaMemsetAsync(sums.data(), 0, sizeof(double) * nv, h.stream));
+        if (c.nnz > 0)
+          B200_LAUNCH(h, (k_out_weight<T>), std::min(grid_for(c.nnz), 148 * 16), kBlock, 0, c.indices.as<int32_t>(),
+                      c.weights.as<T>(), (long long)c.nnz, sums.as<double>());
+        B200_LAUNCH(h, (k_cast<double, T>), grid_for(nv), kBlock, 0, sums.as<double>(), nv, ow.as<T>());
+      } else {
+        dbuf deg = make_dbuf<int32_t>(nv, h.stream);
+        CUDA_TRY(cudaMemsetAsync(deg.data(), 0, sizeof(int32_t) * nv, h.stream));
+        if (c.nnz > 0)
+          B200_LAUNCH(h, k_out_degree, std::min(grid_for(c.nnz), 148 * 16), kBlock, 0, c.indices.as<int32_t>(),
+                      (long long)c.nnz, deg.as<int32_t>());
+        B200_LAUNCH(h, (k_cast<int32_t, T>), grid_for(nv), kBlock, 0, deg.as<int32_t>(), nv, ow.as<T>());
+      }
       sync(h);
-    } else {
-      dbuf deg = make_dbuf<int32_t>(nv, h.stream);
-      CUDA_TRY(cudaMemsetAsync(deg.data(), 0, sizeof(int32_t) * nv, h.stream));
-      if (c.nnz > 0)
-        B200_LAUNCH(h, k_out_degree, std::min(grid_for(c.nnz), 148 * 16), kBlock, 0, c.indices.as<int32_t>(),
-                    (long long)c.nnz, deg.as<int32_t>());
-      B200_LAUNCH(h, (k_cast<int32_t, T>), grid_for(nv), kBlock, 0, deg.as<int32_t>(), nv, out_w.as<T>());
-      sync(h);
+      c.out_w = std::move(ow);
     }
+    out_w = c.out_w.as<T>();
   }
   if (a.expensive && weighted && c.nnz > 0) {
     dbuf neg = make_dbuf<int>(1, h.stream);
@@ -218,7 +224,8 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
   }
 
   // state
-  dbuf pr_a = make_dbuf<T>(nv, h.stream), pr_b = make_dbuf<T>(nv, h.stream), x = make_dbuf<T>(nv, h.stream);
+  dbuf pr_a = make_dbuf<T>(nv, h.stream), pr_b = make_dbuf<T>(nv, h.stream);
+  dbuf x    = make_dbuf<T>(padded_x_elems(nv, sizeof(T)), h.stream);  // whole smem slices are TMA-copied
   dbuf acc_hi = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
   CUDA_TRY(cudaMemsetAsync(acc_hi.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
   dbuf state = make_dbuf<pr_state_t>(1, h.stream);
@@ -237,7 +244,7 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
   const int vgrid = std::min(grid_for(nv), h.sm_count * 8);
   const int max_it = (int)std::min<size_t>(a.max_iterations, 0x7fffffff);
   // prologue: x and dangling sum of the starting vector, init for sweep 1
-  B200_LAUNCH(h, (k_vertex_pass<T>), vgrid, kBlock, 0, pr_a.as<T>(), (T const*)nullptr, out_w.as<T>(), x.as<T>(), nv, st);
+  B200_LAUNCH(h, (k_vertex_pass<T>), vgrid, kBlock, 0, pr_a.as<T>(), (T const*)nullptr, out_w, x.as<T>(), nv, st);
   B200_LAUNCH(h, k_finalize, 1, 1, 0, st, a.alpha, a.epsilon, nv, n_pers > 0 ? 1 : 0, 0, max_it);
 
   T* cur = pr_a.as<T>();
@@ -253,11 +260,11 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
     int todo = std::min(batch, std::max(max_it, 1) - enqueued);
     for (int k = 0; k < todo; ++k) {
       if (c.offs64) launch_pull_sweep<int64_t, T>(h, c, x.as<T>(), nxt, acc_hi.as<double>(), a.alpha, st);
-      else launch_pull_sweep<int32_t, T>(h, c, x.as<T>(), nxt, acc_hi.as<double>(), a.alpha, st);
+      else launch_pull_sweep_auto<int32_t, T>(h, c, nv, x.as<T>(), nxt, acc_hi.as<double>(), a.alpha, st);
       if (n_pers > 0)
         B200_LAUNCH(h, (k_personalize<T>), grid_for(n_pers), kBlock, 0, pers_idx.as<int32_t>(), (T const*)a.pers_val->data,
                     n_pers, pers_sum, nxt, st);
-      B200_LAUNCH(h, (k_vertex_pass<T>), vgrid, kBlock, 0, nxt, cur, out_w.as<T>(), x.as<T>(), nv, st);
+      B200_LAUNCH(h, (k_vertex_pass<T>), vgrid, kBlock, 0, nxt, cur, out_w, x.as<T>(), nv, st);
       B200_LAUNCH(h, k_finalize, 1, 1, 0, st, a.alpha, a.epsilon, nv, n_pers > 0 ? 1 : 0, 1, max_it);
       std::swap(cur, nxt);
       ++enqueued;
@@ -441,7 +448,7 @@ cugraph_error_code_t cugraph_b200_time_pull_spmv(const cugraph_resource_handle_t
     B200_EXPECTS(g->weight_type == FLOAT32, CUGRAPH_NOT_IMPLEMENTED, "time_pull_spmv: float32 graphs only");
     csx_t const& c = pull_view(h, *g);
     int32_t nv     = g->n_vertices;
-    dbuf x = make_dbuf<float>(nv, h.stream), y = make_dbuf<float>(nv, h.stream);
+    dbuf x = make_dbuf<float>(padded_x_elems(nv, sizeof(float)), h.stream), y = make_dbuf<float>(nv, h.stream);
     B200_LAUNCH(h, (k_fill<float>), grid_for(nv), kBlock, 0, x.as<float>(), nv, 1.0f / (float)nv);
     dbuf acc = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
     CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
@@ -449,7 +456,7 @@ cugraph_error_code_t cugraph_b200_time_pull_spmv(const cugraph_resource_handle_t
     CUDA_TRY(cudaMemsetAsync(state.data(), 0, sizeof(pr_state_t), h.stream));
     auto sweep = [&] {
       if (c.offs64) launch_pull_sweep<int64_t, float>(h, c, x.as<float>(), y.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
-      else launch_pull_sweep<int32_t, float>(h, c, x.as<float>(), y.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
+      else launch_pull_sweep_auto<int32_t, float>(h, c, nv, x.as<float>(), y.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
     };
     for (int k = 0; k < 3; ++k) sweep();
     cudaEvent_t e0, e1;

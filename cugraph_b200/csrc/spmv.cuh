@@ -140,6 +140,11 @@ struct low_bins_t {
   int32_t block_begin[kNumSeg];  // first block of bin b; [6] = total blocks
 };
 
+// lanes per row in low bin b (degree in [16,32) [8,16) [4,8) [2,4) [1,2)): every lane owns up to 8
+// edges and issues all of their loads back to back — these rows are latency-bound (offsets -> indices
+// -> x is a chain of three dependent loads), so work per lane, not lanes per row, buys throughput.
+__host__ __device__ __forceinline__ int low_bin_lanes(int b) { return b == 0 ? 4 : (b == 1 ? 2 : 1); }
+
 template <typename O, typename T, bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 k_spmv_low(O const* __restrict__ offsets, int32_t const* __restrict__ indices, T const* __restrict__ weights,
@@ -158,18 +163,31 @@ k_spmv_low(O const* __restrict__ offsets, int32_t const* __restrict__ indices, T
     if (r < bins.row_begin[b + 1]) y[row_vertex ? row_vertex[r] : r] = (T)init;
     return;
   }
-  const int g   = 16 >> b;  // lanes per row
+  const int g   = low_bin_lanes(b);
   const int sub = threadIdx.x & (g - 1);
   const int r   = bins.row_begin[b] + blk * (256 / g) + (threadIdx.x / g);
   double acc    = 0.0;
   const bool in = r < bins.row_begin[b + 1];
   if (in) {
-    long long lo = (long long)offsets[r], hi = (long long)offsets[r + 1];
-    for (long long i = lo + sub; i < hi; i += g) {
-      T xv = x[ld_stream(indices + i)];
-      if (WEIGHTED) xv *= ld_stream(weights + i);
-      acc += (double)xv;
+    const long long lo = (long long)offsets[r], hi = (long long)offsets[r + 1];
+    constexpr int kR = 8;  // degree < 32 and g in {4,2,1} => at most 8 edges per lane
+    int c[kR];
+    T wv[kR];
+#pragma unroll
+    for (int k = 0; k < kR; ++k) {
+      const long long e = lo + sub + (long long)k * g;
+      c[k]              = 0;
+      wv[k]             = (T)0;
+      if (e < hi) {
+        c[k]  = ld_stream(indices + e);
+        wv[k] = WEIGHTED ? ld_stream(weights + e) : (T)1;
+      }
     }
+    T v[kR];
+#pragma unroll
+    for (int k = 0; k < kR; ++k) v[k] = x[c[k]] * wv[k];
+    acc = (((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3])) +
+          (((double)v[4] + (double)v[5]) + ((double)v[6] + (double)v[7]));
   }
   for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (in && sub == 0) y[row_vertex ? row_vertex[r] : r] = (T)(acc * alpha + init);
@@ -186,7 +204,7 @@ inline low_bins_t make_low_bins(csx_t const& c)
     b.row_begin[k]   = c.seg[k];
     b.block_begin[k] = blocks;
     int rows         = c.seg[k + 1] - c.seg[k];
-    int per_block    = (k == kNumSeg - 2) ? 256 : 256 / (16 >> k);
+    int per_block    = (k == kNumSeg - 2) ? 256 : 256 / low_bin_lanes(k);
     blocks += (rows + per_block - 1) / per_block;
   }
   b.row_begin[kNumSeg - 1]   = c.seg[kNumSeg];
