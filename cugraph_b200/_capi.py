@@ -105,6 +105,13 @@ def lib():
     _sig(L.cugraph_b200_comm_create, i32, [vp, i32, i32, pvp, pvp])
     _sig(L.cugraph_b200_comm_free, None, [vp])
     _sig(L.cugraph_b200_time_pull_spmv, i32, [vp, vp, sz, C.POINTER(dbl), C.POINTER(dbl), pvp])
+    _sig(L.cugraph_b200_create_resource_handle_on_stream, vp, [vp])
+    _sig(L.cugraph_b200_padded_elems, sz, [sz, sz])
+    _sig(L.cugraph_b200_block_create, i32, [vp, sz, sz, vp, vp, vp, pvp, pvp])
+    _sig(L.cugraph_b200_block_free, None, [vp])
+    _sig(L.cugraph_b200_block_span, sz, [vp])
+    _sig(L.cugraph_b200_block_pull_sweep, i32, [vp, vp, vp, vp, dbl, pvp])
+    _sig(L.cugraph_b200_pagerank_vertex_step, i32, [vp, vp, vp, vp, vp, sz, dbl, dbl, i32, vp, vp, pvp])
     _lib = L
     return L
 

@@ -101,7 +101,7 @@ void cugraph_free_resource_handle(cugraph_resource_handle_t* handle)
   unregister_stream(h->aux_stream);
   cudaEventDestroy(h->ev_a);
   cudaEventDestroy(h->ev_b);
-  cudaStreamDestroy(h->stream);
+  if (!h->borrowed_stream) cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->aux_stream);
   cudaFreeHost(h->pinned);
   delete h;

@@ -96,6 +96,7 @@ struct comm_impl;
 struct handle_impl {
   int device{0};
   cudaStream_t stream{nullptr};
+  bool borrowed_stream{false};        // stream belongs to the caller (torch): never destroyed here
   cudaStream_t aux_stream{nullptr};  // overlap of independent kernels / collectives
   cudaEvent_t ev_a{nullptr}, ev_b{nullptr};
   int sm_count{148};

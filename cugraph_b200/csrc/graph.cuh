@@ -136,6 +136,9 @@ dbuf collect_vertex_values(handle_impl const& h, graph_impl const& g,
                            device_array_view_impl const* verts, device_array_view_impl const* vals,
                            T fill);
 
+std::unique_ptr<csx_t> build_binned_rows(handle_impl const& h, int32_t const* major, int32_t const* minor, void const* w,
+                                         cugraph_data_type_id_t wtype, int64_t n, int32_t nv);
+
 // ---- multi-GPU hooks (mg.cu) ----
 struct mg_pr_args {
   double alpha;

@@ -889,31 +889,39 @@ void expand_offsets_to_rows(handle_impl const& h, void const* offsets, cugraph_d
 // ---------------------------------------------------------------------------------------------
 // orientation accessors
 // ---------------------------------------------------------------------------------------------
+// (major, minor[, w]) -> compressed rows whose PHYSICAL order is descending degree (row_vertex maps a
+// physical row back to its major id), binned and chunked for the pull kernels.  Used for the lazily
+// built transpose of a CSR graph and for the rectangular edge blocks of the multi-GPU partition.
+std::unique_ptr<csx_t> build_binned_rows(handle_impl const& h, int32_t const* major, int32_t const* minor, void const* w,
+                                         cugraph_data_type_id_t wtype, int64_t n, int32_t nv)
+{
+  dbuf deg = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+  CUDA_TRY(cudaMemsetAsync(deg.data(), 0, sizeof(int32_t) * std::max(nv, 1), h.stream));
+  if (n > 0) B200_LAUNCH(h, k_degree, grid_for(n, 4), kBlock, 0, major, n, deg.as<int32_t>());
+  dbuf dk = make_dbuf<uint64_t>(std::max(nv, 1), h.stream), dk2 = make_dbuf<uint64_t>(std::max(nv, 1), h.stream);
+  auto c        = std::make_unique<csx_t>();
+  c->row_vertex = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+  dbuf row_of_v = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+  if (nv > 0) {
+    B200_LAUNCH(h, k_degree_keys, grid_for(nv), kBlock, 0, deg.as<int32_t>(), nv, dk.as<uint64_t>());
+    sort_keys<uint64_t>(h, dk.as<uint64_t>(), dk2.as<uint64_t>(), nv, 0, 64);
+    B200_LAUNCH(h, k_perm_from_keys, grid_for(nv), kBlock, 0, dk2.as<uint64_t>(), nv, c->row_vertex.as<int32_t>(),
+                row_of_v.as<int32_t>());
+  }
+  build_csx(h, *c, major, minor, w, wtype, n, nv, row_of_v.as<int32_t>(), nullptr, false, false);
+  finish_binning(h, *c);
+  return c;
+}
+
 csx_t const& pull_view(handle_impl const& h, graph_impl& g)
 {
   if (g.store_transposed || g.is_symmetric) return *g.primary;
   if (!g.pull_alt) {
     // transpose the primary CSR; physical rows re-sorted by in-degree so that the binned kernels apply
     csx_t const& p = *g.primary;
-    int32_t nv     = g.n_vertices;
     dbuf maj       = expand_majors(h, p);  // sources
-    dbuf deg       = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
-    CUDA_TRY(cudaMemsetAsync(deg.data(), 0, sizeof(int32_t) * std::max(nv, 1), h.stream));
-    if (p.nnz > 0) B200_LAUNCH(h, k_degree, grid_for(p.nnz, 4), kBlock, 0, p.indices.as<int32_t>(), p.nnz, deg.as<int32_t>());
-    dbuf dk = make_dbuf<uint64_t>(std::max(nv, 1), h.stream), dk2 = make_dbuf<uint64_t>(std::max(nv, 1), h.stream);
-    auto c        = std::make_unique<csx_t>();
-    c->row_vertex = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
-    dbuf row_of_v = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
-    if (nv > 0) {
-      B200_LAUNCH(h, k_degree_keys, grid_for(nv), kBlock, 0, deg.as<int32_t>(), nv, dk.as<uint64_t>());
-      sort_keys<uint64_t>(h, dk.as<uint64_t>(), dk2.as<uint64_t>(), nv, 0, 64);
-      B200_LAUNCH(h, k_perm_from_keys, grid_for(nv), kBlock, 0, dk2.as<uint64_t>(), nv, c->row_vertex.as<int32_t>(),
-                  row_of_v.as<int32_t>());
-    }
-    build_csx(h, *c, p.indices.as<int32_t>(), maj.as<int32_t>(), g.weighted ? p.weights.data() : nullptr,
-              g.weight_type, p.nnz, nv, row_of_v.as<int32_t>(), nullptr, false, false);
-    finish_binning(h, *c);
-    g.pull_alt = std::move(c);
+    g.pull_alt     = build_binned_rows(h, p.indices.as<int32_t>(), maj.as<int32_t>(), g.weighted ? p.weights.data() : nullptr,
+                                       g.weight_type, p.nnz, g.n_vertices);
   }
   return *g.pull_alt;
 }

@@ -1,0 +1,270 @@
+"""Multi-GPU PageRank: 2D edge partition over one process per GPU (torch.distributed, NCCL on NVLink 5).
+
+What the reference does: P = R x C GPUs, vertex -> GPU by hash
+(cpp/include/cugraph/utilities/graph_partition_utils.cuh:30-43, 101-128), every GPU holds the edge
+block (row block of destinations) x (column block of sources); per PageRank iteration the scaled
+ranks are all-gathered inside the column group (update_edge_src_property, grouped ncclBroadcast,
+update_edge_src_dst_property.cuh:550-579), the local pull sweep runs, and the partial sums are reduced
+to their owners inside the row group (grouped ncclReduce, per_v_transform_reduce_e.cuh:3389-3407).
+
+Here: the same partition, but the exchange is ONE all_gather_into_tensor + ONE reduce_scatter_tensor
+per iteration on equal-sized (padded) vertex partitions, the dangling / convergence scalars travel in
+one 2-element all_reduce and never touch the host unless epsilon > 0, and the local sweep is the
+same column-blocked shared-memory kernel as on one GPU (C-ABI: cugraph_b200_block_*).
+
+`partition_edges` (pure torch, device agnostic: exercised on CPU with the gloo backend in
+tests/test_mg_partition_cpu.py) builds the blocks; `MGGraph` / `pagerank` need CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+# ----------------------------------------------------------------------------------------------
+# process grid (reference: cpp/tests/utilities/mg_utilities.cpp:49-53, partition_manager.hpp:106-114)
+# ----------------------------------------------------------------------------------------------
+def grid_shape(world: int):
+    """(R, C): R = largest divisor <= sqrt(world) = size of the all-gather (column) group,
+    C = world / R = size of the reduce (row) group.  2 -> 1x2, 4 -> 2x2, 8 -> 2x4."""
+    r = int(math.isqrt(world))
+    while world % r:
+        r -= 1
+    return r, world // r
+
+
+def vertex_owner(ext: torch.Tensor, world: int) -> torch.Tensor:
+    """Balanced vertex -> GPU map (the role of murmurhash3_32(ext) % P in the reference)."""
+    x = ext.to(torch.int64)
+    x = (x ^ (x >> 30)) * -4658895280553007687   # 0xbf58476d1ce4e5b9 as int64
+    x = (x ^ (x >> 27)) * -7723592293110705685   # 0x94d049bb133111eb as int64
+    x = x ^ (x >> 31)
+    return (x & 0x7FFFFFFFFFFFFFFF) % world
+
+
+@dataclass
+class Groups:
+    world: int
+    rank: int
+    R: int
+    C: int
+    r: int
+    c: int
+    row_group: object   # ranks (r, *)  : reduce-scatter of partial y
+    col_group: object   # ranks (*, c)  : all-gather of x
+
+
+def make_groups() -> Groups:
+    world, rank = dist.get_world_size(), dist.get_rank()
+    R, Cc = grid_shape(world)
+    r, c = rank // Cc, rank % Cc
+    row_group = col_group = None
+    for rr in range(R):
+        g = dist.new_group([rr * Cc + cc for cc in range(Cc)])
+        if rr == r:
+            row_group = g
+    for cc in range(Cc):
+        g = dist.new_group([rr * Cc + cc for rr in range(R)])
+        if cc == c:
+            col_group = g
+    return Groups(world, rank, R, Cc, r, c, row_group, col_group)
+
+
+# ----------------------------------------------------------------------------------------------
+# collectives that also run on gloo (CPU tests)
+# ----------------------------------------------------------------------------------------------
+def _is_nccl(group=None):
+    return dist.get_backend(group) == "nccl"
+
+
+def exchange(tensors, dest: torch.Tensor, world: int):
+    """all-to-all-v: element i of every tensor goes to rank dest[i]. Returns received tensors."""
+    order = torch.argsort(dest, stable=True)
+    send_counts = torch.bincount(dest, minlength=world).to(torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    out = []
+    for t in tensors:
+        ts = t[order].contiguous()
+        tr = torch.empty(sum(rc), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(tr, ts, output_split_sizes=rc, input_split_sizes=sc)
+        out.append(tr)
+    return out, order, sc, rc
+
+
+def all_gather_into(out: torch.Tensor, inp: torch.Tensor, group):
+    if _is_nccl(group):
+        dist.all_gather_into_tensor(out, inp, group=group)
+    else:
+        n = dist.get_world_size(group)
+        parts = [torch.empty_like(inp) for _ in range(n)]
+        dist.all_gather(parts, inp, group=group)
+        out.copy_(torch.cat(parts))
+
+
+def reduce_scatter_into(out: torch.Tensor, inp: torch.Tensor, group):
+    if _is_nccl(group):
+        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+    else:
+        tmp = inp.clone()
+        dist.all_reduce(tmp, group=group)
+        k = dist.get_rank(group)
+        out.copy_(tmp[k * out.numel():(k + 1) * out.numel()])
+
+
+# ----------------------------------------------------------------------------------------------
+# 2D partition
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Partition:
+    groups: Groups
+    rows: torch.Tensor        # int32, local destination slot of every local edge: c_v * maxpart + lid
+    cols: torch.Tensor        # int32, local source slot: r_u * maxpart + lid
+    weights: object           # tensor or None
+    vertices: torch.Tensor    # external ids of the vertices this rank owns (sorted)
+    n_local: int
+    maxpart: int
+    n_global: int
+
+
+def partition_edges(src: torch.Tensor, dst: torch.Tensor, weights=None, groups: Groups | None = None) -> Partition:
+    """Shuffle this rank's share of the edge list into the 2D partition and renumber.
+    Edge (u -> v) is stored on GPU (r(owner(v)), c(owner(u)))  (graph_partition_utils.cuh:101-128)."""
+    g = groups or make_groups()
+    P, Cc = g.world, g.C
+    so, do = vertex_owner(src, P), vertex_owner(dst, P)
+    target = (do // Cc) * Cc + (so % Cc)
+    payload = [src, dst] + ([weights] if weights is not None else [])
+    recv, _, _, _ = exchange(payload, target, P)
+    src_e, dst_e = recv[0], recv[1]
+    w_e = recv[2] if weights is not None else None
+    # vertices referenced here -> their owners (owner keeps the sorted union = its local numbering)
+    u = torch.unique(torch.cat([src_e, dst_e]))
+    ou = vertex_owner(u, P)
+    (recv_ids,), order, sc, rc = exchange([u], ou, P)
+    mine = torch.unique(recv_ids)                       # sorted external ids owned by this rank
+    n_local = int(mine.numel())
+    pos = torch.searchsorted(mine, recv_ids)            # local id of every requested vertex
+    back = torch.empty(sum(sc), dtype=pos.dtype, device=pos.device)
+    dist.all_to_all_single(back, pos.contiguous(), output_split_sizes=sc, input_split_sizes=rc)
+    lid = torch.empty_like(back)
+    lid[order] = back                                   # lid[k] = local id (at its owner) of u[k]
+    t = torch.tensor([n_local, n_local], dtype=torch.int64, device=src.device)
+    mx = t[:1].clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    tot = t[1:].clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    maxpart = max(int(mx.item()), 1)
+    ks, kd = torch.searchsorted(u, src_e), torch.searchsorted(u, dst_e)
+    rows = ((ou[kd] % Cc) * maxpart + lid[kd]).to(torch.int32)
+    cols = ((ou[ks] // Cc) * maxpart + lid[ks]).to(torch.int32)
+    return Partition(g, rows, cols, w_e, mine, n_local, maxpart, int(tot.item()))
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA side
+# ----------------------------------------------------------------------------------------------
+def _view(t):
+    from cugraph_b200.pylibcugraph.utils import View
+    return View(t)
+
+
+class MGGraph:
+    """This rank's edge block of a 2D-partitioned graph (pull orientation: rows = destinations)."""
+
+    def __init__(self, src, dst, weights=None, groups: Groups | None = None, dtype=torch.float32):
+        from cugraph_b200 import _capi
+        from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
+        assert src.is_cuda, "MGGraph needs CUDA tensors"
+        self.lib = _capi.lib()
+        self._capi = _capi
+        self.dtype = dtype if weights is None else weights.dtype
+        self.part = partition_edges(src, dst, weights, groups)
+        p = self.part
+        g = p.groups
+        self.handle = ResourceHandle(stream=torch.cuda.current_stream().cuda_stream)
+        self.n_rows, self.n_cols = g.C * p.maxpart, g.R * p.maxpart
+        rv, cv, wv = _view(p.rows), _view(p.cols), _view(p.weights)
+        blk, err = C.c_void_p(), C.c_void_p()
+        code = self.lib.cugraph_b200_block_create(self.handle.ptr, self.n_rows, self.n_cols, rv.ptr, cv.ptr, wv.ptr,
+                                                  C.byref(blk), C.byref(err))
+        for v in (rv, cv, wv):
+            v.free()
+        _capi.check(code, err, "cugraph_b200_block_create")
+        self.block = blk.value
+        self.span = int(self.lib.cugraph_b200_block_span(self.block))
+        es = 4 if self.dtype == torch.float32 else 8
+        self.x_elems = int(self.lib.cugraph_b200_padded_elems(self.span, es))
+        # out-weight sums of the owned vertices: partial per column slot, reduce-scattered in the column group
+        ones = p.weights.to(torch.float64) if p.weights is not None else torch.ones(p.cols.numel(), dtype=torch.float64, device=src.device)
+        partial = torch.zeros(self.n_cols, dtype=torch.float64, device=src.device)
+        partial.index_add_(0, p.cols.long(), ones)
+        ow = torch.empty(p.maxpart, dtype=torch.float64, device=src.device)
+        reduce_scatter_into(ow, partial, g.col_group)
+        self.out_w = ow.to(self.dtype)
+        self.num_edges_local = int(p.rows.numel())
+        p.rows = p.cols = p.weights = None  # the block owns its own copy
+        torch.cuda.synchronize()
+
+    def __del__(self):
+        try:
+            if getattr(self, "block", None):
+                self.lib.cugraph_b200_block_free(self.block)
+                self.block = None
+        except Exception:
+            pass
+
+    # one PageRank iteration = all-gather(x) -> block sweep -> reduce-scatter(y) -> vertex step -> all-reduce(2 scalars)
+    def pagerank(self, alpha=0.85, epsilon=1e-5, max_iterations=100, time_iterations=False):
+        p, g, L, capi = self.part, self.part.groups, self.lib, self._capi
+        dev, dt, mp = self.out_w.device, self.dtype, p.maxpart
+        pr = torch.zeros(mp, dtype=dt, device=dev)
+        pr[:p.n_local] = 1.0 / p.n_global
+        x_local = torch.zeros(mp, dtype=dt, device=dev)
+        xg = torch.zeros(self.x_elems, dtype=dt, device=dev)
+        ypart = torch.zeros(self.span, dtype=dt, device=dev)
+        yred = torch.zeros(mp, dtype=dt, device=dev)
+        tot = torch.zeros(2, dtype=torch.float64, device=dev)
+        part = torch.zeros(2, dtype=torch.float64, device=dev)
+        views = {k: _view(v) for k, v in dict(pr=pr, x=x_local, xg=xg, yp=ypart, yr=yred, ow=self.out_w).items()}
+        err = C.c_void_p()
+
+        def vertex_step(first):
+            part.zero_()
+            code = L.cugraph_b200_pagerank_vertex_step(self.handle.ptr, views["yr"].ptr, views["pr"].ptr, views["ow"].ptr,
+                                                       views["x"].ptr, p.n_local, float(alpha), float(p.n_global),
+                                                       1 if first else 0, C.c_void_p(tot.data_ptr()),
+                                                       C.c_void_p(part.data_ptr()), C.byref(err))
+            capi.check(code, err, "cugraph_b200_pagerank_vertex_step")
+            dist.all_reduce(part)
+
+        vertex_step(True)
+        tot, part = part, tot
+        iters, converged = 0, False
+        for _ in range(int(max_iterations)):
+            all_gather_into(xg[:self.n_cols], x_local, g.col_group)
+            code = L.cugraph_b200_block_pull_sweep(self.handle.ptr, self.block, views["xg"].ptr, views["yp"].ptr,
+                                                   float(alpha), C.byref(err))
+            capi.check(code, err, "cugraph_b200_block_pull_sweep")
+            reduce_scatter_into(yred, ypart[:self.n_rows], g.row_group)
+            vertex_step(False)
+            tot, part = part, tot
+            iters += 1
+            if epsilon > 0.0 and float(tot[0].item()) < epsilon:   # host sync only when a tolerance is requested
+                break
+        converged = iters < max_iterations
+        for v in views.values():
+            v.free()
+        return p.vertices, pr[:p.n_local].clone(), iters, converged
+
+
+def pagerank(graph: MGGraph, alpha=0.85, epsilon=1e-5, max_iterations=100):
+    """Returns (vertices, pageranks, converged) for the vertices owned by this rank
+    (the MG contract of pylibcugraph.pagerank: every rank gets its local part)."""
+    v, p, it, conv = graph.pagerank(alpha, epsilon, max_iterations)
+    return v, p, conv

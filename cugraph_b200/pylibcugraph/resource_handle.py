@@ -6,9 +6,14 @@ class ResourceHandle:
     """Owns a cugraph_resource_handle_t.  `handle_ptr` None -> single-GPU handle on the current
     device; otherwise the integer address of a cugraph_b200_comm_t (see comms.py)."""
 
-    def __init__(self, handle_ptr=None):
+    def __init__(self, handle_ptr=None, stream=None):
         self._lib = _capi.lib()
-        self._ptr = self._lib.cugraph_create_resource_handle(handle_ptr)
+        if stream is not None:
+            # bind to the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream): library
+            # kernels and torch.distributed collectives are then ordered without host synchronisation
+            self._ptr = self._lib.cugraph_b200_create_resource_handle_on_stream(stream)
+        else:
+            self._ptr = self._lib.cugraph_create_resource_handle(handle_ptr)
         if not self._ptr:
             raise RuntimeError("cugraph_create_resource_handle failed (is a CUDA device available?)")
 

@@ -42,6 +42,34 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_time_pull_spmv(
   const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, size_t iterations,
   double* ms_per_sweep, double* algorithmic_bytes_per_sweep, cugraph_error_t** error);
 
+/*
+ * ---- multi-GPU building blocks (orchestrated by cugraph_b200/mg.py over torch.distributed) ----
+ * The reference keeps its 2D-partitioned edge blocks inside graph_t and runs the exchange inside the
+ * prims (update_edge_src_property / per_v_transform_reduce_e MG paths).  Here the launcher owns the
+ * process groups; the library provides the device pieces.  Every call below only enqueues work on
+ * the handle's stream (create the handle on the caller's stream so that collectives and kernels
+ * are ordered without host synchronisation).
+ */
+typedef struct { int32_t align_; } cugraph_b200_block_t;
+
+CUGRAPH_EXPORT cugraph_resource_handle_t* cugraph_b200_create_resource_handle_on_stream(void* cuda_stream);
+CUGRAPH_EXPORT size_t cugraph_b200_padded_elems(size_t n, size_t elem_size);
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_block_create(
+  const cugraph_resource_handle_t* handle, size_t n_rows, size_t n_cols,
+  const cugraph_type_erased_device_array_view_t* rows, const cugraph_type_erased_device_array_view_t* cols,
+  const cugraph_type_erased_device_array_view_t* weights, cugraph_b200_block_t** block, cugraph_error_t** error);
+CUGRAPH_EXPORT void cugraph_b200_block_free(cugraph_b200_block_t* block);
+CUGRAPH_EXPORT size_t cugraph_b200_block_span(const cugraph_b200_block_t* block);
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_block_pull_sweep(
+  const cugraph_resource_handle_t* handle, cugraph_b200_block_t* block,
+  const cugraph_type_erased_device_array_view_t* x, cugraph_type_erased_device_array_view_t* y, double alpha,
+  cugraph_error_t** error);
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_pagerank_vertex_step(
+  const cugraph_resource_handle_t* handle, const cugraph_type_erased_device_array_view_t* y,
+  cugraph_type_erased_device_array_view_t* pr, const cugraph_type_erased_device_array_view_t* out_w,
+  cugraph_type_erased_device_array_view_t* x, size_t n_local, double alpha, double n_vertices_global, bool_t first,
+  const double* totals_prev_device, double* partial_out_device, cugraph_error_t** error);
+
 #ifdef __cplusplus
 }
 #endif

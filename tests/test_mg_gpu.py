@@ -1,0 +1,84 @@
+"""2-GPU NCCL run of the multi-GPU PageRank (skipped when fewer than 2 GPUs are visible): MG result ==
+oracle on the gathered graph, as the reference's mg_pagerank_test.cpp:158-248 compares MG with SG."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, scale, weighted, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from cugraph_b200 import mg
+    from oracle.rmat import rmat_edgelist
+    s, d = rmat_edgelist(scale, 16 << scale, seed=5)
+    E = s.shape[0]
+    w_all = np.random.default_rng(3).random(E).astype(np.float32) + 0.1
+    lo, hi = rank * E // world, (rank + 1) * E // world
+    w = torch.as_tensor(w_all[lo:hi]).cuda() if weighted else None
+    G = mg.MGGraph(torch.as_tensor(s[lo:hi]).cuda(), torch.as_tensor(d[lo:hi]).cuda(), w)
+    verts, pr, iters, conv = G.pagerank(0.85, 0.0, 40)
+    res = [None] * world
+    dist.all_gather_object(res, (verts.cpu().numpy(), pr.cpu().numpy()))
+    # converging run: iteration count must agree on all ranks and with the scalar exchange
+    v2, p2, it2, c2 = G.pagerank(0.85, 1e-6, 500)
+    if rank == 0:
+        q.put((res, it2, c2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_mg_pagerank_two_gpus(weighted):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import oracle
+    from oracle.rmat import rmat_edgelist
+    scale, world = 14, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, scale, weighted, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, it2, c2 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s, d = rmat_edgelist(scale, 16 << scale, seed=5)
+    w_all = np.random.default_rng(3).random(s.shape[0]).astype(np.float32) + 0.1
+    present = np.unique(np.concatenate([s, d]))
+    remap = -np.ones(1 << scale, dtype=np.int64)
+    remap[present] = np.arange(present.size)
+    ref, _, _ = oracle.pagerank(remap[s], remap[d], present.size, w_all if weighted else None, alpha=0.85, epsilon=0.0,
+                                max_iterations=40)
+    got = np.zeros(present.size)
+    n = 0
+    for verts, vals in res:
+        got[remap[verts]] = vals
+        n += verts.size
+    assert n == present.size
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-12)
+    _, it_ref, conv_ref = oracle.pagerank(remap[s], remap[d], present.size, w_all if weighted else None, alpha=0.85,
+                                          epsilon=1e-6, max_iterations=500)
+    assert c2 == conv_ref and abs(it2 - it_ref) <= 1
