@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json configs[1]): PageRank on RMAT scale-24 edge-factor-16 (Graph500 a,b,c,
 multi-edges and self-loops kept, scrambled ids, unweighted, int32 ids / float32 scores), alpha 0.85,
-epsilon 0 (never converges), 100 iterations, graph stored transposed.  N>1: scale-27, 2D edge partition.
+epsilon 0 (never converges), 100 iterations, graph stored transposed.  N>1: weak scaling with 2^28 edge
+draws per GPU (scale 24 + log2 N; N = 8 is BASELINE's scale-27 configuration), 2D edge partition.
 
 A STEP is one call of `cugraph_pagerank_allow_nonconvergence` (100 iterations) through the C-ABI.
   value  = MTEPS = E * iterations * steps / time, graph already resident in HBM (graph creation is
@@ -253,7 +254,17 @@ def run_multi(args):
     run_mg_pagerank(args, METRIC, ALPHA, ITERS, ClockSampler, _peaks)
 
 
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun children) write to fd 1; the contract is ONE JSON line on
+    stdout.  Route fd 1 to stderr for the run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -265,9 +276,7 @@ def main():
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
-        if args.scale is None:
-            args.scale = 27
-        return run_multi(args)
+        return run_multi(args)  # weak scaling: scale 24 + log2(N); N = 8 is BASELINE's scale-27 configuration
     if args.scale is None:
         args.scale = 24
     return run_single(args)

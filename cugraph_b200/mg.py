@@ -117,6 +117,17 @@ def reduce_scatter_into(out: torch.Tensor, inp: torch.Tensor, group):
         out.copy_(tmp[k * out.numel():(k + 1) * out.numel()])
 
 
+def _unique_big(tensors, chunk=1 << 29):
+    """sorted unique of the concatenation, in pieces (torch.unique is limited to < 2^31 elements)."""
+    parts = []
+    for t in tensors:
+        for i in range(0, max(t.numel(), 1), chunk):
+            parts.append(torch.unique(t[i:i + chunk]))
+    while len(parts) > 1:
+        parts = [torch.unique(torch.cat(parts[i:i + 2])) for i in range(0, len(parts), 2)]
+    return parts[0]
+
+
 # ----------------------------------------------------------------------------------------------
 # 2D partition
 # ----------------------------------------------------------------------------------------------
@@ -124,9 +135,9 @@ def reduce_scatter_into(out: torch.Tensor, inp: torch.Tensor, group):
 class Partition:
     groups: Groups
     rows: torch.Tensor        # int32, local destination slot of every local edge: c_v * maxpart + lid
-    cols: torch.Tensor        # int32, local source slot: r_u * maxpart + lid
+    cols: torch.Tensor        # int32, local source slot: lid * R + r_u (interleaved)
     weights: object           # tensor or None
-    vertices: torch.Tensor    # external ids of the vertices this rank owns (sorted)
+    vertices: torch.Tensor    # external ids of the vertices this rank owns, in local-id order
     n_local: int
     maxpart: int
     n_global: int
@@ -143,13 +154,23 @@ def partition_edges(src: torch.Tensor, dst: torch.Tensor, weights=None, groups: 
     recv, _, _, _ = exchange(payload, target, P)
     src_e, dst_e = recv[0], recv[1]
     w_e = recv[2] if weights is not None else None
-    # vertices referenced here -> their owners (owner keeps the sorted union = its local numbering)
-    u = torch.unique(torch.cat([src_e, dst_e]))
+    # vertices referenced here -> their owners, together with how often each is a SOURCE here; the owner
+    # numbers its vertices by descending global out-degree so that hot sources get the lowest local ids
+    # (the column-blocked sweep keeps the lowest column ids in shared memory) — the role of the
+    # reference's per-GPU degree-descending renumbering (renumber_edgelist_impl.cuh:732-738)
+    u = _unique_big([src_e, dst_e])
+    ks = torch.searchsorted(u, src_e)
+    cnt = torch.bincount(ks, minlength=u.numel()).to(torch.int64)
     ou = vertex_owner(u, P)
-    (recv_ids,), order, sc, rc = exchange([u], ou, P)
-    mine = torch.unique(recv_ids)                       # sorted external ids owned by this rank
+    (recv_ids, recv_cnt), order, sc, rc = exchange([u, cnt], ou, P)
+    mine, inv = torch.unique(recv_ids, return_inverse=True)   # sorted external ids owned by this rank
     n_local = int(mine.numel())
-    pos = torch.searchsorted(mine, recv_ids)            # local id of every requested vertex
+    deg = torch.zeros(n_local, dtype=torch.int64, device=src.device).index_add_(0, inv, recv_cnt)
+    by_deg = torch.argsort(-deg, stable=True)                  # by_deg[l] = index into `mine` of local id l
+    lid_of_mine = torch.empty_like(by_deg)
+    lid_of_mine[by_deg] = torch.arange(n_local, device=src.device)
+    pos = lid_of_mine[inv]                                     # local id of every requested vertex
+    mine = mine[by_deg]                                        # external ids in local-id order
     back = torch.empty(sum(sc), dtype=pos.dtype, device=pos.device)
     dist.all_to_all_single(back, pos.contiguous(), output_split_sizes=sc, input_split_sizes=rc)
     lid = torch.empty_like(back)
@@ -160,9 +181,11 @@ def partition_edges(src: torch.Tensor, dst: torch.Tensor, weights=None, groups: 
     tot = t[1:].clone()
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     maxpart = max(int(mx.item()), 1)
-    ks, kd = torch.searchsorted(u, src_e), torch.searchsorted(u, dst_e)
+    kd = torch.searchsorted(u, dst_e)
     rows = ((ou[kd] % Cc) * maxpart + lid[kd]).to(torch.int32)
-    cols = ((ou[ks] // Cc) * maxpart + lid[ks]).to(torch.int32)
+    # columns are INTERLEAVED across the R partitions of the column group (slot = lid * R + r_u): the hot
+    # sources of every partition share the lowest column ids
+    cols = (lid[ks] * g.R + (ou[ks] // Cc)).to(torch.int32)
     return Partition(g, rows, cols, w_e, mine, n_local, maxpart, int(tot.item()))
 
 
@@ -204,6 +227,7 @@ class MGGraph:
         ones = p.weights.to(torch.float64) if p.weights is not None else torch.ones(p.cols.numel(), dtype=torch.float64, device=src.device)
         partial = torch.zeros(self.n_cols, dtype=torch.float64, device=src.device)
         partial.index_add_(0, p.cols.long(), ones)
+        partial = partial.view(p.maxpart, g.R).t().contiguous().view(-1)   # interleaved -> partition-major
         ow = torch.empty(p.maxpart, dtype=torch.float64, device=src.device)
         reduce_scatter_into(ow, partial, g.col_group)
         self.out_w = ow.to(self.dtype)
@@ -227,6 +251,7 @@ class MGGraph:
         pr[:p.n_local] = 1.0 / p.n_global
         x_local = torch.zeros(mp, dtype=dt, device=dev)
         xg = torch.zeros(self.x_elems, dtype=dt, device=dev)
+        xseg = torch.zeros(self.n_cols, dtype=dt, device=dev)
         ypart = torch.zeros(self.span, dtype=dt, device=dev)
         yred = torch.zeros(mp, dtype=dt, device=dev)
         tot = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -247,7 +272,11 @@ class MGGraph:
         tot, part = part, tot
         iters, converged = 0, False
         for _ in range(int(max_iterations)):
-            all_gather_into(xg[:self.n_cols], x_local, g.col_group)
+            if g.R == 1:
+                xg[:mp].copy_(x_local)
+            else:
+                all_gather_into(xseg, x_local, g.col_group)              # [R, maxpart] partition-major
+                xg[:self.n_cols].view(mp, g.R).copy_(xseg.view(g.R, mp).t())  # -> interleaved column order
             code = L.cugraph_b200_block_pull_sweep(self.handle.ptr, self.block, views["xg"].ptr, views["yp"].ptr,
                                                    float(alpha), C.byref(err))
             capi.check(code, err, "cugraph_b200_block_pull_sweep")

@@ -46,15 +46,16 @@ def _worker(rank, world, port, scale, weighted, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("weighted", [False, True])
-def test_mg_pagerank_two_gpus(weighted):
+def test_mg_pagerank_multi_gpu(weighted, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     import oracle
     from oracle.rmat import rmat_edgelist
-    scale, world = 14, 2
+    scale = 14
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
