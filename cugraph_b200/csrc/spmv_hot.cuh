@@ -66,82 +66,68 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 
 // One chunk = up to 1024 consecutive edges of one block = n_seg (row, block) segments.
 // HOT: gather from the shared-memory slice; else (cold block) from global x.
-// Software pipeline over the passes of a lane group: while pass n is consumed, the index loads of pass
-// n+1 and the segment bounds of pass n+2 are already in flight (the kernel is bound by the latency of the
-// index stream, not by bandwidth: profiles/r01_notes.md).
 template <typename T, bool WEIGHTED, bool HOT>
 __device__ __forceinline__ void hot_process_chunk(int cb, int ce, int seg0, int n_seg, int lg,
                                                   int32_t const* __restrict__ seg_start,
                                                   int32_t const* __restrict__ seg_row,
-                                                  uint16_t const* __restrict__ tile /* idx16, indexed by position */,
+                                                  uint16_t const* __restrict__ tile /* smem, index 0 = edge cb */,
                                                   int32_t const* __restrict__ idx32,
                                                   int cold_base, T const* __restrict__ w, T const* __restrict__ x,
                                                   T const* __restrict__ sx, double* __restrict__ acc_hi, int lane)
 {
-  constexpr int kR      = 8;  // edges per lane per round
-  const uint16_t* idx16 = tile;
-  const int g           = 1 << lg;
-  const int sub         = lane & (g - 1);
-  const int groups      = 32 >> lg;
-
-  auto bounds = [&](int jj, int& lo, int& hi, int& row) {
-    lo = ce; hi = ce; row = 0;
-    if (jj < n_seg) {
-      lo  = seg_start[seg0 + jj];
-      hi  = seg_start[seg0 + jj + 1];
-      row = seg_row[seg0 + jj];
+  const uint16_t* idx16 = tile;  // idx16[i] is the column of permuted position i
+  const int g      = 1 << lg;
+  const int sub    = lane & (g - 1);
+  const int groups = 32 >> lg;
+  int j            = lane >> lg;
+  // bounds of this group's first segment (afterwards prefetched one pass ahead)
+  int lo = ce, hi = ce, row = 0;
+  if (j < n_seg) {
+    lo  = seg_start[seg0 + j];
+    hi  = seg_start[seg0 + j + 1];
+    row = seg_row[seg0 + j];
+  }
+  while (__any_sync(0xffffffffu, j < n_seg)) {
+    const int jn = j + groups;
+    int lo_n = ce, hi_n = ce, row_n = 0;
+    if (jn < n_seg) {
+      lo_n  = seg_start[seg0 + jn];
+      hi_n  = seg_start[seg0 + jn + 1];
+      row_n = seg_row[seg0 + jn];
     }
-  };
-  auto issue = [&](int first, int hi, unsigned (&c)[kR], T (&wv)[kR]) {
+    lo = lo < cb ? cb : lo;
+    hi = hi > ce ? ce : hi;
+    double acc = 0.0;
+    // rounds of kR predicated edges per lane: all index loads of a round are issued back to back
+    // (no serial remainder loop: every load of the round is in flight together)
+    constexpr int kR = 8;
+    for (int i = lo + sub; i < hi; i += kR * g) {
+      unsigned c[kR];
+      T wv[kR];
 #pragma unroll
-    for (int k = 0; k < kR; ++k) {
-      const int e = first + k * g;
-      c[k]        = 0;
-      wv[k]       = (T)0;
-      if (e < hi) {
-        c[k]  = HOT ? (unsigned)idx16[e] : (unsigned)idx32[e - cold_base];
-        wv[k] = WEIGHTED ? w[e] : (T)1;
+      for (int k = 0; k < kR; ++k) {
+        const int e = i + k * g;
+        c[k]        = 0;
+        wv[k]       = (T)0;
+        if (e < hi) {
+          c[k]  = HOT ? (unsigned)idx16[e] : (unsigned)idx32[e - cold_base];
+          wv[k] = WEIGHTED ? w[e] : (T)1;
+        }
       }
-    }
-  };
-  auto gather_sum = [&](unsigned const (&c)[kR], T const (&wv)[kR]) {
-    T v[kR];
+      T v[kR];
 #pragma unroll
-    for (int k = 0; k < kR; ++k) v[k] = (HOT ? sx[c[k]] : x[c[k]]) * wv[k];
-    return (((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3])) +
-           (((double)v[4] + (double)v[5]) + ((double)v[6] + (double)v[7]));
-  };
-
-  int j0 = lane >> lg, j1 = j0 + groups;
-  int lo0, hi0, row0, lo1, hi1, row1;
-  bounds(j0, lo0, hi0, row0);
-  bounds(j1, lo1, hi1, row1);
-  lo0 = lo0 < cb ? cb : lo0;
-  hi0 = hi0 > ce ? ce : hi0;
-  unsigned c0[kR], c1[kR];
-  T w0[kR], w1[kR];
-  issue(lo0 + sub, hi0, c0, w0);
-  while (__any_sync(0xffffffffu, j0 < n_seg)) {
-    const int j2 = j1 + groups;
-    int lo2, hi2, row2;
-    bounds(j2, lo2, hi2, row2);          // bounds two passes ahead
-    lo1 = lo1 < cb ? cb : lo1;
-    hi1 = hi1 > ce ? ce : hi1;
-    issue(lo1 + sub, hi1, c1, w1);       // indices one pass ahead
-    double acc = gather_sum(c0, w0);
-    for (int i = lo0 + sub + kR * g; i < hi0; i += kR * g) {  // rare: segment longer than one round
-      issue(i, hi0, c0, w0);
-      acc += gather_sum(c0, w0);
+      for (int k = 0; k < kR; ++k) v[k] = (HOT ? sx[c[k]] : x[c[k]]) * wv[k];
+      double part = 0.0;
+#pragma unroll
+      for (int k = 0; k < kR; k += 4) part += ((double)v[k] + (double)v[k + 1]) + ((double)v[k + 2] + (double)v[k + 3]);
+      acc += part;
     }
     for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0 && hi0 > lo0) atomicAdd(acc_hi + row0, acc);
-    j0 = j1; lo0 = lo1; hi0 = hi1; row0 = row1;
-#pragma unroll
-    for (int k = 0; k < kR; ++k) {
-      c0[k] = c1[k];
-      w0[k] = w1[k];
-    }
-    j1 = j2; lo1 = lo2; hi1 = hi2; row1 = row2;
+    if (sub == 0 && hi > lo) atomicAdd(acc_hi + row, acc);
+    j   = jn;
+    lo  = lo_n;
+    hi  = hi_n;
+    row = row_n;
   }
 }
 
