@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -317,6 +318,7 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   // Beamer's switch points (the reference: bfs_impl.cuh:291-297, alpha ~ E/V*0.267, beta = 24)
   const double alpha = 14.0, beta = 24.0;
   const int full_grid = h.sm_count * 8;
+  const bool trace    = std::getenv("CUGRAPH_B200_BFS_TRACE") != nullptr;
   while (n_f > 0 && level < depth_limit) {
     if (direction_optimizing) {
       unsigned long long m_u = m_total - std::min(m_vis, m_total);
@@ -357,6 +359,9 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
     }
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
     sync(h);
+    if (trace)
+      std::fprintf(stderr, "bfs level %d %s n_f=%d m_f=%llu m_vis=%llu n_vis=%lld -> next n_f=%d m_f=%llu\n", level,
+                   bottom_up ? "bottom-up" : "top-down", n_f, m_f, m_vis, n_vis, hc->n_small + hc->n_large, hc->m_f);
     prev_n_f = n_f;
     n_small  = hc->n_small;
     n_large  = hc->n_large;
@@ -504,7 +509,9 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   sync(h);
   const double avg_w   = hsum / (double)c.nnz;
   const double avg_deg = (double)c.nnz / (double)nv;
-  T delta              = (T)(32.0 * avg_w / std::max(avg_deg, 1e-30));
+  double delta_scale = 1.0;  // tuning knob (results do not depend on it)
+  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_DELTA_SCALE")) delta_scale = std::atof(e);
+  T delta = (T)(32.0 * avg_w / std::max(avg_deg, 1e-30) * delta_scale);
   if (!(delta > (T)0)) delta = (T)1;
 
   dbuf stamp = make_dbuf<int32_t>(nv, h.stream), far_stamp = make_dbuf<int32_t>(nv, h.stream);
