@@ -17,6 +17,8 @@
 //    hubs first), the next-frontier word is assembled with a ballot — no atomics.
 #include "graph.cuh"
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <cfloat>
 #include <climits>
@@ -28,7 +30,6 @@ namespace b200 {
 namespace {
 
 constexpr int kBlock       = 256;
-constexpr int kLargeDegree = 8192;
 
 inline int grid_for(int64_t n) { return (int)std::min<int64_t>(std::max<int64_t>((n + kBlock - 1) / kBlock, 1), 1 << 22); }
 
@@ -62,80 +63,140 @@ __device__ __forceinline__ void warp_add_u64(unsigned long long* target, unsigne
 }
 
 // ------------------------------------------------------------------------------------------
-// generic load-balanced advance over a queue of frontier vertices
+// generic load-balanced advance over a queue of frontier vertices (merge-path style):
+//   1. degrees of the queue entries -> exclusive scan (CUB, library code for the tiny per-level scan)
+//   2. the summed edge range is cut into tiles of kTileEdges; a CTA finds the vertices of its tile by
+//      binary search, stages their scan / offsets in shared memory and strides over the tile's edges.
+// Every CTA gets the same number of edges whatever the degree mix (a 400k-edge hub is spread over
+// ~200 CTAs, 2000 degree-1 vertices share one).
 // Op: __device__ void edge(int src, long long e, int nbr)
 // ------------------------------------------------------------------------------------------
-template <typename O, typename Op, bool SKIP_LARGE>
+constexpr int kTileEdges = 2048;
+constexpr int kTileVerts = 2048;
+
+template <typename O>
+__global__ void k_queue_degrees(O const* __restrict__ off, int32_t const* __restrict__ q, int n, int32_t* __restrict__ deg)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) deg[i] = (int32_t)((long long)off[q[i] + 1] - (long long)off[q[i]]);
+  if (i == n) deg[i] = 0;
+}
+
+__device__ __forceinline__ int upper_bound_minus1(int32_t const* a, int n, int key)
+{
+  int lo = 0, hi = n;  // first index with a[idx] > key
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] <= key) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+// IDENT: the queue is the identity (vertex k is queue entry k) and `scan` are the row offsets themselves
+template <typename O, typename Op, bool IDENT>
 __global__ void __launch_bounds__(kBlock)
 k_advance(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ frontier,
-          int n_frontier, Op op)
+          int n_frontier, int32_t const* __restrict__ scan /* n_frontier + 1 */, Op op)
 {
-  __shared__ int s_scan[kBlock + 1];
-  __shared__ long long s_beg[kBlock];
-  __shared__ int s_src[kBlock];
+  __shared__ int s_scan[kTileVerts + 1];
+  __shared__ int s_owner[kTileEdges];
   __shared__ int s_warp[kBlock / 32];
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  for (int base = blockIdx.x * kBlock; base < n_frontier; base += gridDim.x * kBlock) {
-    int v = -1, deg = 0;
-    long long beg = 0;
-    if (base + t < n_frontier) {
-      v   = frontier[base + t];
-      beg = (long long)off[v];
-      deg = (int)((long long)off[v + 1] - beg);
-      if (SKIP_LARGE && deg >= kLargeDegree) deg = 0;  // such vertices sit in the large queue
+  __shared__ int s_k0, s_k1;
+  constexpr int kPer = kTileEdges / kBlock;  // consecutive slots per thread in the owner fill
+  const int total    = scan[n_frontier];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int tile = blockIdx.x; (long long)tile * kTileEdges < total; tile += gridDim.x) {
+    const int e0 = tile * kTileEdges;
+    const int e1 = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
+    if (threadIdx.x == 0) {
+      s_k0 = upper_bound_minus1(scan, n_frontier, e0);
+      s_k1 = upper_bound_minus1(scan, n_frontier, e1 - 1);
     }
-    // block exclusive scan of deg
-    int incl = deg;
+    for (int i = threadIdx.x; i < kTileEdges; i += kBlock) s_owner[i] = -1;
+    __syncthreads();
+    const int k0 = s_k0, k1 = s_k1;
+    const int nv = k1 - k0 + 1;
+    const bool staged = nv <= kTileVerts;
+    if (staged)
+      for (int i = threadIdx.x; i <= nv; i += kBlock) s_scan[i] = scan[k0 + i];
+    __syncthreads();
+    // mark the first slot of every queue entry of the tile (empty entries share a slot with their
+    // successor: the largest index wins), then fill forward with a block-wide max-scan
+    for (int k = k0 + threadIdx.x; k <= k1; k += kBlock) {
+      const int start = staged ? s_scan[k - k0] : scan[k];
+      const int p     = (start > e0 ? start : e0) - e0;
+      if (p < e1 - e0) atomicMax(s_owner + p, k);
+    }
+    __syncthreads();
+    int own[kPer];
+    int run = -1;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int o = s_owner[threadIdx.x * kPer + j];
+      run         = o > run ? o : run;
+      own[j]      = run;
+    }
+    int incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl = y > incl ? y : incl;
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    if (wid == 0) {
-      int w = (lane < kBlock / 32) ? s_warp[lane] : 0;
+    int before = -1;  // max over all previous threads
+    for (int wv = 0; wv < wid; ++wv) before = s_warp[wv] > before ? s_warp[wv] : before;
+    const int prev_lane = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane > 0) before = prev_lane > before ? prev_lane : before;
 #pragma unroll
-      for (int o = 1; o < kBlock / 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += y;
-      }
-      if (lane < kBlock / 32) s_warp[lane] = w;  // inclusive over warps
-    }
+    for (int j = 0; j < kPer; ++j) s_owner[threadIdx.x * kPer + j] = own[j] > before ? own[j] : before;
     __syncthreads();
-    int warp_off = wid > 0 ? s_warp[wid - 1] : 0;
-    s_scan[t]    = warp_off + incl - deg;
-    s_beg[t]     = beg;
-    s_src[t]     = v;
-    if (t == kBlock - 1) s_scan[kBlock] = warp_off + incl;
-    __syncthreads();
-    const int total = s_scan[kBlock];
-    for (int i = t; i < total; i += kBlock) {
-      int lo = 0, hi = kBlock;  // last k with s_scan[k] <= i
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (s_scan[mid] <= i) lo = mid; else hi = mid;
-      }
-      long long e = s_beg[lo] + (i - s_scan[lo]);
-      op.edge(s_src[lo], e, idx[e]);
+    for (int e = e0 + threadIdx.x; e < e1; e += kBlock) {
+      const int k   = s_owner[e - e0];
+      const int v   = IDENT ? k : frontier[k];
+      const int beg = staged ? s_scan[k - k0] : scan[k];
+      const long long pos = (long long)off[v] + (e - beg);
+      op.edge(v, pos, idx[pos]);
     }
     __syncthreads();
   }
 }
 
-// hubs: every vertex of the large queue is expanded edge-parallel by the whole grid
-template <typename O, typename Op>
-__global__ void __launch_bounds__(kBlock)
-k_advance_large(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ frontier,
-                int n_frontier, Op op)
-{
-  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long nt  = (long long)gridDim.x * blockDim.x;
-  for (int j = 0; j < n_frontier; ++j) {
-    int v         = frontier[j];
-    long long beg = (long long)off[v], end = (long long)off[v + 1];
-    for (long long e = beg + tid; e < end; e += nt) op.edge(v, e, idx[e]);
+// per-algorithm scratch for the advance
+struct advance_scratch_t {
+  dbuf deg, scan, tmp;
+  size_t tmp_bytes{0};
+  void init(handle_impl const& h, int32_t nv)
+  {
+    deg  = make_dbuf<int32_t>((size_t)nv + 1, h.stream);
+    scan = make_dbuf<int32_t>((size_t)nv + 1, h.stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg.as<int32_t>(), scan.as<int32_t>(), nv + 1, h.stream);
+    tmp = dbuf(tmp_bytes, h.stream);
   }
+};
+
+// total_edges = sum of the degrees of the queue entries (known on the host from the previous level)
+template <typename O, typename Op>
+void advance(handle_impl const& h, advance_scratch_t& sc, O const* off, int32_t const* idx, int32_t const* queue, int n,
+             unsigned long long total_edges, Op op)
+{
+  if (n <= 0) return;
+  B200_EXPECTS(total_edges < (1ull << 31), CUGRAPH_UNKNOWN_ERROR, "frontier too large for one advance");
+  B200_LAUNCH(h, (k_queue_degrees<O>), (n + 1 + kBlock - 1) / kBlock, kBlock, 0, off, queue, n, sc.deg.as<int32_t>());
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(sc.tmp.data(), sc.tmp_bytes, sc.deg.as<int32_t>(), sc.scan.as<int32_t>(), n + 1, h.stream));
+  h.launches += 2;
+  if (total_edges == 0) return;
+  int grid = (int)std::min<unsigned long long>((total_edges + kTileEdges - 1) / kTileEdges, (unsigned long long)h.sm_count * 8);
+  B200_LAUNCH(h, (k_advance<O, Op, false>), grid, kBlock, 0, off, idx, queue, n, sc.scan.as<int32_t>(), op);
+}
+
+// every edge of the graph, edge-balanced: the row offsets are the scan of the identity queue
+template <typename Op>
+void advance_all_edges(handle_impl const& h, int32_t const* off, int32_t const* idx, int32_t n_vertices, long long nnz, Op op)
+{
+  if (nnz <= 0) return;
+  int grid = (int)std::min<long long>((nnz + kTileEdges - 1) / kTileEdges, (long long)h.sm_count * 8);
+  B200_LAUNCH(h, (k_advance<int32_t, Op, true>), grid, kBlock, 0, off, idx, (int32_t const*)nullptr, n_vertices, off, op);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -147,8 +208,8 @@ __device__ __forceinline__ unsigned enqueue_by_degree(O const* off, int v, int32
                                                       frontier_counters_t* cnt)
 {
   const unsigned d = (unsigned)((long long)off[v + 1] - (long long)off[v]);
-  if (d >= (unsigned)kLargeDegree) q_large[warp_append(&cnt->n_large)] = v;
-  else q_small[warp_append(&cnt->n_small)] = v;
+  (void)q_large;  // the merge-path advance balances any degree mix: one queue
+  q_small[warp_append(&cnt->n_small)] = v;
   return d;
 }
 
@@ -319,6 +380,8 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   const double alpha = 14.0, beta = 24.0;
   const int full_grid = h.sm_count * 8;
   const bool trace    = std::getenv("CUGRAPH_B200_BFS_TRACE") != nullptr;
+  advance_scratch_t adv;
+  adv.init(h, nv);
   while (n_f > 0 && level < depth_limit) {
     if (direction_optimizing) {
       unsigned long long m_u = m_total - std::min(m_vis, m_total);
@@ -335,12 +398,7 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
         mixed_queue        = true;
       }
       bfs_topdown_op<O> op{off, visited.as<uint32_t>(), dist, pred, nxt, nxt_l, dc, level};
-      if (n_small > 0) {
-        int grid = std::min((n_small + kBlock - 1) / kBlock, full_grid);
-        if (mixed_queue) B200_LAUNCH(h, (k_advance<O, bfs_topdown_op<O>, false>), grid, kBlock, 0, off, idx, cur, n_small, op);
-        else B200_LAUNCH(h, (k_advance<O, bfs_topdown_op<O>, true>), grid, kBlock, 0, off, idx, cur, n_small, op);
-      }
-      if (n_large > 0) B200_LAUNCH(h, (k_advance_large<O, bfs_topdown_op<O>>), full_grid, kBlock, 0, off, idx, cur_l, n_large, op);
+      advance<O>(h, adv, off, idx, cur, n_small, m_f, op);
       std::swap(cur, nxt);
       std::swap(cur_l, nxt_l);
       mixed_queue = false;
@@ -408,7 +466,10 @@ struct sssp_relax_op {
     const T old = atomic_min_nonneg(dist + nbr, nd);
     if (!(nd < old)) return;
     if (nd < threshold) {
-      if (atomicExch(stamp + nbr, round) != round) enqueue_by_degree(off, nbr, next_near, next_near_large, cnt);
+      if (atomicExch(stamp + nbr, round) != round) {
+        const unsigned d = enqueue_by_degree(off, nbr, next_near, next_near_large, cnt);
+        warp_add_u64(&cnt->m_f, d);
+      }
     } else {
       if (atomicExch(far_stamp + nbr, window) != window) far[warp_append(&cnt->n_far)] = nbr;
     }
@@ -428,7 +489,10 @@ __global__ void k_split_far(O const* __restrict__ off, int32_t const* __restrict
   T d   = dist[v];
   if (d < lo) return;  // settled through the near pile meanwhile
   if (d < hi) {
-    if (atomicExch(stamp + v, round) != round) enqueue_by_degree(off, v, near_out, near_large_out, cnt);
+    if (atomicExch(stamp + v, round) != round) {
+      const unsigned d = enqueue_by_degree(off, v, near_out, near_large_out, cnt);
+      warp_add_u64(&cnt->m_f, d);
+    }
   } else {
     if (atomicExch(far_stamp + v, window) != window) far_out[warp_append(&cnt->n_far)] = v;
   }
@@ -467,6 +531,20 @@ __global__ void k_sssp_pred(O const* __restrict__ off, int32_t const* __restrict
     }
   }
 }
+
+template <typename T>
+struct sssp_pred_op {
+  T const* w;
+  T const* dist;
+  int32_t* pred;
+  int32_t source;
+  T unreached;
+  __device__ __forceinline__ void edge(int src, long long e, int nbr) const
+  {
+    const T du = dist[src];
+    if (du != unreached && nbr != source && nbr != src && du + w[e] == dist[nbr]) pred[nbr] = src;
+  }
+};
 
 template <typename T>
 __global__ void k_sum_weights(T const* __restrict__ w, long long n, double* out)
@@ -531,30 +609,39 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   int32_t *near_l = la.as<int32_t>(), *next_near_l = lb.as<int32_t>();
   int32_t *far = fa.as<int32_t>(), *far2 = fb.as<int32_t>();
   int n_near = 1, n_near_l = 0, n_far = 0, round = 1, window = 1;
-  bool mixed = true;  // the seed may be a hub sitting in the small queue
+  bool mixed = true;
+  (void)mixed;
+  unsigned long long near_edges = (unsigned long long)c.nnz < (1ull << 31) ? (1ull << 31) - 1 : 0;  // seed: unknown -> full grid
+  advance_scratch_t adv;
+  adv.init(h, nv);
   T lo = (T)0, hi = delta;
   const int full_grid = h.sm_count * 8;
+  const bool trace    = std::getenv("CUGRAPH_B200_SSSP_TRACE") != nullptr;
+  unsigned long long tr_edges = 0;
+  int tr_rounds = 0;
   while (true) {
     while (n_near + n_near_l > 0) {
       ++round;
+      ++tr_rounds;
+      if (near_edges < (1ull << 31) - 1) tr_edges += near_edges;
       CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_small, n_large; n_far keeps running
+      CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
       sssp_relax_op<O, T> op{off, w, dist, stamp.as<int32_t>(), far_stamp.as<int32_t>(), next_near, next_near_l, far,
                              dc, hi, cutoff, round, window};
-      if (n_near > 0) {
-        int grid = std::min((n_near + kBlock - 1) / kBlock, full_grid);
-        if (mixed) B200_LAUNCH(h, (k_advance<O, sssp_relax_op<O, T>, false>), grid, kBlock, 0, off, idx, near, n_near, op);
-        else B200_LAUNCH(h, (k_advance<O, sssp_relax_op<O, T>, true>), grid, kBlock, 0, off, idx, near, n_near, op);
-      }
-      if (n_near_l > 0) B200_LAUNCH(h, (k_advance_large<O, sssp_relax_op<O, T>>), full_grid, kBlock, 0, off, idx, near_l, n_near_l, op);
+      advance<O>(h, adv, off, idx, near, n_near, near_edges, op);
       CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
       sync(h);
-      n_near   = hc->n_small;
-      n_near_l = hc->n_large;
-      n_far    = hc->n_far;
-      mixed    = false;
+      n_near     = hc->n_small;
+      n_near_l   = hc->n_large;
+      n_far      = hc->n_far;
+      near_edges = hc->m_f;
+      mixed      = false;
       std::swap(near, next_near);
       std::swap(near_l, next_near_l);
     }
+    if (trace)
+      std::fprintf(stderr, "sssp window %d hi=%g: rounds so far %d, edges relaxed so far %llu, far pile %d\n", window,
+                   (double)hi, tr_rounds, tr_edges, n_far);
     if (n_far == 0) break;
     // advance the window to the smallest pending distance, then split the far pile
     T inf = (T)INFINITY;
@@ -574,13 +661,19 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
                 far_stamp.as<int32_t>(), round, window, near, near_l, far2, dc);
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
     sync(h);
-    n_near   = hc->n_small;
-    n_near_l = hc->n_large;
-    n_far    = hc->n_far;
+    n_near     = hc->n_small;
+    n_near_l   = hc->n_large;
+    n_far      = hc->n_far;
+    near_edges = hc->m_f;
     std::swap(far, far2);
   }
   if (pred) {
-    B200_LAUNCH(h, (k_sssp_pred<O, T>), h.sm_count * 16, kBlock, 0, off, idx, w, dist, nv, source, unreached, pred);
+    if (sizeof(O) == 4) {
+      sssp_pred_op<T> pop{w, dist, pred, source, unreached};
+      advance_all_edges(h, (int32_t const*)off, idx, nv, (long long)c.nnz, pop);
+    } else {
+      B200_LAUNCH(h, (k_sssp_pred<O, T>), h.sm_count * 16, kBlock, 0, off, idx, w, dist, nv, source, unreached, pred);
+    }
   }
   check_last("sssp");
 }
