@@ -32,24 +32,25 @@ constexpr int kWarpsPerCta = 8;
 // keep their neighbours sorted by source id, a row's adjacency is already partitioned by block; the
 // copy stores the segments block-major: all (row, block 0) segments, then block 1, ...
 // Hot blocks store 16-bit local column ids (halves the index stream), the cold block 32-bit ids.
+// Every (row, block) segment is cut into LANE SLOTS of 8 entries (16 bytes of ids: one 128-bit load per
+// lane); the last slot of a segment is padded with a column that reads 0, so the kernel is predicate-free.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHotSliceBytes = 192 * 1024;  // x slice a CTA keeps in shared memory
+constexpr int kHotZeroPad    = 64;          // trailing elements of the slice that hold zeros (padding target)
+constexpr int kHotSlot       = 8;           // entries per lane slot
 
 struct hot_layout_t {
-  int W{0};
-  int B{0};
+  int W{0};      // source columns per hot block (= slice elements - kHotZeroPad)
+  int B{0};      // hot blocks; the cold block (sources >= B*W) is block B
   int32_t n_hi{0};
   int64_t nnz_hi{0};
-  int64_t nnz_hot{0};
-  dbuf idx16;        // nnz_hot x uint16 : column id - block*W, block-major permuted order
-  dbuf idx32;        // (nnz_hi - nnz_hot) x int32 : column ids of the cold block
-  dbuf w;            // nnz_hi x T in permuted order, or empty
-  dbuf block_start;  // (B+2) x int32 : first permuted position of each block (cold = block B), 8-aligned
-  dbuf seg_row;      // row of every non-empty segment, block-major
-  dbuf seg_start;    // (n_segments+1) x int32 : permuted position where each non-empty segment starts
-  dbuf chunks;       // (n_chunks+1) x int32 : index of the segment that contains the chunk's first edge
-  int32_t n_chunks{0};
-  dbuf units;        // n_units x hot_unit_t (spmv_hot.cuh): <= 128 consecutive chunks of one block
+  int64_t n_hot_slots{0};
+  int64_t n_slots{0};
+  dbuf slot_idx16;   // n_hot_slots x 8 x uint16 : column - block*W, padding -> W (the slice's zero column)
+  dbuf slot_idx32;   // (n_slots - n_hot_slots) x 8 x int32 : cold columns, padding -> n_vertices (x is 0 there)
+  dbuf slot_w;       // n_slots x 8 x T, padding 0; or empty
+  dbuf slot_row;     // n_slots x int32 : row of the slot's segment
+  dbuf units;        // n_units x hot_unit_t (spmv_hot.cuh): <= 8192 consecutive slots of one block
   int32_t n_units{0};
   dbuf unit_counter; // 1 x int : dynamic work distribution cursor (reset by the finish kernel)
   int n_cta{0};

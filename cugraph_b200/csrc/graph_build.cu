@@ -944,21 +944,23 @@ csx_t const& push_view(handle_impl const& h, graph_impl& g)
 }
 
 // ---------------------------------------------------------------------------------------------
-// column-blocked copy of the degree>=32 prefix (hot_layout_t, consumed by spmv_hot.cuh)
+// column-blocked, slotted copy of the degree>=32 prefix (hot_layout_t, consumed by spmv_hot.cuh)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kHotBytes    = kHotSliceBytes;  // graph.cuh: shared-memory x slice of the blocked sweep
-constexpr int kHotChunkLen = 1024;
-constexpr int kHotMaxB     = 24;
+constexpr int kHotMaxB = 24;
 
 // one thread per (block, row): segment = edges of row r whose source lies in block b
 template <typename O>
 __global__ void k_hot_segments(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t n_hi, int B, int W,
-                               int32_t* __restrict__ seg_pos, int32_t* __restrict__ seg_len)
+                               int32_t* __restrict__ seg_pos, int32_t* __restrict__ seg_len, int32_t* __restrict__ seg_slots)
 {
   const long long total = (long long)(B + 1) * n_hi;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p <= total; p += (long long)gridDim.x * blockDim.x) {
+    if (p == total) {
+      seg_slots[p] = 0;
+      continue;
+    }
     const int b = (int)(p / n_hi), r = (int)(p - (long long)b * n_hi);
     const int beg = (int)off[r], end = (int)off[r + 1];
     auto lower = [&](int key) {
@@ -973,163 +975,98 @@ __global__ void k_hot_segments(O const* __restrict__ off, int32_t const* __restr
     const int hi = (b == B) ? end : lower((b + 1) * W);
     seg_pos[p]   = lo;
     seg_len[p]   = hi - lo;
+    seg_slots[p] = (hi - lo + kHotSlot - 1) / kHotSlot;  // 8-entry lane slots this segment needs
   }
 }
 
-// one warp per (block, row) segment: copy into block-major order (block b shifted so that it starts
-// on a multiple of 8 positions: TMA bulk copies of index tiles need 16-byte aligned sources)
+// one warp per (block, row) segment: cut it into 8-entry lane slots; the last slot is padded with the
+// block's zero column (weight 0), so the kernel needs no per-entry predicate
 template <typename T>
-__global__ void k_hot_permute(int32_t const* __restrict__ idx, T const* __restrict__ w, int32_t const* __restrict__ seg_pos,
-                              int32_t const* __restrict__ boff, int32_t const* __restrict__ seg_index,
-                              int32_t const* __restrict__ shift, int32_t n_hi, int B, int W, int cold_base,
-                              uint16_t* __restrict__ idx16, int32_t* __restrict__ idx32, T* __restrict__ w_out,
-                              int32_t* __restrict__ seg_row, int32_t* __restrict__ seg_start)
+__global__ void k_hot_fill_slots(int32_t const* __restrict__ idx, T const* __restrict__ w,
+                                 int32_t const* __restrict__ seg_pos, int32_t const* __restrict__ seg_len,
+                                 int32_t const* __restrict__ slot_off, int32_t n_hi, int B, int W, int zero_col_hot,
+                                 int zero_col_cold, int cold_slot0, uint16_t* __restrict__ idx16,
+                                 int32_t* __restrict__ idx32, T* __restrict__ w_out, int32_t* __restrict__ slot_row)
 {
   const long long total = (long long)(B + 1) * n_hi;
   const int lane        = threadIdx.x & 31;
   for (long long p = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; p < total;
        p += ((long long)gridDim.x * blockDim.x) >> 5) {
-    const int b   = (int)(p / n_hi);
-    const int r   = (int)(p - (long long)b * n_hi);
-    const int src = seg_pos[p], dst = boff[p] + shift[b], len = boff[p + 1] - boff[p];
+    const int len = seg_len[p];
     if (len == 0) continue;
-    if (lane == 0) {
-      seg_row[seg_index[p]]   = r;
-      seg_start[seg_index[p]] = dst;
+    const int b = (int)(p / n_hi), r = (int)(p - (long long)b * n_hi);
+    const int src = seg_pos[p], s0 = slot_off[p], ns = (len + kHotSlot - 1) / kHotSlot;
+    for (int k = lane; k < ns; k += 32) {
+      const int s  = s0 + k;
+      slot_row[s]  = r;
+#pragma unroll
+      for (int j = 0; j < kHotSlot; ++j) {
+        const int e   = k * kHotSlot + j;
+        const bool in = e < len;
+        if (b < B) idx16[(size_t)s * kHotSlot + j] = (uint16_t)(in ? idx[src + e] - b * W : zero_col_hot);
+        else idx32[(size_t)(s - cold_slot0) * kHotSlot + j] = in ? idx[src + e] : zero_col_cold;
+        if (w_out) w_out[(size_t)s * kHotSlot + j] = in ? w[src + e] : (T)0;
+      }
     }
-    for (int i = lane; i < len; i += 32) {
-      const int col = idx[src + i];
-      if (b < B) idx16[dst + i] = (uint16_t)(col - b * W);
-      else idx32[dst + i - cold_base] = col;
-      if (w_out) w_out[dst + i] = w[src + i];
-    }
-  }
-}
-
-__global__ void k_nonempty(int32_t const* __restrict__ len, long long n, int32_t* __restrict__ flag)
-{
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p <= n; p += (long long)gridDim.x * blockDim.x)
-    flag[p] = (p < n && len[p] > 0) ? 1 : 0;
-}
-
-// chunk k of block b starts at block_start[b] + (k - bcb[b]) * 1024; record the segment it starts in
-__global__ void k_hot_chunks(int32_t const* __restrict__ boff, int32_t const* __restrict__ seg_index, int32_t n_hi, int B,
-                             int32_t const* __restrict__ bcb, int32_t* __restrict__ chunks)
-{
-  const int n_chunks = bcb[B + 1];
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_chunks; k += gridDim.x * blockDim.x) {
-    int b = 0;
-    while (b < B && k >= bcb[b + 1]) ++b;
-    const int32_t* bo = boff + (size_t)b * n_hi;
-    const int begin   = bo[0] + (k - bcb[b]) * kHotChunkLen;
-    int lo = 0, hi = n_hi;  // first r with bo[r] > begin
-    while (lo < hi) {
-      int mid = lo + ((hi - lo) >> 1);
-      if (bo[mid] <= begin) lo = mid + 1; else hi = mid;
-    }
-    const int r0 = lo - 1;  // the non-empty row segment that contains `begin`
-    chunks[k]    = seg_index[(size_t)b * n_hi + r0];
   }
 }
 
 struct hot_unit_host_t {  // mirrors hot_unit_t (spmv_hot.cuh)
-  int32_t chunk_begin, chunk_end, block, pos_begin, block_end, head_begin, pad0, pad1;
+  int32_t slot_begin, slot_end, block, pad;
 };
-constexpr int kHotUnitChunks = 128;
+constexpr int kHotUnitSlots = 8192;  // lane slots per work unit (<= 64 K edges)
 
 template <typename O>
 std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const& c, int32_t nv, size_t es)
 {
-  const int W        = (int)(kHotBytes / es);
+  const int W        = (int)(kHotSliceBytes / es) - kHotZeroPad;  // columns per hot block; the pad holds zeros
   const int32_t n_hi = c.seg[0];
   const int B        = (int)std::min<int64_t>(kHotMaxB, ((int64_t)nv + W - 1) / W);
   auto L             = std::make_unique<hot_layout_t>();
   L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = c.nnz_hi;
   const int64_t n_seg = (int64_t)(B + 1) * n_hi;
-  dbuf seg_pos = make_dbuf<int32_t>(n_seg, h.stream), seg_len = make_dbuf<int32_t>(n_seg + 1, h.stream);
-  CUDA_TRY(cudaMemsetAsync(seg_len.as<int32_t>() + n_seg, 0, sizeof(int32_t), h.stream));
-  B200_LAUNCH(h, (k_hot_segments<O>), grid_for(n_seg), kBlock, 0, c.offsets.as<O>(), c.indices.as<int32_t>(), n_hi, B, W,
-              seg_pos.as<int32_t>(), seg_len.as<int32_t>());
-  dbuf boff = make_dbuf<int32_t>(n_seg + 1, h.stream);
-  exclusive_scan_i32(h, seg_len.as<int32_t>(), boff.as<int32_t>(), n_seg + 1);
-  // non-empty segments get consecutive indices (block-major)
-  dbuf flag = make_dbuf<int32_t>(n_seg + 1, h.stream), seg_index = make_dbuf<int32_t>(n_seg + 1, h.stream);
-  B200_LAUNCH(h, k_nonempty, grid_for(n_seg + 1), kBlock, 0, seg_len.as<int32_t>(), (long long)n_seg, flag.as<int32_t>());
-  exclusive_scan_i32(h, flag.as<int32_t>(), seg_index.as<int32_t>(), n_seg + 1);
-  seg_len.release();
-  flag.release();
-  int32_t n_nonempty = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n_nonempty, seg_index.as<int32_t>() + n_seg, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
-  // block boundaries -> chunk counts, head-word bases, work units (host)
-  std::vector<int32_t> bstart(B + 2);
+  dbuf seg_pos = make_dbuf<int32_t>(n_seg, h.stream), seg_len = make_dbuf<int32_t>(n_seg, h.stream);
+  dbuf seg_slots = make_dbuf<int32_t>(n_seg + 1, h.stream), slot_off = make_dbuf<int32_t>(n_seg + 1, h.stream);
+  B200_LAUNCH(h, (k_hot_segments<O>), grid_for(n_seg + 1), kBlock, 0, c.offsets.as<O>(), c.indices.as<int32_t>(), n_hi, B, W,
+              seg_pos.as<int32_t>(), seg_len.as<int32_t>(), seg_slots.as<int32_t>());
+  exclusive_scan_i32(h, seg_slots.as<int32_t>(), slot_off.as<int32_t>(), n_seg + 1);
+  seg_slots.release();
+  std::vector<int32_t> bslot(B + 2);  // first slot of every block (cold = block B), total at [B+1]
   for (int b = 0; b <= B + 1; ++b)
-    CUDA_TRY(cudaMemcpyAsync(&bstart[b], boff.as<int32_t>() + (size_t)std::min<int64_t>((int64_t)b * n_hi, n_seg),
+    CUDA_TRY(cudaMemcpyAsync(&bslot[b], slot_off.as<int32_t>() + (size_t)std::min<int64_t>((int64_t)b * n_hi, n_seg),
                              sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
   sync(h);
-  // shifted block starts: every block begins on a multiple of 8 permuted positions
-  std::vector<int32_t> shift(B + 2, 0), sstart(B + 2, 0);
-  for (int b = 0; b <= B; ++b) {
-    int s      = bstart[b] + shift[b];
-    int pad    = (8 - (s & 7)) & 7;
-    shift[b]   = shift[b] + pad;
-    sstart[b]  = bstart[b] + shift[b];
-    shift[b + 1] = shift[b];
-  }
-  sstart[B + 1]       = bstart[B + 1] + shift[B];
-  const int total_pos = sstart[B + 1];
-  L->nnz_hot          = sstart[B];  // first permuted position of the cold block
-  std::vector<int32_t> bcb(B + 2, 0);
+  L->n_hot_slots = bslot[B];
+  L->n_slots     = bslot[B + 1];
   std::vector<hot_unit_host_t> units;
-  for (int b = 0; b <= B; ++b) {
-    const int tb = bstart[b + 1] - bstart[b];
-    int nch      = (tb + kHotChunkLen - 1) / kHotChunkLen;
-    bcb[b + 1]   = bcb[b] + nch;
-    for (int k = 0; k < nch; k += kHotUnitChunks)
-      units.push_back({bcb[b] + k, bcb[b] + std::min(k + kHotUnitChunks, nch), b, sstart[b] + k * kHotChunkLen,
-                       sstart[b] + tb, 0, 0, 0});
-  }
-  L->n_chunks = bcb[B + 1];
-  L->n_units  = (int32_t)units.size();
-  L->block_start = make_dbuf<int32_t>(B + 2, h.stream);
-  dbuf d_bcb     = make_dbuf<int32_t>(B + 2, h.stream);
-  dbuf d_shift   = make_dbuf<int32_t>(B + 2, h.stream);
-  CUDA_TRY(cudaMemcpyAsync(L->block_start.data(), sstart.data(), sizeof(int32_t) * (B + 2), cudaMemcpyHostToDevice, h.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_bcb.data(), bcb.data(), sizeof(int32_t) * (B + 2), cudaMemcpyHostToDevice, h.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_shift.data(), shift.data(), sizeof(int32_t) * (B + 2), cudaMemcpyHostToDevice, h.stream));
-  L->units = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
+  for (int b = 0; b <= B; ++b)
+    for (int s = bslot[b]; s < bslot[b + 1]; s += kHotUnitSlots)
+      units.push_back({s, std::min(s + kHotUnitSlots, bslot[b + 1]), b, 0});
+  L->n_units = (int32_t)units.size();
+  L->units   = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
   if (!units.empty())
     CUDA_TRY(cudaMemcpyAsync(L->units.data(), units.data(), sizeof(hot_unit_host_t) * units.size(), cudaMemcpyHostToDevice, h.stream));
   L->unit_counter = make_dbuf<int>(1, h.stream);
   CUDA_TRY(cudaMemsetAsync(L->unit_counter.data(), 0, sizeof(int), h.stream));
-  L->seg_row   = make_dbuf<int32_t>(std::max(n_nonempty, 1), h.stream);
-  L->seg_start = make_dbuf<int32_t>((size_t)n_nonempty + 2, h.stream);
-  {
-    int32_t end_pos[2] = {total_pos, total_pos};  // sentinels: one past the last segment
-    CUDA_TRY(cudaMemcpyAsync(L->seg_start.as<int32_t>() + n_nonempty, end_pos, sizeof(end_pos), cudaMemcpyHostToDevice, h.stream));
-    sync(h);
-  }
-  // permuted indices / weights, segment rows and starts (index tiles are copied in 16-byte multiples:
-  // keep 8 spare entries behind the last hot position)
-  L->idx16 = make_dbuf<uint16_t>((size_t)L->nnz_hot + 16, h.stream);
-  CUDA_TRY(cudaMemsetAsync(L->idx16.data(), 0, sizeof(uint16_t) * ((size_t)L->nnz_hot + 16), h.stream));
-  L->idx32 = make_dbuf<int32_t>(std::max<int64_t>(total_pos - L->nnz_hot, 1), h.stream);
+  L->slot_row   = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots, 1), h.stream);
+  L->slot_idx16 = make_dbuf<uint16_t>(std::max<int64_t>(L->n_hot_slots, 1) * kHotSlot, h.stream);
+  L->slot_idx32 = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots - L->n_hot_slots, 1) * kHotSlot, h.stream);
   const bool weighted = c.weights.data() != nullptr;
-  if (weighted) L->w = dbuf((size_t)total_pos * es, h.stream);
+  if (weighted) L->slot_w = dbuf((size_t)std::max<int64_t>(L->n_slots, 1) * kHotSlot * es, h.stream);
+  // padded entries of the cold block read x[zero_col_cold] with weight 0; unweighted cold padding needs a
+  // real zero in x: the caller's x buffer holds zeros behind n_vertices (padded_x_elems)
+  const int zero_col_cold = nv;
   int pgrid = (int)std::min<int64_t>((n_seg * 32 + kBlock - 1) / kBlock, 1 << 20);
   if (es == 4)
-    B200_LAUNCH(h, (k_hot_permute<float>), pgrid, kBlock, 0, c.indices.as<int32_t>(), c.weights.as<float>(),
-                seg_pos.as<int32_t>(), boff.as<int32_t>(), seg_index.as<int32_t>(), d_shift.as<int32_t>(), n_hi, B, W,
-                (int)L->nnz_hot, L->idx16.as<uint16_t>(), L->idx32.as<int32_t>(), L->w.as<float>(),
-                L->seg_row.as<int32_t>(), L->seg_start.as<int32_t>());
+    B200_LAUNCH(h, (k_hot_fill_slots<float>), pgrid, kBlock, 0, c.indices.as<int32_t>(), c.weights.as<float>(),
+                seg_pos.as<int32_t>(), seg_len.as<int32_t>(), slot_off.as<int32_t>(), n_hi, B, W, W, zero_col_cold,
+                (int)L->n_hot_slots, L->slot_idx16.as<uint16_t>(), L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(),
+                L->slot_row.as<int32_t>());
   else
-    B200_LAUNCH(h, (k_hot_permute<double>), pgrid, kBlock, 0, c.indices.as<int32_t>(), c.weights.as<double>(),
-                seg_pos.as<int32_t>(), boff.as<int32_t>(), seg_index.as<int32_t>(), d_shift.as<int32_t>(), n_hi, B, W,
-                (int)L->nnz_hot, L->idx16.as<uint16_t>(), L->idx32.as<int32_t>(), L->w.as<double>(),
-                L->seg_row.as<int32_t>(), L->seg_start.as<int32_t>());
-  L->chunks = make_dbuf<int32_t>((size_t)L->n_chunks + 1, h.stream);
-  CUDA_TRY(cudaMemcpyAsync(L->chunks.as<int32_t>() + L->n_chunks, &n_nonempty, sizeof(int32_t), cudaMemcpyHostToDevice, h.stream));
-  B200_LAUNCH(h, k_hot_chunks, grid_for(L->n_chunks), kBlock, 0, boff.as<int32_t>(), seg_index.as<int32_t>(), n_hi, B,
-              d_bcb.as<int32_t>(), L->chunks.as<int32_t>());
+    B200_LAUNCH(h, (k_hot_fill_slots<double>), pgrid, kBlock, 0, c.indices.as<int32_t>(), c.weights.as<double>(),
+                seg_pos.as<int32_t>(), seg_len.as<int32_t>(), slot_off.as<int32_t>(), n_hi, B, W, W, zero_col_cold,
+                (int)L->n_hot_slots, L->slot_idx16.as<uint16_t>(), L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(),
+                L->slot_row.as<int32_t>());
   check_last("hot layout");
   L->n_cta = h.sm_count;
   sync(h);
@@ -1146,10 +1083,11 @@ hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_v
   tried = true;
   long long min_edges = 1ll << 22;
   if (const char* e = std::getenv("CUGRAPH_B200_HOT_MIN_EDGES")) min_edges = std::atoll(e);
-  const int W = (int)(kHotBytes / elem_size);
+  const int W = (int)(kHotSliceBytes / elem_size) - kHotZeroPad;
   const int B = (int)std::min<int64_t>(kHotMaxB, ((int64_t)n_vertices + W - 1) / W);
+  // slots are at most nnz_hi/8 + one per (row, block) segment
   if (!c.degree_sorted || c.seg[0] <= 0 || c.nnz_hi < min_edges || c.offs64 || c.nnz_hi >= (1ll << 31) - 4096 ||
-      (int64_t)(B + 1) * c.seg[0] >= (1ll << 31) - 2)
+      (int64_t)(B + 1) * c.seg[0] + c.nnz_hi / kHotSlot >= (1ll << 31) - 2)
     return nullptr;
   slot = build_hot_layout<int32_t>(h, c, n_vertices, elem_size);
   return slot.get();

@@ -226,6 +226,7 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
   // state
   dbuf pr_a = make_dbuf<T>(nv, h.stream), pr_b = make_dbuf<T>(nv, h.stream);
   dbuf x    = make_dbuf<T>(padded_x_elems(nv, sizeof(T)), h.stream);  // whole smem slices are TMA-copied
+  CUDA_TRY(cudaMemsetAsync(x.data(), 0, padded_x_elems(nv, sizeof(T)) * sizeof(T), h.stream));  // zeros behind nv
   dbuf acc_hi = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
   CUDA_TRY(cudaMemsetAsync(acc_hi.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
   dbuf state = make_dbuf<pr_state_t>(1, h.stream);
@@ -449,6 +450,7 @@ cugraph_error_code_t cugraph_b200_time_pull_spmv(const cugraph_resource_handle_t
     csx_t const& c = pull_view(h, *g);
     int32_t nv     = g->n_vertices;
     dbuf x = make_dbuf<float>(padded_x_elems(nv, sizeof(float)), h.stream), y = make_dbuf<float>(nv, h.stream);
+    CUDA_TRY(cudaMemsetAsync(x.data(), 0, padded_x_elems(nv, sizeof(float)) * sizeof(float), h.stream));
     B200_LAUNCH(h, (k_fill<float>), grid_for(nv), kBlock, 0, x.as<float>(), nv, 1.0f / (float)nv);
     dbuf acc = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
     CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));

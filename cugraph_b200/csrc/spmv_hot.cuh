@@ -5,30 +5,27 @@
 // l1tex 73 %, DRAM 16 % — profiles/r01_ncu_k_spmv_hi_v1.csv).  The source space is therefore cut into
 // B hot blocks of W vertices whose x-slice (192 KiB) a persistent CTA keeps in shared memory, filled by
 // TMA bulk copies (cp.async.bulk + mbarrier).  Rows keep their neighbours sorted by source id, so a
-// row's adjacency is already partitioned by block; staging stores the (row, block) segments block-major
-// with 16-bit local column ids plus, for every non-empty segment, its start and its row
-// (hot_layout_t, graph.cuh).
+// row's adjacency is already partitioned by block; staging stores the (row, block) segments block-major,
+// cut into LANE SLOTS of 8 entries with 16-bit local column ids (hot_layout_t, graph.cuh): a lane reads
+// its 8 ids with one 128-bit load, gathers 8 values from shared memory and adds them in fp64 — no
+// per-entry predicates (padding entries read a zero), no segment walk.
 //
-// Execution: work units (128 chunks of 1024 edges, all of one block) are handed out dynamically
-// through one atomic counter (the next unit is fetched while the current one is processed); a CTA
-// refills its shared memory only when its next unit belongs to another block.  A warp owns a chunk;
-// g = 1..32 lanes cooperate on one segment (g from the chunk's average segment length:
-// vertex-group-per-warp), each lane keeps four gathers in flight, partial sums are folded with log2(g)
-// shuffles and ONE fp64 atomic per segment piece goes to acc_hi[row].  The cold block
-// (sources >= B*W) runs through the same code with global gathers.
+// Execution: work units (<= 8192 slots of one block) are handed out dynamically through one atomic
+// counter (the next unit is fetched while the current one is processed); a CTA refills its shared
+// memory only when its next unit belongs to another block.  A warp handles 32 consecutive slots per
+// step.  If the 32 slots belong to one row (hub segments) the partials are folded with shuffles into ONE
+// fp64 atomic; otherwise lanes first combine with their right neighbours of the same row (3 shuffle
+// steps) and the surviving heads issue one fp64 atomic each into acc_hi[row] — the only atomics on
+// the path.  The cold block (sources >= B*W) runs through the same code with global gathers.
 #pragma once
 #include "spmv.cuh"
 
 namespace b200 {
 
-constexpr bool kHotStageTiles = false;  // TMA-staged index tiles measured slower (16 warps): r01 notes
-constexpr int kHotThreads   = kHotStageTiles ? 512 : 1024;
-constexpr int kHotWarps     = kHotThreads / 32;
-constexpr int kHotChunk     = 1024;
-constexpr int kHotSmemBytes = kHotSliceBytes;  // x slice (graph.cuh)
-constexpr int kHotTileBytes = kHotChunk * 2;   // one chunk of 16-bit column ids
-constexpr int kHotDynSmem   = kHotSmemBytes + (kHotStageTiles ? kHotWarps * 2 * kHotTileBytes : 0);  // slice (+ index tiles)
-constexpr int kHotTmaPiece  = 16 * 1024;       // bytes per bulk copy of the slice
+constexpr int kHotThreads  = 1024;
+constexpr int kHotWarps    = kHotThreads / 32;
+constexpr int kHotDynSmem  = kHotSliceBytes;
+constexpr int kHotTmaPiece = 16 * 1024;  // bytes per bulk copy of the slice
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,110 +61,115 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                : "memory");
 }
 
-// One chunk = up to 1024 consecutive edges of one block = n_seg (row, block) segments.
-// HOT: gather from the shared-memory slice; else (cold block) from global x.
-template <typename T, bool WEIGHTED, bool HOT>
-__device__ __forceinline__ void hot_process_chunk(int cb, int ce, int seg0, int n_seg, int lg,
-                                                  int32_t const* __restrict__ seg_start,
-                                                  int32_t const* __restrict__ seg_row,
-                                                  uint16_t const* __restrict__ tile /* smem, index 0 = edge cb */,
-                                                  int32_t const* __restrict__ idx32,
-                                                  int cold_base, T const* __restrict__ w, T const* __restrict__ x,
-                                                  T const* __restrict__ sx, double* __restrict__ acc_hi, int lane)
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p)
 {
-  const uint16_t* idx16 = tile;  // idx16[i] is the column of permuted position i
-  const int g      = 1 << lg;
-  const int sub    = lane & (g - 1);
-  const int groups = 32 >> lg;
-  int j            = lane >> lg;
-  // bounds of this group's first segment (afterwards prefetched one pass ahead)
-  int lo = ce, hi = ce, row = 0;
-  if (j < n_seg) {
-    lo  = seg_start[seg0 + j];
-    hi  = seg_start[seg0 + j + 1];
-    row = seg_row[seg0 + j];
-  }
-  while (__any_sync(0xffffffffu, j < n_seg)) {
-    const int jn = j + groups;
-    int lo_n = ce, hi_n = ce, row_n = 0;
-    if (jn < n_seg) {
-      lo_n  = seg_start[seg0 + jn];
-      hi_n  = seg_start[seg0 + jn + 1];
-      row_n = seg_row[seg0 + jn];
-    }
-    lo = lo < cb ? cb : lo;
-    hi = hi > ce ? ce : hi;
-    double acc = 0.0;
-    // rounds of kR predicated edges per lane: all index loads of a round are issued back to back
-    // (no serial remainder loop: every load of the round is in flight together)
-    constexpr int kR = 8;
-    for (int i = lo + sub; i < hi; i += kR * g) {
-      unsigned c[kR];
-      T wv[kR];
-#pragma unroll
-      for (int k = 0; k < kR; ++k) {
-        const int e = i + k * g;
-        c[k]        = 0;
-        wv[k]       = (T)0;
-        if (e < hi) {
-          c[k]  = HOT ? (unsigned)idx16[e] : (unsigned)idx32[e - cold_base];
-          wv[k] = WEIGHTED ? w[e] : (T)1;
-        }
-      }
-      T v[kR];
-#pragma unroll
-      for (int k = 0; k < kR; ++k) v[k] = (HOT ? sx[c[k]] : x[c[k]]) * wv[k];
-      double part = 0.0;
-#pragma unroll
-      for (int k = 0; k < kR; k += 4) part += ((double)v[k] + (double)v[k + 1]) + ((double)v[k + 2] + (double)v[k + 3]);
-      acc += part;
-    }
-    for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0 && hi > lo) atomicAdd(acc_hi + row, acc);
-    j   = jn;
-    lo  = lo_n;
-    hi  = hi_n;
-    row = row_n;
-  }
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 
-// a work unit: up to 128 consecutive chunks of one block (mirrored by hot_unit_host_t, graph_build.cu)
+// a work unit: consecutive lane slots of one block (mirrored by hot_unit_host_t, graph_build.cu)
 struct hot_unit_t {
-  int32_t chunk_begin;
-  int32_t chunk_end;
+  int32_t slot_begin;
+  int32_t slot_end;
   int32_t block;
-  int32_t pos_begin;   // permuted position of the first chunk's first edge
-  int32_t block_end;   // permuted position one past the block's last edge
-  int32_t head_begin;  // (unused by the kernel) head word of the first chunk
-  int32_t pad0, pad1;
+  int32_t pad;
 };
+
+// the 8 column ids of lane slot s: one 128-bit load (hot, 16-bit ids) or two (cold, 32-bit ids)
+struct slot_ids_t {
+  uint4 a, b;
+};
+template <bool HOT>
+__device__ __forceinline__ slot_ids_t hot_slot_load(long long s, bool valid, uint16_t const* __restrict__ idx16,
+                                                    int32_t const* __restrict__ idx32, long long cold_slot0)
+{
+  slot_ids_t r;
+  r.a = make_uint4(0, 0, 0, 0);
+  r.b = make_uint4(0, 0, 0, 0);
+  if (valid) {
+    if (HOT) {
+      r.a = ld_stream_v4(idx16 + s * kHotSlot);
+    } else {
+      r.a = ld_stream_v4(idx32 + (s - cold_slot0) * kHotSlot);
+      r.b = ld_stream_v4(idx32 + (s - cold_slot0) * kHotSlot + 4);
+    }
+  }
+  return r;
+}
+
+// sum of the 8 entries of a lane slot (fp64); an invalid slot has all-zero ids and row -1: its value is
+// never emitted
+template <typename T, bool WEIGHTED, bool HOT>
+__device__ __forceinline__ double hot_slot_sum(slot_ids_t const& ids, long long s, bool valid, T const* __restrict__ w,
+                                               T const* __restrict__ x, T const* __restrict__ sx)
+{
+  unsigned c[kHotSlot];
+  if (HOT) {
+    c[0] = ids.a.x & 0xffffu; c[1] = ids.a.x >> 16; c[2] = ids.a.y & 0xffffu; c[3] = ids.a.y >> 16;
+    c[4] = ids.a.z & 0xffffu; c[5] = ids.a.z >> 16; c[6] = ids.a.w & 0xffffu; c[7] = ids.a.w >> 16;
+  } else {
+    c[0] = ids.a.x; c[1] = ids.a.y; c[2] = ids.a.z; c[3] = ids.a.w;
+    c[4] = ids.b.x; c[5] = ids.b.y; c[6] = ids.b.z; c[7] = ids.b.w;
+  }
+  T v[kHotSlot];
+#pragma unroll
+  for (int k = 0; k < kHotSlot; ++k) v[k] = HOT ? sx[c[k]] : x[c[k]];
+  if (WEIGHTED) {
+#pragma unroll
+    for (int k = 0; k < kHotSlot; ++k) v[k] *= valid ? ld_stream(w + s * kHotSlot + k) : (T)0;
+  }
+  return (((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3])) +
+         (((double)v[4] + (double)v[5]) + ((double)v[6] + (double)v[7]));
+}
+
+// fold the 32 per-slot partials of a warp step into acc_hi[row]
+__device__ __forceinline__ void hot_emit(double acc, int row, double* __restrict__ acc_hi, int lane)
+{
+  const int r0 = __shfl_sync(0xffffffffu, row, 0);
+  if (__all_sync(0xffffffffu, row == r0)) {  // one row (hub segment, or 32 padding slots)
+    acc = warp_sum(acc);
+    if (lane == 0 && r0 >= 0) atomicAdd(acc_hi + r0, acc);
+    return;
+  }
+  // slots of a row are consecutive lanes: combine with right neighbours of the same row (runs up to 8
+  // collapse into their head lane), then one atomic per surviving head
+  bool alive = row >= 0;
+#pragma unroll
+  for (int o = 1; o <= 4; o <<= 1) {
+    const double nb  = __shfl_down_sync(0xffffffffu, acc, o);
+    const int rn     = __shfl_down_sync(0xffffffffu, row, o);
+    const bool nb_al = __shfl_down_sync(0xffffffffu, (int)alive, o) != 0;
+    const bool head  = (lane & (2 * o - 1)) == 0;      // lanes that may absorb at this step
+    const bool take  = head && alive && nb_al && (lane + o < 32) && rn == row;
+    if (take) acc += nb;
+    // the absorbed lane retires (it is at lane+o of a head that took it)
+    const bool taken = __shfl_up_sync(0xffffffffu, (int)take, o) != 0;
+    if (((lane & (2 * o - 1)) == o) && taken) alive = false;
+  }
+  if (alive) atomicAdd(acc_hi + row, acc);
+}
 
 template <typename T, bool WEIGHTED>
 __global__ void __launch_bounds__(kHotThreads, 1)
 k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restrict__ unit_counter,
-               int32_t const* __restrict__ chunk_seg0, int cold_base, int32_t const* __restrict__ seg_start,
-               int32_t const* __restrict__ seg_row, uint16_t const* __restrict__ idx16,
-               int32_t const* __restrict__ idx32, T const* __restrict__ w, T const* __restrict__ x,
-               double* __restrict__ acc_hi, int W, int B, pr_state_t const* __restrict__ st)
+               int32_t const* __restrict__ slot_row, uint16_t const* __restrict__ idx16,
+               int32_t const* __restrict__ idx32, long long cold_slot0, T const* __restrict__ w,
+               T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, pr_state_t const* __restrict__ st)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* sx = reinterpret_cast<T*>(smem_raw);
-  __shared__ uint64_t bar;                      // slice fill
-  __shared__ uint64_t tile_bar[kHotWarps][2];   // per-warp index tiles, double buffered
+  __shared__ uint64_t bar;
   __shared__ int s_next;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint16_t* my_tiles = reinterpret_cast<uint16_t*>(smem_raw + kHotSmemBytes + warp * 2 * kHotTileBytes);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
-    for (int i = 0; i < kHotWarps; ++i) {
-      mbar_init(&tile_bar[i][0], 1);
-      mbar_init(&tile_bar[i][1], 1);
-    }
     s_next = atomicAdd(unit_counter, 1);
   }
-  unsigned phase = 0, tphase0 = 0, tphase1 = 0;
-  int cur_block = -1;
+  if (threadIdx.x < kHotZeroPad) sx[W + threadIdx.x] = (T)0;  // the padding column(s) of every slice
+  unsigned phase = 0;
+  int cur_block  = -1;
   while (true) {
     __syncthreads();  // s_next is published; everyone is done with the previous unit's slice
     const int u = s_next;
@@ -177,16 +179,6 @@ k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restric
     const hot_unit_t un = units[u];
     const int b         = un.block;
     const bool hot      = b < B;
-    int k               = un.chunk_begin + warp;
-    // first index tile of this warp: in flight while the slice is (re)filled
-    int buf = 0;
-    if (kHotStageTiles && hot && k < un.chunk_end && lane == 0) {
-      const int cb = un.pos_begin + (k - un.chunk_begin) * kHotChunk;
-      const int ce = (cb + kHotChunk < un.block_end) ? cb + kHotChunk : un.block_end;
-      const unsigned bytes = (unsigned)(((ce - cb) * 2 + 15) & ~15);
-      mbar_expect_tx(&tile_bar[warp][0], bytes);
-      tma_bulk_g2s(my_tiles, idx16 + cb, bytes, &tile_bar[warp][0]);
-    }
     if (hot && b != cur_block) {
       if (threadIdx.x == 0) {
         const unsigned bytes = (unsigned)(W * sizeof(T));
@@ -199,56 +191,42 @@ k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restric
       mbar_wait(&bar, phase);
       phase ^= 1;
     }
-    int seg0 = 0, seg1 = 0;
-    if (k < un.chunk_end) {
-      seg0 = chunk_seg0[k];
-      seg1 = chunk_seg0[k + 1];
+    // two warp steps (64 slots) per iteration, software pipelined: the index vectors and rows of the next
+    // iteration are loaded before the current one is gathered and reduced
+    const int stride = kHotWarps * 64;
+    int s0           = un.slot_begin + warp * 64;
+    slot_ids_t ia, ib;
+    int ra = -1, rb = -1;
+    {
+      const int sa = s0 + lane, sb = s0 + 32 + lane;
+      const bool va = sa < un.slot_end, vb = sb < un.slot_end;
+      if (hot) { ia = hot_slot_load<true>(sa, va, idx16, idx32, cold_slot0); ib = hot_slot_load<true>(sb, vb, idx16, idx32, cold_slot0); }
+      else { ia = hot_slot_load<false>(sa, va, idx16, idx32, cold_slot0); ib = hot_slot_load<false>(sb, vb, idx16, idx32, cold_slot0); }
+      ra = va ? slot_row[sa] : -1;
+      rb = vb ? slot_row[sb] : -1;
     }
-    while (k < un.chunk_end) {
-      const int cb = un.pos_begin + (k - un.chunk_begin) * kHotChunk;
-      const int ce = (cb + kHotChunk < un.block_end) ? cb + kHotChunk : un.block_end;
-      const int kn  = k + kHotWarps;  // next chunk of this warp: prefetch its metadata and its index tile
-      int seg0_next = 0, seg1_next = 0;
-      if (kn < un.chunk_end) {
-        seg0_next = chunk_seg0[kn];
-        seg1_next = chunk_seg0[kn + 1];
-        if (kHotStageTiles && hot) {
-          __syncwarp();  // every lane is done reading the tile that is about to be overwritten
-          if (lane == 0) {
-            const int cbn = un.pos_begin + (kn - un.chunk_begin) * kHotChunk;
-            const int cen = (cbn + kHotChunk < un.block_end) ? cbn + kHotChunk : un.block_end;
-            const unsigned bytes = (unsigned)(((cen - cbn) * 2 + 15) & ~15);
-            mbar_expect_tx(&tile_bar[warp][buf ^ 1], bytes);
-            tma_bulk_g2s(my_tiles + (buf ^ 1) * kHotChunk, idx16 + cbn, bytes, &tile_bar[warp][buf ^ 1]);
-          }
-        }
-      }
-      const int n_seg = seg1 - seg0 + 1;  // segments overlapping the chunk (the last may be empty here)
-      const int avg   = (ce - cb) / n_seg;
-      int lg          = 0;  // lanes per segment: 4-8 edges per lane (8-16 measured slower)
-      while (lg < 5 && (8 << lg) <= avg) ++lg;
+    for (; s0 < un.slot_end; s0 += stride) {
+      const int sa = s0 + lane, sb = s0 + 32 + lane;
+      const bool va = sa < un.slot_end, vb = sb < un.slot_end;
+      // prefetch the next iteration
+      const int na = sa + stride, nb = sb + stride;
+      const bool nva = na < un.slot_end, nvb = nb < un.slot_end;
+      slot_ids_t ja, jb;
+      if (hot) { ja = hot_slot_load<true>(na, nva, idx16, idx32, cold_slot0); jb = hot_slot_load<true>(nb, nvb, idx16, idx32, cold_slot0); }
+      else { ja = hot_slot_load<false>(na, nva, idx16, idx32, cold_slot0); jb = hot_slot_load<false>(nb, nvb, idx16, idx32, cold_slot0); }
+      const int nra = nva ? slot_row[na] : -1;
+      const int nrb = nvb ? slot_row[nb] : -1;
+      double aa, ab;
       if (hot) {
-        const uint16_t* tile = idx16;
-        if (kHotStageTiles) {
-          if (buf == 0) {
-            mbar_wait(&tile_bar[warp][0], tphase0);
-            tphase0 ^= 1;
-          } else {
-            mbar_wait(&tile_bar[warp][1], tphase1);
-            tphase1 ^= 1;
-          }
-          tile = my_tiles + buf * kHotChunk - cb;
-          buf ^= 1;
-        }
-        hot_process_chunk<T, WEIGHTED, true>(cb, ce, seg0, n_seg, lg, seg_start, seg_row, tile, idx32, cold_base, w, x, sx,
-                                             acc_hi, lane);
+        aa = hot_slot_sum<T, WEIGHTED, true>(ia, sa, va, w, x, sx);
+        ab = hot_slot_sum<T, WEIGHTED, true>(ib, sb, vb, w, x, sx);
       } else {
-        hot_process_chunk<T, WEIGHTED, false>(cb, ce, seg0, n_seg, lg, seg_start, seg_row, nullptr, idx32, cold_base, w, x,
-                                              sx, acc_hi, lane);
+        aa = hot_slot_sum<T, WEIGHTED, false>(ia, sa, va, w, x, sx);
+        ab = hot_slot_sum<T, WEIGHTED, false>(ib, sb, vb, w, x, sx);
       }
-      k    = kn;
-      seg0 = seg0_next;
-      seg1 = seg1_next;
+      hot_emit(aa, ra, acc_hi, lane);
+      if (s0 + 32 < un.slot_end) hot_emit(ab, rb, acc_hi, lane);
+      ia = ja; ib = jb; ra = nra; rb = nrb;
     }
   }
 }
@@ -281,7 +259,8 @@ void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, dou
                 c.weights.as<T>(), x, y, c.row_vertex.as<int32_t>(), bins, alpha, st);
 }
 
-// x must be readable up to roundup(n_vertices, W) elements (the TMA fill copies whole slices)
+// x must hold padded_x_elems() elements, zero behind n_vertices (slices are copied whole; the cold
+// block's padding entries read x[n_vertices])
 template <typename O, typename T>
 void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_t const& L, T const* x, T* y,
                                double* acc_hi, double alpha, pr_state_t const* st)
@@ -293,14 +272,14 @@ void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_
     attr_set = true;
   }
   const int grid = std::min(L.n_cta, L.n_units);
-  if (L.w.data())
+  if (L.slot_w.data())
     B200_LAUNCH(h, (k_spmv_blocked<T, true>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
-                L.unit_counter.as<int>(), L.chunks.as<int32_t>(), (int)L.nnz_hot, L.seg_start.as<int32_t>(),
-                L.seg_row.as<int32_t>(), L.idx16.as<uint16_t>(), L.idx32.as<int32_t>(), L.w.as<T>(), x, acc_hi, L.W, L.B, st);
+                L.unit_counter.as<int>(), L.slot_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
+                (long long)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, st);
   else
     B200_LAUNCH(h, (k_spmv_blocked<T, false>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
-                L.unit_counter.as<int>(), L.chunks.as<int32_t>(), (int)L.nnz_hot, L.seg_start.as<int32_t>(),
-                L.seg_row.as<int32_t>(), L.idx16.as<uint16_t>(), L.idx32.as<int32_t>(), L.w.as<T>(), x, acc_hi, L.W, L.B, st);
+                L.unit_counter.as<int>(), L.slot_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
+                (long long)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, st);
   B200_LAUNCH(h, (k_spmv_blocked_finish<T>), (L.n_hi + 255) / 256, 256, 0, acc_hi, L.n_hi, y, c.row_vertex.as<int32_t>(),
               alpha, L.unit_counter.as<int>(), st);
   launch_low_rows<O, T>(h, c, x, y, alpha, st);
@@ -316,11 +295,13 @@ void launch_pull_sweep_auto(handle_impl const& h, csx_t const& c, int32_t n_vert
   else launch_pull_sweep<O, T>(h, c, x, y, acc_hi, alpha, st);
 }
 
-// number of elements an x buffer needs so that whole shared-memory slices can be copied
+// elements an x buffer needs: whole slices are TMA-copied and x[n_vertices] must be a readable zero.
+// The buffer must be zero-filled once at allocation; only [0, n_vertices) is ever written afterwards.
 inline size_t padded_x_elems(int32_t n_vertices, size_t elem_size)
 {
-  size_t W = kHotSmemBytes / elem_size;
-  return (((size_t)n_vertices + W - 1) / W) * W;
+  const size_t slice = kHotSliceBytes / elem_size;
+  const size_t W     = slice - kHotZeroPad;
+  return ((size_t)n_vertices / W + 2) * slice;
 }
 
 }  // namespace b200
