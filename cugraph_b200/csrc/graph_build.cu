@@ -948,7 +948,12 @@ csx_t const& push_view(handle_impl const& h, graph_impl& g)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kHotMaxB = 24;
+constexpr int kHotMaxBDefault = 48;  // measured on RMAT-24: 8 -> 0.627 ms, 24 -> 0.571, 48 -> 0.549, 96 -> 0.563
+inline int hot_max_blocks()
+{
+  if (const char* e = std::getenv("CUGRAPH_B200_HOT_BLOCKS")) return std::max(1, std::min(std::atoi(e), 250));
+  return kHotMaxBDefault;
+}
 
 // one thread per (block, row): segment = edges of row r whose source lies in block b
 template <typename O>
@@ -1012,7 +1017,7 @@ __global__ void k_hot_fill_slots(int32_t const* __restrict__ idx, T const* __res
 }
 
 struct hot_unit_host_t {  // mirrors hot_unit_t (spmv_hot.cuh)
-  int32_t slot_begin, slot_end, block, pad;
+  int32_t slot_begin, slot_end, block, combine;
 };
 constexpr int kHotUnitSlots = 8192;  // lane slots per work unit (<= 64 K edges)
 
@@ -1021,7 +1026,7 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
 {
   const int W        = (int)(kHotSliceBytes / es) - kHotZeroPad;  // columns per hot block; the pad holds zeros
   const int32_t n_hi = c.seg[0];
-  const int B        = (int)std::min<int64_t>(kHotMaxB, ((int64_t)nv + W - 1) / W);
+  const int B        = (int)std::min<int64_t>(hot_max_blocks(), ((int64_t)nv + W - 1) / W);
   auto L             = std::make_unique<hot_layout_t>();
   L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = c.nnz_hi;
   const int64_t n_seg = (int64_t)(B + 1) * n_hi;
@@ -1039,9 +1044,12 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   L->n_hot_slots = bslot[B];
   L->n_slots     = bslot[B + 1];
   std::vector<hot_unit_host_t> units;
-  for (int b = 0; b <= B; ++b)
+  for (int b = 0; b <= B; ++b) {
+    // blocks whose rows mostly own a single slot gain nothing from combining neighbouring lanes
+    const int combine = (double)(bslot[b + 1] - bslot[b]) >= 1.2 * (double)n_hi ? 1 : 0;
     for (int s = bslot[b]; s < bslot[b + 1]; s += kHotUnitSlots)
-      units.push_back({s, std::min(s + kHotUnitSlots, bslot[b + 1]), b, 0});
+      units.push_back({s, std::min(s + kHotUnitSlots, bslot[b + 1]), b, combine});
+  }
   L->n_units = (int32_t)units.size();
   L->units   = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
   if (!units.empty())
@@ -1084,7 +1092,7 @@ hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_v
   long long min_edges = 1ll << 22;
   if (const char* e = std::getenv("CUGRAPH_B200_HOT_MIN_EDGES")) min_edges = std::atoll(e);
   const int W = (int)(kHotSliceBytes / elem_size) - kHotZeroPad;
-  const int B = (int)std::min<int64_t>(kHotMaxB, ((int64_t)n_vertices + W - 1) / W);
+  const int B = (int)std::min<int64_t>(hot_max_blocks(), ((int64_t)n_vertices + W - 1) / W);
   // slots are at most nnz_hi/8 + one per (row, block) segment
   if (!c.degree_sorted || c.seg[0] <= 0 || c.nnz_hi < min_edges || c.offs64 || c.nnz_hi >= (1ll << 31) - 4096 ||
       (int64_t)(B + 1) * c.seg[0] + c.nnz_hi / kHotSlot >= (1ll << 31) - 2)

@@ -73,7 +73,7 @@ struct hot_unit_t {
   int32_t slot_begin;
   int32_t slot_end;
   int32_t block;
-  int32_t pad;
+  int32_t combine;  // 1: segments of this block span several slots, combine neighbours before the atomics
 };
 
 // the 8 column ids of lane slot s: one 128-bit load (hot, 16-bit ids) or two (cold, 32-bit ids)
@@ -123,7 +123,11 @@ __device__ __forceinline__ double hot_slot_sum(slot_ids_t const& ids, long long 
          (((double)v[4] + (double)v[5]) + ((double)v[6] + (double)v[7]));
 }
 
-// fold the 32 per-slot partials of a warp step into acc_hi[row]
+// fold the 32 per-slot partials of a warp step into acc_hi[row] (row < 0: nothing to emit).
+// The kernel is bound by the MIO pipe (shared-memory gathers + shuffles, profiles/r01_ncu_k_spmv_blocked_v4.csv),
+// so the combine uses one packed shuffle for (row, alive) and a vote instead of a shuffle for the retire
+// flag, and is skipped for units whose segments are mostly single slots (COMBINE = false).
+template <bool COMBINE>
 __device__ __forceinline__ void hot_emit(double acc, int row, double* __restrict__ acc_hi, int lane)
 {
   const int r0 = __shfl_sync(0xffffffffu, row, 0);
@@ -132,22 +136,19 @@ __device__ __forceinline__ void hot_emit(double acc, int row, double* __restrict
     if (lane == 0 && r0 >= 0) atomicAdd(acc_hi + r0, acc);
     return;
   }
-  // slots of a row are consecutive lanes: combine with right neighbours of the same row (runs up to 8
-  // collapse into their head lane), then one atomic per surviving head
-  bool alive = row >= 0;
+  if (COMBINE) {
+    // slots of a row are consecutive lanes: aligned runs of up to 8 collapse into their head lane
 #pragma unroll
-  for (int o = 1; o <= 4; o <<= 1) {
-    const double nb  = __shfl_down_sync(0xffffffffu, acc, o);
-    const int rn     = __shfl_down_sync(0xffffffffu, row, o);
-    const bool nb_al = __shfl_down_sync(0xffffffffu, (int)alive, o) != 0;
-    const bool head  = (lane & (2 * o - 1)) == 0;      // lanes that may absorb at this step
-    const bool take  = head && alive && nb_al && (lane + o < 32) && rn == row;
-    if (take) acc += nb;
-    // the absorbed lane retires (it is at lane+o of a head that took it)
-    const bool taken = __shfl_up_sync(0xffffffffu, (int)take, o) != 0;
-    if (((lane & (2 * o - 1)) == o) && taken) alive = false;
+    for (int o = 1; o <= 4; o <<= 1) {
+      const double nb = __shfl_down_sync(0xffffffffu, acc, o);
+      const int rn    = __shfl_down_sync(0xffffffffu, row, o);  // -1 when the neighbour is retired / padding
+      const bool take = ((lane & (2 * o - 1)) == 0) && row >= 0 && rn == row;
+      if (take) acc += nb;
+      const unsigned takes = __ballot_sync(0xffffffffu, take);
+      if (lane >= o && ((takes >> (lane - o)) & 1u)) row = -1;  // absorbed by the head at lane - o
+    }
   }
-  if (alive) atomicAdd(acc_hi + row, acc);
+  if (row >= 0) atomicAdd(acc_hi + row, acc);
 }
 
 template <typename T, bool WEIGHTED>
@@ -224,8 +225,13 @@ k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restric
         aa = hot_slot_sum<T, WEIGHTED, false>(ia, sa, va, w, x, sx);
         ab = hot_slot_sum<T, WEIGHTED, false>(ib, sb, vb, w, x, sx);
       }
-      hot_emit(aa, ra, acc_hi, lane);
-      if (s0 + 32 < un.slot_end) hot_emit(ab, rb, acc_hi, lane);
+      if (un.combine) {
+        hot_emit<true>(aa, ra, acc_hi, lane);
+        if (s0 + 32 < un.slot_end) hot_emit<true>(ab, rb, acc_hi, lane);
+      } else {
+        hot_emit<false>(aa, ra, acc_hi, lane);
+        if (s0 + 32 < un.slot_end) hot_emit<false>(ab, rb, acc_hi, lane);
+      }
       ia = ja; ib = jb; ra = nra; rb = nrb;
     }
   }
