@@ -15,9 +15,10 @@ A STEP is one call of `cugraph_pagerank_allow_nonconvergence` (100 iterations) t
   e2e    = the same metric for the whole reference-facing call sequence with HOST buffers inside the
            timed region: pinned edge list -> H2D -> cugraph_graph_create_with_times_sg -> pagerank ->
            D2H of (vertices, scores)
-  roofline = the pull-SpMV sweep (kernels k_spmv_hi + k_spmv_hi_finish + k_spmv_low = one
+  roofline = the pull-SpMV sweep (kernels k_spmv_blocked + k_spmv_blocked_finish + k_spmv_low = one
            per_v_transform_reduce_incoming_e) timed alone with CUDA events on the handle's stream;
-           algorithmic bytes per sweep = 4E + 4(V+1) + 4V + 4V
+           algorithmic bytes per sweep = 4E + 4(V+1) + 4V + 4V; traffic = DRAM bytes of
+           the three kernels from the ncu launch list (profiles/spmv_traffic.json)
   cpu_baseline = oracle port (oracle/oracle.c, OpenMP) on a bounded sample, host cores stated
 Synthetic data, random seed 0.  Inputs (1.2 GB per sweep) exceed the 126 MB L2, so no explicit L2 flush
 is needed between timed iterations (stated in config.l2).
@@ -211,7 +212,7 @@ def run_single(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "pull sweep: k_spmv_hi+k_spmv_hi_finish+k_spmv_low",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "pull sweep: k_spmv_blocked+k_spmv_blocked_finish+k_spmv_low",
                 "ms_per_sweep": ms.value, "algorithmic_bytes_per_sweep": by.value,
                 "sweep_mteps": E / (ms.value * 1e-3) / 1e6}
 
@@ -219,13 +220,19 @@ def run_single(args):
     del G
     torch.cuda.empty_cache()
     e2e_steps = max(1, min(args.steps, 3))
+    # pinned host buffers for the result (a pageable .cpu() costs 20-30 ms for 134 MB)
+    h_v = torch.empty(nv, dtype=torch.int32).pin_memory()
+    h_p = torch.empty(nv, dtype=torch.float32).pin_memory()
 
     def e2e_step():
         s = h_src.cuda(non_blocking=True)
         d = h_dst.cuda(non_blocking=True)
         g = plc.SGGraph(h, props, s, d, store_transposed=True, renumber=True)
         vv, pp, _ = plc.pagerank(h, g, None, None, None, None, ALPHA, 0.0, ITERS, False, fail_on_nonconvergence=False)
-        return vv.cpu(), pp.cpu()
+        h_v.copy_(vv, non_blocking=True)
+        h_p.copy_(pp, non_blocking=True)
+        torch.cuda.synchronize()
+        return h_v, h_p
 
     e2e_step()
     torch.cuda.synchronize()
@@ -236,7 +243,7 @@ def run_single(args):
     e2e_wall = time.perf_counter() - t0
     e2e = {"value": E * ITERS * e2e_steps / e2e_wall / 1e6, "unit": "MTEPS", "h2d_bytes_per_step": 2 * E * 4,
            "d2h_bytes_per_step": nv * 8, "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
-           "includes": "pinned H2D of edge list, graph staging, 100 iterations, D2H of vertices+scores"}
+           "includes": "pinned H2D of edge list, graph staging, 100 iterations, D2H of vertices+scores into pinned buffers"}
 
     cpu = _cpu_baseline()
     out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

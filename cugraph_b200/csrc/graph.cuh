@@ -46,14 +46,20 @@ struct hot_layout_t {
   int64_t nnz_hi{0};
   int64_t n_hot_slots{0};
   int64_t n_slots{0};
+  // A (row, block) segment is cut into PIECES of <= 64 entries = <= 8 lane slots of 8 entries.  Pieces are
+  // ordered by (block, slots per piece); 32 consecutive pieces of one class form a GROUP = the work of one
+  // warp (lane = piece).  Slots of a group are stored step-major: slot (step j, lane l) at group_base + 32 j + l.
   dbuf slot_idx16;   // n_hot_slots x 8 x uint16 : column - block*W, padding -> W (the slice's zero column)
   dbuf slot_idx32;   // (n_slots - n_hot_slots) x 8 x int32 : cold columns, padding -> n_vertices (x is 0 there)
   dbuf slot_w;       // n_slots x 8 x T, padding 0; or empty
-  dbuf slot_row;     // n_slots x int32 : row of the slot's segment
-  dbuf units;        // n_units x hot_unit_t (spmv_hot.cuh): <= 8192 consecutive slots of one block
+  dbuf seg_row;      // per (group, lane): row of the piece, -1 for the unused lanes of a class's last group
+  dbuf subs;         // n_subs x hot_sub_t (spmv_hot.cuh): consecutive groups of one class
+  dbuf units;        // n_units x hot_unit_t: consecutive sub-units of one block, about 8192 slots
+  int32_t n_subs{0};
   int32_t n_units{0};
-  dbuf unit_counter; // 1 x int : dynamic work distribution cursor (reset by the finish kernel)
-  int n_cta{0};
+  dbuf cta_range;    // (n_cta + 1) x int32 : CTA c owns units [cta_range[c], cta_range[c+1]) (cost-balanced)
+  dbuf unit_counter; // n_cta x int : per-range cursors, also used for stealing (reset by the finish kernel)
+  int n_cta{0};      // CTAs of the persistent kernel = min(SM count, n_units)
 };
 
 // One orientation: compressed rows over `n_rows` physical rows.

@@ -7,8 +7,10 @@
 #include "graph.cuh"
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -17,6 +19,38 @@ namespace b200 {
 namespace {
 
 constexpr int kBlock = 256;
+
+// CUGRAPH_B200_BUILD_TRACE=1: print the time of every staging phase (stream-synchronised) to stderr
+struct phase_trace {
+  handle_impl const& h;
+  bool on;
+  cudaEvent_t e0{}, e1{};
+  explicit phase_trace(handle_impl const& hh) : h(hh), on(std::getenv("CUGRAPH_B200_BUILD_TRACE") != nullptr)
+  {
+    if (on) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, h.stream);
+    }
+  }
+  void mark(const char* what)
+  {
+    if (!on) return;
+    cudaEventRecord(e1, h.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::fprintf(stderr, "[build] %-28s %8.3f ms\n", what, ms);
+    std::swap(e0, e1);
+  }
+  ~phase_trace()
+  {
+    if (on) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+  }
+};
 
 inline int grid_for(int64_t n, int per_thread = 1)
 {
@@ -415,6 +449,7 @@ void build_csx_typed(handle_impl const& h, csx_t& out, int32_t const* major, int
                      int64_t n, int32_t nv, int32_t const* relabel_major, int32_t const* relabel_minor,
                      bool dedupe, bool keep_min_weight)
 {
+  phase_trace tr(h);
   int bits = bits_for(std::max<int64_t>(nv, 2));
   B200_EXPECTS(2 * bits <= 64, CUGRAPH_INVALID_INPUT, "too many vertices");
   dbuf keys  = make_dbuf<uint64_t>(n, h.stream);
@@ -448,6 +483,7 @@ void build_csx_typed(handle_impl const& h, csx_t& out, int32_t const* major, int
     B200_LAUNCH(h, (k_gather<W>), grid_for(n, 4), kBlock, 0, w, perm2.as<uint32_t>(), n, wsorted.as<W>());
   }
   keys.release();
+  tr.mark("csx: pack + sort");
   int64_t m = n;
   if (dedupe && n > 0) {
     dbuf head = make_dbuf<uint8_t>(n, h.stream);
@@ -484,6 +520,7 @@ void build_csx_typed(handle_impl const& h, csx_t& out, int32_t const* major, int
     }
   }
   check_last("build_csx");
+  tr.mark("csx: indices + offsets");
 }
 
 void build_csx(handle_impl const& h, csx_t& out, int32_t const* major, int32_t const* minor, void const* w,
@@ -788,6 +825,7 @@ void stage_graph_typed(handle_impl const& h, graph_impl& g, device_array_view_im
                        device_array_view_impl const* wv, bool renumber, bool drop_self_loops, bool drop_multi_edges,
                        bool symmetrize)
 {
+  phase_trace tr(h);
   int64_t n = (int64_t)src->size;
   // working copies in VT (inputs may legally be any integer width equal to the graph's vertex type)
   dbuf s_ext = make_dbuf<VT>(n, h.stream), d_ext = make_dbuf<VT>(n, h.stream);
@@ -817,10 +855,12 @@ void stage_graph_typed(handle_impl const& h, graph_impl& g, device_array_view_im
     d_ext = std::move(d2);
     n     = m;
   }
+  tr.mark("stage: copies/self-loops");
   staged_ids ranks = compute_ranks<VT>(h, verts ? (VT const*)verts->data : nullptr, verts ? (int64_t)verts->size : 0,
                                  s_ext.as<VT>(), d_ext.as<VT>(), n, renumber);
   s_ext.release();
   d_ext.release();
+  tr.mark("stage: ranks");
   int32_t nv = ranks.nv;
   g.n_vertices = nv;
   g.renumbered = renumber;
@@ -863,13 +903,16 @@ void stage_graph_typed(handle_impl const& h, graph_impl& g, device_array_view_im
     B200_LAUNCH(h, (k_gather_ext<VT>), grid_for(nv), kBlock, 0, renumber ? ranks.sorted_ext.as<VT>() : (VT const*)nullptr,
                 rank_of_int.as<int32_t>(), nv, g.ext_of_int.as<VT>());
   if (renumber) g.sorted_ext = std::move(ranks.sorted_ext);
+  tr.mark("stage: degree order");
 
   g.primary = std::make_unique<csx_t>();
   build_csx(h, *g.primary, major, minor, wptr, g.weight_type, n, nv, g.int_of_rank.as<int32_t>(),
             g.int_of_rank.as<int32_t>(), false, false);
   g.n_edges = g.primary->nnz;
+  tr.mark("stage: build_csx");
   finish_binning(h, *g.primary);
   sync(h);
+  tr.mark("stage: binning");
 }
 
 void stage_graph(handle_impl const& h, graph_impl& g, device_array_view_impl const* verts,
@@ -948,136 +991,371 @@ csx_t const& push_view(handle_impl const& h, graph_impl& g)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kHotMaxBDefault = 48;  // measured on RMAT-24: 8 -> 0.627 ms, 24 -> 0.571, 48 -> 0.549, 96 -> 0.563
+// Hot blocks by default: ALL of the source space (a cold block only exists beyond 2048 slices = 100 M
+// float columns).  Measured on RMAT-24 (8.87 M non-isolated vertices = 181 slices) with the piece layout, pull
+// sweep: B = 48 -> 0.535 ms, 96 -> 0.538, 160 -> 0.520, 181 (all) -> 0.456 (profiles/r01_notes.md); since every
+// CTA owns a contiguous range of units, more blocks cost no extra slice fills (1-2 slices per CTA).
+constexpr int kHotMaxBDefault = 2048;
 inline int hot_max_blocks()
 {
-  if (const char* e = std::getenv("CUGRAPH_B200_HOT_BLOCKS")) return std::max(1, std::min(std::atoi(e), 250));
+  if (const char* e = std::getenv("CUGRAPH_B200_HOT_BLOCKS")) return std::max(1, std::min(std::atoi(e), 2048));
   return kHotMaxBDefault;
 }
 
-// one thread per (block, row): segment = edges of row r whose source lies in block b
+// ---- staging of the piece layout (hot_layout_t, graph.cuh).  All passes are O(nnz_hi + #segments):
+//   1. head flags: an edge starts a (row, block) segment if it starts its row or its source lies in another
+//      block than its predecessor's (neighbours are sorted by source id)
+//   2. segments = compacted head positions; each is cut into pieces of <= 64 entries (<= 8 lane slots)
+//   3. pieces are ordered (stable radix sort) by (block, slots-per-piece); 32 consecutive pieces of one
+//      class form a GROUP that one warp processes, lane = piece
+//   4. slots are written step-major inside a group, so every warp step is one coalesced 512-byte read
+
+__device__ __forceinline__ int hot_block_of(int col, int W, int B)
+{
+  const int b = col / W;
+  return b < B ? b : B;
+}
+
 template <typename O>
-__global__ void k_hot_segments(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t n_hi, int B, int W,
-                               int32_t* __restrict__ seg_pos, int32_t* __restrict__ seg_len, int32_t* __restrict__ seg_slots)
+__global__ void k_hot_row_starts(O const* __restrict__ off, int32_t n_hi, uint8_t* __restrict__ flag)
 {
-  const long long total = (long long)(B + 1) * n_hi;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p <= total; p += (long long)gridDim.x * blockDim.x) {
-    if (p == total) {
-      seg_slots[p] = 0;
-      continue;
-    }
-    const int b = (int)(p / n_hi), r = (int)(p - (long long)b * n_hi);
-    const int beg = (int)off[r], end = (int)off[r + 1];
-    auto lower = [&](int key) {
-      int lo = beg, hi = end;
-      while (lo < hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        if (idx[mid] < key) lo = mid + 1; else hi = mid;
-      }
-      return lo;
-    };
-    const int lo = (b == 0) ? beg : lower(b * W);
-    const int hi = (b == B) ? end : lower((b + 1) * W);
-    seg_pos[p]   = lo;
-    seg_len[p]   = hi - lo;
-    seg_slots[p] = (hi - lo + kHotSlot - 1) / kHotSlot;  // 8-entry lane slots this segment needs
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_hi) flag[(size_t)off[r]] = 1;  // degree >= 32 rows are never empty
+}
+
+__global__ void k_hot_heads(int32_t const* __restrict__ idx, long long nnz_hi, int W, int B, uint8_t* __restrict__ flag)
+{
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nnz_hi; e += (long long)gridDim.x * blockDim.x) {
+    if (e > 0 && !flag[e] && hot_block_of(idx[e], W, B) != hot_block_of(idx[e - 1], W, B)) flag[e] = 1;
   }
 }
 
-// one warp per (block, row) segment: cut it into 8-entry lane slots; the last slot is padded with the
-// block's zero column (weight 0), so the kernel needs no per-entry predicate
-template <typename T>
-__global__ void k_hot_fill_slots(int32_t const* __restrict__ idx, T const* __restrict__ w,
-                                 int32_t const* __restrict__ seg_pos, int32_t const* __restrict__ seg_len,
-                                 int32_t const* __restrict__ slot_off, int32_t n_hi, int B, int W, int zero_col_hot,
-                                 int zero_col_cold, int cold_slot0, uint16_t* __restrict__ idx16,
-                                 int32_t* __restrict__ idx32, T* __restrict__ w_out, int32_t* __restrict__ slot_row)
+constexpr int kHotPieceSlots   = 8;                          // slots per piece (= steps per group) at most
+constexpr int kHotPieceEntries = kHotPieceSlots * kHotSlot;  // 64
+
+// per segment: its row (binary search in the offsets) and how many pieces it yields
+template <typename O>
+__global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz_hi,
+                                   O const* __restrict__ off, int32_t n_hi, int32_t* __restrict__ seg_row,
+                                   int32_t* __restrict__ seg_pieces)
 {
-  const long long total = (long long)(B + 1) * n_hi;
-  const int lane        = threadIdx.x & 31;
-  for (long long p = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; p < total;
-       p += ((long long)gridDim.x * blockDim.x) >> 5) {
-    const int len = seg_len[p];
-    if (len == 0) continue;
-    const int b = (int)(p / n_hi), r = (int)(p - (long long)b * n_hi);
-    const int src = seg_pos[p], s0 = slot_off[p], ns = (len + kHotSlot - 1) / kHotSlot;
-    for (int k = lane; k < ns; k += 32) {
-      const int s  = s0 + k;
-      slot_row[s]  = r;
-#pragma unroll
-      for (int j = 0; j < kHotSlot; ++j) {
-        const int e   = k * kHotSlot + j;
-        const bool in = e < len;
-        if (b < B) idx16[(size_t)s * kHotSlot + j] = (uint16_t)(in ? idx[src + e] - b * W : zero_col_hot);
-        else idx32[(size_t)(s - cold_slot0) * kHotSlot + j] = in ? idx[src + e] : zero_col_cold;
-        if (w_out) w_out[(size_t)s * kHotSlot + j] = in ? w[src + e] : (T)0;
-      }
-    }
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_segs) return;
+  if (k == n_segs) {
+    seg_pieces[k] = 0;
+    return;
+  }
+  const long long start = head_pos[k];
+  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz_hi;
+  int lo = 0, hi = n_hi;  // last row r with off[r] <= start
+  while (hi - lo > 1) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((long long)off[mid] <= start) lo = mid; else hi = mid;
+  }
+  seg_row[k]    = lo;
+  seg_pieces[k] = (int)((end - start + kHotPieceEntries - 1) / kHotPieceEntries);
+}
+
+// per segment: write its pieces (start edge, entries, row) and their class key = block * 8 + (slots - 1)
+__global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz_hi,
+                                  int32_t const* __restrict__ idx, int W, int B, int32_t const* __restrict__ seg_row,
+                                  int32_t const* __restrict__ piece_off, uint32_t* __restrict__ piece_key,
+                                  int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
+                                  int32_t* __restrict__ piece_row)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_segs) return;
+  const long long start = head_pos[k];
+  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz_hi;
+  const int b           = hot_block_of(idx[start], W, B);
+  const int row         = seg_row[k];
+  int p                 = piece_off[k];
+  for (long long s = start; s < end; s += kHotPieceEntries, ++p) {
+    const int len  = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
+    const int cls  = (len + kHotSlot - 1) / kHotSlot;  // 1..8
+    piece_key[p]   = (uint32_t)(b * kHotPieceSlots + cls - 1);
+    piece_start[p] = (int32_t)s;
+    piece_len[p]   = len;
+    piece_row[p]   = row;
   }
 }
 
-struct hot_unit_host_t {  // mirrors hot_unit_t (spmv_hot.cuh)
-  int32_t slot_begin, slot_end, block, combine;
+__global__ void k_hot_class_starts(uint32_t const* __restrict__ sorted_key, int32_t n_pieces, int n_keys,
+                                   int32_t* __restrict__ class_start)
+{
+  const int key = blockIdx.x * blockDim.x + threadIdx.x;
+  if (key > n_keys) return;
+  int lo = 0, hi = n_pieces;  // first piece with sorted_key >= key
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if (sorted_key[mid] < (uint32_t)key) lo = mid + 1; else hi = mid;
+  }
+  class_start[key] = lo;
+}
+
+struct hot_sub_host_t {  // mirrors hot_sub_t (spmv_hot.cuh)
+  int32_t slot_begin, row_begin, n_groups, cls;
 };
-constexpr int kHotUnitSlots = 8192;  // lane slots per work unit (<= 64 K edges)
+struct hot_unit_host_t {  // mirrors hot_unit_t (spmv_hot.cuh)
+  int32_t sub_begin, sub_end, block, pad;
+};
+struct hot_fill_t {  // build-time companion of a sub-unit
+  int32_t piece_begin, piece_end, block, pad;
+};
+
+// one CTA per sub-unit, one warp per group, lane = piece: write the group's slots step-major
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict__ fills, int32_t const* __restrict__ perm,
+           int32_t const* __restrict__ piece_start, int32_t const* __restrict__ piece_len,
+           int32_t const* __restrict__ piece_row, int32_t const* __restrict__ idx, T const* __restrict__ w, int W, int B,
+           int zero_col_cold, long long cold_slot0, uint16_t* __restrict__ idx16, int32_t* __restrict__ idx32,
+           T* __restrict__ w_out, int32_t* __restrict__ seg_row_out)
+{
+  const hot_sub_host_t sb = subs[blockIdx.x];
+  const hot_fill_t fl     = fills[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool hot = fl.block < B;
+  for (int q = warp; q < sb.n_groups; q += 8) {
+    const int pi     = fl.piece_begin + q * 32 + lane;
+    const bool valid = pi < fl.piece_end;
+    int st = 0, ln = 0, row = -1;
+    if (valid) {
+      const int p = perm[pi];
+      st          = piece_start[p];
+      ln          = piece_len[p];
+      row         = piece_row[p];
+    }
+    seg_row_out[(size_t)sb.row_begin + (size_t)q * 32 + lane] = row;
+    for (int j = 0; j < sb.cls; ++j) {
+      const long long slot = (long long)sb.slot_begin + ((long long)q * sb.cls + j) * 32 + lane;
+      int col[kHotSlot];
+#pragma unroll
+      for (int k = 0; k < kHotSlot; ++k) {
+        const int e   = j * kHotSlot + k;
+        const bool in = e < ln;
+        col[k]        = in ? idx[st + e] : -1;
+        if (w_out) w_out[(size_t)slot * kHotSlot + k] = in ? w[st + e] : (T)0;
+      }
+      if (hot) {
+        unsigned v[kHotSlot];
+#pragma unroll
+        for (int k = 0; k < kHotSlot; ++k) v[k] = col[k] >= 0 ? (unsigned)(col[k] - fl.block * W) : (unsigned)W;
+        uint4 o = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        reinterpret_cast<uint4*>(idx16)[slot] = o;
+      } else {
+        int v[kHotSlot];
+#pragma unroll
+        for (int k = 0; k < kHotSlot; ++k) v[k] = col[k] >= 0 ? col[k] : zero_col_cold;
+        int4* dst = reinterpret_cast<int4*>(idx32) + (slot - cold_slot0) * 2;
+        dst[0]    = make_int4(v[0], v[1], v[2], v[3]);
+        dst[1]    = make_int4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+}
+
+// slots per work unit, about (a unit is a run of sub-units of one block; sub-units are at most this long)
+inline int hot_unit_slots()
+{
+  if (const char* e = std::getenv("CUGRAPH_B200_HOT_UNIT_SLOTS")) return std::max(1024, std::min(std::atoi(e), 1 << 20));
+  return 8192;
+}
 
 template <typename O>
 std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const& c, int32_t nv, size_t es)
 {
+  phase_trace tr(h);
   const int W        = (int)(kHotSliceBytes / es) - kHotZeroPad;  // columns per hot block; the pad holds zeros
   const int32_t n_hi = c.seg[0];
   const int B        = (int)std::min<int64_t>(hot_max_blocks(), ((int64_t)nv + W - 1) / W);
+  const int64_t nnz  = c.nnz_hi;
   auto L             = std::make_unique<hot_layout_t>();
-  L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = c.nnz_hi;
-  const int64_t n_seg = (int64_t)(B + 1) * n_hi;
-  dbuf seg_pos = make_dbuf<int32_t>(n_seg, h.stream), seg_len = make_dbuf<int32_t>(n_seg, h.stream);
-  dbuf seg_slots = make_dbuf<int32_t>(n_seg + 1, h.stream), slot_off = make_dbuf<int32_t>(n_seg + 1, h.stream);
-  B200_LAUNCH(h, (k_hot_segments<O>), grid_for(n_seg + 1), kBlock, 0, c.offsets.as<O>(), c.indices.as<int32_t>(), n_hi, B, W,
-              seg_pos.as<int32_t>(), seg_len.as<int32_t>(), seg_slots.as<int32_t>());
-  exclusive_scan_i32(h, seg_slots.as<int32_t>(), slot_off.as<int32_t>(), n_seg + 1);
-  seg_slots.release();
-  std::vector<int32_t> bslot(B + 2);  // first slot of every block (cold = block B), total at [B+1]
-  for (int b = 0; b <= B + 1; ++b)
-    CUDA_TRY(cudaMemcpyAsync(&bslot[b], slot_off.as<int32_t>() + (size_t)std::min<int64_t>((int64_t)b * n_hi, n_seg),
-                             sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
-  sync(h);
-  L->n_hot_slots = bslot[B];
-  L->n_slots     = bslot[B + 1];
-  std::vector<hot_unit_host_t> units;
-  for (int b = 0; b <= B; ++b) {
-    // blocks whose rows mostly own a single slot gain nothing from combining neighbouring lanes
-    const int combine = (double)(bslot[b + 1] - bslot[b]) >= 1.2 * (double)n_hi ? 1 : 0;
-    for (int s = bslot[b]; s < bslot[b + 1]; s += kHotUnitSlots)
-      units.push_back({s, std::min(s + kHotUnitSlots, bslot[b + 1]), b, combine});
+  L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = nnz;
+  int32_t const* idx = c.indices.as<int32_t>();
+
+  // 1. segment heads
+  dbuf flag = make_dbuf<uint8_t>(nnz, h.stream);
+  CUDA_TRY(cudaMemsetAsync(flag.data(), 0, nnz, h.stream));
+  B200_LAUNCH(h, (k_hot_row_starts<O>), grid_for(n_hi), kBlock, 0, c.offsets.as<O>(), n_hi, flag.as<uint8_t>());
+  B200_LAUNCH(h, k_hot_heads, std::min(grid_for(nnz, 4), 148 * 32), kBlock, 0, idx, (long long)nnz, W, B, flag.as<uint8_t>());
+  dbuf head_pos = make_dbuf<int32_t>(nnz, h.stream);
+  int64_t n_segs64;
+  {
+    dbuf d_count = make_dbuf<int64_t>(1, h.stream);
+    thrust::counting_iterator<int32_t> iota(0);
+    size_t bytes = 0;
+    CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, bytes, iota, flag.as<uint8_t>(), head_pos.as<int32_t>(), d_count.as<int64_t>(),
+                                        nnz, h.stream));
+    dbuf tmp(bytes, h.stream);
+    CUDA_TRY(cub::DeviceSelect::Flagged(tmp.data(), bytes, iota, flag.as<uint8_t>(), head_pos.as<int32_t>(),
+                                        d_count.as<int64_t>(), nnz, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(&n_segs64, d_count.data(), sizeof(int64_t), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
   }
-  L->n_units = (int32_t)units.size();
-  L->units   = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
-  if (!units.empty())
+  flag.release();
+  const int32_t n_segs = (int32_t)n_segs64;
+  tr.mark("hot: segment heads");
+
+  // 2. pieces
+  dbuf seg_row = make_dbuf<int32_t>(n_segs, h.stream), seg_pieces = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
+  dbuf piece_off = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
+  B200_LAUNCH(h, (k_hot_segment_info<O>), grid_for((int64_t)n_segs + 1), kBlock, 0, head_pos.as<int32_t>(), n_segs,
+              (long long)nnz, c.offsets.as<O>(), n_hi, seg_row.as<int32_t>(), seg_pieces.as<int32_t>());
+  exclusive_scan_i32(h, seg_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_segs + 1);
+  int32_t n_pieces = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_segs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  seg_pieces.release();
+  dbuf piece_key = make_dbuf<uint32_t>(n_pieces, h.stream), piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
+  dbuf piece_start = make_dbuf<int32_t>(n_pieces, h.stream), piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
+  dbuf piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
+  B200_LAUNCH(h, k_hot_emit_pieces, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W, B,
+              seg_row.as<int32_t>(), piece_off.as<int32_t>(), piece_key.as<uint32_t>(), piece_start.as<int32_t>(),
+              piece_len.as<int32_t>(), piece_row.as<int32_t>());
+  head_pos.release();
+  seg_row.release();
+  piece_off.release();
+  tr.mark("hot: pieces");
+
+  // 3. order pieces by class
+  const int n_keys = (B + 1) * kHotPieceSlots;
+  dbuf perm = make_dbuf<uint32_t>(n_pieces, h.stream), perm2 = make_dbuf<uint32_t>(n_pieces, h.stream);
+  B200_LAUNCH(h, k_iota64, grid_for(n_pieces, 4), kBlock, 0, (int64_t)n_pieces, perm.as<uint32_t>());
+  sort_pairs<uint32_t, uint32_t>(h, piece_key.as<uint32_t>(), piece_key2.as<uint32_t>(), perm.as<uint32_t>(),
+                                 perm2.as<uint32_t>(), n_pieces, 0, bits_for(n_keys + 1));
+  dbuf class_start = make_dbuf<int32_t>((size_t)n_keys + 1, h.stream);
+  B200_LAUNCH(h, k_hot_class_starts, grid_for(n_keys + 1), kBlock, 0, piece_key2.as<uint32_t>(), n_pieces, n_keys,
+              class_start.as<int32_t>());
+  std::vector<int32_t> cstart((size_t)n_keys + 1);
+  CUDA_TRY(cudaMemcpyAsync(cstart.data(), class_start.data(), sizeof(int32_t) * cstart.size(), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  piece_key.release();
+  piece_key2.release();
+  perm.release();
+  tr.mark("hot: class sort");
+  if (tr.on) {  // layout statistics: pieces by class and by entries, per range of blocks
+    std::vector<int32_t> hlen(n_pieces), hperm(n_pieces);
+    CUDA_TRY(cudaMemcpy(hlen.data(), piece_len.data(), sizeof(int32_t) * n_pieces, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hperm.data(), perm2.data(), sizeof(int32_t) * n_pieces, cudaMemcpyDeviceToHost));
+    const int edges[] = {0, 1, 4, 16, 64, 160, 250, B, B + 1};
+    std::fprintf(stderr, "[hot] B=%d W=%d n_hi=%d nnz_hi=%lld segments=%d pieces=%d\n", B, W, n_hi, (long long)nnz, n_segs, n_pieces);
+    for (int k = 0; k + 1 < 9; ++k) {
+      const int b0 = std::min(edges[k], B + 1), b1 = std::min(edges[k + 1], B + 1);
+      if (b1 <= b0) continue;
+      long long by_len[9] = {0}, by_cls[9] = {0}, entries = 0;
+      for (int key = b0 * kHotPieceSlots; key < b1 * kHotPieceSlots; ++key)
+        for (int p = cstart[key]; p < cstart[key + 1]; ++p) {
+          const int ln = hlen[hperm[p]];
+          entries += ln;
+          by_cls[key % kHotPieceSlots + 1]++;
+          if (ln <= 8) by_len[ln]++;
+        }
+      std::fprintf(stderr, "[hot] blocks [%d,%d)%s entries %lld  pieces by slots:", b0, b1, b1 == B + 1 && b0 == B ? " (cold)" : "", entries);
+      for (int c2 = 1; c2 <= 8; ++c2) std::fprintf(stderr, " %lld", by_cls[c2]);
+      std::fprintf(stderr, "  1-slot pieces by entries:");
+      for (int c2 = 1; c2 <= 8; ++c2) std::fprintf(stderr, " %lld", by_len[c2]);
+      std::fprintf(stderr, "\n");
+    }
+  }
+
+  // 4. sub-units (runs of groups of one class), units (runs of sub-units of one block), CTA ranges
+  std::vector<hot_sub_host_t> subs;
+  std::vector<hot_fill_t> fills;
+  std::vector<hot_unit_host_t> units;
+  std::vector<double> unit_cost;
+  double cold_cost = 2.0;
+  if (const char* e = std::getenv("CUGRAPH_B200_HOT_COLD_COST")) cold_cost = std::atof(e);
+  const int kHotUnitSlots = hot_unit_slots();
+  int64_t slot_run = 0, row_run = 0, cold_slot0 = 0;
+  for (int b = 0; b <= B; ++b) {
+    if (b == B) cold_slot0 = slot_run;
+    int64_t unit_slots = 0;
+    int unit_sub0      = (int)subs.size();
+    auto close_unit = [&]() {
+      if ((int)subs.size() > unit_sub0) {
+        units.push_back({unit_sub0, (int32_t)subs.size(), b, 0});
+        unit_cost.push_back((double)unit_slots * (b == B ? cold_cost : 1.0) + 64.0);
+      }
+      unit_sub0  = (int)subs.size();
+      unit_slots = 0;
+    };
+    for (int cls = 1; cls <= kHotPieceSlots; ++cls) {
+      const int key   = b * kHotPieceSlots + cls - 1;
+      int32_t p       = cstart[key];
+      const int32_t pe = cstart[key + 1];
+      const int max_groups = std::max(1, kHotUnitSlots / (32 * cls));
+      while (p < pe) {
+        const int groups = (int)std::min<int64_t>(max_groups, ((int64_t)(pe - p) + 31) / 32);
+        if (slot_run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return nullptr;  // 32-bit slot ids
+        subs.push_back({(int32_t)slot_run, (int32_t)row_run, groups, cls});
+        fills.push_back({p, std::min<int32_t>(pe, p + groups * 32), b, 0});
+        slot_run += (int64_t)groups * 32 * cls;
+        row_run += (int64_t)groups * 32;
+        unit_slots += (int64_t)groups * 32 * cls;
+        p += groups * 32;
+        if (unit_slots >= kHotUnitSlots) close_unit();
+      }
+    }
+    close_unit();
+  }
+  L->n_hot_slots = cold_slot0;
+  L->n_slots     = slot_run;
+  L->n_units     = (int32_t)units.size();
+  L->n_subs      = (int32_t)subs.size();
+  L->n_cta       = (int)std::max<size_t>(1, std::min<size_t>((size_t)h.sm_count, units.size()));
+  std::vector<int32_t> range(L->n_cta + 1, 0);
+  {
+    std::vector<double> cost(units.size() + 1, 0.0);
+    for (size_t u = 0; u < units.size(); ++u) cost[u + 1] = cost[u] + unit_cost[u];
+    size_t u = 0;
+    for (int cta = 1; cta < L->n_cta; ++cta) {
+      const double target = cost[units.size()] * cta / L->n_cta;
+      while (u < units.size() && cost[u + 1] <= target) ++u;
+      range[cta] = (int32_t)u;
+    }
+    range[L->n_cta] = (int32_t)units.size();
+  }
+  L->units     = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
+  L->subs      = make_dbuf<hot_sub_host_t>(std::max<size_t>(subs.size(), 1), h.stream);
+  L->cta_range = make_dbuf<int32_t>(range.size(), h.stream);
+  dbuf d_fills = make_dbuf<hot_fill_t>(std::max<size_t>(fills.size(), 1), h.stream);
+  if (!units.empty()) {
     CUDA_TRY(cudaMemcpyAsync(L->units.data(), units.data(), sizeof(hot_unit_host_t) * units.size(), cudaMemcpyHostToDevice, h.stream));
-  L->unit_counter = make_dbuf<int>(1, h.stream);
-  CUDA_TRY(cudaMemsetAsync(L->unit_counter.data(), 0, sizeof(int), h.stream));
-  L->slot_row   = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots, 1), h.stream);
+    CUDA_TRY(cudaMemcpyAsync(L->subs.data(), subs.data(), sizeof(hot_sub_host_t) * subs.size(), cudaMemcpyHostToDevice, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_fills.data(), fills.data(), sizeof(hot_fill_t) * fills.size(), cudaMemcpyHostToDevice, h.stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(L->cta_range.data(), range.data(), sizeof(int32_t) * range.size(), cudaMemcpyHostToDevice, h.stream));
+  sync(h);  // the host vectors are pageable
+  L->unit_counter = make_dbuf<int>(L->n_cta, h.stream);
+  CUDA_TRY(cudaMemsetAsync(L->unit_counter.data(), 0, sizeof(int) * L->n_cta, h.stream));
+
+  // 5. slots
+  L->seg_row    = make_dbuf<int32_t>(std::max<int64_t>(row_run, 1), h.stream);
   L->slot_idx16 = make_dbuf<uint16_t>(std::max<int64_t>(L->n_hot_slots, 1) * kHotSlot, h.stream);
   L->slot_idx32 = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots - L->n_hot_slots, 1) * kHotSlot, h.stream);
   const bool weighted = c.weights.data() != nullptr;
   if (weighted) L->slot_w = dbuf((size_t)std::max<int64_t>(L->n_slots, 1) * kHotSlot * es, h.stream);
-  // padded entries of the cold block read x[zero_col_cold] with weight 0; unweighted cold padding needs a
-  // real zero in x: the caller's x buffer holds zeros behind n_vertices (padded_x_elems)
-  const int zero_col_cold = nv;
-  int pgrid = (int)std::min<int64_t>((n_seg * 32 + kBlock - 1) / kBlock, 1 << 20);
-  if (es == 4)
-    B200_LAUNCH(h, (k_hot_fill_slots<float>), pgrid, kBlock, 0, c.indices.as<int32_t>(), c.weights.as<float>(),
-                seg_pos.as<int32_t>(), seg_len.as<int32_t>(), slot_off.as<int32_t>(), n_hi, B, W, W, zero_col_cold,
-                (int)L->n_hot_slots, L->slot_idx16.as<uint16_t>(), L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(),
-                L->slot_row.as<int32_t>());
-  else
-    B200_LAUNCH(h, (k_hot_fill_slots<double>), pgrid, kBlock, 0, c.indices.as<int32_t>(), c.weights.as<double>(),
-                seg_pos.as<int32_t>(), seg_len.as<int32_t>(), slot_off.as<int32_t>(), n_hi, B, W, W, zero_col_cold,
-                (int)L->n_hot_slots, L->slot_idx16.as<uint16_t>(), L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(),
-                L->slot_row.as<int32_t>());
+  // padding entries of the cold block read x[n_vertices], which the caller keeps at zero (padded_x_elems)
+  if (!subs.empty()) {
+    if (es == 4)
+      B200_LAUNCH(h, (k_hot_fill<float>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+                  perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
+                  c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
+                  L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>());
+    else
+      B200_LAUNCH(h, (k_hot_fill<double>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+                  perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
+                  c.weights.as<double>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
+                  L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(), L->seg_row.as<int32_t>());
+  }
   check_last("hot layout");
-  L->n_cta = h.sm_count;
   sync(h);
+  tr.mark("hot: fill slots");
+  if (tr.on)
+    std::fprintf(stderr, "[hot] slots %lld (hot %lld) = %.1f MB ids, seg rows %lld, units %d, subs %d\n", (long long)L->n_slots,
+                 (long long)L->n_hot_slots, (double)(L->n_hot_slots * 16 + (L->n_slots - L->n_hot_slots) * 32) / 1e6,
+                 (long long)row_run, L->n_units, L->n_subs);
   return L;
 }
 
@@ -1091,12 +1369,8 @@ hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_v
   tried = true;
   long long min_edges = 1ll << 22;
   if (const char* e = std::getenv("CUGRAPH_B200_HOT_MIN_EDGES")) min_edges = std::atoll(e);
-  const int W = (int)(kHotSliceBytes / elem_size) - kHotZeroPad;
-  const int B = (int)std::min<int64_t>(hot_max_blocks(), ((int64_t)n_vertices + W - 1) / W);
-  // slots are at most nnz_hi/8 + one per (row, block) segment
-  if (!c.degree_sorted || c.seg[0] <= 0 || c.nnz_hi < min_edges || c.offs64 || c.nnz_hi >= (1ll << 31) - 4096 ||
-      (int64_t)(B + 1) * c.seg[0] + c.nnz_hi / kHotSlot >= (1ll << 31) - 2)
-    return nullptr;
+  // 32-bit edge positions / slot numbers; build_hot_layout itself gives up (nullptr) if the slots overflow
+  if (!c.degree_sorted || c.seg[0] <= 0 || c.nnz_hi < min_edges || c.offs64 || c.nnz_hi >= (1ll << 31) - 4096) return nullptr;
   slot = build_hot_layout<int32_t>(h, c, n_vertices, elem_size);
   return slot.get();
 }

@@ -5,18 +5,22 @@
 // l1tex 73 %, DRAM 16 % — profiles/r01_ncu_k_spmv_hi_v1.csv).  The source space is therefore cut into
 // B hot blocks of W vertices whose x-slice (192 KiB) a persistent CTA keeps in shared memory, filled by
 // TMA bulk copies (cp.async.bulk + mbarrier).  Rows keep their neighbours sorted by source id, so a
-// row's adjacency is already partitioned by block; staging stores the (row, block) segments block-major,
-// cut into LANE SLOTS of 8 entries with 16-bit local column ids (hot_layout_t, graph.cuh): a lane reads
-// its 8 ids with one 128-bit load, gathers 8 values from shared memory and adds them in fp64 — no
-// per-entry predicates (padding entries read a zero), no segment walk.
+// row's adjacency is already partitioned by block.  Staging (graph_build.cu) cuts every (row, block)
+// segment into PIECES of <= 64 entries, stored as <= 8 LANE SLOTS of 8 entries with 16-bit local column
+// ids, and orders the pieces by (block, slots per piece).  32 consecutive pieces of one class are a
+// GROUP: one warp, lane = piece.  Per step a lane reads its 8 ids with one 128-bit load (the warp reads
+// 512 contiguous bytes), gathers 8 values from shared memory and adds them in fp64 into a register;
+// after the group's <= 8 steps every lane issues ONE fp64 atomic into acc_hi[row] — no per-entry
+// predicates (padding entries read a zero), no per-step shuffles.  Only the class of full 64-entry pieces
+// can hold several pieces of one row in a group; there a segmented shuffle reduction runs first.
 //
-// Execution: work units (<= 8192 slots of one block) are handed out dynamically through one atomic
-// counter (the next unit is fetched while the current one is processed); a CTA refills its shared
-// memory only when its next unit belongs to another block.  A warp handles 32 consecutive slots per
-// step.  If the 32 slots belong to one row (hub segments) the partials are folded with shuffles into ONE
-// fp64 atomic; otherwise lanes first combine with their right neighbours of the same row (3 shuffle
-// steps) and the surviving heads issue one fp64 atomic each into acc_hi[row] — the only atomics on
-// the path.  The cold block (sources >= B*W) runs through the same code with global gathers.
+// Execution: work units (sub-units of one block, about 8192 slots) are ordered by block and every CTA owns
+// a contiguous, cost-balanced range of them, so a CTA refills its shared memory only a couple of times
+// per sweep (one atomic cursor for ALL CTAs made every CTA walk every block: 148 x B slice fills were
+// 43 % of the shared-memory wavefronts, profiles/r01_ncu_k_spmv_blocked_v4.csv).  A CTA that runs out
+// of units steals from the ranges of the following CTAs (per-range atomic cursors; the next unit is
+// fetched while the current one is processed).  The cold block (sources >= B*W) runs through the same
+// code with global gathers.
 #pragma once
 #include "spmv.cuh"
 
@@ -68,171 +72,290 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p)
   return v;
 }
 
-// a work unit: consecutive lane slots of one block (mirrored by hot_unit_host_t, graph_build.cu)
+// consecutive groups of one class (mirrored by hot_sub_host_t, graph_build.cu)
+struct hot_sub_t {
+  int32_t slot_begin;  // first slot of group 0; group q starts at slot_begin + q * 32 * cls
+  int32_t row_begin;   // seg_row index of (group 0, lane 0)
+  int32_t n_groups;
+  int32_t cls;         // slots per piece = steps per group, 1..8
+};
+// a work unit: consecutive sub-units of one block (mirrored by hot_unit_host_t)
 struct hot_unit_t {
-  int32_t slot_begin;
-  int32_t slot_end;
+  int32_t sub_begin;
+  int32_t sub_end;
   int32_t block;
-  int32_t combine;  // 1: segments of this block span several slots, combine neighbours before the atomics
+  int32_t pad;
 };
 
-// the 8 column ids of lane slot s: one 128-bit load (hot, 16-bit ids) or two (cold, 32-bit ids)
+// the 8 column ids of a lane slot: one 128-bit load (hot, 16-bit ids) or two (cold, 32-bit ids)
 struct slot_ids_t {
   uint4 a, b;
 };
 template <bool HOT>
-__device__ __forceinline__ slot_ids_t hot_slot_load(long long s, bool valid, uint16_t const* __restrict__ idx16,
-                                                    int32_t const* __restrict__ idx32, long long cold_slot0)
+__device__ __forceinline__ slot_ids_t hot_slot_load(int s, uint16_t const* __restrict__ idx16,
+                                                    int32_t const* __restrict__ idx32, int cold_slot0)
 {
   slot_ids_t r;
-  r.a = make_uint4(0, 0, 0, 0);
-  r.b = make_uint4(0, 0, 0, 0);
-  if (valid) {
-    if (HOT) {
-      r.a = ld_stream_v4(idx16 + s * kHotSlot);
-    } else {
-      r.a = ld_stream_v4(idx32 + (s - cold_slot0) * kHotSlot);
-      r.b = ld_stream_v4(idx32 + (s - cold_slot0) * kHotSlot + 4);
-    }
+  if (HOT) {
+    r.a = ld_stream_v4(idx16 + (size_t)(unsigned)s * kHotSlot);
+    r.b = r.a;
+  } else {
+    r.a = ld_stream_v4(idx32 + (size_t)(unsigned)(s - cold_slot0) * kHotSlot);
+    r.b = ld_stream_v4(idx32 + (size_t)(unsigned)(s - cold_slot0) * kHotSlot + 4);
   }
   return r;
 }
 
-// sum of the 8 entries of a lane slot (fp64); an invalid slot has all-zero ids and row -1: its value is
-// never emitted
+// sum of the 8 entries of a lane slot (fp64)
 template <typename T, bool WEIGHTED, bool HOT>
-__device__ __forceinline__ double hot_slot_sum(slot_ids_t const& ids, long long s, bool valid, T const* __restrict__ w,
+__device__ __forceinline__ double hot_slot_sum(slot_ids_t const& ids, int s, T const* __restrict__ w,
                                                T const* __restrict__ x, T const* __restrict__ sx)
 {
-  unsigned c[kHotSlot];
-  if (HOT) {
-    c[0] = ids.a.x & 0xffffu; c[1] = ids.a.x >> 16; c[2] = ids.a.y & 0xffffu; c[3] = ids.a.y >> 16;
-    c[4] = ids.a.z & 0xffffu; c[5] = ids.a.z >> 16; c[6] = ids.a.w & 0xffffu; c[7] = ids.a.w >> 16;
-  } else {
-    c[0] = ids.a.x; c[1] = ids.a.y; c[2] = ids.a.z; c[3] = ids.a.w;
-    c[4] = ids.b.x; c[5] = ids.b.y; c[6] = ids.b.z; c[7] = ids.b.w;
-  }
   T v[kHotSlot];
-#pragma unroll
-  for (int k = 0; k < kHotSlot; ++k) v[k] = HOT ? sx[c[k]] : x[c[k]];
+  if (HOT) {
+    // byte offsets into the slice: (id16 << 2), extracted with one shift + one mask each
+    const unsigned m = 0x3fffcu;
+    const char* base = reinterpret_cast<const char*>(sx);
+    v[0] = *reinterpret_cast<const T*>(base + (((ids.a.x << 2) & m) * (sizeof(T) / 4)));
+    v[1] = *reinterpret_cast<const T*>(base + (((ids.a.x >> 14) & m) * (sizeof(T) / 4)));
+    v[2] = *reinterpret_cast<const T*>(base + (((ids.a.y << 2) & m) * (sizeof(T) / 4)));
+    v[3] = *reinterpret_cast<const T*>(base + (((ids.a.y >> 14) & m) * (sizeof(T) / 4)));
+    v[4] = *reinterpret_cast<const T*>(base + (((ids.a.z << 2) & m) * (sizeof(T) / 4)));
+    v[5] = *reinterpret_cast<const T*>(base + (((ids.a.z >> 14) & m) * (sizeof(T) / 4)));
+    v[6] = *reinterpret_cast<const T*>(base + (((ids.a.w << 2) & m) * (sizeof(T) / 4)));
+    v[7] = *reinterpret_cast<const T*>(base + (((ids.a.w >> 14) & m) * (sizeof(T) / 4)));
+  } else {
+    v[0] = x[ids.a.x]; v[1] = x[ids.a.y]; v[2] = x[ids.a.z]; v[3] = x[ids.a.w];
+    v[4] = x[ids.b.x]; v[5] = x[ids.b.y]; v[6] = x[ids.b.z]; v[7] = x[ids.b.w];
+  }
   if (WEIGHTED) {
 #pragma unroll
-    for (int k = 0; k < kHotSlot; ++k) v[k] *= valid ? ld_stream(w + s * kHotSlot + k) : (T)0;
+    for (int k = 0; k < kHotSlot; ++k) v[k] *= ld_stream(w + (size_t)(unsigned)s * kHotSlot + k);
   }
   return (((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3])) +
          (((double)v[4] + (double)v[5]) + ((double)v[6] + (double)v[7]));
 }
 
-// fold the 32 per-slot partials of a warp step into acc_hi[row] (row < 0: nothing to emit).
-// The kernel is bound by the MIO pipe (shared-memory gathers + shuffles, profiles/r01_ncu_k_spmv_blocked_v4.csv),
-// so the combine uses one packed shuffle for (row, alive) and a vote instead of a shuffle for the retire
-// flag, and is skipped for units whose segments are mostly single slots (COMBINE = false).
-template <bool COMBINE>
+// end of a group: one fp64 atomic per lane.  SAME_ROW_RUNS (class of full pieces): consecutive lanes may
+// hold pieces of the same row — suffix-sum inside the runs first, run heads emit.
+template <bool SAME_ROW_RUNS>
 __device__ __forceinline__ void hot_emit(double acc, int row, double* __restrict__ acc_hi, int lane)
 {
-  const int r0 = __shfl_sync(0xffffffffu, row, 0);
-  if (__all_sync(0xffffffffu, row == r0)) {  // one row (hub segment, or 32 padding slots)
-    acc = warp_sum(acc);
-    if (lane == 0 && r0 >= 0) atomicAdd(acc_hi + r0, acc);
-    return;
-  }
-  if (COMBINE) {
-    // slots of a row are consecutive lanes: aligned runs of up to 8 collapse into their head lane
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-      const double nb = __shfl_down_sync(0xffffffffu, acc, o);
-      const int rn    = __shfl_down_sync(0xffffffffu, row, o);  // -1 when the neighbour is retired / padding
-      const bool take = ((lane & (2 * o - 1)) == 0) && row >= 0 && rn == row;
-      if (take) acc += nb;
-      const unsigned takes = __ballot_sync(0xffffffffu, take);
-      if (lane >= o && ((takes >> (lane - o)) & 1u)) row = -1;  // absorbed by the head at lane - o
+  if (SAME_ROW_RUNS) {
+    const int r0 = __shfl_sync(0xffffffffu, row, 0);
+    if (__all_sync(0xffffffffu, row == r0)) {  // 32 pieces of one hub row
+      acc = warp_sum(acc);
+      if (lane == 0 && r0 >= 0) atomicAdd(acc_hi + r0, acc);
+      return;
     }
+    const int left = __shfl_up_sync(0xffffffffu, row, 1);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double nb = __shfl_down_sync(0xffffffffu, acc, o);
+      const int rn    = __shfl_down_sync(0xffffffffu, row, o);
+      if (lane + o < 32 && rn == row) acc += nb;
+    }
+    if (lane > 0 && left == row) row = -1;  // not the head of its run
   }
   if (row >= 0) atomicAdd(acc_hi + row, acc);
+}
+
+// all groups of one sub-unit that fall to this warp (q = q0, q0 + 32, ...); the first ids / row of the
+// next group are requested before the current group is reduced
+template <typename T, bool WEIGHTED, bool HOT>
+__device__ __forceinline__ void hot_run_groups(hot_sub_t const sb, int q, int lane, int32_t const* __restrict__ seg_row,
+                                               uint16_t const* __restrict__ idx16, int32_t const* __restrict__ idx32,
+                                               int cold_slot0, T const* __restrict__ w, T const* __restrict__ x,
+                                               T const* __restrict__ sx, double* __restrict__ acc_hi)
+{
+  if (q >= sb.n_groups) return;
+  const int cls    = sb.cls;
+  const int gslots = 32 * cls;  // slot numbers fit 31 bits (checked at staging)
+  int s            = sb.slot_begin + q * gslots + lane;
+  int ri           = sb.row_begin + q * 32 + lane;
+  slot_ids_t ids         = hot_slot_load<HOT>(s, idx16, idx32, cold_slot0);
+  int row                = ld_stream(seg_row + ri);
+  while (true) {
+    double acc = 0.0;
+    for (int j = 1; j < cls; ++j) {
+      const slot_ids_t nx = hot_slot_load<HOT>(s + 32 * j, idx16, idx32, cold_slot0);
+      acc += hot_slot_sum<T, WEIGHTED, HOT>(ids, s + 32 * (j - 1), w, x, sx);
+      ids = nx;
+    }
+    q += 32;
+    const bool more = q < sb.n_groups;
+    slot_ids_t nx   = ids;
+    int nrow        = -1;
+    if (more) {
+      nx   = hot_slot_load<HOT>(s + 32 * gslots, idx16, idx32, cold_slot0);
+      nrow = ld_stream(seg_row + ri + 1024);
+    }
+    acc += hot_slot_sum<T, WEIGHTED, HOT>(ids, s + 32 * (cls - 1), w, x, sx);
+    if (cls == kHotSlot) hot_emit<true>(acc, row, acc_hi, lane);
+    else hot_emit<false>(acc, row, acc_hi, lane);
+    if (!more) break;
+    s += 32 * gslots;
+    ri += 1024;
+    ids = nx;
+    row = nrow;
+  }
+}
+
+// class of one-slot pieces (the bulk of the pieces once every column block is hot): one step per group, so
+// there is nothing to pipeline inside a group.  The warp keeps FOUR groups in flight instead: 4 id vectors + 4
+// rows are requested before the first gather (ncu on the one-group-ahead version: 22 % of all stall samples
+// sat on the move that consumes the prefetched ids, profiles/r01_ncu_k_spmv_blocked_v5.csv).
+template <typename T, bool WEIGHTED, bool HOT>
+__device__ __forceinline__ void hot_run_groups_c1(hot_sub_t const sb, int q, int lane, int32_t const* __restrict__ seg_row,
+                                                  uint16_t const* __restrict__ idx16, int32_t const* __restrict__ idx32,
+                                                  int cold_slot0, T const* __restrict__ w, T const* __restrict__ x,
+                                                  T const* __restrict__ sx, double* __restrict__ acc_hi)
+{
+  constexpr int K = HOT ? 4 : 2;  // cold ids are 32-bit: twice the registers per slot
+  for (; q < sb.n_groups; q += 32 * K) {
+    slot_ids_t ids[K];
+    int row[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int qk = q + 32 * k;
+      row[k]       = -1;
+      if (qk < sb.n_groups) {  // warp-uniform
+        ids[k] = hot_slot_load<HOT>(sb.slot_begin + qk * 32 + lane, idx16, idx32, cold_slot0);
+        row[k] = ld_stream(seg_row + sb.row_begin + qk * 32 + lane);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int qk = q + 32 * k;
+      if (qk < sb.n_groups) {
+        const double acc = hot_slot_sum<T, WEIGHTED, HOT>(ids[k], sb.slot_begin + qk * 32 + lane, w, x, sx);
+        if (row[k] >= 0) atomicAdd(acc_hi + row[k], acc);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int ld_volatile(const int* p)
+{
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// next units for this CTA (called by all lanes of warp 0): own range first — `claim` consecutive units per
+// atomic, they are processed without a CTA barrier in between — then single units of the following CTAs'
+// ranges.  victim_off = how many ranges (starting with the own one) are known to be exhausted.
+// Returns the first unit (n_units when everything is done) and sets count.
+__device__ __forceinline__ int hot_fetch_unit(int* __restrict__ cursor, int32_t const* __restrict__ cta_range, int n_cta,
+                                              int n_units, int claim, int& victim_off, int& count, int lane)
+{
+  while (victim_off < n_cta) {
+    int v = (int)blockIdx.x + victim_off;
+    if (v >= n_cta) v -= n_cta;
+    const int want = victim_off == 0 ? claim : 1;
+    int u = -1, c = 0;
+    if (lane == 0) {
+      u             = cta_range[v] + atomicAdd(cursor + v, want);
+      const int end = cta_range[v + 1];
+      c             = end - u < want ? end - u : want;
+      if (c <= 0) u = -1;
+    }
+    u = __shfl_sync(0xffffffffu, u, 0);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (u >= 0) {
+      count = c;
+      return u;
+    }
+    ++victim_off;
+    while (victim_off < n_cta) {  // look 32 ranges ahead at a time for one that still has units
+      int vv         = (int)blockIdx.x + victim_off + lane;
+      const bool inr = victim_off + lane < n_cta;
+      if (vv >= n_cta) vv -= n_cta;
+      const bool has   = inr && ld_volatile(cursor + vv) < cta_range[vv + 1] - cta_range[vv];
+      const unsigned m = __ballot_sync(0xffffffffu, has);
+      if (m) {
+        victim_off += __ffs(m) - 1;
+        break;
+      }
+      victim_off += 32;
+    }
+  }
+  count = 0;
+  return n_units;
 }
 
 template <typename T, bool WEIGHTED>
 __global__ void __launch_bounds__(kHotThreads, 1)
 k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restrict__ unit_counter,
-               int32_t const* __restrict__ slot_row, uint16_t const* __restrict__ idx16,
-               int32_t const* __restrict__ idx32, long long cold_slot0, T const* __restrict__ w,
-               T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, pr_state_t const* __restrict__ st)
+               int32_t const* __restrict__ cta_range, hot_sub_t const* __restrict__ subs,
+               int32_t const* __restrict__ seg_row, uint16_t const* __restrict__ idx16,
+               int32_t const* __restrict__ idx32, int cold_slot0, T const* __restrict__ w,
+               T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, int c1_wide,
+               int claim, pr_state_t const* __restrict__ st)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* sx = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
-  __shared__ int s_next;
+  __shared__ int s_next, s_count;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    s_next = atomicAdd(unit_counter, 1);
+  int victim_off = 0;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (warp == 0) {
+    int cnt     = 0;
+    const int n = hot_fetch_unit(unit_counter, cta_range, (int)gridDim.x, n_units, claim, victim_off, cnt, lane);
+    if (lane == 0) {
+      s_next  = n;
+      s_count = cnt;
+    }
   }
   if (threadIdx.x < kHotZeroPad) sx[W + threadIdx.x] = (T)0;  // the padding column(s) of every slice
   unsigned phase = 0;
   int cur_block  = -1;
   while (true) {
-    __syncthreads();  // s_next is published; everyone is done with the previous unit's slice
-    const int u = s_next;
+    __syncthreads();  // s_next is published; everyone is done with the previous units' slice
+    const int u0 = s_next, ucnt = s_count;
     __syncthreads();
-    if (u >= n_units) break;
-    if (threadIdx.x == 0) s_next = atomicAdd(unit_counter, 1);  // fetch the next unit while working
-    const hot_unit_t un = units[u];
-    const int b         = un.block;
-    const bool hot      = b < B;
-    if (hot && b != cur_block) {
-      if (threadIdx.x == 0) {
-        const unsigned bytes = (unsigned)(W * sizeof(T));
-        mbar_expect_tx(&bar, bytes);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(x + (size_t)b * W);
-        for (unsigned o = 0; o < bytes; o += kHotTmaPiece)
-          tma_bulk_g2s(smem_raw + o, src + o, (bytes - o) < (unsigned)kHotTmaPiece ? (bytes - o) : (unsigned)kHotTmaPiece, &bar);
+    if (u0 >= n_units) break;
+    if (warp == 0) {  // fetch the next claim while working
+      int cnt     = 0;
+      const int n = hot_fetch_unit(unit_counter, cta_range, (int)gridDim.x, n_units, claim, victim_off, cnt, lane);
+      if (lane == 0) {
+        s_next  = n;
+        s_count = cnt;
       }
-      cur_block = b;
-      mbar_wait(&bar, phase);
-      phase ^= 1;
     }
-    // two warp steps (64 slots) per iteration, software pipelined: the index vectors and rows of the next
-    // iteration are loaded before the current one is gathered and reduced
-    const int stride = kHotWarps * 64;
-    int s0           = un.slot_begin + warp * 64;
-    slot_ids_t ia, ib;
-    int ra = -1, rb = -1;
-    {
-      const int sa = s0 + lane, sb = s0 + 32 + lane;
-      const bool va = sa < un.slot_end, vb = sb < un.slot_end;
-      if (hot) { ia = hot_slot_load<true>(sa, va, idx16, idx32, cold_slot0); ib = hot_slot_load<true>(sb, vb, idx16, idx32, cold_slot0); }
-      else { ia = hot_slot_load<false>(sa, va, idx16, idx32, cold_slot0); ib = hot_slot_load<false>(sb, vb, idx16, idx32, cold_slot0); }
-      ra = va ? slot_row[sa] : -1;
-      rb = vb ? slot_row[sb] : -1;
-    }
-    for (; s0 < un.slot_end; s0 += stride) {
-      const int sa = s0 + lane, sb = s0 + 32 + lane;
-      const bool va = sa < un.slot_end, vb = sb < un.slot_end;
-      // prefetch the next iteration
-      const int na = sa + stride, nb = sb + stride;
-      const bool nva = na < un.slot_end, nvb = nb < un.slot_end;
-      slot_ids_t ja, jb;
-      if (hot) { ja = hot_slot_load<true>(na, nva, idx16, idx32, cold_slot0); jb = hot_slot_load<true>(nb, nvb, idx16, idx32, cold_slot0); }
-      else { ja = hot_slot_load<false>(na, nva, idx16, idx32, cold_slot0); jb = hot_slot_load<false>(nb, nvb, idx16, idx32, cold_slot0); }
-      const int nra = nva ? slot_row[na] : -1;
-      const int nrb = nvb ? slot_row[nb] : -1;
-      double aa, ab;
-      if (hot) {
-        aa = hot_slot_sum<T, WEIGHTED, true>(ia, sa, va, w, x, sx);
-        ab = hot_slot_sum<T, WEIGHTED, true>(ib, sb, vb, w, x, sx);
-      } else {
-        aa = hot_slot_sum<T, WEIGHTED, false>(ia, sa, va, w, x, sx);
-        ab = hot_slot_sum<T, WEIGHTED, false>(ib, sb, vb, w, x, sx);
+    int dealt = 0;  // groups are dealt round-robin to the warps, continuing across sub-units and units
+    for (int u = u0; u < u0 + ucnt; ++u) {
+      const hot_unit_t un = units[u];
+      const int b         = un.block;
+      const bool hot      = b < B;
+      if (hot && b != cur_block) {
+        if (u != u0) __syncthreads();  // warps of this claim may still gather from the old slice
+        if (threadIdx.x == 0) {
+          const unsigned bytes = (unsigned)(W * sizeof(T));
+          mbar_expect_tx(&bar, bytes);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(x + (size_t)b * W);
+          for (unsigned o = 0; o < bytes; o += kHotTmaPiece)
+            tma_bulk_g2s(smem_raw + o, src + o, (bytes - o) < (unsigned)kHotTmaPiece ? (bytes - o) : (unsigned)kHotTmaPiece, &bar);
+        }
+        cur_block = b;
+        mbar_wait(&bar, phase);
+        phase ^= 1;
       }
-      if (un.combine) {
-        hot_emit<true>(aa, ra, acc_hi, lane);
-        if (s0 + 32 < un.slot_end) hot_emit<true>(ab, rb, acc_hi, lane);
-      } else {
-        hot_emit<false>(aa, ra, acc_hi, lane);
-        if (s0 + 32 < un.slot_end) hot_emit<false>(ab, rb, acc_hi, lane);
+      for (int si = un.sub_begin; si < un.sub_end; ++si) {
+        const hot_sub_t sb = subs[si];
+        const int q0       = (warp - dealt) & (kHotWarps - 1);
+        dealt += sb.n_groups;
+        if (c1_wide && sb.cls == 1) {
+          if (hot) hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
+          else hot_run_groups_c1<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
+        } else if (hot) {
+          hot_run_groups<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
+        } else {
+          hot_run_groups<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
+        }
       }
-      ia = ja; ib = jb; ra = nra; rb = nrb;
     }
   }
 }
@@ -241,11 +364,11 @@ k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restric
 template <typename T>
 __global__ void k_spmv_blocked_finish(double* __restrict__ acc_hi, int n_hi, T* __restrict__ y,
                                       int32_t const* __restrict__ row_vertex, double alpha, int* unit_counter,
-                                      pr_state_t const* __restrict__ st)
+                                      int n_cta, pr_state_t const* __restrict__ st)
 {
   if (st->done) return;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r == 0) *unit_counter = 0;
+  if (r < n_cta) unit_counter[r] = 0;
   if (r >= n_hi) return;
   y[row_vertex ? row_vertex[r] : r] = (T)(acc_hi[r] * alpha + st->init);
   acc_hi[r]                          = 0.0;
@@ -259,10 +382,25 @@ void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, dou
   if (lblocks <= 0) return;
   if (c.weights.data())
     B200_LAUNCH(h, (k_spmv_low<O, T, true>), lblocks, 256, 0, c.offsets.as<O>(), c.indices.as<int32_t>(),
-                c.weights.as<T>(), x, y, c.row_vertex.as<int32_t>(), bins, alpha, st);
+                c.weights.as<T>(), x, y, c.row_vertex.as<int32_t>(), bins, alpha, st, low_mode());
   else
     B200_LAUNCH(h, (k_spmv_low<O, T, false>), lblocks, 256, 0, c.offsets.as<O>(), c.indices.as<int32_t>(),
-                c.weights.as<T>(), x, y, c.row_vertex.as<int32_t>(), bins, alpha, st);
+                c.weights.as<T>(), x, y, c.row_vertex.as<int32_t>(), bins, alpha, st, low_mode());
+}
+
+// CUGRAPH_B200_HOT_C1: 1 = four one-slot groups in flight per warp (hot_run_groups_c1), 0 = generic group loop
+inline int hot_c1_wide()
+{
+  const char* e = std::getenv("CUGRAPH_B200_HOT_C1");
+  return e ? std::atoi(e) : 0;
+}
+
+// CUGRAPH_B200_HOT_CLAIM: units of its own range a CTA takes per atomic (processed without a CTA barrier in between)
+inline int hot_claim()
+{
+  const char* e = std::getenv("CUGRAPH_B200_HOT_CLAIM");
+  const int c   = e ? std::atoi(e) : 1;
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
 }
 
 // x must hold padded_x_elems() elements, zero behind n_vertices (slices are copied whole; the cold
@@ -277,17 +415,17 @@ void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_
     CUDA_TRY(cudaFuncSetAttribute(k_spmv_blocked<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotDynSmem));
     attr_set = true;
   }
-  const int grid = std::min(L.n_cta, L.n_units);
+  const int grid = L.n_cta;
   if (L.slot_w.data())
     B200_LAUNCH(h, (k_spmv_blocked<T, true>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
-                L.unit_counter.as<int>(), L.slot_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
-                (long long)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, st);
+                L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
+                (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, hot_c1_wide(), hot_claim(), st);
   else
     B200_LAUNCH(h, (k_spmv_blocked<T, false>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
-                L.unit_counter.as<int>(), L.slot_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
-                (long long)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, st);
+                L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
+                (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, hot_c1_wide(), hot_claim(), st);
   B200_LAUNCH(h, (k_spmv_blocked_finish<T>), (L.n_hi + 255) / 256, 256, 0, acc_hi, L.n_hi, y, c.row_vertex.as<int32_t>(),
-              alpha, L.unit_counter.as<int>(), st);
+              alpha, L.unit_counter.as<int>(), L.n_cta, st);
   launch_low_rows<O, T>(h, c, x, y, alpha, st);
 }
 
