@@ -33,6 +33,7 @@ def pagerank(resource_handle, graph, precomputed_vertex_out_weight_vertices, pre
                                initial_guess_vertices, initial_guess_values)]
     res = C.c_void_p()
     err = C.c_void_p()
+    resource_handle.order_after_caller()
     code = _capi.lib().cugraph_pagerank_allow_nonconvergence(
         resource_handle.ptr, graph.ptr, views[0].ptr, views[1].ptr, views[2].ptr, views[3].ptr,
         float(alpha), float(epsilon), int(max_iterations), int(bool(do_expensive_check)), C.byref(res), C.byref(err))
@@ -58,6 +59,7 @@ def personalized_pagerank(resource_handle, graph, precomputed_vertex_out_weight_
                                personalization_values)]
     res = C.c_void_p()
     err = C.c_void_p()
+    resource_handle.order_after_caller()
     code = _capi.lib().cugraph_personalized_pagerank_allow_nonconvergence(
         resource_handle.ptr, graph.ptr, *[v.ptr for v in views], float(alpha), float(epsilon),
         int(max_iterations), int(bool(do_expensive_check)), C.byref(res), C.byref(err))
@@ -89,6 +91,7 @@ def bfs(handle, graph, sources, direction_optimizing, depth_limit, compute_prede
     sv = View(sources)
     res = C.c_void_p()
     err = C.c_void_p()
+    handle.order_after_caller()
     code = _capi.lib().cugraph_bfs(handle.ptr, graph.ptr, sv.ptr, int(bool(direction_optimizing)), int(depth_limit),
                                    int(bool(compute_predecessors)), int(bool(do_expensive_check)),
                                    C.byref(res), C.byref(err))
@@ -102,6 +105,7 @@ def sssp(resource_handle, graph, source, cutoff, compute_predecessors, do_expens
     """Returns (vertices, distances, predecessors) — sssp.pyx:120-170."""
     res = C.c_void_p()
     err = C.c_void_p()
+    resource_handle.order_after_caller()
     code = _capi.lib().cugraph_sssp(resource_handle.ptr, graph.ptr, int(source), float(cutoff),
                                     int(bool(compute_predecessors)), int(bool(do_expensive_check)),
                                     C.byref(res), C.byref(err))

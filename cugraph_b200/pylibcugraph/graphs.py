@@ -59,6 +59,7 @@ class SGGraph(_GPUGraph):
         g = C.c_void_p()
         err = C.c_void_p()
         L = self._lib
+        resource_handle.order_after_caller()
         if input_array_format == "COO":
             code = L.cugraph_graph_create_with_times_sg(
                 resource_handle.ptr, C.byref(graph_properties.c), v, s, d, w, eid, ety, t0, t1,
