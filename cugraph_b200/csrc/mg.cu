@@ -7,7 +7,7 @@
 // the C ABI: a resource handle bound to the caller's CUDA stream, rectangular edge blocks with the
 // same binned / column-blocked layout as the single-GPU graph, the block pull sweep and the fused
 // per-iteration vertex step.  All calls only ENQUEUE work on the handle's stream.
-#include "spmv_hot.cuh"
+#include "spmv_hot_x.cuh"
 
 #include <algorithm>
 

@@ -201,40 +201,6 @@ __device__ __forceinline__ void hot_run_groups(hot_sub_t const sb, int q, int la
   }
 }
 
-// class of one-slot pieces (the bulk of the pieces once every column block is hot): one step per group, so
-// there is nothing to pipeline inside a group.  The warp keeps FOUR groups in flight instead: 4 id vectors + 4
-// rows are requested before the first gather (ncu on the one-group-ahead version: 22 % of all stall samples
-// sat on the move that consumes the prefetched ids, profiles/r01_ncu_k_spmv_blocked_v5.csv).
-template <typename T, bool WEIGHTED, bool HOT>
-__device__ __forceinline__ void hot_run_groups_c1(hot_sub_t const sb, int q, int lane, int32_t const* __restrict__ seg_row,
-                                                  uint16_t const* __restrict__ idx16, int32_t const* __restrict__ idx32,
-                                                  int cold_slot0, T const* __restrict__ w, T const* __restrict__ x,
-                                                  T const* __restrict__ sx, double* __restrict__ acc_hi)
-{
-  constexpr int K = HOT ? 4 : 2;  // cold ids are 32-bit: twice the registers per slot
-  for (; q < sb.n_groups; q += 32 * K) {
-    slot_ids_t ids[K];
-    int row[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int qk = q + 32 * k;
-      row[k]       = -1;
-      if (qk < sb.n_groups) {  // warp-uniform
-        ids[k] = hot_slot_load<HOT>(sb.slot_begin + qk * 32 + lane, idx16, idx32, cold_slot0);
-        row[k] = ld_stream(seg_row + sb.row_begin + qk * 32 + lane);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int qk = q + 32 * k;
-      if (qk < sb.n_groups) {
-        const double acc = hot_slot_sum<T, WEIGHTED, HOT>(ids[k], sb.slot_begin + qk * 32 + lane, w, x, sx);
-        if (row[k] >= 0) atomicAdd(acc_hi + row[k], acc);
-      }
-    }
-  }
-}
-
 __device__ __forceinline__ int ld_volatile(const int* p)
 {
   int v;
@@ -242,30 +208,21 @@ __device__ __forceinline__ int ld_volatile(const int* p)
   return v;
 }
 
-// next units for this CTA (called by all lanes of warp 0): own range first — `claim` consecutive units per
-// atomic, they are processed without a CTA barrier in between — then single units of the following CTAs'
-// ranges.  victim_off = how many ranges (starting with the own one) are known to be exhausted.
-// Returns the first unit (n_units when everything is done) and sets count.
+// next unit for this CTA (called by all lanes of warp 0): own range first, then the ranges of the
+// following CTAs.  victim_off = how many ranges (starting with the own one) are known to be exhausted.
 __device__ __forceinline__ int hot_fetch_unit(int* __restrict__ cursor, int32_t const* __restrict__ cta_range, int n_cta,
-                                              int n_units, int claim, int& victim_off, int& count, int lane)
+                                              int n_units, int& victim_off, int lane)
 {
   while (victim_off < n_cta) {
     int v = (int)blockIdx.x + victim_off;
     if (v >= n_cta) v -= n_cta;
-    const int want = victim_off == 0 ? claim : 1;
-    int u = -1, c = 0;
+    int u = -1;
     if (lane == 0) {
-      u             = cta_range[v] + atomicAdd(cursor + v, want);
-      const int end = cta_range[v + 1];
-      c             = end - u < want ? end - u : want;
-      if (c <= 0) u = -1;
+      u = cta_range[v] + atomicAdd(cursor + v, 1);
+      if (u >= cta_range[v + 1]) u = -1;
     }
     u = __shfl_sync(0xffffffffu, u, 0);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (u >= 0) {
-      count = c;
-      return u;
-    }
+    if (u >= 0) return u;
     ++victim_off;
     while (victim_off < n_cta) {  // look 32 ranges ahead at a time for one that still has units
       int vv         = (int)blockIdx.x + victim_off + lane;
@@ -280,7 +237,6 @@ __device__ __forceinline__ int hot_fetch_unit(int* __restrict__ cursor, int32_t 
       victim_off += 32;
     }
   }
-  count = 0;
   return n_units;
 }
 
@@ -290,72 +246,55 @@ k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restric
                int32_t const* __restrict__ cta_range, hot_sub_t const* __restrict__ subs,
                int32_t const* __restrict__ seg_row, uint16_t const* __restrict__ idx16,
                int32_t const* __restrict__ idx32, int cold_slot0, T const* __restrict__ w,
-               T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, int c1_wide,
-               int claim, pr_state_t const* __restrict__ st)
+               T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, pr_state_t const* __restrict__ st)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* sx = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
-  __shared__ int s_next, s_count;
+  __shared__ int s_next;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int victim_off = 0;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   if (warp == 0) {
-    int cnt     = 0;
-    const int n = hot_fetch_unit(unit_counter, cta_range, (int)gridDim.x, n_units, claim, victim_off, cnt, lane);
-    if (lane == 0) {
-      s_next  = n;
-      s_count = cnt;
-    }
+    const int n = hot_fetch_unit(unit_counter, cta_range, (int)gridDim.x, n_units, victim_off, lane);
+    if (lane == 0) s_next = n;
   }
   if (threadIdx.x < kHotZeroPad) sx[W + threadIdx.x] = (T)0;  // the padding column(s) of every slice
   unsigned phase = 0;
   int cur_block  = -1;
   while (true) {
-    __syncthreads();  // s_next is published; everyone is done with the previous units' slice
-    const int u0 = s_next, ucnt = s_count;
+    __syncthreads();  // s_next is published; everyone is done with the previous unit's slice
+    const int u = s_next;
     __syncthreads();
-    if (u0 >= n_units) break;
-    if (warp == 0) {  // fetch the next claim while working
-      int cnt     = 0;
-      const int n = hot_fetch_unit(unit_counter, cta_range, (int)gridDim.x, n_units, claim, victim_off, cnt, lane);
-      if (lane == 0) {
-        s_next  = n;
-        s_count = cnt;
-      }
+    if (u >= n_units) break;
+    if (warp == 0) {  // fetch the next unit while working
+      const int n = hot_fetch_unit(unit_counter, cta_range, (int)gridDim.x, n_units, victim_off, lane);
+      if (lane == 0) s_next = n;
     }
-    int dealt = 0;  // groups are dealt round-robin to the warps, continuing across sub-units and units
-    for (int u = u0; u < u0 + ucnt; ++u) {
-      const hot_unit_t un = units[u];
-      const int b         = un.block;
-      const bool hot      = b < B;
-      if (hot && b != cur_block) {
-        if (u != u0) __syncthreads();  // warps of this claim may still gather from the old slice
-        if (threadIdx.x == 0) {
-          const unsigned bytes = (unsigned)(W * sizeof(T));
-          mbar_expect_tx(&bar, bytes);
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(x + (size_t)b * W);
-          for (unsigned o = 0; o < bytes; o += kHotTmaPiece)
-            tma_bulk_g2s(smem_raw + o, src + o, (bytes - o) < (unsigned)kHotTmaPiece ? (bytes - o) : (unsigned)kHotTmaPiece, &bar);
-        }
-        cur_block = b;
-        mbar_wait(&bar, phase);
-        phase ^= 1;
+    const hot_unit_t un = units[u];
+    const int b         = un.block;
+    const bool hot      = b < B;
+    if (hot && b != cur_block) {
+      if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)(W * sizeof(T));
+        mbar_expect_tx(&bar, bytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(x + (size_t)b * W);
+        for (unsigned o = 0; o < bytes; o += kHotTmaPiece)
+          tma_bulk_g2s(smem_raw + o, src + o, (bytes - o) < (unsigned)kHotTmaPiece ? (bytes - o) : (unsigned)kHotTmaPiece, &bar);
       }
-      for (int si = un.sub_begin; si < un.sub_end; ++si) {
-        const hot_sub_t sb = subs[si];
-        const int q0       = (warp - dealt) & (kHotWarps - 1);
-        dealt += sb.n_groups;
-        if (c1_wide && sb.cls == 1) {
-          if (hot) hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
-          else hot_run_groups_c1<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
-        } else if (hot) {
-          hot_run_groups<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
-        } else {
-          hot_run_groups<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
-        }
-      }
+      cur_block = b;
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    // groups are dealt round-robin to the warps, continuing across the sub-units of the unit
+    int dealt = 0;
+    for (int si = un.sub_begin; si < un.sub_end; ++si) {
+      const hot_sub_t sb = subs[si];
+      const int q0       = (warp - dealt) & (kHotWarps - 1);
+      dealt += sb.n_groups;
+      if (hot) hot_run_groups<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
+      else hot_run_groups<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
     }
   }
 }
@@ -388,21 +327,6 @@ void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, dou
                 c.weights.as<T>(), x, y, c.row_vertex.as<int32_t>(), bins, alpha, st, low_mode());
 }
 
-// CUGRAPH_B200_HOT_C1: 1 = four one-slot groups in flight per warp (hot_run_groups_c1), 0 = generic group loop
-inline int hot_c1_wide()
-{
-  const char* e = std::getenv("CUGRAPH_B200_HOT_C1");
-  return e ? std::atoi(e) : 0;
-}
-
-// CUGRAPH_B200_HOT_CLAIM: units of its own range a CTA takes per atomic (processed without a CTA barrier in between)
-inline int hot_claim()
-{
-  const char* e = std::getenv("CUGRAPH_B200_HOT_CLAIM");
-  const int c   = e ? std::atoi(e) : 1;
-  return c < 1 ? 1 : (c > 64 ? 64 : c);
-}
-
 // x must hold padded_x_elems() elements, zero behind n_vertices (slices are copied whole; the cold
 // block's padding entries read x[n_vertices])
 template <typename O, typename T>
@@ -419,25 +343,17 @@ void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_
   if (L.slot_w.data())
     B200_LAUNCH(h, (k_spmv_blocked<T, true>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
                 L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
-                (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, hot_c1_wide(), hot_claim(), st);
+                (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, st);
   else
     B200_LAUNCH(h, (k_spmv_blocked<T, false>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
                 L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(), L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(),
-                (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, hot_c1_wide(), hot_claim(), st);
+                (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W, L.B, st);
   B200_LAUNCH(h, (k_spmv_blocked_finish<T>), (L.n_hi + 255) / 256, 256, 0, acc_hi, L.n_hi, y, c.row_vertex.as<int32_t>(),
               alpha, L.unit_counter.as<int>(), L.n_cta, st);
   launch_low_rows<O, T>(h, c, x, y, alpha, st);
 }
 
-// dispatch: blocked layout when it exists for this graph, else the plain edge-balanced sweep
-template <typename O, typename T>
-void launch_pull_sweep_auto(handle_impl const& h, csx_t const& c, int32_t n_vertices, T const* x, T* y, double* acc_hi,
-                            double alpha, pr_state_t const* st)
-{
-  hot_layout_t const* L = hot_layout(h, c, n_vertices, sizeof(T));
-  if (L) launch_pull_sweep_blocked<O, T>(h, c, *L, x, y, acc_hi, alpha, st);
-  else launch_pull_sweep<O, T>(h, c, x, y, acc_hi, alpha, st);
-}
+// (the dispatcher launch_pull_sweep_auto lives in spmv_hot_x.cuh, next to the experimental kernel variant)
 
 // elements an x buffer needs: whole slices are TMA-copied and x[n_vertices] must be a readable zero.
 // The buffer must be zero-filled once at allocation; only [0, n_vertices) is ever written afterwards.
