@@ -227,23 +227,28 @@ def run_single(args):
     def e2e_step():
         s = h_src.cuda(non_blocking=True)
         d = h_dst.cuda(non_blocking=True)
-        g = plc.SGGraph(h, props, s, d, store_transposed=True, renumber=True)
+        g = plc.SGGraph(h, props, s, d, store_transposed=True, renumber=True)  # waits for the two copies first
         vv, pp, _ = plc.pagerank(h, g, None, None, None, None, ALPHA, 0.0, ITERS, False, fail_on_nonconvergence=False)
+        assert vv.numel() == nv, f"e2e graph has {vv.numel()} vertices, the resident one {nv}"
         h_v.copy_(vv, non_blocking=True)
         h_p.copy_(pp, non_blocking=True)
         torch.cuda.synchronize()
         return h_v, h_p
 
-    e2e_step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    try:
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_wall = time.perf_counter() - t0
-    e2e = {"value": E * ITERS * e2e_steps / e2e_wall / 1e6, "unit": "MTEPS", "h2d_bytes_per_step": 2 * E * 4,
-           "d2h_bytes_per_step": nv * 8, "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
-           "includes": "pinned H2D of edge list, graph staging, 100 iterations, D2H of vertices+scores into pinned buffers"}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_wall = time.perf_counter() - t0
+        e2e = {"value": E * ITERS * e2e_steps / e2e_wall / 1e6, "unit": "MTEPS", "h2d_bytes_per_step": 2 * E * 4,
+               "d2h_bytes_per_step": nv * 8, "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
+               "includes": "pinned H2D of edge list, graph staging, 100 iterations, D2H of vertices+scores into pinned buffers"}
+    except Exception as ex:  # keep the device-resident measurement even if the host-buffer arm fails
+        e2e = {"value": None, "unit": "MTEPS", "h2d_bytes_per_step": 2 * E * 4, "d2h_bytes_per_step": nv * 8,
+               "error": f"{type(ex).__name__}: {ex}"[:300]}
 
     cpu = _cpu_baseline()
     out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
