@@ -263,4 +263,37 @@ inline void check_last(const char* what)
 
 inline void sync(handle_impl const& h) { CUDA_TRY(cudaStreamSynchronize(h.stream)); }
 
+// CUGRAPH_B200_BUILD_TRACE=1: print the time of every staging phase (stream-synchronised) to stderr
+struct phase_trace {
+  handle_impl const& h;
+  bool on;
+  cudaEvent_t e0{}, e1{};
+  explicit phase_trace(handle_impl const& hh) : h(hh), on(std::getenv("CUGRAPH_B200_BUILD_TRACE") != nullptr)
+  {
+    if (on) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, h.stream);
+    }
+  }
+  void mark(const char* what)
+  {
+    if (!on) return;
+    cudaEventRecord(e1, h.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::fprintf(stderr, "[build] %-28s %8.3f ms\n", what, ms);
+    std::swap(e0, e1);
+  }
+  ~phase_trace()
+  {
+    if (on) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+  }
+};
+
+
 }  // namespace b200

@@ -62,6 +62,18 @@ struct hot_layout_t {
   int n_cta{0};      // CTAs of the persistent kernel = min(SM count, n_units)
 };
 
+// EXPERIMENTAL (CUGRAPH_B200_LOW_ELL=1): exact-degree classes of the degree < 32 rows.  Rows are degree-descending, so
+// the rows of degree d are the contiguous range [row_begin[d], row_begin[d] + n[d]) and their adjacency is a dense
+// n[d] x d matrix starting at indices[off0[d]]; `idx` holds it TRANSPOSED (entry k of row i at off0[d] - off0[31] +
+// k * n[d] + i): a lane per row reads coalesced, needs no offsets, and can own several rows.
+struct low_ell_t {
+  int32_t row_begin[32]{};
+  int32_t n[32]{};
+  long long base[32]{};  // start of class d inside idx / w
+  dbuf idx;              // (nnz - nnz_hi) x int32
+  dbuf w;                // same x T, or empty
+};
+
 // One orientation: compressed rows over `n_rows` physical rows.
 // row_vertex == nullptr  -> physical row r is vertex r (rows are degree-descending by construction)
 // row_vertex != nullptr  -> physical row r is vertex row_vertex[r] (a lazily built transpose whose
@@ -86,6 +98,8 @@ struct csx_t {
   mutable std::unique_ptr<hot_layout_t> hot4, hot8;
   mutable bool hot4_tried{false}, hot8_tried{false};
   mutable dbuf out_w;  // n_vertices x T : per-source sum of edge weights (or out-degree), T = weight type
+  mutable std::unique_ptr<low_ell_t> low_ell;
+  mutable bool low_ell_tried{false};
 };
 
 struct graph_impl {
@@ -125,6 +139,8 @@ inline graph_impl* G(cugraph_graph_t* g)
 csx_t const& pull_view(handle_impl const& h, graph_impl& g);  // rows = destinations, indices = sources
 // column-blocked copy for elements of `elem_size` bytes, or nullptr when the graph is too small for it
 hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size);
+// exact-degree ELL copy of the degree < 32 rows; nullptr unless CUGRAPH_B200_LOW_ELL=1 (graph_build.cu)
+low_ell_t const* low_ell_layout(handle_impl const& h, csx_t const& c, size_t elem_size);
 csx_t const& push_view(handle_impl const& h, graph_impl& g);  // rows = sources, vertex-indexed offsets
 
 // external <-> internal id helpers (graph_build.cu)

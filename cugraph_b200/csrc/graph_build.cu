@@ -20,38 +20,6 @@ namespace {
 
 constexpr int kBlock = 256;
 
-// CUGRAPH_B200_BUILD_TRACE=1: print the time of every staging phase (stream-synchronised) to stderr
-struct phase_trace {
-  handle_impl const& h;
-  bool on;
-  cudaEvent_t e0{}, e1{};
-  explicit phase_trace(handle_impl const& hh) : h(hh), on(std::getenv("CUGRAPH_B200_BUILD_TRACE") != nullptr)
-  {
-    if (on) {
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      cudaEventRecord(e0, h.stream);
-    }
-  }
-  void mark(const char* what)
-  {
-    if (!on) return;
-    cudaEventRecord(e1, h.stream);
-    cudaEventSynchronize(e1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    std::fprintf(stderr, "[build] %-28s %8.3f ms\n", what, ms);
-    std::swap(e0, e1);
-  }
-  ~phase_trace()
-  {
-    if (on) {
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
-    }
-  }
-};
-
 inline int grid_for(int64_t n, int per_thread = 1)
 {
   int64_t b = (n + (int64_t)kBlock * per_thread - 1) / ((int64_t)kBlock * per_thread);
@@ -1373,6 +1341,86 @@ hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_v
   if (!c.degree_sorted || c.seg[0] <= 0 || c.nnz_hi < min_edges || c.offs64 || c.nnz_hi >= (1ll << 31) - 4096) return nullptr;
   slot = build_hot_layout<int32_t>(h, c, n_vertices, elem_size);
   return slot.get();
+}
+
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL exact-degree ELL copy of the degree < 32 rows (low_ell_t, consumed by k_spmv_low_ell)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// P[d] = number of rows with degree >= d (rows are degree-descending), d = 0..32
+template <typename O>
+__global__ void k_low_class_bounds(O const* __restrict__ off, int32_t n_rows, int32_t* __restrict__ P)
+{
+  const int d = threadIdx.x;
+  if (d > 32) return;
+  int lo = 0, hi = n_rows;  // first row with degree < d
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((long long)(off[mid + 1] - off[mid]) >= d) lo = mid + 1; else hi = mid;
+  }
+  P[d] = lo;
+}
+
+// out[k * n + i] = in[i * d + k]  (one degree class)
+template <typename V>
+__global__ void k_low_transpose(V const* __restrict__ in, V* __restrict__ out, int32_t n, int d)
+{
+  const long long total = (long long)n * d;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e / n), i = (int)(e - (long long)k * n);
+    out[e]      = in[(long long)i * d + k];
+  }
+}
+
+template <typename O>
+std::unique_ptr<low_ell_t> build_low_ell(handle_impl const& h, csx_t const& c, size_t es)
+{
+  auto L = std::make_unique<low_ell_t>();
+  dbuf dP = make_dbuf<int32_t>(33, h.stream);
+  B200_LAUNCH(h, (k_low_class_bounds<O>), 1, 64, 0, c.offsets.as<O>(), c.n_rows, dP.as<int32_t>());
+  int32_t P[33];
+  CUDA_TRY(cudaMemcpyAsync(P, dP.data(), sizeof(P), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  const int64_t low_nnz = c.nnz - c.nnz_hi;
+  L->idx = make_dbuf<int32_t>(std::max<int64_t>(low_nnz, 1), h.stream);
+  const bool weighted = c.weights.data() != nullptr;
+  if (weighted) L->w = dbuf((size_t)std::max<int64_t>(low_nnz, 1) * es, h.stream);
+  long long run = 0;  // classes in row order: degree 31 first
+  for (int d = 31; d >= 0; --d) {
+    L->row_begin[d] = P[d + 1];
+    L->n[d]         = P[d] - P[d + 1];
+    L->base[d]      = run;
+    if (d == 0 || L->n[d] == 0) continue;
+    // the class's rows are contiguous and all have d entries: a dense n x d matrix at offsets[row_begin]
+    const long long src0 = c.nnz_hi + run;  // = offsets[row_begin[d]]
+    const int grid       = (int)std::min<long long>(((long long)L->n[d] * d + 255) / 256, 148 * 64);
+    B200_LAUNCH(h, (k_low_transpose<int32_t>), grid, 256, 0, c.indices.as<int32_t>() + src0, L->idx.as<int32_t>() + run,
+                L->n[d], d);
+    if (weighted) {
+      if (es == 4)
+        B200_LAUNCH(h, (k_low_transpose<float>), grid, 256, 0, c.weights.as<float>() + src0, L->w.as<float>() + run, L->n[d], d);
+      else
+        B200_LAUNCH(h, (k_low_transpose<double>), grid, 256, 0, c.weights.as<double>() + src0, L->w.as<double>() + run, L->n[d], d);
+    }
+    run += (long long)L->n[d] * d;
+  }
+  B200_EXPECTS(run == low_nnz, CUGRAPH_UNKNOWN_ERROR, "internal: degree classes do not add up");
+  check_last("low ell");
+  sync(h);
+  return L;
+}
+
+}  // namespace
+
+low_ell_t const* low_ell_layout(handle_impl const& h, csx_t const& c, size_t elem_size)
+{
+  if (c.low_ell_tried) return c.low_ell.get();
+  c.low_ell_tried = true;
+  const char* e   = std::getenv("CUGRAPH_B200_LOW_ELL");
+  if (!e || std::atoi(e) == 0 || !c.degree_sorted || c.n_rows <= c.seg[0]) return nullptr;
+  c.low_ell = c.offs64 ? build_low_ell<int64_t>(h, c, elem_size) : build_low_ell<int32_t>(h, c, elem_size);
+  return c.low_ell.get();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -142,6 +142,7 @@ struct pr_args {
 template <typename T>
 void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centrality_result_impl& res)
 {
+  phase_trace tr(h);
   const int32_t nv = g.n_vertices;
   // argument checks of pagerank_impl.cuh:79-88
   B200_EXPECTS(a.alpha >= 0.0 && a.alpha <= 1.0, CUGRAPH_UNKNOWN_ERROR, "Invalid input argument: alpha should be in [0.0, 1.0].");
@@ -187,6 +188,7 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
     }
     out_w = c.out_w.as<T>();
   }
+  tr.mark("pagerank: pull view + out-weights");
   if (a.expensive && weighted && c.nnz > 0) {
     dbuf neg = make_dbuf<int>(1, h.stream);
     CUDA_TRY(cudaMemsetAsync(neg.data(), 0, sizeof(int), h.stream));
@@ -242,6 +244,7 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
     B200_LAUNCH(h, (k_fill<T>), grid_for(nv), kBlock, 0, pr_a.as<T>(), nv, (T)((T)1 / (T)nv));
   }
 
+  tr.mark("pagerank: state setup");
   const int vgrid = std::min(grid_for(nv), h.sm_count * 8);
   const int max_it = (int)std::min<size_t>(a.max_iterations, 0x7fffffff);
   // prologue: x and dangling sum of the starting vector, init for sweep 1
@@ -276,6 +279,7 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
     iters = hst->iter;
     if (hst->done || enqueued >= std::max(max_it, 1)) break;
   }
+  tr.mark("pagerank: iterations (+ layout staging on the first call)");
   // after `iters` real iterations the newest vector sits in pr_a when iters is even, pr_b when odd
   T* final_pr = (iters % 2 == 0) ? pr_a.as<T>() : pr_b.as<T>();
 
@@ -284,6 +288,7 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
   res.iterations = (size_t)iters;
   res.converged  = (size_t)iters < a.max_iterations;  // pagerank_impl.cuh:329
   sync(h);
+  tr.mark("pagerank: result gather");
 }
 
 cugraph_error_code_t pagerank_entry(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, pr_args a,

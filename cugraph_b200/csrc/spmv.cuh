@@ -196,6 +196,144 @@ k_spmv_low(O const* __restrict__ offsets, int32_t const* __restrict__ indices, T
 }
 
 // ------------------------------------------------------------------------------------------
+// EXPERIMENTAL (CUGRAPH_B200_LOW_ELL=1): degree < 32 rows from the exact-degree ELL copy (low_ell_t).  One lane per
+// row, no offsets load, coalesced index reads; a thread owns R rows of its class (R = 4 for degree <= 4, 2 for <= 8)
+// so that 8..16 independent index loads, then as many gathers, are in flight per lane.
+// ------------------------------------------------------------------------------------------
+struct low_ell_args_t {
+  int32_t row_begin[32];
+  int32_t n[32];
+  long long base[32];
+  int32_t block_begin[33];  // in class order 31, 30, ..., 0; [32] = total
+};
+
+__host__ __device__ __forceinline__ int low_ell_rows_per_thread(int d) { return d <= 4 ? 4 : (d <= 8 ? 2 : 1); }
+
+// D entries of R rows per thread, fully unrolled
+template <typename T, bool WEIGHTED, int D, int R>
+__device__ __forceinline__ void low_ell_rows(int32_t const* __restrict__ ell, T const* __restrict__ ellw, int n, int i0,
+                                             T const* __restrict__ x, double (&acc)[4])
+{
+  int c[R][D];
+  T wv[R][D];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int i = i0 + j * 256;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      c[j][k]  = -1;
+      wv[j][k] = (T)1;
+      if (i < n) {
+        c[j][k] = ld_stream(ell + (long long)k * n + i);
+        if (WEIGHTED) wv[j][k] = ld_stream(ellw + (long long)k * n + i);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      if (c[j][k] >= 0) a += (double)(x[c[j][k]] * wv[j][k]);
+    acc[j] = a;
+  }
+}
+
+template <typename T, bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T const* __restrict__ x, T* __restrict__ y,
+               int32_t const* __restrict__ row_vertex, low_ell_args_t L, double alpha, pr_state_t const* __restrict__ st)
+{
+  if (st->done) return;
+  int d = 31;  // class of this block
+#pragma unroll 1
+  for (int k = 1; k < 32; ++k)
+    if ((int)blockIdx.x >= L.block_begin[k]) d = 31 - k;
+  const double init = st->init;
+  const int blk     = blockIdx.x - L.block_begin[31 - d];
+  const int n       = L.n[d];
+  const int R       = low_ell_rows_per_thread(d);
+  const int i0      = blk * 256 * R + threadIdx.x;
+  double acc[4]     = {0.0, 0.0, 0.0, 0.0};
+  if (d > 0) {
+    int32_t const* e = ell + L.base[d];
+    T const* ew      = WEIGHTED ? ellw + L.base[d] : nullptr;
+    switch (d) {
+      case 1: low_ell_rows<T, WEIGHTED, 1, 4>(e, ew, n, i0, x, acc); break;
+      case 2: low_ell_rows<T, WEIGHTED, 2, 4>(e, ew, n, i0, x, acc); break;
+      case 3: low_ell_rows<T, WEIGHTED, 3, 4>(e, ew, n, i0, x, acc); break;
+      case 4: low_ell_rows<T, WEIGHTED, 4, 4>(e, ew, n, i0, x, acc); break;
+      case 5: low_ell_rows<T, WEIGHTED, 5, 2>(e, ew, n, i0, x, acc); break;
+      case 6: low_ell_rows<T, WEIGHTED, 6, 2>(e, ew, n, i0, x, acc); break;
+      case 7: low_ell_rows<T, WEIGHTED, 7, 2>(e, ew, n, i0, x, acc); break;
+      case 8: low_ell_rows<T, WEIGHTED, 8, 2>(e, ew, n, i0, x, acc); break;
+      default: {  // 9..31: eight entries at a time
+        if (i0 < n) {
+          double a = 0.0;
+          for (int k0 = 0; k0 < d; k0 += 8) {
+            int c[8];
+            T wv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              c[k]  = -1;
+              wv[k] = (T)1;
+              if (k0 + k < d) {
+                c[k] = ld_stream(e + (long long)(k0 + k) * n + i0);
+                if (WEIGHTED) wv[k] = ld_stream(ew + (long long)(k0 + k) * n + i0);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (c[k] >= 0) a += (double)(x[c[k]] * wv[k]);
+          }
+          acc[0] = a;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = i0 + j * 256;
+    if (j < R && i < n) {
+      const int r                    = L.row_begin[d] + i;
+      y[row_vertex ? row_vertex[r] : r] = (T)(acc[j] * alpha + init);
+    }
+  }
+}
+
+inline low_ell_args_t make_low_ell_args(low_ell_t const& E)
+{
+  low_ell_args_t a{};
+  int blocks = 0;
+  for (int k = 0; k < 32; ++k) {
+    const int d      = 31 - k;
+    a.row_begin[d]   = E.row_begin[d];
+    a.n[d]           = E.n[d];
+    a.base[d]        = E.base[d];
+    a.block_begin[k] = blocks;
+    const int per    = 256 * low_ell_rows_per_thread(d);
+    blocks += (E.n[d] + per - 1) / per;
+  }
+  a.block_begin[32] = blocks;
+  return a;
+}
+
+template <typename T>
+void launch_low_rows_ell(handle_impl const& h, csx_t const& c, low_ell_t const& E, T const* x, T* y, double alpha,
+                         pr_state_t const* st)
+{
+  low_ell_args_t a = make_low_ell_args(E);
+  const int blocks = a.block_begin[32];
+  if (blocks <= 0) return;
+  if (E.w.data())
+    B200_LAUNCH(h, (k_spmv_low_ell<T, true>), blocks, 256, 0, E.idx.as<int32_t>(), E.w.as<T>(), x, y,
+                c.row_vertex.as<int32_t>(), a, alpha, st);
+  else
+    B200_LAUNCH(h, (k_spmv_low_ell<T, false>), blocks, 256, 0, E.idx.as<int32_t>(), E.w.as<T>(), x, y,
+                c.row_vertex.as<int32_t>(), a, alpha, st);
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launcher of one full sweep
 // ------------------------------------------------------------------------------------------
 // 1 (default): index / weight loads of the low rows allocate in L1 — a lane walks 4..32 consecutive bytes of
@@ -243,6 +381,10 @@ void launch_pull_sweep(handle_impl const& h, csx_t const& c, T const* x, T* y, d
     if (c.n_split > 0)
       B200_LAUNCH(h, (k_spmv_hi_finish<T>), (c.n_split + 255) / 256, 256, 0, c.split_rows.as<int32_t>(), c.n_split,
                   acc_hi, y, rv, alpha, st);
+  }
+  if (low_ell_t const* E = low_ell_layout(h, c, sizeof(T))) {
+    launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
+    return;
   }
   low_bins_t bins = make_low_bins(c);
   int lblocks     = bins.block_begin[kNumSeg - 1];

@@ -316,6 +316,10 @@ __global__ void k_spmv_blocked_finish(double* __restrict__ acc_hi, int n_hi, T* 
 template <typename O, typename T>
 void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, double alpha, pr_state_t const* st)
 {
+  if (low_ell_t const* E = low_ell_layout(h, c, sizeof(T))) {  // experimental, CUGRAPH_B200_LOW_ELL=1
+    launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
+    return;
+  }
   low_bins_t bins = make_low_bins(c);
   int lblocks     = bins.block_begin[kNumSeg - 1];
   if (lblocks <= 0) return;

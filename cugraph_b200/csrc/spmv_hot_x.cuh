@@ -150,9 +150,8 @@ k_spmv_blocked_x(hot_unit_t const* __restrict__ units, int n_units, int* __restr
         const hot_sub_t sb = subs[si];
         const int q0       = (warp - dealt) & (kHotWarps - 1);
         dealt += sb.n_groups;
-        if (c1_wide && sb.cls == 1) {
-          if (hot) hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
-          else hot_run_groups_c1<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
+        if (c1_wide && sb.cls == 1 && hot) {  // the cold block (if any) stays on the generic loop
+          hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
         } else if (hot) {
           hot_run_groups<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
         } else {
