@@ -1029,7 +1029,7 @@ __global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t 
                                   int32_t const* __restrict__ idx, int W, int B, int32_t const* __restrict__ seg_row,
                                   int32_t const* __restrict__ piece_off, uint32_t* __restrict__ piece_key,
                                   int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
-                                  int32_t* __restrict__ piece_row)
+                                  int32_t* __restrict__ piece_row, int narrow, int kinds)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_segs) return;
@@ -1041,7 +1041,9 @@ __global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t 
   for (long long s = start; s < end; s += kHotPieceEntries, ++p) {
     const int len  = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
     const int cls  = (len + kHotSlot - 1) / kHotSlot;  // 1..8
-    piece_key[p]   = (uint32_t)(b * kHotPieceSlots + cls - 1);
+    int code       = cls - 1;
+    if (narrow) code = (b < B && len <= 2) ? 0 : ((b < B && len <= 4) ? 1 : cls + 1);  // kinds: Q, H, 1..8
+    piece_key[p]   = (uint32_t)(b * kinds + code);
     piece_start[p] = (int32_t)s;
     piece_len[p]   = len;
     piece_row[p]   = row;
@@ -1078,7 +1080,7 @@ k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict
            int32_t const* __restrict__ piece_start, int32_t const* __restrict__ piece_len,
            int32_t const* __restrict__ piece_row, int32_t const* __restrict__ idx, T const* __restrict__ w, int W, int B,
            int zero_col_cold, long long cold_slot0, uint16_t* __restrict__ idx16, int32_t* __restrict__ idx32,
-           T* __restrict__ w_out, int32_t* __restrict__ seg_row_out)
+           T* __restrict__ w_out, int32_t* __restrict__ seg_row_out, uint2* __restrict__ idx_h, uint32_t* __restrict__ idx_q)
 {
   const hot_sub_host_t sb = subs[blockIdx.x];
   const hot_fill_t fl     = fills[blockIdx.x];
@@ -1095,6 +1097,15 @@ k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict
       row         = piece_row[p];
     }
     seg_row_out[(size_t)sb.row_begin + (size_t)q * 32 + lane] = row;
+    if (sb.cls > kHotPieceSlots) {  // narrow classes: one step, 4 (cls 16) or 2 (cls 32) ids per slot, hot blocks only
+      const size_t slot = (size_t)sb.slot_begin + (size_t)q * 32 + lane;
+      unsigned v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = k < ln ? (unsigned)(idx[st + k] - fl.block * W) : (unsigned)W;
+      if (sb.cls == 16) idx_h[slot] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+      else idx_q[slot] = v[0] | (v[1] << 16);
+      continue;
+    }
     for (int j = 0; j < sb.cls; ++j) {
       const long long slot = (long long)sb.slot_begin + ((long long)q * sb.cls + j) * 32 + lane;
       int col[kHotSlot];
@@ -1141,6 +1152,11 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   auto L             = std::make_unique<hot_layout_t>();
   L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = nnz;
   int32_t const* idx = c.indices.as<int32_t>();
+  // experimental narrow slots (graph.cuh): unweighted only; needs k_spmv_blocked_x
+  bool narrow = false;
+  if (const char* e = std::getenv("CUGRAPH_B200_HOT_NARROW")) narrow = std::atoi(e) != 0 && c.weights.data() == nullptr;
+  const int kinds = narrow ? kHotPieceSlots + 2 : kHotPieceSlots;
+  L->narrow       = narrow;
 
   // 1. segment heads
   dbuf flag = make_dbuf<uint8_t>(nnz, h.stream);
@@ -1180,14 +1196,14 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   dbuf piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
   B200_LAUNCH(h, k_hot_emit_pieces, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W, B,
               seg_row.as<int32_t>(), piece_off.as<int32_t>(), piece_key.as<uint32_t>(), piece_start.as<int32_t>(),
-              piece_len.as<int32_t>(), piece_row.as<int32_t>());
+              piece_len.as<int32_t>(), piece_row.as<int32_t>(), narrow ? 1 : 0, kinds);
   head_pos.release();
   seg_row.release();
   piece_off.release();
   tr.mark("hot: pieces");
 
   // 3. order pieces by class
-  const int n_keys = (B + 1) * kHotPieceSlots;
+  const int n_keys = (B + 1) * kinds;
   dbuf perm = make_dbuf<uint32_t>(n_pieces, h.stream), perm2 = make_dbuf<uint32_t>(n_pieces, h.stream);
   B200_LAUNCH(h, k_iota64, grid_for(n_pieces, 4), kBlock, 0, (int64_t)n_pieces, perm.as<uint32_t>());
   sort_pairs<uint32_t, uint32_t>(h, piece_key.as<uint32_t>(), piece_key2.as<uint32_t>(), perm.as<uint32_t>(),
@@ -1212,11 +1228,11 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
       const int b0 = std::min(edges[k], B + 1), b1 = std::min(edges[k + 1], B + 1);
       if (b1 <= b0) continue;
       long long by_len[9] = {0}, by_cls[9] = {0}, entries = 0;
-      for (int key = b0 * kHotPieceSlots; key < b1 * kHotPieceSlots; ++key)
+      for (int key = b0 * kinds; key < b1 * kinds; ++key)
         for (int p = cstart[key]; p < cstart[key + 1]; ++p) {
           const int ln = hlen[hperm[p]];
           entries += ln;
-          by_cls[key % kHotPieceSlots + 1]++;
+          by_cls[std::min(8, narrow ? std::max(1, key % kinds - 1) : key % kinds + 1)]++;
           if (ln <= 8) by_len[ln]++;
         }
       std::fprintf(stderr, "[hot] blocks [%d,%d)%s entries %lld  pieces by slots:", b0, b1, b1 == B + 1 && b0 == B ? " (cold)" : "", entries);
@@ -1235,7 +1251,7 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   double cold_cost = 2.0;
   if (const char* e = std::getenv("CUGRAPH_B200_HOT_COLD_COST")) cold_cost = std::atof(e);
   const int kHotUnitSlots = hot_unit_slots();
-  int64_t slot_run = 0, row_run = 0, cold_slot0 = 0;
+  int64_t slot_run = 0, row_run = 0, cold_slot0 = 0, hslot_run = 0, qslot_run = 0;
   for (int b = 0; b <= B; ++b) {
     if (b == B) cold_slot0 = slot_run;
     int64_t unit_slots = 0;
@@ -1248,19 +1264,29 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
       unit_sub0  = (int)subs.size();
       unit_slots = 0;
     };
-    for (int cls = 1; cls <= kHotPieceSlots; ++cls) {
-      const int key   = b * kHotPieceSlots + cls - 1;
-      int32_t p       = cstart[key];
+    for (int kind = 0; kind < kinds; ++kind) {
+      // steps per group and the sub-unit's class code: 1..8 = full 8-entry slots; narrow layouts put the
+      // one-step kinds Q (code 32: 2 ids per slot) and H (code 16: 4 ids) in front
+      int cls = kind + 1, code = kind + 1;
+      if (narrow) {
+        cls  = kind < 2 ? 1 : kind - 1;
+        code = kind == 0 ? 32 : (kind == 1 ? 16 : kind - 1);
+      }
+      const bool is_narrow = code > kHotPieceSlots;
+      const int key    = b * kinds + kind;
+      int32_t p        = cstart[key];
       const int32_t pe = cstart[key + 1];
-      const int max_groups = std::max(1, kHotUnitSlots / (32 * cls));
+      // narrow slots count half towards the size of a unit
+      const int max_groups = is_narrow ? std::max(1, kHotUnitSlots / 16) : std::max(1, kHotUnitSlots / (32 * cls));
+      int64_t& run         = is_narrow ? (code == 16 ? hslot_run : qslot_run) : slot_run;
       while (p < pe) {
         const int groups = (int)std::min<int64_t>(max_groups, ((int64_t)(pe - p) + 31) / 32);
-        if (slot_run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return nullptr;  // 32-bit slot ids
-        subs.push_back({(int32_t)slot_run, (int32_t)row_run, groups, cls});
+        if (run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return nullptr;  // 32-bit slot ids
+        subs.push_back({(int32_t)run, (int32_t)row_run, groups, code});
         fills.push_back({p, std::min<int32_t>(pe, p + groups * 32), b, 0});
-        slot_run += (int64_t)groups * 32 * cls;
+        run += (int64_t)groups * 32 * cls;
         row_run += (int64_t)groups * 32;
-        unit_slots += (int64_t)groups * 32 * cls;
+        unit_slots += is_narrow ? (int64_t)groups * 16 : (int64_t)groups * 32 * cls;
         p += groups * 32;
         if (unit_slots >= kHotUnitSlots) close_unit();
       }
@@ -1302,6 +1328,8 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   L->seg_row    = make_dbuf<int32_t>(std::max<int64_t>(row_run, 1), h.stream);
   L->slot_idx16 = make_dbuf<uint16_t>(std::max<int64_t>(L->n_hot_slots, 1) * kHotSlot, h.stream);
   L->slot_idx32 = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots - L->n_hot_slots, 1) * kHotSlot, h.stream);
+  L->slot_idx_h = make_dbuf<uint2>(std::max<int64_t>(hslot_run, 1), h.stream);
+  L->slot_idx_q = make_dbuf<uint32_t>(std::max<int64_t>(qslot_run, 1), h.stream);
   const bool weighted = c.weights.data() != nullptr;
   if (weighted) L->slot_w = dbuf((size_t)std::max<int64_t>(L->n_slots, 1) * kHotSlot * es, h.stream);
   // padding entries of the cold block read x[n_vertices], which the caller keeps at zero (padded_x_elems)
@@ -1310,19 +1338,22 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
       B200_LAUNCH(h, (k_hot_fill<float>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
                   c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
-                  L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>());
+                  L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
+                  L->slot_idx_q.as<uint32_t>());
     else
       B200_LAUNCH(h, (k_hot_fill<double>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
                   c.weights.as<double>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
-                  L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(), L->seg_row.as<int32_t>());
+                  L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
+                  L->slot_idx_q.as<uint32_t>());
   }
   check_last("hot layout");
   sync(h);
   tr.mark("hot: fill slots");
   if (tr.on)
-    std::fprintf(stderr, "[hot] slots %lld (hot %lld) = %.1f MB ids, seg rows %lld, units %d, subs %d\n", (long long)L->n_slots,
-                 (long long)L->n_hot_slots, (double)(L->n_hot_slots * 16 + (L->n_slots - L->n_hot_slots) * 32) / 1e6,
+    std::fprintf(stderr, "[hot] slots %lld (hot %lld) + %lld half + %lld quarter = %.1f MB ids, seg rows %lld, units %d, subs %d\n",
+                 (long long)L->n_slots, (long long)L->n_hot_slots, (long long)hslot_run, (long long)qslot_run,
+                 (double)(L->n_hot_slots * 16 + (L->n_slots - L->n_hot_slots) * 32 + hslot_run * 8 + qslot_run * 4) / 1e6,
                  (long long)row_run, L->n_units, L->n_subs);
   return L;
 }

@@ -3,7 +3,7 @@
 #   bash scripts/test_variants.sh
 set -u
 T="tests/test_pagerank_gpu.py tests/test_edge_cases_gpu.py"
-run() { echo "== $*"; env "$@" CUGRAPH_B200_HOT_MIN_EDGES=0 python -m pytest $T -x -q 2>&1 | tail -2; }
+run() { echo "== $*"; env CUGRAPH_B200_HOT_MIN_EDGES=0 "$@" python -m pytest $T -x -q 2>&1 | tail -2; }
 run CUGRAPH_B200_HOT_X=1
 run CUGRAPH_B200_HOT_X=1 CUGRAPH_B200_HOT_C1=0 CUGRAPH_B200_HOT_CLAIM=8
 run CUGRAPH_B200_HOT_X=1 CUGRAPH_B200_HOT_UNIT_SLOTS=2048
@@ -11,3 +11,5 @@ run CUGRAPH_B200_LOW_ELL=1
 run CUGRAPH_B200_LOW_ELL=1 CUGRAPH_B200_HOT_MIN_EDGES=1000000000
 run CUGRAPH_B200_HOT_BLOCKS=1
 run CUGRAPH_B200_LOW_MODE=0
+run CUGRAPH_B200_HOT_NARROW=1
+run CUGRAPH_B200_HOT_NARROW=1 CUGRAPH_B200_LOW_ELL=1 CUGRAPH_B200_HOT_CLAIM=2
