@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -212,16 +213,35 @@ class MGGraph:
         g = p.groups
         self.handle = ResourceHandle(stream=torch.cuda.current_stream().cuda_stream)
         self.n_rows, self.n_cols = g.C * p.maxpart, g.R * p.maxpart
-        rv, cv, wv = _view(p.rows), _view(p.cols), _view(p.weights)
-        blk, err = C.c_void_p(), C.c_void_p()
-        code = self.lib.cugraph_b200_block_create(self.handle.ptr, self.n_rows, self.n_cols, rv.ptr, cv.ptr, wv.ptr,
-                                                  C.byref(blk), C.byref(err))
-        for v in (rv, cv, wv):
-            v.free()
-        _capi.check(code, err, "cugraph_b200_block_create")
-        self.block = blk.value
-        self.span = int(self.lib.cugraph_b200_block_span(self.block))
         es = 4 if self.dtype == torch.float32 else 8
+        # EXPERIMENTAL (CUGRAPH_B200_MG_SPLIT=1): one block per destination partition of the row group, so that the
+        # reduction of partition j's partial sums runs under the sweep of partition j+1 (pagerank_split)
+        self.split = os.environ.get("CUGRAPH_B200_MG_SPLIT", "0") == "1" and g.C > 1
+        self.block, self.blocks = None, []
+
+        def make_block(rows, cols, w, n_rows):
+            rv, cv, wv = _view(rows), _view(cols), _view(w)
+            blk, err = C.c_void_p(), C.c_void_p()
+            code = self.lib.cugraph_b200_block_create(self.handle.ptr, n_rows, self.n_cols, rv.ptr, cv.ptr, wv.ptr,
+                                                      C.byref(blk), C.byref(err))
+            for v in (rv, cv, wv):
+                v.free()
+            _capi.check(code, err, "cugraph_b200_block_create")
+            return blk.value
+
+        if self.split:
+            part_of = torch.div(p.rows, p.maxpart, rounding_mode="floor")
+            for j in range(g.C):
+                m = part_of == j
+                rj = (p.rows[m] - j * p.maxpart).to(p.rows.dtype).contiguous()
+                cj = p.cols[m].contiguous()
+                wj = p.weights[m].contiguous() if p.weights is not None else None
+                self.blocks.append(make_block(rj, cj, wj, p.maxpart))
+            self.spans = [int(self.lib.cugraph_b200_block_span(b)) for b in self.blocks]
+            self.span = max(self.spans)
+        else:
+            self.block = make_block(p.rows, p.cols, p.weights, self.n_rows)
+            self.span = int(self.lib.cugraph_b200_block_span(self.block))
         self.x_elems = int(self.lib.cugraph_b200_padded_elems(self.span, es))
         # out-weight sums of the owned vertices: partial per column slot, reduce-scattered in the column group
         ones = p.weights.to(torch.float64) if p.weights is not None else torch.ones(p.cols.numel(), dtype=torch.float64, device=src.device)
@@ -240,11 +260,16 @@ class MGGraph:
             if getattr(self, "block", None):
                 self.lib.cugraph_b200_block_free(self.block)
                 self.block = None
+            for b in getattr(self, "blocks", []):
+                self.lib.cugraph_b200_block_free(b)
+            self.blocks = []
         except Exception:
             pass
 
     # one PageRank iteration = all-gather(x) -> block sweep -> reduce-scatter(y) -> vertex step -> all-reduce(2 scalars)
     def pagerank(self, alpha=0.85, epsilon=1e-5, max_iterations=100, time_iterations=False):
+        if self.split:
+            return self.pagerank_split(alpha, epsilon, max_iterations)
         p, g, L, capi = self.part, self.part.groups, self.lib, self._capi
         dev, dt, mp = self.out_w.device, self.dtype, p.maxpart
         pr = torch.zeros(mp, dtype=dt, device=dev)
@@ -290,6 +315,65 @@ class MGGraph:
         for v in views.values():
             v.free()
         return p.vertices, pr[:p.n_local].clone(), iters, converged
+
+
+# EXPERIMENTAL: same iteration, but the block is split by destination partition: sweep j, then an asynchronous
+# reduce of its partial sums to member j of the row group while sweep j+1 runs (the reference's per-block
+# ncclReduce, per_v_transform_reduce_e.cuh:3389-3407).  Only the last reduce and the all-gather stay exposed.
+def _pagerank_split(self, alpha=0.85, epsilon=1e-5, max_iterations=100):
+    p, g, L, capi = self.part, self.part.groups, self.lib, self._capi
+    dev, dt, mp = self.out_w.device, self.dtype, p.maxpart
+    pr = torch.zeros(mp, dtype=dt, device=dev)
+    pr[:p.n_local] = 1.0 / p.n_global
+    x_local = torch.zeros(mp, dtype=dt, device=dev)
+    xg = torch.zeros(self.x_elems, dtype=dt, device=dev)
+    xseg = torch.zeros(self.n_cols, dtype=dt, device=dev)
+    ybufs = [torch.zeros(sp, dtype=dt, device=dev) for sp in self.spans]
+    ymine = ybufs[g.c][:mp]                      # the reduction for this rank's vertices lands here
+    tot = torch.zeros(2, dtype=torch.float64, device=dev)
+    part = torch.zeros(2, dtype=torch.float64, device=dev)
+    views = {k: _view(v) for k, v in dict(pr=pr, x=x_local, xg=xg, yr=ymine, ow=self.out_w).items()}
+    yviews = [_view(y) for y in ybufs]
+    err = C.c_void_p()
+
+    def vertex_step(first):
+        part.zero_()
+        code = L.cugraph_b200_pagerank_vertex_step(self.handle.ptr, views["yr"].ptr, views["pr"].ptr, views["ow"].ptr,
+                                                   views["x"].ptr, p.n_local, float(alpha), float(p.n_global),
+                                                   1 if first else 0, C.c_void_p(tot.data_ptr()),
+                                                   C.c_void_p(part.data_ptr()), C.byref(err))
+        capi.check(code, err, "cugraph_b200_pagerank_vertex_step")
+        dist.all_reduce(part)
+
+    vertex_step(True)
+    tot, part = part, tot
+    iters = 0
+    for _ in range(int(max_iterations)):
+        if g.R == 1:
+            xg[:mp].copy_(x_local)
+        else:
+            all_gather_into(xseg, x_local, g.col_group)
+            xg[:self.n_cols].view(mp, g.R).copy_(xseg.view(g.R, mp).t())
+        works = []
+        for j in range(g.C):
+            code = L.cugraph_b200_block_pull_sweep(self.handle.ptr, self.blocks[j], views["xg"].ptr, yviews[j].ptr,
+                                                   float(alpha), C.byref(err))
+            capi.check(code, err, "cugraph_b200_block_pull_sweep")
+            works.append(dist.reduce(ybufs[j][:mp], dst=g.r * g.C + j, group=g.row_group, async_op=True))
+        for wk in works:
+            wk.wait()
+        vertex_step(False)
+        tot, part = part, tot
+        iters += 1
+        if epsilon > 0.0 and float(tot[0].item()) < epsilon:
+            break
+    converged = iters < max_iterations
+    for v in list(views.values()) + yviews:
+        v.free()
+    return p.vertices, pr[:p.n_local].clone(), iters, converged
+
+
+MGGraph.pagerank_split = _pagerank_split
 
 
 def pagerank(graph: MGGraph, alpha=0.85, epsilon=1e-5, max_iterations=100):

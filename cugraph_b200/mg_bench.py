@@ -114,6 +114,7 @@ def run_mg_pagerank(args, metric, alpha, iters, ClockSampler, peaks):
                           "num_edges": E_total, "edges_per_gpu": E_local, "alpha": alpha, "iterations": iters,
                           "partition": f"2D {R}x{Cc} (all-gather group {R}, reduce-scatter group {Cc})",
                           "mass": float(mass.item()),
+                          "mg_split": os.environ.get("CUGRAPH_B200_MG_SPLIT", "0") == "1",
                           "l2": "inputs per sweep exceed the 126 MB L2; no explicit flush"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None}
         print(json.dumps(out), flush=True)
