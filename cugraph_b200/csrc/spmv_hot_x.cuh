@@ -250,6 +250,8 @@ void launch_pull_sweep_blocked_x(handle_impl const& h, csx_t const& c, hot_layou
     attr_set = true;
   }
   const int grid = L.n_cta;
+  const bool la  = low_async() && h.aux_stream != nullptr;  // experimental: low rows on the second stream
+  if (la) CUDA_TRY(cudaEventRecord(h.ev_a, h.stream));      // x and the loop state are ready here
   if (L.slot_w.data())
     B200_LAUNCH(h, (k_spmv_blocked_x<T, true>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
                 L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(),
@@ -260,9 +262,19 @@ void launch_pull_sweep_blocked_x(handle_impl const& h, csx_t const& c, hot_layou
                 L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(),
                 L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(), (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W,
                 L.B, hot_c1_wide(), hot_claim(), L.slot_idx_h.as<uint2>(), L.slot_idx_q.as<uint32_t>(), st);
+  if (la) {  // queued behind the persistent kernel: its blocks fill the SMs that the blocked kernel's tail frees
+    CUDA_TRY(cudaStreamWaitEvent(h.aux_stream, h.ev_a, 0));
+    handle_impl ha = h;
+    ha.stream      = h.aux_stream;
+    ha.launches    = 0;
+    launch_low_rows<O, T>(ha, c, x, y, alpha, st);
+    h.launches += ha.launches;
+    CUDA_TRY(cudaEventRecord(h.ev_b, h.aux_stream));
+  }
   B200_LAUNCH(h, (k_spmv_blocked_finish<T>), (L.n_hi + 255) / 256, 256, 0, acc_hi, L.n_hi, y, c.row_vertex.as<int32_t>(),
               alpha, L.unit_counter.as<int>(), L.n_cta, st);
-  launch_low_rows<O, T>(h, c, x, y, alpha, st);
+  if (la) CUDA_TRY(cudaStreamWaitEvent(h.stream, h.ev_b, 0));
+  else launch_low_rows<O, T>(h, c, x, y, alpha, st);
 }
 
 // dispatch: blocked layout when it exists for this graph, else the plain edge-balanced sweep

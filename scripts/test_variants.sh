@@ -13,3 +13,4 @@ run CUGRAPH_B200_HOT_BLOCKS=1
 run CUGRAPH_B200_LOW_MODE=0
 run CUGRAPH_B200_HOT_NARROW=1
 run CUGRAPH_B200_HOT_NARROW=1 CUGRAPH_B200_LOW_ELL=1 CUGRAPH_B200_HOT_CLAIM=2
+run CUGRAPH_B200_LOW_ASYNC=1
