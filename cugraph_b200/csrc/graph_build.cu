@@ -1073,6 +1073,90 @@ struct hot_fill_t {  // build-time companion of a sub-unit
   int32_t piece_begin, piece_end, block, pad;
 };
 
+// Host-side plan of the blocked sweep's work structure, from the per-class piece counts alone (class_start[key] =
+// first piece of class key = block * kinds + kind, pieces ordered by key; kinds = 8, or 10 for narrow layouts where
+// kind 0 / 1 are the quarter / half slot classes):
+//   sub-unit = consecutive groups (32 pieces each) of one class, at most `unit_slots` slots;
+//   unit     = consecutive sub-units of one block, closed once it holds >= unit_slots slots (narrow slots count half);
+//   range    = contiguous units per persistent CTA, balanced by slots (cold block weighted by cold_cost).
+// Pure host code: exercised on CPU through cugraph_b200_debug_plan_hot_units (tests/test_hot_plan_cpu.py).
+struct hot_plan_t {
+  std::vector<hot_sub_host_t> subs;
+  std::vector<hot_fill_t> fills;
+  std::vector<hot_unit_host_t> units;
+  std::vector<int32_t> range;
+  int64_t slot_run{0}, row_run{0}, cold_slot0{0}, hslot_run{0}, qslot_run{0};
+  int n_cta{1};
+};
+
+bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int unit_slots_target, int sm_count,
+                    double cold_cost, hot_plan_t& P)
+{
+  const int kinds         = narrow ? kHotPieceSlots + 2 : kHotPieceSlots;
+  const int kHotUnitSlots = unit_slots_target;
+  auto& subs  = P.subs;
+  auto& fills = P.fills;
+  auto& units = P.units;
+  std::vector<double> unit_cost;
+  int64_t &slot_run = P.slot_run, &row_run = P.row_run, &cold_slot0 = P.cold_slot0, &hslot_run = P.hslot_run,
+          &qslot_run = P.qslot_run;
+  for (int b = 0; b <= B; ++b) {
+    if (b == B) cold_slot0 = slot_run;
+    int64_t unit_slots = 0;
+    int unit_sub0      = (int)subs.size();
+    auto close_unit = [&]() {
+      if ((int)subs.size() > unit_sub0) {
+        units.push_back({unit_sub0, (int32_t)subs.size(), b, 0});
+        unit_cost.push_back((double)unit_slots * (b == B ? cold_cost : 1.0) + 64.0);
+      }
+      unit_sub0  = (int)subs.size();
+      unit_slots = 0;
+    };
+    for (int kind = 0; kind < kinds; ++kind) {
+      // steps per group and the sub-unit's class code: 1..8 = full 8-entry slots; narrow layouts put the
+      // one-step kinds Q (code 32: 2 ids per slot) and H (code 16: 4 ids) in front
+      int cls = kind + 1, code = kind + 1;
+      if (narrow) {
+        cls  = kind < 2 ? 1 : kind - 1;
+        code = kind == 0 ? 32 : (kind == 1 ? 16 : kind - 1);
+      }
+      const bool is_narrow = code > kHotPieceSlots;
+      const int key    = b * kinds + kind;
+      int32_t p        = cstart[key];
+      const int32_t pe = cstart[key + 1];
+      // narrow slots count half towards the size of a unit
+      const int max_groups = is_narrow ? std::max(1, kHotUnitSlots / 16) : std::max(1, kHotUnitSlots / (32 * cls));
+      int64_t& run         = is_narrow ? (code == 16 ? hslot_run : qslot_run) : slot_run;
+      while (p < pe) {
+        const int groups = (int)std::min<int64_t>(max_groups, ((int64_t)(pe - p) + 31) / 32);
+        if (run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return false;  // 32-bit slot ids
+        subs.push_back({(int32_t)run, (int32_t)row_run, groups, code});
+        fills.push_back({p, std::min<int32_t>(pe, p + groups * 32), b, 0});
+        run += (int64_t)groups * 32 * cls;
+        row_run += (int64_t)groups * 32;
+        unit_slots += is_narrow ? (int64_t)groups * 16 : (int64_t)groups * 32 * cls;
+        p += groups * 32;
+        if (unit_slots >= kHotUnitSlots) close_unit();
+      }
+    }
+    close_unit();
+  }
+  P.n_cta = (int)std::max<size_t>(1, std::min<size_t>((size_t)sm_count, units.size()));
+  P.range.assign(P.n_cta + 1, 0);
+  {
+    std::vector<double> cost(units.size() + 1, 0.0);
+    for (size_t u = 0; u < units.size(); ++u) cost[u + 1] = cost[u] + unit_cost[u];
+    size_t u = 0;
+    for (int cta = 1; cta < P.n_cta; ++cta) {
+      const double target = cost[units.size()] * cta / P.n_cta;
+      while (u < units.size() && cost[u + 1] <= target) ++u;
+      P.range[cta] = (int32_t)u;
+    }
+    P.range[P.n_cta] = (int32_t)units.size();
+  }
+  return true;
+}
+
 // one CTA per sub-unit, one warp per group, lane = piece: write the group's slots step-major
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1244,72 +1328,20 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   }
 
   // 4. sub-units (runs of groups of one class), units (runs of sub-units of one block), CTA ranges
-  std::vector<hot_sub_host_t> subs;
-  std::vector<hot_fill_t> fills;
-  std::vector<hot_unit_host_t> units;
-  std::vector<double> unit_cost;
   double cold_cost = 2.0;
   if (const char* e = std::getenv("CUGRAPH_B200_HOT_COLD_COST")) cold_cost = std::atof(e);
-  const int kHotUnitSlots = hot_unit_slots();
-  int64_t slot_run = 0, row_run = 0, cold_slot0 = 0, hslot_run = 0, qslot_run = 0;
-  for (int b = 0; b <= B; ++b) {
-    if (b == B) cold_slot0 = slot_run;
-    int64_t unit_slots = 0;
-    int unit_sub0      = (int)subs.size();
-    auto close_unit = [&]() {
-      if ((int)subs.size() > unit_sub0) {
-        units.push_back({unit_sub0, (int32_t)subs.size(), b, 0});
-        unit_cost.push_back((double)unit_slots * (b == B ? cold_cost : 1.0) + 64.0);
-      }
-      unit_sub0  = (int)subs.size();
-      unit_slots = 0;
-    };
-    for (int kind = 0; kind < kinds; ++kind) {
-      // steps per group and the sub-unit's class code: 1..8 = full 8-entry slots; narrow layouts put the
-      // one-step kinds Q (code 32: 2 ids per slot) and H (code 16: 4 ids) in front
-      int cls = kind + 1, code = kind + 1;
-      if (narrow) {
-        cls  = kind < 2 ? 1 : kind - 1;
-        code = kind == 0 ? 32 : (kind == 1 ? 16 : kind - 1);
-      }
-      const bool is_narrow = code > kHotPieceSlots;
-      const int key    = b * kinds + kind;
-      int32_t p        = cstart[key];
-      const int32_t pe = cstart[key + 1];
-      // narrow slots count half towards the size of a unit
-      const int max_groups = is_narrow ? std::max(1, kHotUnitSlots / 16) : std::max(1, kHotUnitSlots / (32 * cls));
-      int64_t& run         = is_narrow ? (code == 16 ? hslot_run : qslot_run) : slot_run;
-      while (p < pe) {
-        const int groups = (int)std::min<int64_t>(max_groups, ((int64_t)(pe - p) + 31) / 32);
-        if (run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return nullptr;  // 32-bit slot ids
-        subs.push_back({(int32_t)run, (int32_t)row_run, groups, code});
-        fills.push_back({p, std::min<int32_t>(pe, p + groups * 32), b, 0});
-        run += (int64_t)groups * 32 * cls;
-        row_run += (int64_t)groups * 32;
-        unit_slots += is_narrow ? (int64_t)groups * 16 : (int64_t)groups * 32 * cls;
-        p += groups * 32;
-        if (unit_slots >= kHotUnitSlots) close_unit();
-      }
-    }
-    close_unit();
-  }
-  L->n_hot_slots = cold_slot0;
-  L->n_slots     = slot_run;
+  hot_plan_t plan;
+  if (!plan_hot_units(cstart, B, narrow, hot_unit_slots(), h.sm_count, cold_cost, plan)) return nullptr;  // slots overflow 31 bits
+  auto& subs  = plan.subs;
+  auto& fills = plan.fills;
+  auto& units = plan.units;
+  auto& range = plan.range;
+  const int64_t row_run = plan.row_run, hslot_run = plan.hslot_run, qslot_run = plan.qslot_run, cold_slot0 = plan.cold_slot0;
+  L->n_hot_slots = plan.cold_slot0;
+  L->n_slots     = plan.slot_run;
   L->n_units     = (int32_t)units.size();
   L->n_subs      = (int32_t)subs.size();
-  L->n_cta       = (int)std::max<size_t>(1, std::min<size_t>((size_t)h.sm_count, units.size()));
-  std::vector<int32_t> range(L->n_cta + 1, 0);
-  {
-    std::vector<double> cost(units.size() + 1, 0.0);
-    for (size_t u = 0; u < units.size(); ++u) cost[u + 1] = cost[u] + unit_cost[u];
-    size_t u = 0;
-    for (int cta = 1; cta < L->n_cta; ++cta) {
-      const double target = cost[units.size()] * cta / L->n_cta;
-      while (u < units.size() && cost[u + 1] <= target) ++u;
-      range[cta] = (int32_t)u;
-    }
-    range[L->n_cta] = (int32_t)units.size();
-  }
+  L->n_cta       = plan.n_cta;
   L->units     = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
   L->subs      = make_dbuf<hot_sub_host_t>(std::max<size_t>(subs.size(), 1), h.stream);
   L->cta_range = make_dbuf<int32_t>(range.size(), h.stream);
@@ -1359,6 +1391,22 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
 }
 
 }  // namespace
+
+// flat copy of plan_hot_units' result for the debug C entry (CPU tests)
+bool debug_plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int unit_slots, int sm_count, double cold_cost,
+                          int64_t totals[6], std::vector<int32_t>& subs4, std::vector<int32_t>& fills4,
+                          std::vector<int32_t>& units4, std::vector<int32_t>& range)
+{
+  hot_plan_t P;
+  if (!plan_hot_units(cstart, B, narrow, unit_slots, sm_count, cold_cost, P)) return false;
+  totals[0] = P.slot_run; totals[1] = P.row_run; totals[2] = P.cold_slot0; totals[3] = P.hslot_run; totals[4] = P.qslot_run;
+  totals[5] = P.n_cta;
+  for (auto const& x : P.subs) subs4.insert(subs4.end(), {x.slot_begin, x.row_begin, x.n_groups, x.cls});
+  for (auto const& x : P.fills) fills4.insert(fills4.end(), {x.piece_begin, x.piece_end, x.block, x.pad});
+  for (auto const& x : P.units) units4.insert(units4.end(), {x.sub_begin, x.sub_end, x.block, x.pad});
+  range = P.range;
+  return true;
+}
 
 hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size)
 {
@@ -1550,3 +1598,31 @@ template dbuf collect_vertex_values<double>(handle_impl const&, graph_impl const
                                             device_array_view_impl const*, double);
 
 }  // namespace b200
+
+extern "C" cugraph_error_code_t cugraph_b200_debug_plan_hot_units(
+  const int32_t* class_start, int n_hot_blocks, bool_t narrow, int unit_slots, int sm_count, double cold_cost,
+  int64_t* totals, int32_t* subs, int32_t* fills, size_t subs_capacity, size_t* n_subs, int32_t* units,
+  size_t units_capacity, size_t* n_units, int32_t* range, size_t range_capacity, cugraph_error_t** error)
+{
+  using namespace b200;
+  return guarded(error, [&] {
+    B200_EXPECTS(class_start && totals && subs && fills && units && range && n_subs && n_units, CUGRAPH_INVALID_INPUT,
+                 "null argument");
+    B200_EXPECTS(n_hot_blocks >= 0 && unit_slots >= 32 && sm_count >= 1, CUGRAPH_INVALID_INPUT, "bad parameter");
+    const int kinds = narrow == TRUE ? 10 : 8;
+    std::vector<int32_t> cstart(class_start, class_start + (size_t)(n_hot_blocks + 1) * kinds + 1);
+    std::vector<int32_t> s4, f4, u4, r;
+    int64_t t[6];
+    B200_EXPECTS(debug_plan_hot_units(cstart, n_hot_blocks, narrow == TRUE, unit_slots, sm_count, cold_cost, t, s4, f4, u4, r),
+                 CUGRAPH_INVALID_INPUT, "slot numbers overflow 31 bits");
+    B200_EXPECTS(s4.size() / 4 <= subs_capacity && u4.size() / 4 <= units_capacity && r.size() <= range_capacity,
+                 CUGRAPH_INVALID_INPUT, "output capacity too small");
+    std::copy(t, t + 6, totals);
+    std::copy(s4.begin(), s4.end(), subs);
+    std::copy(f4.begin(), f4.end(), fills);
+    std::copy(u4.begin(), u4.end(), units);
+    std::copy(r.begin(), r.end(), range);
+    *n_subs  = s4.size() / 4;
+    *n_units = u4.size() / 4;
+  });
+}

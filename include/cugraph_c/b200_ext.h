@@ -70,6 +70,17 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_pagerank_vertex_step(
   cugraph_type_erased_device_array_view_t* x, size_t n_local, double alpha, double n_vertices_global, bool_t first,
   const double* totals_prev_device, double* partial_out_device, cugraph_error_t** error);
 
+/* Host-only planner of the blocked sweep's work structure (sub-units, units, per-CTA unit ranges) from the per-class
+ * piece counts; the function graph staging itself uses.  Needs no GPU: exposed so that the host logic is testable on
+ * CPU (tests/test_hot_plan_cpu.py).  class_start has (n_hot_blocks + 1) * kinds + 1 entries (kinds = 8, narrow: 10).
+ * Outputs: totals[6] = {slots, seg rows, first cold slot, half slots, quarter slots, CTAs}; subs / fills / units are
+ * 4 x int32 records ({slot_begin,row_begin,n_groups,class}, {piece_begin,piece_end,block,0}, {sub_begin,sub_end,block,0});
+ * range has totals[5] + 1 entries.  Returns CUGRAPH_INVALID_INPUT when a capacity is too small. */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_plan_hot_units(
+  const int32_t* class_start, int n_hot_blocks, bool_t narrow, int unit_slots, int sm_count, double cold_cost,
+  int64_t* totals, int32_t* subs, int32_t* fills, size_t subs_capacity, size_t* n_subs, int32_t* units,
+  size_t units_capacity, size_t* n_units, int32_t* range, size_t range_capacity, cugraph_error_t** error);
+
 #ifdef __cplusplus
 }
 #endif
