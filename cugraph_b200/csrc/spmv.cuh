@@ -209,10 +209,25 @@ struct low_ell_args_t {
 
 __host__ __device__ __forceinline__ int low_ell_rows_per_thread(int d) { return d <= 4 ? 4 : (d <= 8 ? 2 : 1); }
 
+// how a kernel reads x[c]: straight from global memory, or (hot variant) from a shared-memory copy of the first
+// `w_hot` entries — the sources with the largest in-degree, which in power-law graphs are also gathered most often
+template <typename T>
+struct gather_global_t {
+  T const* __restrict__ x;
+  __device__ __forceinline__ T operator()(int c) const { return x[c]; }
+};
+template <typename T>
+struct gather_hot_t {
+  T const* __restrict__ x;
+  T const* __restrict__ sx;
+  int w_hot;
+  __device__ __forceinline__ T operator()(int c) const { return c < w_hot ? sx[c] : x[c]; }
+};
+
 // D entries of R rows per thread, fully unrolled
-template <typename T, bool WEIGHTED, int D, int R>
+template <typename T, bool WEIGHTED, int D, int R, typename G>
 __device__ __forceinline__ void low_ell_rows(int32_t const* __restrict__ ell, T const* __restrict__ ellw, int n, int i0,
-                                             T const* __restrict__ x, double (&acc)[4])
+                                             G const& gather, double (&acc)[4])
 {
   int c[R][D];
   T wv[R][D];
@@ -234,39 +249,38 @@ __device__ __forceinline__ void low_ell_rows(int32_t const* __restrict__ ell, T 
     double a = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k)
-      if (c[j][k] >= 0) a += (double)(x[c[j][k]] * wv[j][k]);
+      if (c[j][k] >= 0) a += (double)(gather(c[j][k]) * wv[j][k]);
     acc[j] = a;
   }
 }
 
-template <typename T, bool WEIGHTED>
-__global__ void __launch_bounds__(256)
-k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T const* __restrict__ x, T* __restrict__ y,
-               int32_t const* __restrict__ row_vertex, low_ell_args_t L, double alpha, pr_state_t const* __restrict__ st)
+// one virtual block (256 threads, `vblock` in the block numbering of make_low_ell_args) of the ELL sweep
+template <typename T, bool WEIGHTED, typename G>
+__device__ __forceinline__ void low_ell_block(int vblock, int vtid, int32_t const* __restrict__ ell, T const* __restrict__ ellw,
+                                              G const& gather, T* __restrict__ y, int32_t const* __restrict__ row_vertex,
+                                              low_ell_args_t const& L, double alpha, double init)
 {
-  if (st->done) return;
   int d = 31;  // class of this block
 #pragma unroll 1
   for (int k = 1; k < 32; ++k)
-    if ((int)blockIdx.x >= L.block_begin[k]) d = 31 - k;
-  const double init = st->init;
-  const int blk     = blockIdx.x - L.block_begin[31 - d];
-  const int n       = L.n[d];
-  const int R       = low_ell_rows_per_thread(d);
-  const int i0      = blk * 256 * R + threadIdx.x;
-  double acc[4]     = {0.0, 0.0, 0.0, 0.0};
+    if (vblock >= L.block_begin[k]) d = 31 - k;
+  const int blk = vblock - L.block_begin[31 - d];
+  const int n   = L.n[d];
+  const int R   = low_ell_rows_per_thread(d);
+  const int i0  = blk * 256 * R + vtid;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   if (d > 0) {
     int32_t const* e = ell + L.base[d];
     T const* ew      = WEIGHTED ? ellw + L.base[d] : nullptr;
     switch (d) {
-      case 1: low_ell_rows<T, WEIGHTED, 1, 4>(e, ew, n, i0, x, acc); break;
-      case 2: low_ell_rows<T, WEIGHTED, 2, 4>(e, ew, n, i0, x, acc); break;
-      case 3: low_ell_rows<T, WEIGHTED, 3, 4>(e, ew, n, i0, x, acc); break;
-      case 4: low_ell_rows<T, WEIGHTED, 4, 4>(e, ew, n, i0, x, acc); break;
-      case 5: low_ell_rows<T, WEIGHTED, 5, 2>(e, ew, n, i0, x, acc); break;
-      case 6: low_ell_rows<T, WEIGHTED, 6, 2>(e, ew, n, i0, x, acc); break;
-      case 7: low_ell_rows<T, WEIGHTED, 7, 2>(e, ew, n, i0, x, acc); break;
-      case 8: low_ell_rows<T, WEIGHTED, 8, 2>(e, ew, n, i0, x, acc); break;
+      case 1: low_ell_rows<T, WEIGHTED, 1, 4>(e, ew, n, i0, gather, acc); break;
+      case 2: low_ell_rows<T, WEIGHTED, 2, 4>(e, ew, n, i0, gather, acc); break;
+      case 3: low_ell_rows<T, WEIGHTED, 3, 4>(e, ew, n, i0, gather, acc); break;
+      case 4: low_ell_rows<T, WEIGHTED, 4, 4>(e, ew, n, i0, gather, acc); break;
+      case 5: low_ell_rows<T, WEIGHTED, 5, 2>(e, ew, n, i0, gather, acc); break;
+      case 6: low_ell_rows<T, WEIGHTED, 6, 2>(e, ew, n, i0, gather, acc); break;
+      case 7: low_ell_rows<T, WEIGHTED, 7, 2>(e, ew, n, i0, gather, acc); break;
+      case 8: low_ell_rows<T, WEIGHTED, 8, 2>(e, ew, n, i0, gather, acc); break;
       default: {  // 9..31: eight entries at a time
         if (i0 < n) {
           double a = 0.0;
@@ -284,7 +298,7 @@ k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T co
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (c[k] >= 0) a += (double)(x[c[k]] * wv[k]);
+              if (c[k] >= 0) a += (double)(gather(c[k]) * wv[k]);
           }
           acc[0] = a;
         }
@@ -295,10 +309,26 @@ k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T co
   for (int j = 0; j < 4; ++j) {
     const int i = i0 + j * 256;
     if (j < R && i < n) {
-      const int r                    = L.row_begin[d] + i;
+      const int r                       = L.row_begin[d] + i;
       y[row_vertex ? row_vertex[r] : r] = (T)(acc[j] * alpha + init);
     }
   }
+}
+
+template <typename T, bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T const* __restrict__ x, T* __restrict__ y,
+               int32_t const* __restrict__ row_vertex, low_ell_args_t L, double alpha, pr_state_t const* __restrict__ st)
+{
+  if (st->done) return;
+  gather_global_t<T> g{x};
+  low_ell_block<T, WEIGHTED>((int)blockIdx.x, (int)threadIdx.x, ell, ellw, g, y, row_vertex, L, alpha, st->init);
+}
+
+inline int low_ell_mode()
+{
+  const char* e = std::getenv("CUGRAPH_B200_LOW_ELL");
+  return e ? std::atoi(e) : 0;
 }
 
 inline low_ell_args_t make_low_ell_args(low_ell_t const& E)

@@ -313,6 +313,60 @@ __global__ void k_spmv_blocked_finish(double* __restrict__ acc_hi, int n_hi, T* 
   acc_hi[r]                          = 0.0;
 }
 
+// EXPERIMENTAL (CUGRAPH_B200_LOW_ELL=2): the ELL sweep of the degree < 32 rows as a persistent kernel whose CTAs keep
+// x[0, W) — the first column block, i.e. the sources with the largest in-degree — in shared memory (one TMA fill per
+// CTA and sweep); gathers of those sources are served from shared memory, the rest from L2 as before.
+template <typename T, bool WEIGHTED>
+__global__ void __launch_bounds__(kHotThreads, 1)
+k_spmv_low_ell_hot(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T const* __restrict__ x, T* __restrict__ y,
+                   int32_t const* __restrict__ row_vertex, low_ell_args_t L, int W, double alpha,
+                   pr_state_t const* __restrict__ st)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* sx = reinterpret_cast<T*>(smem_raw);
+  __shared__ uint64_t bar;
+  if (st->done) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    const unsigned bytes = (unsigned)(W * sizeof(T));
+    mbar_expect_tx(&bar, bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x);
+    for (unsigned o = 0; o < bytes; o += kHotTmaPiece)
+      tma_bulk_g2s(smem_raw + o, src + o, (bytes - o) < (unsigned)kHotTmaPiece ? (bytes - o) : (unsigned)kHotTmaPiece, &bar);
+  }
+  __syncthreads();  // the barrier is initialised before anyone waits on it
+  mbar_wait(&bar, 0);
+  gather_hot_t<T> g{x, sx, W};
+  const double init  = st->init;
+  const int n_vblock = L.block_begin[32];
+  const int sub      = threadIdx.x >> 8;  // four virtual 256-thread blocks per CTA
+  for (int vb = (int)blockIdx.x * 4 + sub; vb < n_vblock; vb += (int)gridDim.x * 4)
+    low_ell_block<T, WEIGHTED>(vb, (int)(threadIdx.x & 255), ell, ellw, g, y, row_vertex, L, alpha, init);
+}
+
+template <typename T>
+void launch_low_rows_ell_hot(handle_impl const& h, csx_t const& c, low_ell_t const& E, T const* x, T* y, double alpha,
+                             pr_state_t const* st)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv_low_ell_hot<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotDynSmem));
+    CUDA_TRY(cudaFuncSetAttribute(k_spmv_low_ell_hot<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotDynSmem));
+    attr_set = true;
+  }
+  low_ell_args_t a = make_low_ell_args(E);
+  const int blocks = a.block_begin[32];
+  if (blocks <= 0) return;
+  const int W    = (int)(kHotSliceBytes / sizeof(T)) - kHotZeroPad;  // x holds padded_x_elems(): reading W entries is safe
+  const int grid = std::min(h.sm_count, (blocks + 3) / 4);
+  if (E.w.data())
+    B200_LAUNCH(h, (k_spmv_low_ell_hot<T, true>), grid, kHotThreads, kHotDynSmem, E.idx.as<int32_t>(), E.w.as<T>(), x, y,
+                c.row_vertex.as<int32_t>(), a, W, alpha, st);
+  else
+    B200_LAUNCH(h, (k_spmv_low_ell_hot<T, false>), grid, kHotThreads, kHotDynSmem, E.idx.as<int32_t>(), E.w.as<T>(), x, y,
+                c.row_vertex.as<int32_t>(), a, W, alpha, st);
+}
+
 // EXPERIMENTAL (CUGRAPH_B200_LOW_ASYNC=1): run the degree < 32 rows on the handle's second stream, concurrently with
 // the persistent kernel (disjoint rows of y; both only read x and the loop state)
 inline bool low_async()
@@ -324,8 +378,9 @@ inline bool low_async()
 template <typename O, typename T>
 void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, double alpha, pr_state_t const* st)
 {
-  if (low_ell_t const* E = low_ell_layout(h, c, sizeof(T))) {  // experimental, CUGRAPH_B200_LOW_ELL=1
-    launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
+  if (low_ell_t const* E = low_ell_layout(h, c, sizeof(T))) {  // experimental, CUGRAPH_B200_LOW_ELL=1 | 2
+    if (low_ell_mode() >= 2) launch_low_rows_ell_hot<T>(h, c, *E, x, y, alpha, st);
+    else launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
     return;
   }
   low_bins_t bins = make_low_bins(c);
