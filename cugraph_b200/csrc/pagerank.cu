@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace b200 {
 namespace {
@@ -124,6 +125,32 @@ __global__ void k_count_negative(T const* a, int64_t n, int* out)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     if (a[i] < (T)0) atomicAdd(out, 1);
+}
+
+// ---- debug: compare the configured sweep with the plain reference sweep, row by row
+template <typename T>
+__global__ void k_fill_pattern(T* x, int32_t n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = (T)(0.5 + (double)((unsigned)(i * 2654435761u) >> 16) / 65536.0);
+}
+
+// packed (relative difference bits << 32 | row): atomicMax keeps the worst row of each class
+template <typename O, typename T>
+__global__ void k_compare_rows(O const* __restrict__ off, int32_t const* __restrict__ row_vertex, T const* __restrict__ a,
+                               T const* __restrict__ b, int32_t n_rows, int32_t n_hi, double tol,
+                               unsigned long long* __restrict__ worst /*[2]*/, unsigned long long* __restrict__ n_bad /*[2]*/)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int v        = row_vertex ? row_vertex[r] : r;
+  const double va = (double)a[v], vb = (double)b[v];
+  const double den   = fmax(fabs(va), 1e-300);
+  const float rel    = (float)fmin(fabs(va - vb) / den, 1e30);
+  const int cls      = r < n_hi ? 0 : 1;
+  atomicMax(worst + cls, ((unsigned long long)__float_as_uint(rel) << 32) | (unsigned)r);
+  if (rel > tol) atomicAdd(n_bad + cls, 1ull);
+  (void)off;
 }
 
 struct pr_args {
@@ -483,6 +510,57 @@ cugraph_error_code_t cugraph_b200_time_pull_spmv(const cugraph_resource_handle_t
     if (algorithmic_bytes_per_sweep)
       *algorithmic_bytes_per_sweep = (double)c.nnz * 4.0 * (g->weighted ? 2.0 : 1.0) +
                                      (double)(nv + 1) * (c.offs64 ? 8.0 : 4.0) + (double)nv * 8.0;
+  });
+}
+
+// Debug hook for the experimental sweep variants: y of the configured sweep (environment switches as they are) against
+// the plain reference sweep (k_spmv_hi + k_spmv_low) on the same pseudo-random x.  out[0..3] = degree >= 32 rows:
+// max relative difference, its row, that row's degree, rows above 1e-5; out[4..7] = the same for the degree < 32 rows.
+cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph,
+                                                       double* out, cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    auto* g       = G(graph);
+    B200_EXPECTS(out != nullptr, CUGRAPH_INVALID_INPUT, "out is NULL");
+    B200_EXPECTS(g->mg == nullptr && g->weight_type == FLOAT32, CUGRAPH_NOT_IMPLEMENTED, "single-GPU float32 graphs only");
+    csx_t const& c = pull_view(h, *g);
+    B200_EXPECTS(!c.offs64, CUGRAPH_NOT_IMPLEMENTED, "32-bit offsets only");
+    const int32_t nv = g->n_vertices;
+    const size_t px  = padded_x_elems(nv, sizeof(float));
+    dbuf x = make_dbuf<float>(px, h.stream), y0 = make_dbuf<float>(nv, h.stream), y1 = make_dbuf<float>(nv, h.stream);
+    CUDA_TRY(cudaMemsetAsync(x.data(), 0, px * sizeof(float), h.stream));
+    B200_LAUNCH(h, (k_fill_pattern<float>), grid_for(nv), kBlock, 0, x.as<float>(), nv);
+    dbuf acc = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
+    CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
+    dbuf state = make_dbuf<pr_state_t>(1, h.stream);
+    CUDA_TRY(cudaMemsetAsync(state.data(), 0, sizeof(pr_state_t), h.stream));
+    reference_sweep_only() = true;
+    launch_pull_sweep<int32_t, float>(h, c, x.as<float>(), y0.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
+    reference_sweep_only() = false;
+    launch_pull_sweep_auto<int32_t, float>(h, c, nv, x.as<float>(), y1.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
+    dbuf res = make_dbuf<unsigned long long>(4, h.stream);
+    CUDA_TRY(cudaMemsetAsync(res.data(), 0, 4 * sizeof(unsigned long long), h.stream));
+    B200_LAUNCH(h, (k_compare_rows<int32_t, float>), grid_for(c.n_rows), kBlock, 0, c.offsets.as<int32_t>(),
+                c.row_vertex.as<int32_t>(), y0.as<float>(), y1.as<float>(), c.n_rows, c.seg[0], 1e-5,
+                res.as<unsigned long long>(), res.as<unsigned long long>() + 2);
+    unsigned long long hres[4];
+    CUDA_TRY(cudaMemcpyAsync(hres, res.data(), sizeof(hres), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    for (int k = 0; k < 2; ++k) {
+      const unsigned bits = (unsigned)(hres[k] >> 32);
+      float rel;
+      std::memcpy(&rel, &bits, sizeof(rel));
+      const int32_t row = (int32_t)(hres[k] & 0xffffffffu);
+      int32_t offs[2]   = {0, 0};
+      if (c.n_rows > 0)
+        CUDA_TRY(cudaMemcpy(offs, c.offsets.as<int32_t>() + row, sizeof(offs), cudaMemcpyDeviceToHost));
+      out[4 * k + 0] = rel;
+      out[4 * k + 1] = row;
+      out[4 * k + 2] = offs[1] - offs[0];
+      out[4 * k + 3] = (double)hres[2 + k];
+    }
+    check_last("debug_compare_sweeps");
   });
 }
 

@@ -325,6 +325,14 @@ k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T co
   low_ell_block<T, WEIGHTED>((int)blockIdx.x, (int)threadIdx.x, ell, ellw, g, y, row_vertex, L, alpha, st->init);
 }
 
+// set by cugraph_b200_debug_compare_sweeps while it computes the reference result: launch_pull_sweep then uses
+// k_spmv_hi + k_spmv_low only, whatever experimental switches are on
+inline bool& reference_sweep_only()
+{
+  static thread_local bool v = false;
+  return v;
+}
+
 inline int low_ell_mode()
 {
   const char* e = std::getenv("CUGRAPH_B200_LOW_ELL");
@@ -412,7 +420,7 @@ void launch_pull_sweep(handle_impl const& h, csx_t const& c, T const* x, T* y, d
       B200_LAUNCH(h, (k_spmv_hi_finish<T>), (c.n_split + 255) / 256, 256, 0, c.split_rows.as<int32_t>(), c.n_split,
                   acc_hi, y, rv, alpha, st);
   }
-  if (low_ell_t const* E = low_ell_layout(h, c, sizeof(T))) {
+  if (low_ell_t const* E = reference_sweep_only() ? nullptr : low_ell_layout(h, c, sizeof(T))) {
     launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
     return;
   }

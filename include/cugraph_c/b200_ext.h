@@ -70,6 +70,13 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_pagerank_vertex_step(
   cugraph_type_erased_device_array_view_t* x, size_t n_local, double alpha, double n_vertices_global, bool_t first,
   const double* totals_prev_device, double* partial_out_device, cugraph_error_t** error);
 
+/* Debug hook for the experimental sweep variants: one sweep as configured by the CUGRAPH_B200_* switches against the plain
+ * reference sweep on the same pseudo-random x.  out[0..3] = degree >= 32 rows {max relative difference, its row, that
+ * row's degree, rows above 1e-5}; out[4..7] = the same for the degree < 32 rows.  (scripts/debug_variant.py) */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugraph_resource_handle_t* handle,
+                                                                     cugraph_graph_t* graph, double* out,
+                                                                     cugraph_error_t** error);
+
 /* Host-only planner of the blocked sweep's work structure (sub-units, units, per-CTA unit ranges) from the per-class
  * piece counts; the function graph staging itself uses.  Needs no GPU: exposed so that the host logic is testable on
  * CPU (tests/test_hot_plan_cpu.py).  class_start has (n_hot_blocks + 1) * kinds + 1 entries (kinds = 8, narrow: 10).
