@@ -245,6 +245,7 @@ struct paths_result_impl {
 // ---------------------------------------------------------------------------------------------
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
+#ifndef B200_HOST_EMU
 #define B200_LAUNCH(h, kernel, grid, block, smem, ...)                           \
   do {                                                                           \
     if ((grid) > 0) {                                                            \
@@ -252,6 +253,20 @@ inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) 
       (h).launches++;                                                            \
     }                                                                            \
   } while (0)
+// the lane of a warp that commits a warp-reduced value
+__device__ __forceinline__ bool is_commit_lane() { return (threadIdx.x & 31) == 0; }
+#else
+// host emulation of the staging kernels (emu/cuda_runtime.h, tests/test_emu_staging_cpu.py): every thread of the
+// launch runs to completion, one after the other; warp shuffles are identities, so every thread commits for itself
+#define B200_LAUNCH(h, kernel, grid, block, smem, ...)                           \
+  do {                                                                           \
+    if ((grid) > 0) {                                                            \
+      emu_launch((grid), (block), [&] { kernel(__VA_ARGS__); });                 \
+      (h).launches++;                                                            \
+    }                                                                            \
+  } while (0)
+inline bool is_commit_lane() { return true; }
+#endif
 
 inline void check_last(const char* what)
 {

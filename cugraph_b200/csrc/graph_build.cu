@@ -42,7 +42,7 @@ __global__ void k_minmax(T const* a, int64_t n, long long* mn, long long* mx)
     t = __shfl_xor_sync(0xffffffffu, lmx, o);
     lmx = t > lmx ? t : lmx;
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (is_commit_lane()) {
     atomicMin(mn, lmn);
     atomicMax(mx, lmx);
   }

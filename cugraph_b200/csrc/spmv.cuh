@@ -31,6 +31,7 @@ struct pr_state_t {
   int done;
 };
 
+#ifndef B200_HOST_EMU
 __device__ __forceinline__ int ld_stream(const int* p)
 {
   int v;
@@ -49,6 +50,11 @@ __device__ __forceinline__ double ld_stream(const double* p)
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+#else  // host emulation (emu/cuda_runtime.h): plain loads
+inline int ld_stream(const int* p) { return *p; }
+inline float ld_stream(const float* p) { return *p; }
+inline double ld_stream(const double* p) { return *p; }
+#endif
 
 __device__ __forceinline__ double warp_sum(double v)
 {
