@@ -31,6 +31,7 @@ constexpr int kHotWarps    = kHotThreads / 32;
 constexpr int kHotDynSmem  = kHotSliceBytes;
 constexpr int kHotTmaPiece = 16 * 1024;  // bytes per bulk copy of the slice
 
+#ifndef B200_HOST_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
@@ -71,6 +72,14 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p)
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+#else  // host emulation of the per-lane gather / accumulate code (emu/, tests/test_emu_sweep_cpu.py)
+inline uint4 ld_stream_v4(const void* p)
+{
+  uint4 v;
+  std::memcpy(&v, p, sizeof(v));
+  return v;
+}
+#endif
 
 // consecutive groups of one class (mirrored by hot_sub_host_t, graph_build.cu)
 struct hot_sub_t {
@@ -141,6 +150,11 @@ __device__ __forceinline__ double hot_slot_sum(slot_ids_t const& ids, int s, T c
 template <bool SAME_ROW_RUNS>
 __device__ __forceinline__ void hot_emit(double acc, int row, double* __restrict__ acc_hi, int lane)
 {
+#ifdef B200_HOST_EMU  // lanes run one after the other: the shuffle reduction below is only an optimisation of this
+  (void)lane;
+  if (row >= 0) atomicAdd(acc_hi + row, acc);
+  return;
+#endif
   if (SAME_ROW_RUNS) {
     const int r0 = __shfl_sync(0xffffffffu, row, 0);
     if (__all_sync(0xffffffffu, row == r0)) {  // 32 pieces of one hub row
@@ -201,6 +215,7 @@ __device__ __forceinline__ void hot_run_groups(hot_sub_t const sb, int q, int la
   }
 }
 
+#ifndef B200_HOST_EMU  // kernels and launchers: CUDA only
 __device__ __forceinline__ int ld_volatile(const int* p)
 {
   int v;
@@ -433,6 +448,7 @@ void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_
 }
 
 // (the dispatcher launch_pull_sweep_auto lives in spmv_hot_x.cuh, next to the experimental kernel variant)
+#endif  // !B200_HOST_EMU
 
 // elements an x buffer needs: whole slices are TMA-copied and x[n_vertices] must be a readable zero.
 // The buffer must be zero-filled once at allocation; only [0, n_vertices) is ever written afterwards.

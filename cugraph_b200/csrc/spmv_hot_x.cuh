@@ -47,6 +47,7 @@ __device__ __forceinline__ void hot_run_groups_c1(hot_sub_t const sb, int q, int
   }
 }
 
+#ifndef B200_HOST_EMU
 __device__ __forceinline__ unsigned ld_stream_u32(const uint32_t* p)
 {
   unsigned v;
@@ -59,6 +60,10 @@ __device__ __forceinline__ uint2 ld_stream_v2(const uint2* p)
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
+#else
+inline unsigned ld_stream_u32(const uint32_t* p) { return *p; }
+inline uint2 ld_stream_v2(const uint2* p) { return *p; }
+#endif
 
 // value of the slice entry addressed by the low (HI = false) or high half of a packed pair of 16-bit ids
 template <typename T, bool HI>
@@ -101,6 +106,7 @@ __device__ __forceinline__ void hot_run_groups_narrow(hot_sub_t const sb, int q,
   }
 }
 
+#ifndef B200_HOST_EMU  // kernel and launchers: CUDA only
 // next units for this CTA (called by all lanes of warp 0): own range first — `claim` consecutive units per
 // atomic, they are processed without a CTA barrier in between — then single units of the following CTAs'
 // ranges.  victim_off = how many ranges (starting with the own one) are known to be exhausted.
@@ -287,5 +293,6 @@ void launch_pull_sweep_auto(handle_impl const& h, csx_t const& c, int32_t n_vert
   else if (L->narrow || hot_x_enabled()) launch_pull_sweep_blocked_x<O, T>(h, c, *L, x, y, acc_hi, alpha, st);
   else launch_pull_sweep_blocked<O, T>(h, c, *L, x, y, acc_hi, alpha, st);
 }
+#endif  // !B200_HOST_EMU
 
 }  // namespace b200

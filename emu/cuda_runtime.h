@@ -111,3 +111,8 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 template <typename T> inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <typename T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
 template <typename T> inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+inline int __all_sync(unsigned, int p) { return p; }
+inline int __any_sync(unsigned, int p) { return p; }
+inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+inline void __syncthreads() {}
+inline void __syncwarp(unsigned = 0xffffffffu) {}

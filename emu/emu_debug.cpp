@@ -1,6 +1,9 @@
 // Accessors for the CPU emulation build (libcugraph_c_emu.so): test infrastructure only, see emu/cuda_runtime.h.
 #include "graph.cuh"
-#include "spmv.cuh"
+#include "spmv_hot_x.cuh"
+
+#include <algorithm>
+#include <vector>
 
 namespace b200 {
 void free_mg_graph(graph_impl*) {}
@@ -70,3 +73,75 @@ EMU_EXPORT int emu_low_ell_sweep(const cugraph_resource_handle_t* handle, cugrap
   launch_low_rows_ell<float>(h, c, *E, x, y, alpha, &st);
   return 0;
 }
+
+// Functional model of k_spmv_blocked / k_spmv_blocked_x on the piece layout: the kernels' own per-lane device functions
+// (hot_run_groups, hot_run_groups_c1, hot_run_groups_narrow, hot_slot_sum, hot_emit) called lane by lane, units in order,
+// groups dealt to the 32 warps exactly as in the kernels; the shared-memory slice is a host copy of x[b*W, b*W+W) + zeros.
+// acc[row] receives the fp64 sums of the degree >= 32 rows.  mode bit 0: use the four-groups-in-flight path for the
+// one-slot class (k_spmv_blocked_x); narrow classes are always routed as in k_spmv_blocked_x.
+template <typename T, bool WEIGHTED>
+static void model_blocked(hot_layout_t const& L, T const* x, double* acc, int mode)
+{
+  auto const* units = L.units.as<hot_unit_t>();
+  auto const* subs  = L.subs.as<hot_sub_t>();
+  auto const* seg_row = L.seg_row.as<int32_t>();
+  auto const* idx16 = L.slot_idx16.as<uint16_t>();
+  auto const* idx32 = L.slot_idx32.as<int32_t>();
+  auto const* idx_h = L.slot_idx_h.as<uint2>();
+  auto const* idx_q = L.slot_idx_q.as<uint32_t>();
+  T const* w        = L.slot_w.as<T>();
+  const int cold0   = (int)L.n_hot_slots;
+  std::vector<T> sx((size_t)L.W + kHotZeroPad);
+  int cur_block = -1;
+  for (int u = 0; u < L.n_units; ++u) {
+    const hot_unit_t un = units[u];
+    const bool hot      = un.block < L.B;
+    if (hot && un.block != cur_block) {
+      std::copy(x + (size_t)un.block * L.W, x + (size_t)un.block * L.W + L.W, sx.begin());
+      std::fill(sx.begin() + L.W, sx.end(), (T)0);
+      cur_block = un.block;
+    }
+    int dealt = 0;
+    for (int si = un.sub_begin; si < un.sub_end; ++si) {
+      const hot_sub_t sb = subs[si];
+      for (int warp = 0; warp < kHotWarps; ++warp) {
+        const int q0 = (warp - dealt) & (kHotWarps - 1);
+        for (int lane = 0; lane < 32; ++lane) {
+          if (sb.cls > 8) {
+            if (sb.cls == 16) hot_run_groups_narrow<T, 4>(sb, q0, lane, seg_row, idx_h, idx_q, sx.data(), acc);
+            else hot_run_groups_narrow<T, 2>(sb, q0, lane, seg_row, idx_h, idx_q, sx.data(), acc);
+          } else if ((mode & 1) && sb.cls == 1 && hot) {
+            hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold0, w, x, sx.data(), acc);
+          } else if (hot) {
+            hot_run_groups<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold0, w, x, sx.data(), acc);
+          } else {
+            hot_run_groups<T, WEIGHTED, false>(sb, q0, lane, seg_row, idx16, idx32, cold0, w, x, sx.data(), acc);
+          }
+        }
+      }
+      dealt += sb.n_groups;
+    }
+  }
+}
+
+EMU_EXPORT int emu_blocked_sweep(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, const float* x /* padded */,
+                                 double* acc /* n_hi */, int mode)
+{
+  auto const& h  = H(handle);
+  auto* g        = reinterpret_cast<graph_impl*>(graph);
+  csx_t const& c = *g->primary;
+  if (g->weighted && g->weight_type != FLOAT32) return 3;
+  hot_layout_t const* L = nullptr;
+  try {
+    L = hot_layout(h, c, g->n_vertices, 4);
+  } catch (std::exception const& e) {
+    std::fprintf(stderr, "emu_blocked_sweep: %s\n", e.what());
+    return 2;
+  }
+  if (!L) return 1;
+  if (L->slot_w.data()) model_blocked<float, true>(*L, x, acc, mode);
+  else model_blocked<float, false>(*L, x, acc, mode);
+  return 0;
+}
+
+EMU_EXPORT size_t emu_padded_x_elems(int32_t nv, size_t es) { return padded_x_elems(nv, es); }
