@@ -145,3 +145,37 @@ EMU_EXPORT int emu_blocked_sweep(const cugraph_resource_handle_t* handle, cugrap
 }
 
 EMU_EXPORT size_t emu_padded_x_elems(int32_t nv, size_t es) { return padded_x_elems(nv, es); }
+
+// model of k_spmv_low_ell_hot (spmv_hot.cuh): `grid` persistent CTAs of four virtual 256-thread blocks, gathers of the first
+// W sources served from a copy of x[0, W) (the kernel's shared-memory slice), the rest from x
+EMU_EXPORT int emu_low_ell_hot_sweep(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, const float* x /* padded */,
+                                     float* y, double alpha, double init, int grid)
+{
+  auto const& h  = H(handle);
+  auto* g        = reinterpret_cast<graph_impl*>(graph);
+  csx_t const& c = *g->primary;
+  if (g->weighted && g->weight_type != FLOAT32) return 3;
+  low_ell_t const* E = nullptr;
+  try {
+    E = low_ell_layout(h, c, 4);
+  } catch (std::exception const& e) {
+    std::fprintf(stderr, "emu_low_ell_hot_sweep: %s\n", e.what());
+    return 2;
+  }
+  if (!E) return 1;
+  const int W = (int)(kHotSliceBytes / sizeof(float)) - kHotZeroPad;
+  std::vector<float> sx(x, x + W);
+  gather_hot_t<float> gh{x, sx.data(), W};
+  low_ell_args_t a   = make_low_ell_args(*E);
+  const int n_vblock = a.block_begin[32];
+  for (int cta = 0; cta < grid; ++cta)
+    for (int sub = 0; sub < 4; ++sub)
+      for (int vb = cta * 4 + sub; vb < n_vblock; vb += grid * 4)
+        for (int vtid = 0; vtid < 256; ++vtid) {
+          if (E->w.data())
+            low_ell_block<float, true>(vb, vtid, E->idx.as<int32_t>(), E->w.as<float>(), gh, y, c.row_vertex.as<int32_t>(), a, alpha, init);
+          else
+            low_ell_block<float, false>(vb, vtid, E->idx.as<int32_t>(), E->w.as<float>(), gh, y, c.row_vertex.as<int32_t>(), a, alpha, init);
+        }
+  return 0;
+}

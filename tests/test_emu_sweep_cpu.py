@@ -59,3 +59,31 @@ def test_blocked_sweep_model(emu, monkeypatch, name, env, weighted, mode):  # no
     acc = run_model(emu, g, P, x, mode)
     np.testing.assert_allclose(acc[:P["seg"][0]], expected(P, x), rtol=1e-12, atol=0)
     emu.cugraph_graph_free(g)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_low_ell_hot_model(emu, monkeypatch, weighted):  # noqa: F811
+    """k_spmv_low_ell_hot's loop structure and its shared-memory / global gather split"""
+    monkeypatch.setenv("CUGRAPH_B200_LOW_ELL", "2")
+    src, dst, w = make_edges(140_000, 500_000, seed=77 + weighted, weighted=weighted)
+    g = create_graph(emu, src, dst, w)
+    P = primary(emu, g)
+    nv, n_hi = P["nv"], P["seg"][0]
+    assert nv > 49088                      # sources on both sides of the shared-memory slice
+    emu.emu_padded_x_elems.restype = C.c_size_t
+    emu.emu_padded_x_elems.argtypes = [C.c_int32, C.c_size_t]
+    emu.emu_low_ell_hot_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int]
+    xp = np.zeros(emu.emu_padded_x_elems(nv, 4), dtype=np.float32)
+    xp[:nv] = np.random.default_rng(4).random(nv).astype(np.float32)
+    y = np.full(nv, -3.0, dtype=np.float32)
+    rc = emu.emu_low_ell_hot_sweep(C.c_void_p(emu.handle), g, xp.ctypes.data, y.ctypes.data, 0.85, 0.25, 7)
+    assert rc == 0
+    deg = np.diff(P["off"])
+    rows = np.repeat(np.arange(P["n_rows"]), deg)
+    vals = xp[P["idx"]]
+    if weighted:
+        vals = vals * P["w"]
+    exp = np.bincount(rows, weights=vals.astype(np.float64), minlength=P["n_rows"]) * 0.85 + 0.25
+    assert (y[:n_hi] == -3.0).all()
+    np.testing.assert_allclose(y[n_hi:], exp[n_hi:].astype(np.float32), rtol=2e-6, atol=0)
+    emu.cugraph_graph_free(g)
