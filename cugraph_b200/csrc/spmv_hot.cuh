@@ -72,13 +72,25 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p)
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-#else  // host emulation of the per-lane gather / accumulate code (emu/, tests/test_emu_sweep_cpu.py)
+#else  // host emulation (emu/cuda_runtime.h): a bulk copy is a memcpy by the issuing thread, waiting on the mbarrier is a
+       // CTA barrier (every thread of the CTA waits on it in these kernels)
+inline void mbar_init(uint64_t*, unsigned) {}
+inline void mbar_expect_tx(uint64_t*, unsigned) {}
+inline void mbar_wait(uint64_t*, unsigned) { __syncthreads(); }
+inline void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t*) { std::memcpy(dst_smem, src_gmem, bytes); }
 inline uint4 ld_stream_v4(const void* p)
 {
   uint4 v;
   std::memcpy(&v, p, sizeof(v));
   return v;
 }
+#endif
+
+// the dynamic shared memory of a kernel
+#ifndef B200_HOST_EMU
+#define B200_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#else
+#define B200_DYN_SMEM(name) extern unsigned char name[]  /* one CTA at a time: emu/emu_debug.cpp defines b200::smem_raw */
 #endif
 
 // consecutive groups of one class (mirrored by hot_sub_host_t, graph_build.cu)
@@ -150,10 +162,11 @@ __device__ __forceinline__ double hot_slot_sum(slot_ids_t const& ids, int s, T c
 template <bool SAME_ROW_RUNS>
 __device__ __forceinline__ void hot_emit(double acc, int row, double* __restrict__ acc_hi, int lane)
 {
-#ifdef B200_HOST_EMU  // lanes run one after the other: the shuffle reduction below is only an optimisation of this
-  (void)lane;
-  if (row >= 0) atomicAdd(acc_hi + row, acc);
-  return;
+#ifdef B200_HOST_EMU  // called lane by lane outside a launch (emu_debug.cpp: model_blocked): no warp to reduce with
+  if (!emu::in_fiber()) {
+    if (row >= 0) atomicAdd(acc_hi + row, acc);
+    return;
+  }
 #endif
   if (SAME_ROW_RUNS) {
     const int r0 = __shfl_sync(0xffffffffu, row, 0);
@@ -215,13 +228,16 @@ __device__ __forceinline__ void hot_run_groups(hot_sub_t const sb, int q, int la
   }
 }
 
-#ifndef B200_HOST_EMU  // kernels and launchers: CUDA only
+#ifndef B200_HOST_EMU
 __device__ __forceinline__ int ld_volatile(const int* p)
 {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+#else
+inline int ld_volatile(const int* p) { return *p; }
+#endif
 
 // next unit for this CTA (called by all lanes of warp 0): own range first, then the ranges of the
 // following CTAs.  victim_off = how many ranges (starting with the own one) are known to be exhausted.
@@ -263,7 +279,7 @@ k_spmv_blocked(hot_unit_t const* __restrict__ units, int n_units, int* __restric
                int32_t const* __restrict__ idx32, int cold_slot0, T const* __restrict__ w,
                T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, pr_state_t const* __restrict__ st)
 {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  B200_DYN_SMEM(smem_raw);
   T* sx = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
   __shared__ int s_next;
@@ -337,7 +353,7 @@ k_spmv_low_ell_hot(int32_t const* __restrict__ ell, T const* __restrict__ ellw, 
                    int32_t const* __restrict__ row_vertex, low_ell_args_t L, int W, double alpha,
                    pr_state_t const* __restrict__ st)
 {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  B200_DYN_SMEM(smem_raw);
   T* sx = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
   if (st->done) return;
@@ -448,7 +464,6 @@ void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_
 }
 
 // (the dispatcher launch_pull_sweep_auto lives in spmv_hot_x.cuh, next to the experimental kernel variant)
-#endif  // !B200_HOST_EMU
 
 // elements an x buffer needs: whole slices are TMA-copied and x[n_vertices] must be a readable zero.
 // The buffer must be zero-filled once at allocation; only [0, n_vertices) is ever written afterwards.

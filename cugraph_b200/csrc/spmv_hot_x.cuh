@@ -106,7 +106,6 @@ __device__ __forceinline__ void hot_run_groups_narrow(hot_sub_t const sb, int q,
   }
 }
 
-#ifndef B200_HOST_EMU  // kernel and launchers: CUDA only
 // next units for this CTA (called by all lanes of warp 0): own range first — `claim` consecutive units per
 // atomic, they are processed without a CTA barrier in between — then single units of the following CTAs'
 // ranges.  victim_off = how many ranges (starting with the own one) are known to be exhausted.
@@ -159,7 +158,7 @@ k_spmv_blocked_x(hot_unit_t const* __restrict__ units, int n_units, int* __restr
                int claim, uint2 const* __restrict__ idx_h, uint32_t const* __restrict__ idx_q,
                pr_state_t const* __restrict__ st)
 {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  B200_DYN_SMEM(smem_raw);
   T* sx = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
   __shared__ int s_next, s_count;
@@ -293,6 +292,5 @@ void launch_pull_sweep_auto(handle_impl const& h, csx_t const& c, int32_t n_vert
   else if (L->narrow || hot_x_enabled()) launch_pull_sweep_blocked_x<O, T>(h, c, *L, x, y, acc_hi, alpha, st);
   else launch_pull_sweep_blocked<O, T>(h, c, *L, x, y, acc_hi, alpha, st);
 }
-#endif  // !B200_HOST_EMU
 
 }  // namespace b200

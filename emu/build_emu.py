@@ -1,5 +1,5 @@
-"""Build cugraph_b200/lib/libcugraph_c_emu.so: graph staging (capi_basic.cu, capi_graph.cu, graph_build.cu) compiled as
-plain C++ against the host emulation shim in emu/ — test infrastructure for tests/test_emu_staging_cpu.py."""
+"""Build cugraph_b200/lib/libcugraph_c_emu.so: the single-GPU sources (staging, PageRank, BFS/SSSP) compiled as plain C++
+against the host emulation shim in emu/ — test infrastructure for tests/test_emu_*_cpu.py."""
 import os
 import subprocess
 import sys
@@ -7,7 +7,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "cugraph_b200", "csrc")
 OUT = os.path.join(ROOT, "cugraph_b200", "lib", "libcugraph_c_emu.so")
-SRCS = [os.path.join(CSRC, f) for f in ("capi_basic.cu", "capi_graph.cu", "graph_build.cu")] + [os.path.join(ROOT, "emu", "emu_debug.cpp")]
+SRCS = [os.path.join(CSRC, f) for f in ("capi_basic.cu", "capi_graph.cu", "graph_build.cu", "pagerank.cu", "traverse.cu")] + \
+    [os.path.join(ROOT, "emu", "emu_debug.cpp")]
 
 
 def build(force=False):

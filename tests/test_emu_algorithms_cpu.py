@@ -1,0 +1,172 @@
+"""PageRank, BFS and SSSP on the CPU: the single-GPU sources (pagerank.cu, traverse.cu, spmv*.cuh, graph_build.cu) compiled
+as plain C++ against the SIMT emulation in emu/ (threads of a CTA are fibers; warp collectives and __syncthreads are
+real rendezvous points; TMA copies are memcpys) and called through the C ABI with numpy arrays — kernel LOGIC (work
+distribution, stealing, segmented reductions, frontier queues, device-resident loop state) checked against the oracle
+without a GPU.  Performance, memory-model and scheduling effects are of course only visible on the GPU (`-m gpu`)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.test_emu_staging_cpu import FLOAT32, INT32, Props, create_graph, emu, make_edges  # noqa: F401
+
+
+def _view_to_np(L, view):
+    L.cugraph_type_erased_device_array_view_size.restype = C.c_size_t
+    L.cugraph_type_erased_device_array_view_size.argtypes = [C.c_void_p]
+    L.cugraph_type_erased_device_array_view_type.restype = C.c_int
+    L.cugraph_type_erased_device_array_view_type.argtypes = [C.c_void_p]
+    L.cugraph_type_erased_device_array_view_pointer.restype = C.c_void_p
+    L.cugraph_type_erased_device_array_view_pointer.argtypes = [C.c_void_p]
+    n = L.cugraph_type_erased_device_array_view_size(view)
+    t = L.cugraph_type_erased_device_array_view_type(view)
+    dt = {2: np.int32, 3: np.int64, 8: np.float32, 9: np.float64}[t]
+    p = L.cugraph_type_erased_device_array_view_pointer(view)
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy() if n else np.zeros(0, dt)
+    L.cugraph_type_erased_device_array_view_free(C.c_void_p(view))
+    return out
+
+
+def run_pagerank(L, g, alpha, eps, max_it):
+    res, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_pagerank_allow_nonconvergence(C.c_void_p(L.handle), g, None, None, None, None, C.c_double(alpha),
+                                                   C.c_double(eps), C.c_size_t(max_it), 0, C.byref(res), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    for f in ("cugraph_centrality_result_get_vertices", "cugraph_centrality_result_get_values"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.cugraph_centrality_result_get_num_iterations.restype = C.c_size_t
+    L.cugraph_centrality_result_get_num_iterations.argtypes = [C.c_void_p]
+    L.cugraph_centrality_result_free.argtypes = [C.c_void_p]
+    v = _view_to_np(L, L.cugraph_centrality_result_get_vertices(res))
+    p = _view_to_np(L, L.cugraph_centrality_result_get_values(res))
+    it = L.cugraph_centrality_result_get_num_iterations(res)
+    L.cugraph_centrality_result_free(res)
+    return v, p, int(it)
+
+
+def dense_ids(src, dst):
+    ids, inv = np.unique(np.concatenate([src, dst]), return_inverse=True)
+    return ids, inv[:src.size].astype(np.int32), inv[src.size:].astype(np.int32)
+
+
+PR_CASES = [("plain sweep", "1000000000", False), ("blocked sweep", "0", False), ("blocked sweep weighted", "0", True)]
+
+
+@pytest.mark.parametrize("name,min_edges,weighted", PR_CASES, ids=[c[0] for c in PR_CASES])
+def test_pagerank_emulated(emu, monkeypatch, name, min_edges, weighted):  # noqa: F811
+    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", min_edges)
+    src, dst, w = make_edges(60_000, 250_000, seed=41, weighted=weighted, id_offset=5)
+    g = create_graph(emu, src, dst, w)
+    verts, pr, it = run_pagerank(emu, g, 0.85, 0.0, 20)             # equal iteration counts: the parity protocol
+    ids, s, d = dense_ids(src, dst)
+    ref, ref_it, _ = oracle.pagerank(s, d, ids.size, None if w is None else w.astype(np.float64), alpha=0.85, epsilon=0.0,
+                                     max_iterations=20)
+    assert it == ref_it == 20
+    got = np.zeros(ids.size)
+    got[np.searchsorted(ids, verts)] = pr
+    np.testing.assert_allclose(got, ref, rtol=2e-5 if weighted else 1e-5, atol=0)
+    assert abs(got.sum() - 1.0) < 1e-5
+    emu.cugraph_graph_free(g)
+
+
+def test_pagerank_emulated_experimental_kernel(emu, monkeypatch):  # noqa: F811
+    """k_spmv_blocked_x with multi-unit claims and tiny units: own range, then stealing (CTA 0 drains every range)"""
+    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_HOT_X", "1")
+    monkeypatch.setenv("CUGRAPH_B200_HOT_NARROW", "1")
+    monkeypatch.setenv("CUGRAPH_B200_HOT_CLAIM", "3")
+    monkeypatch.setenv("CUGRAPH_B200_HOT_UNIT_SLOTS", "1024")
+    monkeypatch.setenv("CUGRAPH_B200_LOW_ELL", "2")
+    src, dst, w = make_edges(70_000, 250_000, seed=43)
+    g = create_graph(emu, src, dst, w)
+    verts, pr, it = run_pagerank(emu, g, 0.85, 0.0, 6)
+    ids, s, d = dense_ids(src, dst)
+    ref, _, _ = oracle.pagerank(s, d, ids.size, None, alpha=0.85, epsilon=0.0, max_iterations=6)
+    got = np.zeros(ids.size)
+    got[np.searchsorted(ids, verts)] = pr
+    assert it == 6
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=0)
+    emu.cugraph_graph_free(g)
+
+
+def _paths(L, res):
+    for f in ("cugraph_paths_result_get_vertices", "cugraph_paths_result_get_distances", "cugraph_paths_result_get_predecessors"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.cugraph_paths_result_free.argtypes = [C.c_void_p]
+    v = _view_to_np(L, L.cugraph_paths_result_get_vertices(res))
+    dist = _view_to_np(L, L.cugraph_paths_result_get_distances(res))
+    pred = _view_to_np(L, L.cugraph_paths_result_get_predecessors(res))
+    L.cugraph_paths_result_free(res)
+    return v, dist, pred
+
+
+def symmetric_edges(V, E, seed):
+    src, dst, _ = make_edges(V, E, seed)
+    s = np.concatenate([src, dst]).astype(np.int32)
+    d = np.concatenate([dst, src]).astype(np.int32)
+    return s, d
+
+
+def create_sym_graph(L, s, d, w):
+    views = [L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, t) if a is not None else None
+             for a, t in ((s, INT32), (d, INT32), (w, FLOAT32))]
+    g, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_graph_create_with_times_sg(
+        C.c_void_p(L.handle), C.byref(Props(1, 1)), None, C.c_void_p(views[0]), C.c_void_p(views[1]),
+        C.c_void_p(views[2]) if views[2] else None, None, None, None, None, 0, 1, 0, 0, 0, 0, C.byref(g), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    for v in views:
+        if v:
+            L.cugraph_type_erased_device_array_view_free(v)
+    return g
+
+
+@pytest.mark.parametrize("direction_optimizing", [0, 1])
+def test_bfs_emulated(emu, direction_optimizing):  # noqa: F811
+    s, d = symmetric_edges(20_000, 120_000, seed=51)
+    g = create_sym_graph(emu, s, d, None)
+    ids, ss, dd = dense_ids(s, d)
+    source = int(ids[np.bincount(ss).argmax()])                   # a hub: the bottom-up switch triggers
+    srcs = np.array([source], dtype=np.int32)
+    sv = emu.cugraph_type_erased_device_array_view_create(srcs.ctypes.data, 1, INT32)
+    res, err = C.c_void_p(), C.c_void_p()
+    code = emu.cugraph_bfs(C.c_void_p(emu.handle), g, C.c_void_p(sv), direction_optimizing, C.c_size_t(2**31 - 2), 1, 0,
+                           C.byref(res), C.byref(err))
+    assert code == 0, emu.cugraph_error_message(err)
+    verts, dist, pred = _paths(emu, res)
+    ref_d, _ = oracle.bfs(ss, dd, ids.size, [int(np.searchsorted(ids, source))])
+    got = np.zeros(ids.size, dtype=np.int64)
+    got[np.searchsorted(ids, verts)] = dist
+    unreached = ref_d < 0 if (ref_d < 0).any() else ref_d == np.iinfo(ref_d.dtype).max
+    assert (got[~unreached] == ref_d[~unreached]).all()
+    assert (got[unreached] == np.iinfo(np.int32).max).all()
+    gp = np.zeros(ids.size, dtype=np.int64)
+    gp[np.searchsorted(ids, verts)] = pred
+    has = (~unreached) & (got > 0)
+    pidx = np.searchsorted(ids, gp[has])
+    assert (got[pidx] + 1 == got[has]).all()                      # every predecessor is one level closer
+    emu.cugraph_graph_free(g)
+
+
+def test_sssp_emulated(emu):  # noqa: F811
+    s, d = symmetric_edges(15_000, 90_000, seed=61)
+    r = np.random.default_rng(8)
+    half = s.size // 2
+    wh = (r.random(half).astype(np.float32) + 0.01)
+    w = np.concatenate([wh, wh])                                   # symmetric weights
+    g = create_sym_graph(emu, s, d, w)
+    ids, ss, dd = dense_ids(s, d)
+    source = int(ids[7])
+    res, err = C.c_void_p(), C.c_void_p()
+    emu.cugraph_sssp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    code = emu.cugraph_sssp(C.c_void_p(emu.handle), g, source, float("inf"), 1, 0, C.byref(res), C.byref(err))
+    assert code == 0, emu.cugraph_error_message(err)
+    verts, dist, pred = _paths(emu, res)
+    ref_d, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=True)
+    got = np.zeros(ids.size, dtype=np.float32)
+    got[np.searchsorted(ids, verts)] = dist
+    assert (got == ref_d.astype(np.float32)).all()                 # bit-exact in float, unreached = FLT_MAX on both sides
+    emu.cugraph_graph_free(g)
