@@ -92,31 +92,40 @@ __device__ __forceinline__ int upper_bound_minus1(int32_t const* a, int n, int k
   return lo - 1;
 }
 
+// first and last queue entry of every tile: two binary searches per tile, all tiles in parallel (the merge-path
+// partition).  Done inside k_advance by thread 0 of every CTA they were 2 x log2(n) dependent global loads that the
+// other 255 threads waited for, tile after tile.
+__global__ void k_tile_owners(int32_t const* __restrict__ scan, int n_frontier, int n_tiles, int2* __restrict__ tile_k)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int total = scan[n_frontier];
+  const int e0    = t * kTileEdges;
+  const int e1    = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
+  tile_k[t]       = make_int2(upper_bound_minus1(scan, n_frontier, e0), upper_bound_minus1(scan, n_frontier, e1 - 1));
+}
+
 // IDENT: the queue is the identity (vertex k is queue entry k) and `scan` are the row offsets themselves
 template <typename O, typename Op, bool IDENT>
 __global__ void __launch_bounds__(kBlock)
 k_advance(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ frontier,
-          int n_frontier, int32_t const* __restrict__ scan /* n_frontier + 1 */, Op op)
+          int n_frontier, int32_t const* __restrict__ scan /* n_frontier + 1 */, int2 const* __restrict__ tile_k, int n_tiles,
+          Op op)
 {
   __shared__ int s_scan[kTileVerts + 1];
   __shared__ int s_owner[kTileEdges];
   __shared__ int s_warp[kBlock / 32];
-  __shared__ int s_k0, s_k1;
   constexpr int kPer = kTileEdges / kBlock;  // consecutive slots per thread in the owner fill
   const int total    = scan[n_frontier];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int tile = blockIdx.x; (long long)tile * kTileEdges < total; tile += gridDim.x) {
-    const int e0 = tile * kTileEdges;
-    const int e1 = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
-    if (threadIdx.x == 0) {
-      s_k0 = upper_bound_minus1(scan, n_frontier, e0);
-      s_k1 = upper_bound_minus1(scan, n_frontier, e1 - 1);
-    }
-    for (int i = threadIdx.x; i < kTileEdges; i += kBlock) s_owner[i] = -1;
-    __syncthreads();
-    const int k0 = s_k0, k1 = s_k1;
+  for (int tile = blockIdx.x; tile < n_tiles && (long long)tile * kTileEdges < total; tile += gridDim.x) {
+    const int e0  = tile * kTileEdges;
+    const int e1  = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
+    const int2 kk = tile_k[tile];
+    const int k0 = kk.x, k1 = kk.y;
     const int nv = k1 - k0 + 1;
     const bool staged = nv <= kTileVerts;
+    for (int i = threadIdx.x; i < kTileEdges; i += kBlock) s_owner[i] = -1;
     if (staged)
       for (int i = threadIdx.x; i <= nv; i += kBlock) s_scan[i] = scan[k0 + i];
     __syncthreads();
@@ -186,8 +195,11 @@ void advance(handle_impl const& h, advance_scratch_t& sc, O const* off, int32_t 
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(sc.tmp.data(), sc.tmp_bytes, sc.deg.as<int32_t>(), sc.scan.as<int32_t>(), n + 1, h.stream));
   h.launches += 2;
   if (total_edges == 0) return;
-  int grid = (int)std::min<unsigned long long>((total_edges + kTileEdges - 1) / kTileEdges, (unsigned long long)h.sm_count * 8);
-  B200_LAUNCH(h, (k_advance<O, Op, false>), grid, kBlock, 0, off, idx, queue, n, sc.scan.as<int32_t>(), op);
+  const int n_tiles = (int)((total_edges + kTileEdges - 1) / kTileEdges);
+  dbuf tile_k       = make_dbuf<int2>((size_t)n_tiles, h.stream);
+  B200_LAUNCH(h, k_tile_owners, (n_tiles + kBlock - 1) / kBlock, kBlock, 0, sc.scan.as<int32_t>(), n, n_tiles, tile_k.as<int2>());
+  int grid = (int)std::min<unsigned long long>((unsigned long long)n_tiles, (unsigned long long)h.sm_count * 8);
+  B200_LAUNCH(h, (k_advance<O, Op, false>), grid, kBlock, 0, off, idx, queue, n, sc.scan.as<int32_t>(), tile_k.as<int2>(), n_tiles, op);
 }
 
 // every edge of the graph, edge-balanced: the row offsets are the scan of the identity queue
@@ -195,8 +207,12 @@ template <typename Op>
 void advance_all_edges(handle_impl const& h, int32_t const* off, int32_t const* idx, int32_t n_vertices, long long nnz, Op op)
 {
   if (nnz <= 0) return;
-  int grid = (int)std::min<long long>((nnz + kTileEdges - 1) / kTileEdges, (long long)h.sm_count * 8);
-  B200_LAUNCH(h, (k_advance<int32_t, Op, true>), grid, kBlock, 0, off, idx, (int32_t const*)nullptr, n_vertices, off, op);
+  const int n_tiles = (int)((nnz + kTileEdges - 1) / kTileEdges);
+  dbuf tile_k       = make_dbuf<int2>((size_t)n_tiles, h.stream);
+  B200_LAUNCH(h, k_tile_owners, (n_tiles + kBlock - 1) / kBlock, kBlock, 0, off, n_vertices, n_tiles, tile_k.as<int2>());
+  int grid = (int)std::min<long long>((long long)n_tiles, (long long)h.sm_count * 8);
+  B200_LAUNCH(h, (k_advance<int32_t, Op, true>), grid, kBlock, 0, off, idx, (int32_t const*)nullptr, n_vertices, off,
+              tile_k.as<int2>(), n_tiles, op);
 }
 
 // ------------------------------------------------------------------------------------------

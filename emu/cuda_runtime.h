@@ -27,6 +27,8 @@ struct dim3 {
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct uint2 { unsigned x, y; };
+struct int2 { int x, y; };
+inline int2 make_int2(int a, int b) { return {a, b}; }
 struct uint4 { unsigned x, y, z, w; };
 struct int4 { int x, y, z, w; };
 inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
