@@ -6,12 +6,6 @@
 #include <vector>
 
 namespace b200 {
-void free_mg_graph(graph_impl*) {}
-void attach_comm(handle_impl*, void*) {}
-void mg_pagerank(handle_impl const&, graph_impl&, mg_pr_args const&, centrality_result_impl&)
-{
-  throw capi_exception(CUGRAPH_NOT_IMPLEMENTED, "multi-GPU is not part of the emulation build");
-}
 alignas(128) unsigned char smem_raw[256 * 1024];  // the dynamic shared memory of the one CTA that runs at a time
 }  // namespace b200
 

@@ -4,7 +4,7 @@
 #   bash emu/run_asan.sh [fuzz seconds]
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd); CSRC=$ROOT/cugraph_b200/csrc; OUT=/tmp/libcugraph_c_emu_asan.so
-SRCS=""; for f in capi_basic.cu capi_graph.cu graph_build.cu pagerank.cu traverse.cu; do SRCS="$SRCS -x c++ $CSRC/$f"; done
+SRCS=""; for f in capi_basic.cu capi_graph.cu graph_build.cu pagerank.cu traverse.cu mg.cu; do SRCS="$SRCS -x c++ $CSRC/$f"; done
 /usr/bin/g++ -std=c++17 -O1 -g -fPIC -shared -fvisibility=hidden -DB200_HOST_EMU -fsanitize=address -fno-omit-frame-pointer \
   -I $ROOT/emu -I $ROOT/include -I $CSRC -Wno-attributes $SRCS -x c++ $ROOT/emu/emu_debug.cpp -o $OUT
 export LD_PRELOAD=$(gcc -print-file-name=libasan.so)
@@ -16,6 +16,6 @@ sys.path.insert(0, "$ROOT"); sys.path.insert(0, "$ROOT/emu")
 import build_emu
 build_emu.build = lambda force=False: "$OUT"
 import pytest
-sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "tests/test_emu_staging_cpu.py", "tests/test_emu_sweep_cpu.py", "tests/test_emu_algorithms_cpu.py"]))
+sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "tests/test_emu_staging_cpu.py", "tests/test_emu_sweep_cpu.py", "tests/test_emu_algorithms_cpu.py", "tests/test_emu_mg_cpu.py"]))
 PY
 python emu/fuzz.py ${1:-120} $OUT
