@@ -1306,7 +1306,8 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
     std::vector<int32_t> hlen(n_pieces), hperm(n_pieces);
     CUDA_TRY(cudaMemcpy(hlen.data(), piece_len.data(), sizeof(int32_t) * n_pieces, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(hperm.data(), perm2.data(), sizeof(int32_t) * n_pieces, cudaMemcpyDeviceToHost));
-    const int edges[] = {0, 1, 4, 16, 64, 160, 250, B, B + 1};
+    int edges[] = {0, 1, 4, 16, 64, 160, 250, B, B + 1};
+    for (int k = 0; k < 7; ++k) edges[k] = std::min(edges[k], B);  // ranges of hot blocks, then the cold block [B, B+1)
     std::fprintf(stderr, "[hot] B=%d W=%d n_hi=%d nnz_hi=%lld segments=%d pieces=%d\n", B, W, n_hi, (long long)nnz, n_segs, n_pieces);
     for (int k = 0; k + 1 < 9; ++k) {
       const int b0 = std::min(edges[k], B + 1), b1 = std::min(edges[k + 1], B + 1);
@@ -1316,7 +1317,7 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
         for (int p = cstart[key]; p < cstart[key + 1]; ++p) {
           const int ln = hlen[hperm[p]];
           entries += ln;
-          by_cls[std::min(8, narrow ? std::max(1, key % kinds - 1) : key % kinds + 1)]++;
+          by_cls[(ln + 7) / 8]++;
           if (ln <= 8) by_len[ln]++;
         }
       std::fprintf(stderr, "[hot] blocks [%d,%d)%s entries %lld  pieces by slots:", b0, b1, b1 == B + 1 && b0 == B ? " (cold)" : "", entries);

@@ -178,3 +178,15 @@ EMU_EXPORT int emu_low_ell_hot_sweep(const cugraph_resource_handle_t* handle, cu
         }
   return 0;
 }
+
+// forget the cached layouts of the primary orientation (so that another set of CUGRAPH_B200_* switches can be staged)
+EMU_EXPORT void emu_reset_layouts(cugraph_graph_t* graph)
+{
+  auto* g        = reinterpret_cast<graph_impl*>(graph);
+  csx_t const& c = *g->primary;
+  c.hot4.reset();
+  c.hot8.reset();
+  c.hot4_tried = c.hot8_tried = false;
+  c.low_ell.reset();
+  c.low_ell_tried = false;
+}

@@ -1,0 +1,57 @@
+"""Piece-layout statistics of an RMAT graph on the CPU (emulated staging, CUGRAPH_B200_BUILD_TRACE output): pieces per class
+and per range of blocks, slot counts and bytes, for the default and the narrow layout.   python emu/layout_stats.py [scale]"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "emu"))
+import build_emu  # noqa: E402
+from oracle.rmat import rmat_edgelist  # noqa: E402
+
+scale = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+L = C.CDLL(build_emu.build())
+L.cugraph_create_resource_handle.restype = C.c_void_p
+L.cugraph_create_resource_handle.argtypes = [C.c_void_p]
+L.cugraph_type_erased_device_array_view_create.restype = C.c_void_p
+L.cugraph_type_erased_device_array_view_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+L.cugraph_error_message.restype = C.c_char_p
+L.cugraph_error_message.argtypes = [C.c_void_p]
+L.emu_hot_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+L.emu_reset_layouts.argtypes = [C.c_void_p]
+H = C.c_void_p(L.cugraph_create_resource_handle(None))
+
+
+class Props(C.Structure):
+    _fields_ = [("is_symmetric", C.c_int), ("is_multigraph", C.c_int)]
+
+
+t0 = time.time()
+src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
+src, dst = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)
+print(f"rmat scale {scale}: {src.size} edges in {time.time() - t0:.1f} s", flush=True)
+vs = C.c_void_p(L.cugraph_type_erased_device_array_view_create(src.ctypes.data, src.size, 2))
+vd = C.c_void_p(L.cugraph_type_erased_device_array_view_create(dst.ctypes.data, dst.size, 2))
+g, err = C.c_void_p(), C.c_void_p()
+t0 = time.time()
+code = L.cugraph_graph_create_with_times_sg(H, C.byref(Props(0, 1)), None, vs, vd, None, None, None, None, None, 1, 1, 0, 0, 0, 0,
+                                            C.byref(g), C.byref(err))
+assert code == 0, L.cugraph_error_message(err)
+print(f"emulated staging {time.time() - t0:.1f} s", flush=True)
+os.environ["CUGRAPH_B200_HOT_MIN_EDGES"] = "0"
+os.environ["CUGRAPH_B200_BUILD_TRACE"] = "1"
+for narrow in ("0", "1"):
+    os.environ["CUGRAPH_B200_HOT_NARROW"] = narrow
+    L.emu_reset_layouts(g)
+    ints = (C.c_int64 * 12)()
+    ptrs = (C.c_void_p * 10)()
+    t0 = time.time()
+    sys.stderr.write(f"---- CUGRAPH_B200_HOT_NARROW={narrow}\n")
+    sys.stderr.flush()
+    rc = L.emu_hot_layout(H, g, ints, ptrs)
+    print(f"narrow={narrow}: rc={rc} W={ints[0]} B={ints[1]} n_hi={ints[2]} nnz_hi={ints[3]} hot slots={ints[4]} slots={ints[5]} "
+          f"subs={ints[6]} units={ints[7]} ({time.time() - t0:.1f} s)", flush=True)
