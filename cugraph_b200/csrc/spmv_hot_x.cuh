@@ -73,13 +73,13 @@ __device__ __forceinline__ T hot_gather16(unsigned pair, T const* __restrict__ s
   return *reinterpret_cast<const T*>(reinterpret_cast<const char*>(sx) + off * (sizeof(T) / 4));
 }
 
-// narrow classes (hot blocks, unweighted): one step per group, WIDTH = 2 or 4 ids per lane slot; four groups in flight
+// narrow classes (hot blocks, unweighted): one step per group, WIDTH = 2 or 4 ids per lane slot; 8 / 4 groups in flight
 template <typename T, int WIDTH>
 __device__ __forceinline__ void hot_run_groups_narrow(hot_sub_t const sb, int q, int lane, int32_t const* __restrict__ seg_row,
                                                       uint2 const* __restrict__ idx_h, uint32_t const* __restrict__ idx_q,
                                                       T const* __restrict__ sx, double* __restrict__ acc_hi)
 {
-  constexpr int K = 4;
+  constexpr int K = WIDTH == 2 ? 8 : 4;  // groups in flight: a quarter slot costs one id register per group
   for (; q < sb.n_groups; q += 32 * K) {
     uint2 ids[K];
     int row[K];
