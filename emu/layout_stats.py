@@ -42,6 +42,27 @@ code = L.cugraph_graph_create_with_times_sg(H, C.byref(Props(0, 1)), None, vs, v
                                             C.byref(g), C.byref(err))
 assert code == 0, L.cugraph_error_message(err)
 print(f"emulated staging {time.time() - t0:.1f} s", flush=True)
+# ---- the degree < 32 rows: rows / entries per degree, and how many of their sources fall into the first column blocks
+L.emu_graph_primary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+ints8 = (C.c_int64 * 8)()
+seg = (C.c_int32 * 8)()
+ptrs5 = (C.c_void_p * 5)()
+L.emu_graph_primary(g, ints8, seg, ptrs5)
+n_rows, nnz = int(ints8[0]), int(ints8[1])
+off = np.ctypeslib.as_array(C.cast(ptrs5[0], C.POINTER(C.c_int32)), shape=(n_rows + 1,))
+idx = np.ctypeslib.as_array(C.cast(ptrs5[1], C.POINTER(C.c_int32)), shape=(nnz,))
+n_hi = int(seg[0])
+deg = np.diff(off)
+low_idx = idx[off[n_hi]:]
+print(f"rows {n_rows}, degree>=32 rows {n_hi} with {int(off[n_hi])} entries; degree<32 rows hold {low_idx.size} entries", flush=True)
+hist = np.bincount(deg[n_hi:], minlength=32)
+print("degree<32 rows per degree 0..31:", hist.tolist(), flush=True)
+W = 49088
+for k in (1, 2, 4, 16, 64):
+    print(f"  sources of degree<32 rows inside the first {k} column block(s): {100.0 * (low_idx < k * W).mean():.1f} %", flush=True)
+hi_idx = idx[:off[n_hi]]
+for k in (1, 2, 4, 16, 64):
+    print(f"  sources of degree>=32 rows inside the first {k} column block(s): {100.0 * (hi_idx < k * W).mean():.1f} %", flush=True)
 os.environ["CUGRAPH_B200_HOT_MIN_EDGES"] = "0"
 os.environ["CUGRAPH_B200_BUILD_TRACE"] = "1"
 for narrow in ("0", "1"):
