@@ -91,6 +91,31 @@ def test_pagerank_emulated_experimental_kernel(emu, monkeypatch):  # noqa: F811
     emu.cugraph_graph_free(g)
 
 
+@pytest.mark.parametrize("hot_x", ["0", "1"])
+def test_pagerank_emulated_double_weights(emu, monkeypatch, hot_x):  # noqa: F811
+    """fp64 graphs: 24,512 columns per shared-memory slice, several blocks, base and experimental kernel"""
+    from tests.test_emu_staging_cpu import FLOAT64
+    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_HOT_X", hot_x)
+    src, dst, w32 = make_edges(80_000, 300_000, seed=47, weighted=True)
+    w = w32.astype(np.float64) * 1.000000123
+    L = emu
+    views = [L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, t) for a, t in ((src, INT32), (dst, INT32), (w, FLOAT64))]
+    g, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_graph_create_with_times_sg(C.c_void_p(L.handle), C.byref(Props(0, 1)), None, C.c_void_p(views[0]),
+                                                C.c_void_p(views[1]), C.c_void_p(views[2]), None, None, None, None, 1, 1, 0, 0, 0, 0,
+                                                C.byref(g), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    verts, pr, it = run_pagerank(L, g, 0.85, 0.0, 12)
+    assert pr.dtype == np.float64
+    ids, s, d = dense_ids(src, dst)
+    ref, _, _ = oracle.pagerank(s, d, ids.size, w, alpha=0.85, epsilon=0.0, max_iterations=12)
+    got = np.zeros(ids.size)
+    got[np.searchsorted(ids, verts)] = pr
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
+    L.cugraph_graph_free(g)
+
+
 def _paths(L, res):
     for f in ("cugraph_paths_result_get_vertices", "cugraph_paths_result_get_distances", "cugraph_paths_result_get_predecessors"):
         getattr(L, f).restype = C.c_void_p
