@@ -30,8 +30,10 @@ def view(L, a):
     return C.c_void_p(L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, FLOAT32 if a.dtype == np.float32 else INT32))
 
 
-@pytest.mark.parametrize("R,Cc,weighted,min_edges", [(1, 2, False, "0"), (2, 2, False, "0"), (2, 4, True, "0"), (2, 2, False, "1000000000")])
-def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, min_edges):  # noqa: F811
+@pytest.mark.parametrize("R,Cc,weighted,min_edges,split", [(1, 2, False, "0", False), (2, 2, False, "0", False), (2, 4, True, "0", False),
+                                                            (2, 2, False, "1000000000", False), (2, 4, False, "0", True)])
+def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, min_edges, split):  # noqa: F811
+    """split: one block per destination partition of the row group (the structure of mg.py's CUGRAPH_B200_MG_SPLIT path)"""
     monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", min_edges)
     L = emu
     _api(L)
@@ -53,19 +55,28 @@ def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, m
     # rank (r, c): edges u -> v with r = r_of[v], c = c_of[u]; row = c_of[v] * mp + lid[v]; column = lid[u] * R + r_of[u]
     blocks, spans = {}, {}
     keep = []
+
+    def make_block(rows, cols, ww, nr):
+        keep.extend([rows, cols, ww])
+        blk, err = C.c_void_p(), C.c_void_p()
+        vr, vc, vw = view(L, rows), view(L, cols), (view(L, ww) if ww is not None else None)
+        code = L.cugraph_b200_block_create(handle, nr, n_cols, vr, vc, vw, C.byref(blk), C.byref(err))
+        assert code == 0, L.cugraph_error_message(err)
+        return blk
+
     for r in range(R):
         for c in range(Cc):
             m = (r_of[d] == r) & (c_of[s] == c)
             rows = (c_of[d[m]] * mp + lid[d[m]]).astype(np.int32)
             cols = (lid[s[m]] * R + r_of[s[m]]).astype(np.int32)
             ww = w[m].copy() if weighted else None
-            keep += [rows, cols, ww]
-            blk, err = C.c_void_p(), C.c_void_p()
-            vr, vc, vw = view(L, rows), view(L, cols), (view(L, ww) if weighted else None)
-            code = L.cugraph_b200_block_create(handle, n_rows, n_cols, vr, vc, vw, C.byref(blk), C.byref(err))
-            assert code == 0, L.cugraph_error_message(err)
-            blocks[(r, c)] = blk
-            spans[(r, c)] = L.cugraph_b200_block_span(blk)
+            if not split:
+                blocks[(r, c)] = [make_block(rows, cols, ww, n_rows)]
+            else:  # rows of destination partition j only, renumbered from 0
+                part = rows // mp
+                blocks[(r, c)] = [make_block((rows[part == j] - j * mp).astype(np.int32), cols[part == j].copy(),
+                                             None if ww is None else ww[part == j].copy(), mp) for j in range(Cc)]
+            spans[(r, c)] = max(L.cugraph_b200_block_span(b) for b in blocks[(r, c)])
     span = max(spans.values())
     x_elems = L.cugraph_b200_padded_elems(span, 4)
     # out-weight sums of the owned vertices
@@ -102,10 +113,16 @@ def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, m
                 xg = np.zeros(x_elems, np.float32)                     # all-gather inside the column group, interleaved
                 for rr in range(R):
                     xg[np.arange(mp) * R + rr] = x_loc[rr * Cc + c]
-                yp = np.zeros(span, np.float32)
-                err = C.c_void_p()
-                code = L.cugraph_b200_block_pull_sweep(handle, blocks[(r, c)], view(L, xg), view(L, yp), alpha, C.byref(err))
-                assert code == 0, L.cugraph_error_message(err)
+                yp = np.zeros(max(span, n_rows), np.float32)
+                for j, blk in enumerate(blocks[(r, c)]):
+                    yj = np.zeros(span, np.float32)
+                    err = C.c_void_p()
+                    code = L.cugraph_b200_block_pull_sweep(handle, blk, view(L, xg), view(L, yj), alpha, C.byref(err))
+                    assert code == 0, L.cugraph_error_message(err)
+                    if split:
+                        yp[j * mp:(j + 1) * mp] = yj[:mp]
+                    else:
+                        yp[:span] = yj
                 ypart[(r, c)] = yp
         for r in range(R):                                              # reduce-scatter inside the row group
             total = np.sum([ypart[(r, c)][:n_rows].astype(np.float64) for c in range(Cc)], axis=0)
@@ -118,5 +135,6 @@ def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, m
     ref, _, _ = oracle.pagerank(s.astype(np.int32), d.astype(np.int32), V, None if not weighted else w.astype(np.float64),
                                 alpha=alpha, epsilon=0.0, max_iterations=iters)
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=0)
-    for blk in blocks.values():
-        L.cugraph_b200_block_free(blk)
+    for bl in blocks.values():
+        for blk in bl:
+            L.cugraph_b200_block_free(blk)
