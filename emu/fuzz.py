@@ -87,8 +87,12 @@ r = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "0")))
 t_end = time.time() + budget
 n_cases = 0
 while time.time() < t_end:
-    V = int(r.choice([1, 2, 3, 7, 40, 300, 3000]))
-    E = int(r.integers(0, 12 * V + 2))
+    if os.environ.get("FUZZ_BIG"):   # several column blocks, many work units: slow under emulation, few cases per minute
+        V = int(r.choice([30_000, 60_000, 120_000]))
+        E = int(r.integers(2 * V, 6 * V))
+    else:
+        V = int(r.choice([1, 2, 3, 7, 40, 300, 3000]))
+        E = int(r.integers(0, 12 * V + 2))
     idt = r.choice([np.int32, np.int64])
     wt = r.choice([None, np.float32, np.float64])
     renumber = bool(r.integers(0, 2))
@@ -98,7 +102,7 @@ while time.time() < t_end:
     for k, vals in (("CUGRAPH_B200_HOT_X", "01"), ("CUGRAPH_B200_HOT_NARROW", "01"), ("CUGRAPH_B200_LOW_ELL", "012")):
         os.environ[k] = str(r.choice(list(vals)))
     os.environ["CUGRAPH_B200_HOT_UNIT_SLOTS"] = str(r.choice([1024, 8192]))
-    skew = float(r.choice([1.0, 2.5]))
+    skew = float(r.choice([1.0, 2.5])) if not os.environ.get("FUZZ_BIG") else float(r.choice([2.0, 3.0]))
     src = np.minimum((V * r.random(E) ** skew).astype(np.int64), V - 1).astype(idt)
     dst = np.minimum((V * r.random(E) ** skew).astype(np.int64), V - 1).astype(idt)
     if not renumber and E:
