@@ -185,15 +185,20 @@ struct advance_scratch_t {
 };
 
 // total_edges = sum of the degrees of the queue entries (known on the host from the previous level)
+// ready_deg: degrees of the queue entries if the producer of the queue already wrote them (n + 1 readable elements; the
+// exclusive scan never uses the last one), else nullptr
 template <typename O, typename Op>
 void advance(handle_impl const& h, advance_scratch_t& sc, O const* off, int32_t const* idx, int32_t const* queue, int n,
-             unsigned long long total_edges, Op op)
+             unsigned long long total_edges, Op op, int32_t const* ready_deg = nullptr)
 {
   if (n <= 0) return;
   B200_EXPECTS(total_edges < (1ull << 31), CUGRAPH_UNKNOWN_ERROR, "frontier too large for one advance");
-  B200_LAUNCH(h, (k_queue_degrees<O>), (n + 1 + kBlock - 1) / kBlock, kBlock, 0, off, queue, n, sc.deg.as<int32_t>());
-  CUDA_TRY(cub::DeviceScan::ExclusiveSum(sc.tmp.data(), sc.tmp_bytes, sc.deg.as<int32_t>(), sc.scan.as<int32_t>(), n + 1, h.stream));
-  h.launches += 2;
+  if (!ready_deg) {
+    B200_LAUNCH(h, (k_queue_degrees<O>), (n + 1 + kBlock - 1) / kBlock, kBlock, 0, off, queue, n, sc.deg.as<int32_t>());
+    ready_deg = sc.deg.as<int32_t>();
+  }
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(sc.tmp.data(), sc.tmp_bytes, ready_deg, sc.scan.as<int32_t>(), n + 1, h.stream));
+  h.launches += 1;
   if (total_edges == 0) return;
   const int n_tiles = (int)((total_edges + kTileEdges - 1) / kTileEdges);
   dbuf tile_k       = make_dbuf<int2>((size_t)n_tiles, h.stream);
@@ -236,7 +241,7 @@ struct bfs_topdown_op {
   int32_t* dist;
   int32_t* pred;  // may be null
   int32_t* next_q;
-  int32_t* next_q_large;
+  int32_t* next_q_large;  // degrees of the entries of next_q (BFS uses one queue; this buffer carries their degrees)
   frontier_counters_t* cnt;
   int level;
   __device__ __forceinline__ void edge(int src, long long, int nbr) const
@@ -247,7 +252,11 @@ struct bfs_topdown_op {
     if (old & bit) return;
     dist[nbr] = level + 1;
     if (pred) pred[nbr] = src;
-    const unsigned d = enqueue_by_degree(off, nbr, next_q, next_q_large, cnt);
+    // queue entry and its degree side by side: the next level's scan needs no separate degree pass
+    const unsigned d = (unsigned)((long long)off[nbr + 1] - (long long)off[nbr]);
+    const int pos    = warp_append(&cnt->n_small);
+    next_q[pos]      = nbr;
+    next_q_large[pos] = (int32_t)d;
     warp_add_u64(&cnt->m_f, d);
   }
 };
@@ -255,7 +264,7 @@ struct bfs_topdown_op {
 // 32 consecutive vertices per warp; parents looked up in the frontier bitmap
 template <typename O>
 __global__ void __launch_bounds__(kBlock)
-k_bfs_bottomup(O const* __restrict__ off, int32_t const* __restrict__ idx, uint32_t const* __restrict__ visited,
+k_bfs_bottomup(O const* __restrict__ off, int32_t const* __restrict__ idx, uint32_t* __restrict__ visited,
                uint32_t const* __restrict__ frontier_bm, uint32_t* __restrict__ next_bm, int32_t* __restrict__ dist,
                int32_t* __restrict__ pred, int level, int n_vertices, frontier_counters_t* cnt)
 {
@@ -283,7 +292,10 @@ k_bfs_bottomup(O const* __restrict__ off, int32_t const* __restrict__ idx, uint3
       }
     }
     const uint32_t word = __ballot_sync(0xffffffffu, found);
-    if (lane == 0) next_bm[w] = word;
+    if (lane == 0) {
+      next_bm[w] = word;
+      if (word) visited[w] = vis | word;  // word w belongs to this warp alone: no separate OR pass over the bitmaps
+    }
   }
   my_count = __reduce_add_sync(0xffffffffu, my_count);
   my_deg   = __reduce_add_sync(0xffffffffu, my_deg);
@@ -368,7 +380,7 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   dbuf visited = make_dbuf<uint32_t>(n_words, h.stream), fbm = make_dbuf<uint32_t>(n_words, h.stream),
        nbm = make_dbuf<uint32_t>(n_words, h.stream);
   dbuf qa = make_dbuf<int32_t>(nv, h.stream), qb = make_dbuf<int32_t>(nv, h.stream);
-  dbuf la = make_dbuf<int32_t>(nv, h.stream), lb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf la = make_dbuf<int32_t>((size_t)nv + 1, h.stream), lb = make_dbuf<int32_t>((size_t)nv + 1, h.stream);  // queue degrees
   dbuf cnt = make_dbuf<frontier_counters_t>(1, h.stream);
   frontier_counters_t* dc = cnt.as<frontier_counters_t>();
   CUDA_TRY(cudaMemsetAsync(visited.data(), 0, sizeof(uint32_t) * n_words, h.stream));
@@ -391,6 +403,7 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   int32_t *cur = qa.as<int32_t>(), *nxt = qb.as<int32_t>();
   int32_t *cur_l = la.as<int32_t>(), *nxt_l = lb.as<int32_t>();
   bool bottom_up = false, frontier_is_bitmap = false;
+  bool deg_ready = false;  // cur_l holds the degrees of the entries of cur (written by the top-down level that built it)
   int level = 0, prev_n_f = 0;
   // Beamer's switch points (the reference: bfs_impl.cuh:291-297, alpha ~ E/V*0.267, beta = 24)
   const double alpha = 14.0, beta = 24.0;
@@ -412,12 +425,14 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
         n_small            = n_f;
         n_large            = 0;
         mixed_queue        = true;
+        deg_ready          = false;
       }
       bfs_topdown_op<O> op{off, visited.as<uint32_t>(), dist, pred, nxt, nxt_l, dc, level};
-      advance<O>(h, adv, off, idx, cur, n_small, m_f, op);
+      advance<O>(h, adv, off, idx, cur, n_small, m_f, op, deg_ready ? cur_l : (int32_t const*)nullptr);
       std::swap(cur, nxt);
       std::swap(cur_l, nxt_l);
       mixed_queue = false;
+      deg_ready   = true;
     } else {
       if (!frontier_is_bitmap) {
         CUDA_TRY(cudaMemsetAsync(fbm.data(), 0, sizeof(uint32_t) * n_words, h.stream));
@@ -428,7 +443,6 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
       int grid = std::min(grid_for((int64_t)n_words * 32), h.sm_count * 16);
       B200_LAUNCH(h, (k_bfs_bottomup<O>), grid, kBlock, 0, off, idx, visited.as<uint32_t>(), fbm.as<uint32_t>(),
                   nbm.as<uint32_t>(), dist, pred, level, nv, dc);
-      B200_LAUNCH(h, k_or_words, grid_for(n_words), kBlock, 0, visited.as<uint32_t>(), nbm.as<uint32_t>(), n_words);
       std::swap(fbm, nbm);
     }
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
@@ -613,7 +627,7 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   CUDA_TRY(cudaMemsetAsync(far_stamp.data(), 0, sizeof(int32_t) * nv, h.stream));
   // every queue holds a vertex at most once per round / window (stamps), so V entries suffice
   dbuf qa = make_dbuf<int32_t>(nv, h.stream), qb = make_dbuf<int32_t>(nv, h.stream);
-  dbuf la = make_dbuf<int32_t>(nv, h.stream), lb = make_dbuf<int32_t>(nv, h.stream);
+  dbuf la = make_dbuf<int32_t>((size_t)nv + 1, h.stream), lb = make_dbuf<int32_t>((size_t)nv + 1, h.stream);  // queue degrees
   dbuf fa = make_dbuf<int32_t>(nv, h.stream), fb = make_dbuf<int32_t>(nv, h.stream);
   dbuf cnt = make_dbuf<frontier_counters_t>(1, h.stream);
   frontier_counters_t* dc = cnt.as<frontier_counters_t>();
