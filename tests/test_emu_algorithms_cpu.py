@@ -195,3 +195,56 @@ def test_sssp_emulated(emu):  # noqa: F811
     got[np.searchsorted(ids, verts)] = dist
     assert (got == ref_d.astype(np.float32)).all()                 # bit-exact in float, unreached = FLT_MAX on both sides
     emu.cugraph_graph_free(g)
+
+
+def test_smoke_equivalent_emulated(emu):  # noqa: F811
+    """the sequence of __graft_entry__.smoke() (RMAT-12, vertices_array with isolated vertices, PageRank + BFS + SSSP)"""
+    from oracle.rmat import rmat_edgelist
+    L = emu
+    scale = 12
+    s, d = rmat_edgelist(scale, 16 << scale, seed=3)
+    s, d = np.ascontiguousarray(s, np.int32), np.ascontiguousarray(d, np.int32)
+    V = 1 << scale
+    verts_all = np.arange(V, dtype=np.int32)
+
+    def mk(src, dst, w, sym, transposed):
+        vs = [L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, t) if a is not None else None
+              for a, t in ((verts_all, INT32), (src, INT32), (dst, INT32), (w, FLOAT32))]
+        g, err = C.c_void_p(), C.c_void_p()
+        code = L.cugraph_graph_create_with_times_sg(C.c_void_p(L.handle), C.byref(Props(int(sym), 1)), C.c_void_p(vs[0]),
+                                                    C.c_void_p(vs[1]), C.c_void_p(vs[2]), C.c_void_p(vs[3]) if vs[3] else None,
+                                                    None, None, None, None, int(transposed), 1, 0, 0, 0, 0, C.byref(g), C.byref(err))
+        assert code == 0, L.cugraph_error_message(err)
+        return g
+
+    g = mk(s, d, None, False, True)
+    verts, pr, it = run_pagerank(L, g, 0.85, 0.0, 20)
+    ref, _, _ = oracle.pagerank(s, d, V, None, alpha=0.85, epsilon=0.0, max_iterations=20)
+    got = np.zeros(V)
+    got[verts] = pr
+    assert verts.size == V
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-12)
+    L.cugraph_graph_free(g)
+    s2, d2 = np.concatenate([s, d]), np.concatenate([d, s])
+    wh = np.random.default_rng(0).random(s.shape[0]).astype(np.float32)
+    w2 = np.concatenate([wh, wh])
+    g2 = mk(s2, d2, w2, True, False)
+    src = int(s[0])
+    sarr = np.array([src], dtype=np.int32)
+    sv = L.cugraph_type_erased_device_array_view_create(sarr.ctypes.data, 1, INT32)
+    res, err = C.c_void_p(), C.c_void_p()
+    assert L.cugraph_bfs(C.c_void_p(L.handle), g2, C.c_void_p(sv), 1, C.c_size_t(2**31 - 2), 1, 0, C.byref(res), C.byref(err)) == 0
+    bv, dist, pred = _paths(L, res)
+    rd, _ = oracle.bfs(s2, d2, V, [src])
+    gd = np.zeros(V, dtype=np.int32)
+    gd[bv] = dist
+    assert np.array_equal(gd, rd)
+    L.cugraph_sssp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    res = C.c_void_p()
+    assert L.cugraph_sssp(C.c_void_p(L.handle), g2, src, float("inf"), 1, 0, C.byref(res), C.byref(err)) == 0
+    sv2, sd, sp = _paths(L, res)
+    rs, _ = oracle.sssp(s2, d2, w2, V, src)
+    gs = np.zeros(V)
+    gs[sv2] = sd
+    assert np.array_equal(gs, rs)
+    L.cugraph_graph_free(g2)
