@@ -16,6 +16,6 @@ sys.path.insert(0, "$ROOT"); sys.path.insert(0, "$ROOT/emu")
 import build_emu
 build_emu.build = lambda force=False: "$OUT"
 import pytest
-sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "tests/test_emu_staging_cpu.py", "tests/test_emu_sweep_cpu.py", "tests/test_emu_algorithms_cpu.py", "tests/test_emu_mg_cpu.py"]))
+sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "tests/test_emu_staging_cpu.py", "tests/test_emu_sweep_cpu.py", "tests/test_emu_algorithms_cpu.py", "tests/test_emu_mg_cpu.py", "tests/test_emu_goldens_cpu.py", "tests/test_emu_edge_cases_cpu.py"]))
 PY
 python emu/fuzz.py ${1:-120} $OUT
