@@ -215,6 +215,11 @@ def run_single(args):
                 "traffic": traffic, "peak_source": peak_src, "kernel": "pull sweep: k_spmv_blocked+k_spmv_blocked_finish+k_spmv_low",
                 "ms_per_sweep": ms.value, "algorithmic_bytes_per_sweep": by.value,
                 "sweep_mteps": E / (ms.value * 1e-3) / 1e6}
+    # the same ratio for a whole PageRank iteration (B_iter = B_spmv + 4 V-sized streams of the vertex pass)
+    b_iter = by.value + 16.0 * nv
+    ms_iter = ms_step / ITERS
+    roofline["iteration"] = {"algorithmic_bytes": b_iter, "ms": ms_iter, "achieved": b_iter / (ms_iter * 1e-3) / 1e9,
+                             "frac": b_iter / (ms_iter * 1e-3) / 1e9 / peak}
 
     # e2e: host edge list -> H2D -> graph create -> pagerank -> D2H
     del G
