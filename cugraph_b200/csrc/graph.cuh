@@ -12,6 +12,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 namespace b200 {
@@ -42,8 +44,9 @@ constexpr int kHotSlot       = 8;           // entries per lane slot
 struct hot_layout_t {
   int W{0};      // source columns per hot block (= slice elements - kHotZeroPad)
   int B{0};      // hot blocks; the cold block (sources >= B*W) is block B
-  int32_t n_hi{0};
-  int64_t nnz_hi{0};
+  int32_t n_hi{0};    // rows covered by the layout: the prefix of degree >= 32 rows (seg_k = 0), or, experimentally,
+  int64_t nnz_hi{0};  // the prefix down to a lower degree bound (seg_k > 0: rows [0, seg[seg_k]))
+  int seg_k{0};
   int64_t n_hot_slots{0};
   int64_t n_slots{0};
   // A (row, block) segment is cut into PIECES of <= 64 entries = <= 8 lane slots of 8 entries.  Pieces are
@@ -79,6 +82,17 @@ struct low_ell_t {
   dbuf w;                // same x T, or empty
 };
 
+// EXPERIMENTAL (CUGRAPH_B200_HOT_MIN_DEGREE = 32 | 16 | 8 | 4 | 2 | 1, default 32): rows down to that degree go through the
+// piece layout of the blocked sweep instead of the gather kernel for low rows.  Returns the index into csx_t::seg.
+inline int hot_seg_index()
+{
+  const char* e = std::getenv("CUGRAPH_B200_HOT_MIN_DEGREE");
+  const int d   = e ? std::atoi(e) : 32;
+  for (int k = 0; k < kNumSeg - 1; ++k)
+    if (kSegThreshold[k] == d) return k;
+  return 0;
+}
+
 // One orientation: compressed rows over `n_rows` physical rows.
 // row_vertex == nullptr  -> physical row r is vertex r (rows are degree-descending by construction)
 // row_vertex != nullptr  -> physical row r is vertex row_vertex[r] (a lazily built transpose whose
@@ -106,6 +120,9 @@ struct csx_t {
   mutable std::unique_ptr<low_ell_t> low_ell;
   mutable bool low_ell_tried{false};
 };
+
+// rows that may need an fp64 accumulator in a sweep (callers size acc_hi with it)
+inline int32_t acc_rows(csx_t const& c) { return std::max(std::max(c.seg[0], c.seg[hot_seg_index()]), 1); }
 
 struct graph_impl {
   cugraph_data_type_id_t vertex_type{INT32};

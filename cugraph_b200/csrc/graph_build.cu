@@ -1230,11 +1230,19 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
 {
   phase_trace tr(h);
   const int W        = (int)(kHotSliceBytes / es) - kHotZeroPad;  // columns per hot block; the pad holds zeros
-  const int32_t n_hi = c.seg[0];
+  const int seg_k    = hot_seg_index();  // 0 unless CUGRAPH_B200_HOT_MIN_DEGREE lowers the bound (experimental)
+  const int32_t n_hi = c.seg[seg_k];
   const int B        = (int)std::min<int64_t>(hot_max_blocks(), ((int64_t)nv + W - 1) / W);
-  const int64_t nnz  = c.nnz_hi;
+  int64_t nnz        = c.nnz_hi;
+  if (seg_k > 0) {  // entries of the covered rows = offsets[n_hi]
+    O last = 0;
+    CUDA_TRY(cudaMemcpyAsync(&last, c.offsets.as<O>() + n_hi, sizeof(O), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    nnz = (int64_t)last;
+    if (nnz >= (1ll << 31) - 4096) return nullptr;
+  }
   auto L             = std::make_unique<hot_layout_t>();
-  L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = nnz;
+  L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = nnz; L->seg_k = seg_k;
   int32_t const* idx = c.indices.as<int32_t>();
   // experimental narrow slots (graph.cuh): unweighted only; needs k_spmv_blocked_x
   bool narrow = false;

@@ -142,8 +142,8 @@ cugraph_error_code_t cugraph_b200_block_create(const cugraph_resource_handle_t* 
     b->wtype   = w ? w->type : FLOAT32;
     b->csx     = build_binned_rows(h, (int32_t const*)r->data, (int32_t const*)c->data, w ? w->data : nullptr, b->wtype,
                                    (int64_t)r->size, b->n_span);
-    b->acc_hi  = make_dbuf<double>(std::max(b->csx->seg[0], 1), h.stream);
-    CUDA_TRY(cudaMemsetAsync(b->acc_hi.data(), 0, sizeof(double) * std::max(b->csx->seg[0], 1), h.stream));
+    b->acc_hi  = make_dbuf<double>(acc_rows(*b->csx), h.stream);
+    CUDA_TRY(cudaMemsetAsync(b->acc_hi.data(), 0, sizeof(double) * acc_rows(*b->csx), h.stream));
     b->state = make_dbuf<pr_state_t>(1, h.stream);
     CUDA_TRY(cudaMemsetAsync(b->state.data(), 0, sizeof(pr_state_t), h.stream));
     // build the column-blocked copy now (it is lazily created otherwise, inside the first timed sweep)

@@ -256,8 +256,8 @@ void pagerank_typed(handle_impl const& h, graph_impl& g, pr_args const& a, centr
   dbuf pr_a = make_dbuf<T>(nv, h.stream), pr_b = make_dbuf<T>(nv, h.stream);
   dbuf x    = make_dbuf<T>(padded_x_elems(nv, sizeof(T)), h.stream);  // whole smem slices are TMA-copied
   CUDA_TRY(cudaMemsetAsync(x.data(), 0, padded_x_elems(nv, sizeof(T)) * sizeof(T), h.stream));  // zeros behind nv
-  dbuf acc_hi = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
-  CUDA_TRY(cudaMemsetAsync(acc_hi.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
+  dbuf acc_hi = make_dbuf<double>(acc_rows(c), h.stream);
+  CUDA_TRY(cudaMemsetAsync(acc_hi.data(), 0, sizeof(double) * acc_rows(c), h.stream));
   dbuf state = make_dbuf<pr_state_t>(1, h.stream);
   CUDA_TRY(cudaMemsetAsync(state.data(), 0, sizeof(pr_state_t), h.stream));
   pr_state_t* st = state.as<pr_state_t>();
@@ -484,8 +484,8 @@ cugraph_error_code_t cugraph_b200_time_pull_spmv(const cugraph_resource_handle_t
     dbuf x = make_dbuf<float>(padded_x_elems(nv, sizeof(float)), h.stream), y = make_dbuf<float>(nv, h.stream);
     CUDA_TRY(cudaMemsetAsync(x.data(), 0, padded_x_elems(nv, sizeof(float)) * sizeof(float), h.stream));
     B200_LAUNCH(h, (k_fill<float>), grid_for(nv), kBlock, 0, x.as<float>(), nv, 1.0f / (float)nv);
-    dbuf acc = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
-    CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
+    dbuf acc = make_dbuf<double>(acc_rows(c), h.stream);
+    CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * acc_rows(c), h.stream));
     dbuf state = make_dbuf<pr_state_t>(1, h.stream);
     CUDA_TRY(cudaMemsetAsync(state.data(), 0, sizeof(pr_state_t), h.stream));
     auto sweep = [&] {
@@ -531,8 +531,8 @@ cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugraph_resource_ha
     dbuf x = make_dbuf<float>(px, h.stream), y0 = make_dbuf<float>(nv, h.stream), y1 = make_dbuf<float>(nv, h.stream);
     CUDA_TRY(cudaMemsetAsync(x.data(), 0, px * sizeof(float), h.stream));
     B200_LAUNCH(h, (k_fill_pattern<float>), grid_for(nv), kBlock, 0, x.as<float>(), nv);
-    dbuf acc = make_dbuf<double>(std::max(c.seg[0], 1), h.stream);
-    CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * std::max(c.seg[0], 1), h.stream));
+    dbuf acc = make_dbuf<double>(acc_rows(c), h.stream);
+    CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * acc_rows(c), h.stream));
     dbuf state = make_dbuf<pr_state_t>(1, h.stream);
     CUDA_TRY(cudaMemsetAsync(state.data(), 0, sizeof(pr_state_t), h.stream));
     reference_sweep_only() = true;

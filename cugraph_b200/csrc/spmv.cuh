@@ -345,18 +345,19 @@ inline int low_ell_mode()
   return e ? std::atoi(e) : 0;
 }
 
-inline low_ell_args_t make_low_ell_args(low_ell_t const& E)
+// min_degree_covered: rows of degree >= that are handled by the blocked sweep's piece layout (32 = none of the classes)
+inline low_ell_args_t make_low_ell_args(low_ell_t const& E, int min_degree_covered = 32)
 {
   low_ell_args_t a{};
   int blocks = 0;
   for (int k = 0; k < 32; ++k) {
     const int d      = 31 - k;
     a.row_begin[d]   = E.row_begin[d];
-    a.n[d]           = E.n[d];
+    a.n[d]           = d >= min_degree_covered ? 0 : E.n[d];
     a.base[d]        = E.base[d];
     a.block_begin[k] = blocks;
     const int per    = 256 * low_ell_rows_per_thread(d);
-    blocks += (E.n[d] + per - 1) / per;
+    blocks += (a.n[d] + per - 1) / per;
   }
   a.block_begin[32] = blocks;
   return a;
@@ -364,9 +365,9 @@ inline low_ell_args_t make_low_ell_args(low_ell_t const& E)
 
 template <typename T>
 void launch_low_rows_ell(handle_impl const& h, csx_t const& c, low_ell_t const& E, T const* x, T* y, double alpha,
-                         pr_state_t const* st)
+                         pr_state_t const* st, int min_degree_covered = 32)
 {
-  low_ell_args_t a = make_low_ell_args(E);
+  low_ell_args_t a = make_low_ell_args(E, min_degree_covered);
   const int blocks = a.block_begin[32];
   if (blocks <= 0) return;
   if (E.w.data())
@@ -389,14 +390,15 @@ inline int low_mode()
   return e ? std::atoi(e) : 1;
 }
 
-inline low_bins_t make_low_bins(csx_t const& c)
+// first_bin > 0: bins below it (rows [0, seg[first_bin])) are handled by the blocked sweep's piece layout
+inline low_bins_t make_low_bins(csx_t const& c, int first_bin = 0)
 {
   low_bins_t b{};
   int blocks = 0;
   for (int k = 0; k < kNumSeg - 1; ++k) {
     b.row_begin[k]   = c.seg[k];
     b.block_begin[k] = blocks;
-    int rows         = c.seg[k + 1] - c.seg[k];
+    int rows         = k < first_bin ? 0 : c.seg[k + 1] - c.seg[k];
     int per_block    = (k == kNumSeg - 2) ? 256 : 256 / low_bin_lanes(k);
     blocks += (rows + per_block - 1) / per_block;
   }

@@ -377,7 +377,7 @@ k_spmv_low_ell_hot(int32_t const* __restrict__ ell, T const* __restrict__ ellw, 
 
 template <typename T>
 void launch_low_rows_ell_hot(handle_impl const& h, csx_t const& c, low_ell_t const& E, T const* x, T* y, double alpha,
-                             pr_state_t const* st)
+                             pr_state_t const* st, int min_degree_covered = 32)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -385,7 +385,7 @@ void launch_low_rows_ell_hot(handle_impl const& h, csx_t const& c, low_ell_t con
     CUDA_TRY(cudaFuncSetAttribute(k_spmv_low_ell_hot<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotDynSmem));
     attr_set = true;
   }
-  low_ell_args_t a = make_low_ell_args(E);
+  low_ell_args_t a = make_low_ell_args(E, min_degree_covered);
   const int blocks = a.block_begin[32];
   if (blocks <= 0) return;
   const int W    = (int)(kHotSliceBytes / sizeof(T)) - kHotZeroPad;  // x holds padded_x_elems(): reading W entries is safe
@@ -407,14 +407,16 @@ inline bool low_async()
 }
 
 template <typename O, typename T>
-void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, double alpha, pr_state_t const* st)
+void launch_low_rows(handle_impl const& h, csx_t const& c, T const* x, T* y, double alpha, pr_state_t const* st,
+                     int first_bin = 0)
 {
   if (low_ell_t const* E = low_ell_layout(h, c, sizeof(T))) {  // experimental, CUGRAPH_B200_LOW_ELL=1 | 2
-    if (low_ell_mode() >= 2) launch_low_rows_ell_hot<T>(h, c, *E, x, y, alpha, st);
-    else launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
+    const int covered = kSegThreshold[first_bin];  // rows of degree >= this belong to the piece layout
+    if (low_ell_mode() >= 2) launch_low_rows_ell_hot<T>(h, c, *E, x, y, alpha, st, covered);
+    else launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st, covered);
     return;
   }
-  low_bins_t bins = make_low_bins(c);
+  low_bins_t bins = make_low_bins(c, first_bin);
   int lblocks     = bins.block_begin[kNumSeg - 1];
   if (lblocks <= 0) return;
   if (c.weights.data())
@@ -453,14 +455,14 @@ void launch_pull_sweep_blocked(handle_impl const& h, csx_t const& c, hot_layout_
     handle_impl ha = h;
     ha.stream      = h.aux_stream;
     ha.launches    = 0;
-    launch_low_rows<O, T>(ha, c, x, y, alpha, st);
+    launch_low_rows<O, T>(ha, c, x, y, alpha, st, L.seg_k);
     h.launches += ha.launches;
     CUDA_TRY(cudaEventRecord(h.ev_b, h.aux_stream));
   }
   B200_LAUNCH(h, (k_spmv_blocked_finish<T>), (L.n_hi + 255) / 256, 256, 0, acc_hi, L.n_hi, y, c.row_vertex.as<int32_t>(),
               alpha, L.unit_counter.as<int>(), L.n_cta, st);
   if (la) CUDA_TRY(cudaStreamWaitEvent(h.stream, h.ev_b, 0));
-  else launch_low_rows<O, T>(h, c, x, y, alpha, st);
+  else launch_low_rows<O, T>(h, c, x, y, alpha, st, L.seg_k);
 }
 
 // (the dispatcher launch_pull_sweep_auto lives in spmv_hot_x.cuh, next to the experimental kernel variant)

@@ -272,14 +272,14 @@ void launch_pull_sweep_blocked_x(handle_impl const& h, csx_t const& c, hot_layou
     handle_impl ha = h;
     ha.stream      = h.aux_stream;
     ha.launches    = 0;
-    launch_low_rows<O, T>(ha, c, x, y, alpha, st);
+    launch_low_rows<O, T>(ha, c, x, y, alpha, st, L.seg_k);
     h.launches += ha.launches;
     CUDA_TRY(cudaEventRecord(h.ev_b, h.aux_stream));
   }
   B200_LAUNCH(h, (k_spmv_blocked_finish<T>), (L.n_hi + 255) / 256, 256, 0, acc_hi, L.n_hi, y, c.row_vertex.as<int32_t>(),
               alpha, L.unit_counter.as<int>(), L.n_cta, st);
   if (la) CUDA_TRY(cudaStreamWaitEvent(h.stream, h.ev_b, 0));
-  else launch_low_rows<O, T>(h, c, x, y, alpha, st);
+  else launch_low_rows<O, T>(h, c, x, y, alpha, st, L.seg_k);
 }
 
 // dispatch: blocked layout when it exists for this graph, else the plain edge-balanced sweep

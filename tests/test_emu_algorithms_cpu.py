@@ -116,6 +116,25 @@ def test_pagerank_emulated_double_weights(emu, monkeypatch, hot_x):  # noqa: F81
     L.cugraph_graph_free(g)
 
 
+@pytest.mark.parametrize("min_degree,extra", [("8", {}), ("1", {}), ("4", {"CUGRAPH_B200_HOT_X": "1", "CUGRAPH_B200_HOT_NARROW": "1"}),
+                                              ("16", {"CUGRAPH_B200_LOW_ELL": "1"}), ("2", {"CUGRAPH_B200_LOW_ELL": "2"})])
+def test_pagerank_emulated_lower_degree_bound(emu, monkeypatch, min_degree, extra):  # noqa: F811
+    """CUGRAPH_B200_HOT_MIN_DEGREE: rows down to that degree go through the piece layout, the rest through the low-row kernels"""
+    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_DEGREE", min_degree)
+    for k, v in extra.items():
+        monkeypatch.setenv(k, v)
+    src, dst, w = make_edges(70_000, 260_000, seed=53 + int(min_degree))
+    g = create_graph(emu, src, dst, w)
+    verts, pr, it = run_pagerank(emu, g, 0.85, 0.0, 8)
+    ids, s, d = dense_ids(src, dst)
+    ref, _, _ = oracle.pagerank(s, d, ids.size, None, alpha=0.85, epsilon=0.0, max_iterations=8)
+    got = np.zeros(ids.size)
+    got[np.searchsorted(ids, verts)] = pr
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=0)
+    emu.cugraph_graph_free(g)
+
+
 def _paths(L, res):
     for f in ("cugraph_paths_result_get_vertices", "cugraph_paths_result_get_distances", "cugraph_paths_result_get_predecessors"):
         getattr(L, f).restype = C.c_void_p
