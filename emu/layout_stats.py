@@ -1,5 +1,6 @@
 """Piece-layout statistics of an RMAT graph on the CPU (emulated staging, CUGRAPH_B200_BUILD_TRACE output): pieces per class
-and per range of blocks, slot counts and bytes, for the default and the narrow layout.   python emu/layout_stats.py [scale]"""
+and per range of blocks, slot counts and bytes, for the default and the narrow layout, or for the switch sets given.
+    python emu/layout_stats.py [scale] ["CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=8" ...]"""
 import ctypes as C
 import os
 import sys
@@ -65,13 +66,17 @@ for k in (1, 2, 4, 16, 64):
     print(f"  sources of degree>=32 rows inside the first {k} column block(s): {100.0 * (hi_idx < k * W).mean():.1f} %", flush=True)
 os.environ["CUGRAPH_B200_HOT_MIN_EDGES"] = "0"
 os.environ["CUGRAPH_B200_BUILD_TRACE"] = "1"
-for narrow in ("0", "1"):
-    os.environ["CUGRAPH_B200_HOT_NARROW"] = narrow
+configs = sys.argv[2:] or ["CUGRAPH_B200_HOT_NARROW=0", "CUGRAPH_B200_HOT_NARROW=1"]
+for cfg in configs:
+    for kv in cfg.split(","):
+        k, v = kv.split("=")
+        os.environ[k] = v
+    narrow = cfg
     L.emu_reset_layouts(g)
     ints = (C.c_int64 * 12)()
     ptrs = (C.c_void_p * 10)()
     t0 = time.time()
-    sys.stderr.write(f"---- CUGRAPH_B200_HOT_NARROW={narrow}\n")
+    sys.stderr.write(f"---- {cfg}\n")
     sys.stderr.flush()
     rc = L.emu_hot_layout(H, g, ints, ptrs)
     print(f"narrow={narrow}: rc={rc} W={ints[0]} B={ints[1]} n_hi={ints[2]} nnz_hi={ints[3]} hot slots={ints[4]} slots={ints[5]} "
