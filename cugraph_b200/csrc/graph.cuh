@@ -56,12 +56,14 @@ struct hot_layout_t {
   dbuf slot_idx32;   // (n_slots - n_hot_slots) x 8 x int32 : cold columns, padding -> n_vertices (x is 0 there)
   dbuf slot_w;       // n_slots x 8 x T, padding 0; or empty
   // EXPERIMENTAL narrow classes (CUGRAPH_B200_HOT_NARROW=1, unweighted graphs, hot blocks only; consumed by
-  // k_spmv_blocked_x): pieces of <= 4 entries use an 8-byte slot (4 ids), pieces of <= 2 entries a 4-byte slot
+  // k_spmv_blocked_x): pieces of 3-4 entries use an 8-byte slot (class code 16), of 2 entries a 4-byte slot (32), of 1 entry
+  // a 2-byte slot (64)
   bool narrow{false};
   dbuf slot_idx_h;   // n_hslots x 4 x uint16
   dbuf slot_idx_q;   // n_qslots x 2 x uint16
+  dbuf slot_idx_s;   // n_sslots x 1 x uint16 : one-entry pieces (class code 64)
   dbuf seg_row;      // per (group, lane): row of the piece, -1 for the unused lanes of a class's last group
-  dbuf subs;         // n_subs x hot_sub_t (spmv_hot.cuh): consecutive groups of one class (cls 1..8; 16 / 32 = narrow)
+  dbuf subs;         // n_subs x hot_sub_t (spmv_hot.cuh): consecutive groups of one class (cls 1..8; 16 / 32 / 64 = narrow)
   dbuf units;        // n_units x hot_unit_t: consecutive sub-units of one block, about 8192 slots
   int32_t n_subs{0};
   int32_t n_units{0};

@@ -1042,7 +1042,10 @@ __global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t 
     const int len  = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
     const int cls  = (len + kHotSlot - 1) / kHotSlot;  // 1..8
     int code       = cls - 1;
-    if (narrow) code = (b < B && len <= 2) ? 0 : ((b < B && len <= 4) ? 1 : cls + 1);  // kinds: Q, H, 1..8
+    if (narrow) {  // kinds: S (1 entry), Q (2), H (<= 4), then 1..8 full slots; the cold block only has full slots
+      code = cls + 2;
+      if (b < B && len <= 4) code = len == 1 ? 0 : (len == 2 ? 1 : 2);
+    }
     piece_key[p]   = (uint32_t)(b * kinds + code);
     piece_start[p] = (int32_t)s;
     piece_len[p]   = len;
@@ -1074,8 +1077,8 @@ struct hot_fill_t {  // build-time companion of a sub-unit
 };
 
 // Host-side plan of the blocked sweep's work structure, from the per-class piece counts alone (class_start[key] =
-// first piece of class key = block * kinds + kind, pieces ordered by key; kinds = 8, or 10 for narrow layouts where
-// kind 0 / 1 are the quarter / half slot classes):
+// first piece of class key = block * kinds + kind, pieces ordered by key; kinds = 8, or 11 for narrow layouts where
+// kinds 0 / 1 / 2 are the one-entry (S), quarter (Q) and half (H) slot classes):
 //   sub-unit = consecutive groups (32 pieces each) of one class, at most `unit_slots` slots;
 //   unit     = consecutive sub-units of one block, closed once it holds >= unit_slots slots (narrow slots count half);
 //   range    = contiguous units per persistent CTA, balanced by slots (cold block weighted by cold_cost).
@@ -1085,21 +1088,21 @@ struct hot_plan_t {
   std::vector<hot_fill_t> fills;
   std::vector<hot_unit_host_t> units;
   std::vector<int32_t> range;
-  int64_t slot_run{0}, row_run{0}, cold_slot0{0}, hslot_run{0}, qslot_run{0};
+  int64_t slot_run{0}, row_run{0}, cold_slot0{0}, hslot_run{0}, qslot_run{0}, sslot_run{0};
   int n_cta{1};
 };
 
 bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int unit_slots_target, int sm_count,
                     double cold_cost, hot_plan_t& P)
 {
-  const int kinds         = narrow ? kHotPieceSlots + 2 : kHotPieceSlots;
+  const int kinds         = narrow ? kHotPieceSlots + 3 : kHotPieceSlots;
   const int kHotUnitSlots = unit_slots_target;
   auto& subs  = P.subs;
   auto& fills = P.fills;
   auto& units = P.units;
   std::vector<double> unit_cost;
   int64_t &slot_run = P.slot_run, &row_run = P.row_run, &cold_slot0 = P.cold_slot0, &hslot_run = P.hslot_run,
-          &qslot_run = P.qslot_run;
+          &qslot_run = P.qslot_run, &sslot_run = P.sslot_run;
   for (int b = 0; b <= B; ++b) {
     if (b == B) cold_slot0 = slot_run;
     int64_t unit_slots = 0;
@@ -1114,11 +1117,11 @@ bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int 
     };
     for (int kind = 0; kind < kinds; ++kind) {
       // steps per group and the sub-unit's class code: 1..8 = full 8-entry slots; narrow layouts put the
-      // one-step kinds Q (code 32: 2 ids per slot) and H (code 16: 4 ids) in front
+      // one-step kinds S (code 64: 1 id per slot), Q (code 32: 2 ids) and H (code 16: 4 ids) in front
       int cls = kind + 1, code = kind + 1;
       if (narrow) {
-        cls  = kind < 2 ? 1 : kind - 1;
-        code = kind == 0 ? 32 : (kind == 1 ? 16 : kind - 1);
+        cls  = kind < 3 ? 1 : kind - 2;
+        code = kind == 0 ? 64 : (kind == 1 ? 32 : (kind == 2 ? 16 : kind - 2));
       }
       const bool is_narrow = code > kHotPieceSlots;
       const int key    = b * kinds + kind;
@@ -1126,7 +1129,7 @@ bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int 
       const int32_t pe = cstart[key + 1];
       // narrow slots count half towards the size of a unit
       const int max_groups = is_narrow ? std::max(1, kHotUnitSlots / 16) : std::max(1, kHotUnitSlots / (32 * cls));
-      int64_t& run         = is_narrow ? (code == 16 ? hslot_run : qslot_run) : slot_run;
+      int64_t& run         = is_narrow ? (code == 16 ? hslot_run : (code == 32 ? qslot_run : sslot_run)) : slot_run;
       while (p < pe) {
         const int groups = (int)std::min<int64_t>(max_groups, ((int64_t)(pe - p) + 31) / 32);
         if (run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return false;  // 32-bit slot ids
@@ -1164,7 +1167,8 @@ k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict
            int32_t const* __restrict__ piece_start, int32_t const* __restrict__ piece_len,
            int32_t const* __restrict__ piece_row, int32_t const* __restrict__ idx, T const* __restrict__ w, int W, int B,
            int zero_col_cold, long long cold_slot0, uint16_t* __restrict__ idx16, int32_t* __restrict__ idx32,
-           T* __restrict__ w_out, int32_t* __restrict__ seg_row_out, uint2* __restrict__ idx_h, uint32_t* __restrict__ idx_q)
+           T* __restrict__ w_out, int32_t* __restrict__ seg_row_out, uint2* __restrict__ idx_h, uint32_t* __restrict__ idx_q,
+           uint16_t* __restrict__ idx_s)
 {
   const hot_sub_host_t sb = subs[blockIdx.x];
   const hot_fill_t fl     = fills[blockIdx.x];
@@ -1181,13 +1185,14 @@ k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict
       row         = piece_row[p];
     }
     seg_row_out[(size_t)sb.row_begin + (size_t)q * 32 + lane] = row;
-    if (sb.cls > kHotPieceSlots) {  // narrow classes: one step, 4 (cls 16) or 2 (cls 32) ids per slot, hot blocks only
+    if (sb.cls > kHotPieceSlots) {  // narrow classes: one step, 4 (cls 16), 2 (cls 32) or 1 (cls 64) ids per slot, hot blocks only
       const size_t slot = (size_t)sb.slot_begin + (size_t)q * 32 + lane;
       unsigned v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = k < ln ? (unsigned)(idx[st + k] - fl.block * W) : (unsigned)W;
       if (sb.cls == 16) idx_h[slot] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-      else idx_q[slot] = v[0] | (v[1] << 16);
+      else if (sb.cls == 32) idx_q[slot] = v[0] | (v[1] << 16);
+      else idx_s[slot] = (uint16_t)v[0];
       continue;
     }
     for (int j = 0; j < sb.cls; ++j) {
@@ -1247,7 +1252,7 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   // experimental narrow slots (graph.cuh): unweighted only; needs k_spmv_blocked_x
   bool narrow = false;
   if (const char* e = std::getenv("CUGRAPH_B200_HOT_NARROW")) narrow = std::atoi(e) != 0 && c.weights.data() == nullptr;
-  const int kinds = narrow ? kHotPieceSlots + 2 : kHotPieceSlots;
+  const int kinds = narrow ? kHotPieceSlots + 3 : kHotPieceSlots;
   L->narrow       = narrow;
 
   // 1. segment heads
@@ -1345,7 +1350,8 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   auto& fills = plan.fills;
   auto& units = plan.units;
   auto& range = plan.range;
-  const int64_t row_run = plan.row_run, hslot_run = plan.hslot_run, qslot_run = plan.qslot_run, cold_slot0 = plan.cold_slot0;
+  const int64_t row_run = plan.row_run, hslot_run = plan.hslot_run, qslot_run = plan.qslot_run, sslot_run = plan.sslot_run,
+                cold_slot0 = plan.cold_slot0;
   L->n_hot_slots = plan.cold_slot0;
   L->n_slots     = plan.slot_run;
   L->n_units     = (int32_t)units.size();
@@ -1371,6 +1377,7 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   L->slot_idx32 = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots - L->n_hot_slots, 1) * kHotSlot, h.stream);
   L->slot_idx_h = make_dbuf<uint2>(std::max<int64_t>(hslot_run, 1), h.stream);
   L->slot_idx_q = make_dbuf<uint32_t>(std::max<int64_t>(qslot_run, 1), h.stream);
+  L->slot_idx_s = make_dbuf<uint16_t>(std::max<int64_t>(sslot_run, 1), h.stream);
   const bool weighted = c.weights.data() != nullptr;
   if (weighted) L->slot_w = dbuf((size_t)std::max<int64_t>(L->n_slots, 1) * kHotSlot * es, h.stream);
   // padding entries of the cold block read x[n_vertices], which the caller keeps at zero (padded_x_elems)
@@ -1380,21 +1387,21 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
                   c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
                   L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
-                  L->slot_idx_q.as<uint32_t>());
+                  L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
     else
       B200_LAUNCH(h, (k_hot_fill<double>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
                   c.weights.as<double>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
                   L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
-                  L->slot_idx_q.as<uint32_t>());
+                  L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
   }
   check_last("hot layout");
   sync(h);
   tr.mark("hot: fill slots");
   if (tr.on)
-    std::fprintf(stderr, "[hot] slots %lld (hot %lld) + %lld half + %lld quarter = %.1f MB ids, seg rows %lld, units %d, subs %d\n",
-                 (long long)L->n_slots, (long long)L->n_hot_slots, (long long)hslot_run, (long long)qslot_run,
-                 (double)(L->n_hot_slots * 16 + (L->n_slots - L->n_hot_slots) * 32 + hslot_run * 8 + qslot_run * 4) / 1e6,
+    std::fprintf(stderr, "[hot] slots %lld (hot %lld) + %lld half + %lld quarter + %lld single = %.1f MB ids, seg rows %lld, units %d, subs %d\n",
+                 (long long)L->n_slots, (long long)L->n_hot_slots, (long long)hslot_run, (long long)qslot_run, (long long)sslot_run,
+                 (double)(L->n_hot_slots * 16 + (L->n_slots - L->n_hot_slots) * 32 + hslot_run * 8 + qslot_run * 4 + sslot_run * 2) / 1e6,
                  (long long)row_run, L->n_units, L->n_subs);
   return L;
 }
@@ -1403,13 +1410,14 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
 
 // flat copy of plan_hot_units' result for the debug C entry (CPU tests)
 bool debug_plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int unit_slots, int sm_count, double cold_cost,
-                          int64_t totals[6], std::vector<int32_t>& subs4, std::vector<int32_t>& fills4,
+                          int64_t totals[7], std::vector<int32_t>& subs4, std::vector<int32_t>& fills4,
                           std::vector<int32_t>& units4, std::vector<int32_t>& range)
 {
   hot_plan_t P;
   if (!plan_hot_units(cstart, B, narrow, unit_slots, sm_count, cold_cost, P)) return false;
   totals[0] = P.slot_run; totals[1] = P.row_run; totals[2] = P.cold_slot0; totals[3] = P.hslot_run; totals[4] = P.qslot_run;
   totals[5] = P.n_cta;
+  totals[6] = P.sslot_run;
   for (auto const& x : P.subs) subs4.insert(subs4.end(), {x.slot_begin, x.row_begin, x.n_groups, x.cls});
   for (auto const& x : P.fills) fills4.insert(fills4.end(), {x.piece_begin, x.piece_end, x.block, x.pad});
   for (auto const& x : P.units) units4.insert(units4.end(), {x.sub_begin, x.sub_end, x.block, x.pad});
@@ -1618,15 +1626,15 @@ extern "C" cugraph_error_code_t cugraph_b200_debug_plan_hot_units(
     B200_EXPECTS(class_start && totals && subs && fills && units && range && n_subs && n_units, CUGRAPH_INVALID_INPUT,
                  "null argument");
     B200_EXPECTS(n_hot_blocks >= 0 && unit_slots >= 32 && sm_count >= 1, CUGRAPH_INVALID_INPUT, "bad parameter");
-    const int kinds = narrow == TRUE ? 10 : 8;
+    const int kinds = narrow == TRUE ? 11 : 8;
     std::vector<int32_t> cstart(class_start, class_start + (size_t)(n_hot_blocks + 1) * kinds + 1);
     std::vector<int32_t> s4, f4, u4, r;
-    int64_t t[6];
+    int64_t t[7];
     B200_EXPECTS(debug_plan_hot_units(cstart, n_hot_blocks, narrow == TRUE, unit_slots, sm_count, cold_cost, t, s4, f4, u4, r),
                  CUGRAPH_INVALID_INPUT, "slot numbers overflow 31 bits");
     B200_EXPECTS(s4.size() / 4 <= subs_capacity && u4.size() / 4 <= units_capacity && r.size() <= range_capacity,
                  CUGRAPH_INVALID_INPUT, "output capacity too small");
-    std::copy(t, t + 6, totals);
+    std::copy(t, t + 7, totals);
     std::copy(s4.begin(), s4.end(), subs);
     std::copy(f4.begin(), f4.end(), fills);
     std::copy(u4.begin(), u4.end(), units);

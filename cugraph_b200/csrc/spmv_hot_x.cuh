@@ -5,7 +5,8 @@
 //   * CUGRAPH_B200_HOT_CLAIM (default 4 here): a CTA claims that many units of its own range per atomic and
 //     runs them without a CTA barrier in between
 //   * CUGRAPH_B200_HOT_NARROW=1 (layout option, graph_build.cu; unweighted graphs): pieces of <= 4 / <= 2 entries are
-//     stored in 8-byte / 4-byte slots (classes 16 / 32) instead of a padded 16-byte slot; only this kernel reads them
+//     stored in 8- / 4- / 2-byte slots (classes 16 / 32 / 64: 3-4, 2, 1 entries) instead of a padded 16-byte slot; only this
+//     kernel reads them
 // Measured inside the combined kernel (RMAT-24, same binary): baseline 0.522 ms, C1 0.503, CLAIM=4 0.490,
 // both 0.465.  To be measured as a kernel of its own next.
 #pragma once
@@ -54,6 +55,12 @@ __device__ __forceinline__ unsigned ld_stream_u32(const uint32_t* p)
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ unsigned ld_stream_u16(const uint16_t* p)
+{
+  unsigned short v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint2 ld_stream_v2(const uint2* p)
 {
   uint2 v;
@@ -62,6 +69,7 @@ __device__ __forceinline__ uint2 ld_stream_v2(const uint2* p)
 }
 #else
 inline unsigned ld_stream_u32(const uint32_t* p) { return *p; }
+inline unsigned ld_stream_u16(const uint16_t* p) { return *p; }
 inline uint2 ld_stream_v2(const uint2* p) { return *p; }
 #endif
 
@@ -73,13 +81,14 @@ __device__ __forceinline__ T hot_gather16(unsigned pair, T const* __restrict__ s
   return *reinterpret_cast<const T*>(reinterpret_cast<const char*>(sx) + off * (sizeof(T) / 4));
 }
 
-// narrow classes (hot blocks, unweighted): one step per group, WIDTH = 2 or 4 ids per lane slot; 8 / 4 groups in flight
+// narrow classes (hot blocks, unweighted): one step per group, WIDTH = 1, 2 or 4 ids per lane slot; 8 / 8 / 4 groups in flight
 template <typename T, int WIDTH>
 __device__ __forceinline__ void hot_run_groups_narrow(hot_sub_t const sb, int q, int lane, int32_t const* __restrict__ seg_row,
                                                       uint2 const* __restrict__ idx_h, uint32_t const* __restrict__ idx_q,
-                                                      T const* __restrict__ sx, double* __restrict__ acc_hi)
+                                                      uint16_t const* __restrict__ idx_s, T const* __restrict__ sx,
+                                                      double* __restrict__ acc_hi)
 {
-  constexpr int K = WIDTH == 2 ? 8 : 4;  // groups in flight: a quarter slot costs one id register per group
+  constexpr int K = WIDTH <= 2 ? 8 : 4;  // groups in flight: a quarter / single slot costs one id register per group
   for (; q < sb.n_groups; q += 32 * K) {
     uint2 ids[K];
     int row[K];
@@ -91,14 +100,16 @@ __device__ __forceinline__ void hot_run_groups_narrow(hot_sub_t const sb, int q,
       if (qk < sb.n_groups) {  // warp-uniform
         const size_t s = (size_t)(unsigned)(sb.slot_begin + qk * 32 + lane);
         if (WIDTH == 4) ids[k] = ld_stream_v2(idx_h + s);
-        else ids[k].x = ld_stream_u32(idx_q + s);
+        else if (WIDTH == 2) ids[k].x = ld_stream_u32(idx_q + s);
+        else ids[k].x = ld_stream_u16(idx_s + s);
         row[k] = ld_stream(seg_row + sb.row_begin + qk * 32 + lane);
       }
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (q + 32 * k < sb.n_groups) {
-        double acc = (double)hot_gather16<T, false>(ids[k].x, sx) + (double)hot_gather16<T, true>(ids[k].x, sx);
+        double acc = (double)hot_gather16<T, false>(ids[k].x, sx);
+        if (WIDTH >= 2) acc += (double)hot_gather16<T, true>(ids[k].x, sx);
         if (WIDTH == 4) acc += (double)hot_gather16<T, false>(ids[k].y, sx) + (double)hot_gather16<T, true>(ids[k].y, sx);
         if (row[k] >= 0) atomicAdd(acc_hi + row[k], acc);
       }
@@ -156,7 +167,7 @@ k_spmv_blocked_x(hot_unit_t const* __restrict__ units, int n_units, int* __restr
                int32_t const* __restrict__ idx32, int cold_slot0, T const* __restrict__ w,
                T const* __restrict__ x, double* __restrict__ acc_hi, int W, int B, int c1_wide,
                int claim, uint2 const* __restrict__ idx_h, uint32_t const* __restrict__ idx_q,
-               pr_state_t const* __restrict__ st)
+               uint16_t const* __restrict__ idx_s, pr_state_t const* __restrict__ st)
 {
   B200_DYN_SMEM(smem_raw);
   T* sx = reinterpret_cast<T*>(smem_raw);
@@ -213,8 +224,9 @@ k_spmv_blocked_x(hot_unit_t const* __restrict__ units, int n_units, int* __restr
         const int q0       = (warp - dealt) & (kHotWarps - 1);
         dealt += sb.n_groups;
         if (sb.cls > 8) {  // narrow classes exist only in hot blocks of narrow layouts
-          if (sb.cls == 16) hot_run_groups_narrow<T, 4>(sb, q0, lane, seg_row, idx_h, idx_q, sx, acc_hi);
-          else hot_run_groups_narrow<T, 2>(sb, q0, lane, seg_row, idx_h, idx_q, sx, acc_hi);
+          if (sb.cls == 16) hot_run_groups_narrow<T, 4>(sb, q0, lane, seg_row, idx_h, idx_q, idx_s, sx, acc_hi);
+          else if (sb.cls == 32) hot_run_groups_narrow<T, 2>(sb, q0, lane, seg_row, idx_h, idx_q, idx_s, sx, acc_hi);
+          else hot_run_groups_narrow<T, 1>(sb, q0, lane, seg_row, idx_h, idx_q, idx_s, sx, acc_hi);
         } else if (c1_wide && sb.cls == 1 && hot) {  // the cold block (if any) stays on the generic loop
           hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold_slot0, w, x, sx, acc_hi);
         } else if (hot) {
@@ -261,12 +273,12 @@ void launch_pull_sweep_blocked_x(handle_impl const& h, csx_t const& c, hot_layou
     B200_LAUNCH(h, (k_spmv_blocked_x<T, true>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
                 L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(),
                 L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(), (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W,
-                L.B, hot_c1_wide(), hot_claim(), L.slot_idx_h.as<uint2>(), L.slot_idx_q.as<uint32_t>(), st);
+                L.B, hot_c1_wide(), hot_claim(), L.slot_idx_h.as<uint2>(), L.slot_idx_q.as<uint32_t>(), L.slot_idx_s.as<uint16_t>(), st);
   else
     B200_LAUNCH(h, (k_spmv_blocked_x<T, false>), grid, kHotThreads, kHotDynSmem, L.units.as<hot_unit_t>(), L.n_units,
                 L.unit_counter.as<int>(), L.cta_range.as<int32_t>(), L.subs.as<hot_sub_t>(), L.seg_row.as<int32_t>(),
                 L.slot_idx16.as<uint16_t>(), L.slot_idx32.as<int32_t>(), (int)L.n_hot_slots, L.slot_w.as<T>(), x, acc_hi, L.W,
-                L.B, hot_c1_wide(), hot_claim(), L.slot_idx_h.as<uint2>(), L.slot_idx_q.as<uint32_t>(), st);
+                L.B, hot_c1_wide(), hot_claim(), L.slot_idx_h.as<uint2>(), L.slot_idx_q.as<uint32_t>(), L.slot_idx_s.as<uint16_t>(), st);
   if (la) {  // queued behind the persistent kernel: its blocks fill the SMs that the blocked kernel's tail frees
     CUDA_TRY(cudaStreamWaitEvent(h.aux_stream, h.ev_a, 0));
     handle_impl ha = h;

@@ -47,7 +47,7 @@ EMU_EXPORT int emu_hot_layout(const cugraph_resource_handle_t* handle, cugraph_g
   ints[6] = L->n_subs; ints[7] = L->n_units; ints[8] = L->n_cta; ints[9] = L->narrow; ints[10] = (int64_t)es; ints[11] = 0;
   ptrs[0] = L->slot_idx16.data(); ptrs[1] = L->slot_idx32.data(); ptrs[2] = L->slot_w.data(); ptrs[3] = L->seg_row.data();
   ptrs[4] = L->subs.data(); ptrs[5] = L->units.data(); ptrs[6] = L->cta_range.data(); ptrs[7] = L->slot_idx_h.data();
-  ptrs[8] = L->slot_idx_q.data(); ptrs[9] = nullptr;
+  ptrs[8] = L->slot_idx_q.data(); ptrs[9] = L->slot_idx_s.data();
   return 0;
 }
 
@@ -88,6 +88,7 @@ static void model_blocked(hot_layout_t const& L, T const* x, double* acc, int mo
   auto const* idx32 = L.slot_idx32.as<int32_t>();
   auto const* idx_h = L.slot_idx_h.as<uint2>();
   auto const* idx_q = L.slot_idx_q.as<uint32_t>();
+  auto const* idx_s = L.slot_idx_s.as<uint16_t>();
   T const* w        = L.slot_w.as<T>();
   const int cold0   = (int)L.n_hot_slots;
   std::vector<T> sx((size_t)L.W + kHotZeroPad);
@@ -107,8 +108,9 @@ static void model_blocked(hot_layout_t const& L, T const* x, double* acc, int mo
         const int q0 = (warp - dealt) & (kHotWarps - 1);
         for (int lane = 0; lane < 32; ++lane) {
           if (sb.cls > 8) {
-            if (sb.cls == 16) hot_run_groups_narrow<T, 4>(sb, q0, lane, seg_row, idx_h, idx_q, sx.data(), acc);
-            else hot_run_groups_narrow<T, 2>(sb, q0, lane, seg_row, idx_h, idx_q, sx.data(), acc);
+            if (sb.cls == 16) hot_run_groups_narrow<T, 4>(sb, q0, lane, seg_row, idx_h, idx_q, idx_s, sx.data(), acc);
+            else if (sb.cls == 32) hot_run_groups_narrow<T, 2>(sb, q0, lane, seg_row, idx_h, idx_q, idx_s, sx.data(), acc);
+            else hot_run_groups_narrow<T, 1>(sb, q0, lane, seg_row, idx_h, idx_q, idx_s, sx.data(), acc);
           } else if ((mode & 1) && sb.cls == 1 && hot) {
             hot_run_groups_c1<T, WEIGHTED, true>(sb, q0, lane, seg_row, idx16, idx32, cold0, w, x, sx.data(), acc);
           } else if (hot) {

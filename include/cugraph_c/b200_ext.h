@@ -79,8 +79,8 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugr
 
 /* Host-only planner of the blocked sweep's work structure (sub-units, units, per-CTA unit ranges) from the per-class
  * piece counts; the function graph staging itself uses.  Needs no GPU: exposed so that the host logic is testable on
- * CPU (tests/test_hot_plan_cpu.py).  class_start has (n_hot_blocks + 1) * kinds + 1 entries (kinds = 8, narrow: 10).
- * Outputs: totals[6] = {slots, seg rows, first cold slot, half slots, quarter slots, CTAs}; subs / fills / units are
+ * CPU (tests/test_hot_plan_cpu.py).  class_start has (n_hot_blocks + 1) * kinds + 1 entries (kinds = 8, narrow: 11).
+ * Outputs: totals[7] = {slots, seg rows, first cold slot, half slots, quarter slots, CTAs, single slots}; subs / fills / units are
  * 4 x int32 records ({slot_begin,row_begin,n_groups,class}, {piece_begin,piece_end,block,0}, {sub_begin,sub_end,block,0});
  * range has totals[5] + 1 entries.  Returns CUGRAPH_INVALID_INPUT when a capacity is too small. */
 CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_plan_hot_units(

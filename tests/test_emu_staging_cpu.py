@@ -137,15 +137,17 @@ def hot_pieces(L, g, P):
     sw = as_np(ptrs[2], n_slots * 8, np.float32) if P["w"] is not None else None
     n_h = int(sum(32 * s[2] for s in subs if s[3] == 16))
     n_q = int(sum(32 * s[2] for s in subs if s[3] == 32))
+    n_s = int(sum(32 * s[2] for s in subs if s[3] == 64))
     idx_h = as_np(ptrs[7], n_h * 4, np.uint16)
     idx_q = as_np(ptrs[8], n_q * 2, np.uint16)
+    idx_s = as_np(ptrs[9], n_s, np.uint16)
     sub_block = np.zeros(n_subs, dtype=np.int64)
     for s0, s1, blk, _ in units:
         sub_block[s0:s1] = blk
     out_r, out_c, out_w = [], [], []
     for si, (slot_begin, row_begin, n_groups, code) in enumerate(subs):
         blk = int(sub_block[si])
-        steps, width = (1, 4) if code == 16 else ((1, 2) if code == 32 else (int(code), 8))
+        steps, width = {16: (1, 4), 32: (1, 2), 64: (1, 1)}.get(int(code), (int(code), 8))
         assert narrow or code <= 8
         rows = seg_row[row_begin:row_begin + 32 * n_groups].reshape(n_groups, 32)
         for q in range(n_groups):
@@ -156,6 +158,8 @@ def hot_pieces(L, g, P):
                     ids = idx_h.reshape(-1, 4)[s].astype(np.int64); pad = W
                 elif code == 32:
                     ids = idx_q.reshape(-1, 2)[s].astype(np.int64); pad = W
+                elif code == 64:
+                    ids = idx_s.reshape(-1, 1)[s].astype(np.int64); pad = W
                 elif blk < B:
                     ids = idx16.reshape(-1, 8)[s].astype(np.int64); pad = W
                 else:
@@ -227,7 +231,7 @@ def test_narrow_piece_layout(emu, monkeypatch):
     g = create_graph(emu, src, dst, w)
     P = primary(emu, g)
     H = check_hot(emu, g, P)
-    assert H["narrow"] and (H["subs"][:, 3] == 16).any() and (H["subs"][:, 3] == 32).any()
+    assert H["narrow"] and all((H["subs"][:, 3] == code).any() for code in (16, 32, 64))
     emu.cugraph_graph_free(g)
 
 

@@ -23,7 +23,7 @@ def _plan(counts, narrow, unit_slots=8192, sm_count=148, cold_cost=2.0):
     cstart = np.zeros(nb * kinds + 1, dtype=np.int32)
     cstart[1:] = np.cumsum(counts.reshape(-1))
     cap = int(counts.sum() // 32 + counts.size + 16)
-    totals = np.zeros(6, dtype=np.int64)
+    totals = np.zeros(7, dtype=np.int64)
     subs = np.zeros((cap, 4), dtype=np.int32)
     fills = np.zeros((cap, 4), dtype=np.int32)
     units = np.zeros((cap, 4), dtype=np.int32)
@@ -46,22 +46,22 @@ def _check(counts, narrow, unit_slots=8192, sm_count=148, cold_cost=2.0):
     nb, kinds = counts.shape
     B = nb - 1
     cstart, totals, subs, fills, units, rng = _plan(counts, narrow, unit_slots, sm_count, cold_cost)
-    slots, rows, cold0, hslots, qslots, n_cta = [int(t) for t in totals]
+    slots, rows, cold0, hslots, qslots, n_cta, sslots = [int(t) for t in totals]
     # ---- sub-units
-    run = {"full": 0, "h": 0, "q": 0}
+    run = {"full": 0, "h": 0, "q": 0, "s": 0}
     row_run = 0
     piece = 0
     last_key = -1
     eq_slots = []          # unit-size equivalent of every sub-unit
     for (slot_begin, row_begin, n_groups, code), (p0, p1, blk, _) in zip(subs, fills):
-        kind_space = "h" if code == 16 else ("q" if code == 32 else "full")
+        kind_space = {16: "h", 32: "q", 64: "s"}.get(int(code), "full")
         steps = 1 if code > 8 else code
         assert 1 <= steps <= 8 and n_groups >= 1
         assert slot_begin == run[kind_space] and row_begin == row_run
         assert p0 == piece and p0 < p1 <= p0 + 32 * n_groups and p1 > p0 + 32 * (n_groups - 1)
         # the pieces of a sub-unit belong to one class of one block, classes appear in key order
         if narrow:
-            kind = 0 if code == 32 else (1 if code == 16 else code + 1)
+            kind = {64: 0, 32: 1, 16: 2}.get(int(code), code + 2)
         else:
             kind = code - 1
         key = blk * kinds + kind
@@ -80,9 +80,9 @@ def _check(counts, narrow, unit_slots=8192, sm_count=148, cold_cost=2.0):
         if kind_space == "full":  # full slots of the hot blocks come first, the cold block's (32-bit ids) after them
             assert slot_begin >= cold0 if blk == B else slot_begin + n_slots <= cold0
     assert piece == counts.sum()
-    assert (run["full"], run["h"], run["q"], row_run) == (slots, hslots, qslots, rows)
+    assert (run["full"], run["h"], run["q"], run["s"], row_run) == (slots, hslots, qslots, sslots, rows)
     if not narrow:
-        assert hslots == 0 and qslots == 0
+        assert hslots == 0 and qslots == 0 and sslots == 0
     # ---- units
     eq_slots = np.array(eq_slots, dtype=np.int64)
     nxt = 0
@@ -112,7 +112,7 @@ def _check(counts, narrow, unit_slots=8192, sm_count=148, cold_cost=2.0):
 @pytest.mark.parametrize("narrow", [False, True])
 def test_plan_random_histograms(narrow):
     r = np.random.default_rng(7 + int(narrow))
-    kinds = 10 if narrow else 8
+    kinds = 11 if narrow else 8
     for trial in range(40):
         nb = int(r.integers(1, 40))
         counts = r.integers(0, 3000, size=(nb, kinds)).astype(np.int64)
@@ -120,7 +120,7 @@ def test_plan_random_histograms(narrow):
         if trial % 5 == 0:
             counts[0, kinds - 1] = int(r.integers(50_000, 400_000))   # a heavy class of full pieces in block 0
         if narrow:
-            counts[nb - 1, :2] = 0   # the cold block never holds narrow pieces (graph_build.cu: k_hot_emit_pieces)
+            counts[nb - 1, :3] = 0   # the cold block never holds narrow pieces (graph_build.cu: k_hot_emit_pieces)
         if trial % 7 == 0:
             counts[nb - 1] = 0       # no cold block at all: every column block is hot
         _check(counts, narrow, unit_slots=int(r.choice([1024, 4096, 8192, 32768])), sm_count=int(r.choice([1, 8, 148])))
@@ -128,7 +128,7 @@ def test_plan_random_histograms(narrow):
 
 def test_plan_empty_and_tiny():
     for narrow in (False, True):
-        kinds = 10 if narrow else 8
+        kinds = 11 if narrow else 8
         totals, subs, units, rng = _check(np.zeros((3, kinds), dtype=np.int64), narrow)
         assert len(subs) == 0 and len(units) == 0 and list(rng) == [0, 0]
         one = np.zeros((2, kinds), dtype=np.int64)
