@@ -20,6 +20,11 @@ A STEP is one call of `cugraph_pagerank_allow_nonconvergence` (100 iterations) t
            algorithmic bytes per sweep = 4E + 4(V+1) + 4V + 4V; traffic = DRAM bytes of
            the three kernels from the ncu launch list (profiles/spmv_traffic.json)
   cpu_baseline = oracle port (oracle/oracle.c, OpenMP) on a bounded sample, host cores stated
+  timing = CUDA events recorded on the handle's stream (the stream the library launches on) around the K calls;
+           the wall-clock time of the same region is reported next to it
+  side   = informational extras measured in separate processes under timeouts (scripts/bench_side.py): BFS / SSSP
+           TEPS on the symmetrised RMAT-24 graph (BASELINE.json configs[2], [3]) and the experimental sweep
+           variants; CUGRAPH_B200_BENCH_SIDE=0 skips them
 Synthetic data, random seed 0.  Inputs (1.2 GB per sweep) exceed the 126 MB L2, so no explicit L2 flush
 is needed between timed iterations (stated in config.l2).
 """
@@ -185,18 +190,22 @@ def run_single(args):
     torch.cuda.synchronize()
     sampler.start()
     l0 = h.launch_count()
+    # CUDA events on the stream the library launches on (the handle's own stream, not torch's current stream)
+    hstream = torch.cuda.ExternalStream(int(L.cugraph_b200_handle_stream(h.ptr) or 0))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(hstream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()  # synchronous on return (the C-ABI syncs the handle's stream)
-    e1.record()
+    e1.record(hstream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     launches = h.launch_count() - l0
     clocks = sampler.stop()
-    ms_step = wall / args.steps * 1e3
-    value = E * ITERS * args.steps / wall / 1e6
+    dev_s = e0.elapsed_time(e1) * 1e-3  # device time between the two events; wall is the host's view of the same region
+    timed_s = dev_s if dev_s > 0 else wall
+    ms_step = timed_s / args.steps * 1e3
+    value = E * ITERS * args.steps / timed_s / 1e6
 
     # roofline: the pull sweep alone, CUDA events on the handle's stream inside the library
     ms, by, err = C.c_double(), C.c_double(), C.c_void_p()
@@ -255,15 +264,69 @@ def run_single(args):
         e2e = {"value": None, "unit": "MTEPS", "h2d_bytes_per_step": 2 * E * 4, "d2h_bytes_per_step": nv * 8,
                "error": f"{type(ex).__name__}: {ex}"[:300]}
 
-    cpu = _cpu_baseline()
+    del h_src, h_dst, h_v, h_p
+    torch.cuda.empty_cache()
+    side = _side_measurements(scale) if os.environ.get("CUGRAPH_B200_BENCH_SIDE", "1") != "0" else None
+
+    cpu = _cpu_baseline(sample_scale=args.cpu_sample_scale)
     out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": f"pagerank_rmat{scale}_ef16_100it", "scale": scale, "edge_factor": 16,
                       "num_vertices": nv, "num_edges": E, "alpha": ALPHA, "iterations": ITERS, "vertex_type": "int32",
                       "l2": "inputs (1.2 GB/sweep) exceed the 126 MB L2; no explicit flush"},
+           "timing": {"device_ms_per_step": dev_s / args.steps * 1e3, "wall_ms_per_step": wall / args.steps * 1e3,
+                      "how": "CUDA events recorded on the handle's stream around the K synchronous C-ABI calls"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    if side is not None:
+        out["side"] = side
     print(json.dumps(out), flush=True)
+
+
+# Side measurements (informational; the headline keys above never depend on them).  Each runs in its own process under
+# a timeout: BFS / SSSP of BASELINE.json configs[2] and [3] on the default path, then the experimental sweep variants
+# (off by default, parity-checked against the plain sweep in the same process before they are timed).
+SIDE_VARIANTS = ["-", "CUGRAPH_B200_HOT_X=1", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1", "CUGRAPH_B200_LOW_ELL=1",
+                 "CUGRAPH_B200_LOW_ELL=2", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_LOW_ELL=2",
+                 "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=8",
+                 "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=1", "CUGRAPH_B200_LOW_ASYNC=1"]
+
+
+def _run_side(argv, timeout_s):
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_side.py")] + [str(a) for a in argv]
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s} s"}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": f"exit code {r.returncode}", "stderr_tail": r.stderr[-400:]}
+    try:
+        res = json.loads(lines[-1])
+    except Exception as ex:
+        return {"error": f"unparsable output: {ex}"[:200]}
+    res["process_s"] = time.perf_counter() - t0
+    return res
+
+
+def _side_measurements(scale, budget_s=None):
+    budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "150")) if budget_s is None else budget_s
+    t0 = time.perf_counter()
+    side = {"traversal": _run_side(["traversal", scale, 16, 4], 150), "variants": []}
+    for cfg in SIDE_VARIANTS:
+        if time.perf_counter() - t0 > budget_s:
+            side["variants"].append({"config": cfg, "skipped": f"side budget of {budget_s:.0f} s spent"})
+            continue
+        res = _run_side(["variant", scale, cfg], 75)
+        res.setdefault("config", cfg)
+        side["variants"].append(res)
+    side["seconds"] = time.perf_counter() - t0
+    side["note"] = ("informational: default-path BFS/SSSP (Graph500 TEPS, random sources) and experimental sweep variants "
+                    "(each parity-checked against the plain sweep, then timed); the headline keys use the default path only")
+    return side
 
 
 def run_multi(args):
@@ -288,6 +351,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=int, default=None, help="override RMAT scale (development only)")
+    ap.add_argument("--cpu-sample-scale", type=int, default=21, help="RMAT scale of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

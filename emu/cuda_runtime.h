@@ -7,6 +7,7 @@
 #error "emu/cuda_runtime.h is only for -DB200_HOST_EMU builds"
 #endif
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -237,9 +238,22 @@ inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) 
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)std::malloc(8); return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { return cudaEventCreateWithFlags(e, 0); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
-inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+// an event holds the host time of its record (8 bytes): work is synchronous here, so that IS when the "stream" got there
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
+{
+  const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  std::memcpy(e, &t, sizeof(t));
+  return cudaSuccess;
+}
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
+{
+  double ta, tb;
+  std::memcpy(&ta, a, sizeof(ta));
+  std::memcpy(&tb, b, sizeof(tb));
+  *ms = (float)(tb - ta);
+  return cudaSuccess;
+}
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 // ---- device intrinsics (sequential semantics)
