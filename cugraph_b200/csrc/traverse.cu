@@ -305,12 +305,6 @@ k_bfs_bottomup(O const* __restrict__ off, int32_t const* __restrict__ idx, uint3
   }
 }
 
-__global__ void k_or_words(uint32_t* __restrict__ a, uint32_t const* __restrict__ b, int n)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] |= b[i];
-}
-
 __global__ void k_queue_to_bitmap(int32_t const* __restrict__ q, int n, uint32_t* __restrict__ bm)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,10 +386,9 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   frontier_counters_t* hc = reinterpret_cast<frontier_counters_t*>(h.pinned);
   CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
   sync(h);
-  // the current frontier is either (small queue, large queue) or a bitmap
-  int n_small = hc->n_small, n_large = 0;
-  bool mixed_queue         = true;  // small queue may still hold hubs (seed / bitmap conversion)
-  int n_f                  = n_small;
+  // the current frontier is either a queue (cur, with the entries' degrees in cur_l once a top-down level wrote it) or
+  // a bitmap (fbm)
+  int n_f                  = hc->n_small;
   unsigned long long m_f   = hc->m_f;
   unsigned long long m_vis = m_f;  // edges incident to visited vertices
   long long n_vis          = n_f;
@@ -407,7 +400,6 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   int level = 0, prev_n_f = 0;
   // Beamer's switch points (the reference: bfs_impl.cuh:291-297, alpha ~ E/V*0.267, beta = 24)
   const double alpha = 14.0, beta = 24.0;
-  const int full_grid = h.sm_count * 8;
   const bool trace    = std::getenv("CUGRAPH_B200_BFS_TRACE") != nullptr;
   advance_scratch_t adv;
   adv.init(h, nv);
@@ -422,22 +414,17 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
       if (frontier_is_bitmap) {
         B200_LAUNCH(h, k_bitmap_to_queue, grid_for(n_words), kBlock, 0, fbm.as<uint32_t>(), n_words, cur, &dc->n_conv);
         frontier_is_bitmap = false;
-        n_small            = n_f;
-        n_large            = 0;
-        mixed_queue        = true;
         deg_ready          = false;
       }
       bfs_topdown_op<O> op{off, visited.as<uint32_t>(), dist, pred, nxt, nxt_l, dc, level};
-      advance<O>(h, adv, off, idx, cur, n_small, m_f, op, deg_ready ? cur_l : (int32_t const*)nullptr);
+      advance<O>(h, adv, off, idx, cur, n_f, m_f, op, deg_ready ? cur_l : (int32_t const*)nullptr);
       std::swap(cur, nxt);
       std::swap(cur_l, nxt_l);
-      mixed_queue = false;
-      deg_ready   = true;
+      deg_ready = true;
     } else {
       if (!frontier_is_bitmap) {
         CUDA_TRY(cudaMemsetAsync(fbm.data(), 0, sizeof(uint32_t) * n_words, h.stream));
-        if (n_small > 0) B200_LAUNCH(h, k_queue_to_bitmap, grid_for(n_small), kBlock, 0, cur, n_small, fbm.as<uint32_t>());
-        if (n_large > 0) B200_LAUNCH(h, k_queue_to_bitmap, grid_for(n_large), kBlock, 0, cur_l, n_large, fbm.as<uint32_t>());
+        if (n_f > 0) B200_LAUNCH(h, k_queue_to_bitmap, grid_for(n_f), kBlock, 0, cur, n_f, fbm.as<uint32_t>());
         frontier_is_bitmap = true;
       }
       int grid = std::min(grid_for((int64_t)n_words * 32), h.sm_count * 16);
@@ -449,11 +436,9 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
     sync(h);
     if (trace)
       std::fprintf(stderr, "bfs level %d %s n_f=%d m_f=%llu m_vis=%llu n_vis=%lld -> next n_f=%d m_f=%llu\n", level,
-                   bottom_up ? "bottom-up" : "top-down", n_f, m_f, m_vis, n_vis, hc->n_small + hc->n_large, hc->m_f);
+                   bottom_up ? "bottom-up" : "top-down", n_f, m_f, m_vis, n_vis, hc->n_small, hc->m_f);
     prev_n_f = n_f;
-    n_small  = hc->n_small;
-    n_large  = hc->n_large;
-    n_f      = n_small + n_large;
+    n_f      = hc->n_small;  // both directions count the next frontier in n_small
     m_f      = hc->m_f;
     m_vis += m_f;
     n_vis += n_f;

@@ -123,3 +123,10 @@ def test_bench_side_traversal(surface, capsys):
         assert out[name]["harmonic_mean_mteps"] > 0
         assert all(out[name]["check"][k] for k in ("tree_property", "source_distance_zero",
                                                    "every_reached_vertex_but_the_source_has_a_predecessor")), out[name]
+
+
+def test_graft_entry_smoke(surface, capsys):
+    """__graft_entry__.smoke() itself (scale-12 PageRank + BFS + SSSP against the oracle), kernels emulated"""
+    entry = _load(os.path.join(ROOT, "__graft_entry__.py"), "graft_entry_under_test")
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
