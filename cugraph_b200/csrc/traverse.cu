@@ -606,6 +606,17 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   if (const char* e = std::getenv("CUGRAPH_B200_SSSP_DELTA_SCALE")) delta_scale = std::atof(e);
   T delta = (T)(32.0 * avg_w / std::max(avg_deg, 1e-30) * delta_scale);
   if (!(delta > (T)0)) delta = (T)1;
+  // Window width control (results do not depend on it; CUGRAPH_B200_SSSP_ADAPTIVE=0 keeps the fixed reference width).
+  // Inside one window the near pile is relaxed Bellman-Ford style, so a vertex re-relaxes all its edges every time its
+  // tentative distance improves.  With the reference's width a power-law graph puts nearly every vertex into the first
+  // window (RMAT-24, uniform weights: 90 % of the edge endpoints lie within 0.05 of the source, the width is 0.27) and
+  // the traversal relaxes 6 x E edges in 30 rounds.  The controller starts 64 times narrower and steers the width by
+  // the number of rounds the last window took: <= 2 rounds: twice as wide (sparse stretches cost one cheap window per
+  // doubling), >= 6 rounds: half as wide.
+  bool adaptive = true;
+  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_ADAPTIVE")) adaptive = std::atoi(e) != 0;
+  const T delta_floor = delta / (T)4096;
+  if (adaptive) delta = delta / (T)64;
 
   dbuf stamp = make_dbuf<int32_t>(nv, h.stream), far_stamp = make_dbuf<int32_t>(nv, h.stream);
   CUDA_TRY(cudaMemsetAsync(stamp.data(), 0, sizeof(int32_t) * nv, h.stream));
@@ -633,11 +644,18 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   const int full_grid = h.sm_count * 8;
   const bool trace    = std::getenv("CUGRAPH_B200_SSSP_TRACE") != nullptr;
   unsigned long long tr_edges = 0;
-  int tr_rounds = 0;
+  int tr_rounds = 0, tr_splits = 0;
+  int split_rounds = 1;
+  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_SPLIT_ROUNDS")) split_rounds = std::max(1, std::atoi(e));
+  // a split costs about one round (a kernel + a read-back): only worth it when the pending round is real work
+  unsigned long long split_min_edges = 1ull << 20;
+  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) split_min_edges = std::strtoull(e, nullptr, 10);
   while (true) {
+    int window_rounds = 0;
     while (n_near + n_near_l > 0) {
       ++round;
       ++tr_rounds;
+      ++window_rounds;
       if (near_edges < (1ull << 31) - 1) tr_edges += near_edges;
       CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_small, n_large; n_far keeps running
       CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
@@ -653,11 +671,42 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
       mixed      = false;
       std::swap(near, next_near);
       std::swap(near_l, next_near_l);
+      // A window that is still busy after `split_rounds` rounds is too wide for this stretch of the graph (the hub core
+      // of a power-law graph sits in a very narrow distance band): cut it in half now instead of after the damage.  The
+      // pending near entries at or beyond the new bound join the far pile (same kernel as the window change, reading
+      // the near queue; the far pile keeps growing in place), the rest form the next round's queue.
+      if (adaptive && window_rounds >= split_rounds && n_near > 0 && near_edges >= split_min_edges &&
+          near_edges * 128ull >= (unsigned long long)c.nnz) {
+        const T nhi = lo + (hi - lo) * (T)0.5;
+        if (nhi > lo && nhi < hi) {
+          ++round;
+          CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_far keeps running
+          CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
+          B200_LAUNCH(h, (k_split_far<O, T>), grid_for(n_near), kBlock, 0, off, near, n_near, dist, lo, nhi, stamp.as<int32_t>(),
+                      far_stamp.as<int32_t>(), round, window, next_near, next_near_l, far, dc);
+          CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
+          sync(h);
+          n_near     = hc->n_small;
+          n_near_l   = hc->n_large;
+          n_far      = hc->n_far;
+          near_edges = hc->m_f;
+          std::swap(near, next_near);
+          std::swap(near_l, next_near_l);
+          hi = nhi;
+          if (delta > delta_floor) delta = delta / (T)2;
+          window_rounds = 0;
+          ++tr_splits;
+        }
+      }
     }
     if (trace)
-      std::fprintf(stderr, "sssp window %d hi=%g: rounds so far %d, edges relaxed so far %llu, far pile %d\n", window,
-                   (double)hi, tr_rounds, tr_edges, n_far);
+      std::fprintf(stderr, "sssp window %d hi=%g width %g: %d rounds, rounds so far %d, edges relaxed so far %llu, far pile %d, splits so far %d\n",
+                   window, (double)hi, (double)delta, window_rounds, tr_rounds, tr_edges, n_far, tr_splits);
     if (n_far == 0) break;
+    if (adaptive) {
+      if (window_rounds <= 2) delta = delta * (T)2;
+      else if (window_rounds >= 6 && delta > delta_floor) delta = delta / (T)2;
+    }
     // advance the window to the smallest pending distance, then split the far pile
     T inf = (T)INFINITY;
     CUDA_TRY(cudaMemcpyAsync(dmin.data(), &inf, sizeof(T), cudaMemcpyHostToDevice, h.stream));
@@ -668,7 +717,9 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
     if (!(hmin < inf)) break;  // everything left in the pile was settled earlier
     lo      = hi;
     T steps = std::floor((hmin - hi) / delta);
-    hi      = hi + (steps > (T)0 ? steps : (T)0) * delta + delta;
+    T nhi   = hi + (steps > (T)0 ? steps : (T)0) * delta + delta;
+    if (!(nhi > hmin)) nhi = std::nextafter(hmin, inf);  // rounding must not produce a window without its smallest entry
+    hi      = nhi;
     ++round;
     ++window;
     CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));

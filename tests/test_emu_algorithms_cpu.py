@@ -216,6 +216,51 @@ def test_sssp_emulated(emu):  # noqa: F811
     emu.cugraph_graph_free(g)
 
 
+def _sssp_dist(emu, g, source):  # noqa: F811
+    res, err = C.c_void_p(), C.c_void_p()
+    emu.cugraph_sssp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    code = emu.cugraph_sssp(C.c_void_p(emu.handle), g, source, float("inf"), 1, 0, C.byref(res), C.byref(err))
+    assert code == 0, emu.cugraph_error_message(err)
+    return _paths(emu, res)
+
+
+@pytest.mark.parametrize("weights", ["uniform", "tiny-and-huge", "constant"])
+def test_sssp_window_control_emulated(emu, monkeypatch, capfd, weights):  # noqa: F811
+    """The window-width controller (64x narrower start, doubling / halving by rounds, mid-window split of a busy window)
+    only schedules the work: distances and predecessors' validity do not depend on it.  Hub-heavy graph so that splits
+    happen; weight sets that stress the float arithmetic of the window bounds."""
+    s, d = symmetric_edges(12_000, 150_000, seed=5)
+    r = np.random.default_rng(9)
+    half = s.size // 2
+    if weights == "uniform":
+        wh = r.random(half).astype(np.float32)
+    elif weights == "tiny-and-huge":
+        wh = np.where(r.random(half) < 0.5, 1e-6, 1e6).astype(np.float32) * (1.0 + r.random(half).astype(np.float32))
+    else:
+        wh = np.full(half, 0.25, dtype=np.float32)
+    w = np.concatenate([wh, wh])
+    g = create_sym_graph(emu, s, d, w)
+    ids, ss, dd = dense_ids(s, d)
+    source = int(ids[3])
+    ref_d, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=True)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CUGRAPH_B200_SSSP_ADAPTIVE", mode)
+        monkeypatch.setenv("CUGRAPH_B200_SSSP_TRACE", "1")
+        monkeypatch.setenv("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES", "0")   # the default only splits rounds of >= 2^20 edges
+        capfd.readouterr()
+        verts, dist, pred = _sssp_dist(emu, g, source)
+        trace = capfd.readouterr().err
+        got = np.zeros(ids.size, dtype=np.float32)
+        got[np.searchsorted(ids, verts)] = dist
+        assert (got == ref_d.astype(np.float32)).all(), mode
+        out[mode] = trace
+    last = [ln for ln in out["1"].splitlines() if ln.startswith("sssp window")][-1]
+    if weights == "uniform":
+        assert int(last.split("splits so far")[1]) > 0, last       # the controller did cut a busy window
+    emu.cugraph_graph_free(g)
+
+
 def test_smoke_equivalent_emulated(emu):  # noqa: F811
     """the sequence of __graft_entry__.smoke() (RMAT-12, vertices_array with isolated vertices, PageRank + BFS + SSSP)"""
     from oracle.rmat import rmat_edgelist
