@@ -173,14 +173,17 @@ k_advance(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t co
 
 // per-algorithm scratch for the advance
 struct advance_scratch_t {
-  dbuf deg, scan, tmp;
+  dbuf deg, scan, tmp, tile_k;
   size_t tmp_bytes{0};
-  void init(handle_impl const& h, int32_t nv)
+  size_t tile_cap{0};  // tiles tile_k holds: a queue of distinct vertices never spans more than nnz edges
+  void init(handle_impl const& h, int32_t nv, int64_t nnz)
   {
     deg  = make_dbuf<int32_t>((size_t)nv + 1, h.stream);
     scan = make_dbuf<int32_t>((size_t)nv + 1, h.stream);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg.as<int32_t>(), scan.as<int32_t>(), nv + 1, h.stream);
-    tmp = dbuf(tmp_bytes, h.stream);
+    tmp      = dbuf(tmp_bytes, h.stream);
+    tile_cap = (size_t)(std::min<int64_t>(std::max<int64_t>(nnz, 0), (1ll << 31) - 1) / kTileEdges + 1);
+    tile_k   = make_dbuf<int2>(tile_cap, h.stream);
   }
 };
 
@@ -201,10 +204,15 @@ void advance(handle_impl const& h, advance_scratch_t& sc, O const* off, int32_t 
   h.launches += 1;
   if (total_edges == 0) return;
   const int n_tiles = (int)((total_edges + kTileEdges - 1) / kTileEdges);
-  dbuf tile_k       = make_dbuf<int2>((size_t)n_tiles, h.stream);
-  B200_LAUNCH(h, k_tile_owners, (n_tiles + kBlock - 1) / kBlock, kBlock, 0, sc.scan.as<int32_t>(), n, n_tiles, tile_k.as<int2>());
+  dbuf spill;  // only if the caller's queue held duplicates (more edges than the graph has)
+  int2* tile_k = sc.tile_k.as<int2>();
+  if ((size_t)n_tiles > sc.tile_cap) {
+    spill  = make_dbuf<int2>((size_t)n_tiles, h.stream);
+    tile_k = spill.as<int2>();
+  }
+  B200_LAUNCH(h, k_tile_owners, (n_tiles + kBlock - 1) / kBlock, kBlock, 0, sc.scan.as<int32_t>(), n, n_tiles, tile_k);
   int grid = (int)std::min<unsigned long long>((unsigned long long)n_tiles, (unsigned long long)h.sm_count * 8);
-  B200_LAUNCH(h, (k_advance<O, Op, false>), grid, kBlock, 0, off, idx, queue, n, sc.scan.as<int32_t>(), tile_k.as<int2>(), n_tiles, op);
+  B200_LAUNCH(h, (k_advance<O, Op, false>), grid, kBlock, 0, off, idx, queue, n, sc.scan.as<int32_t>(), tile_k, n_tiles, op);
 }
 
 // every edge of the graph, edge-balanced: the row offsets are the scan of the identity queue
@@ -402,7 +410,7 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   const double alpha = 14.0, beta = 24.0;
   const bool trace    = std::getenv("CUGRAPH_B200_BFS_TRACE") != nullptr;
   advance_scratch_t adv;
-  adv.init(h, nv);
+  adv.init(h, nv, (int64_t)c.nnz);
   while (n_f > 0 && level < depth_limit) {
     if (direction_optimizing) {
       unsigned long long m_u = m_total - std::min(m_vis, m_total);
@@ -639,7 +647,7 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   (void)mixed;
   unsigned long long near_edges = (unsigned long long)c.nnz < (1ull << 31) ? (1ull << 31) - 1 : 0;  // seed: unknown -> full grid
   advance_scratch_t adv;
-  adv.init(h, nv);
+  adv.init(h, nv, (int64_t)c.nnz);
   T lo = (T)0, hi = delta;
   const int full_grid = h.sm_count * 8;
   const bool trace    = std::getenv("CUGRAPH_B200_SSSP_TRACE") != nullptr;
