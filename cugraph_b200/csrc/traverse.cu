@@ -34,8 +34,8 @@ constexpr int kBlock       = 256;
 inline int grid_for(int64_t n) { return (int)std::min<int64_t>(std::max<int64_t>((n + kBlock - 1) / kBlock, 1), 1 << 22); }
 
 struct frontier_counters_t {
-  int n_small;              // entries appended to the next small-degree queue
-  int n_large;              // entries appended to the next large-degree queue
+  int n_small;              // entries appended to the next queue
+  int n_large;              // unused (kept for the layout of the 2-int reset)
   int n_far;                // SSSP: entries appended to the far pile
   int n_conv;               // bitmap -> queue conversion cursor
   unsigned long long m_f;   // sum of degrees of the vertices appended (direction-optimising heuristic)
@@ -231,14 +231,16 @@ void advance_all_edges(handle_impl const& h, int32_t const* off, int32_t const* 
 // ------------------------------------------------------------------------------------------
 // BFS
 // ------------------------------------------------------------------------------------------
-// append v to the small or the large queue according to its degree; returns the degree
+// append v to the queue and its degree to the parallel degree array (the next advance scans the degrees as they are: no
+// degree pass over the queue); returns the degree.  One queue whatever the degree: the merge-path advance balances any mix.
 template <typename O>
-__device__ __forceinline__ unsigned enqueue_by_degree(O const* off, int v, int32_t* q_small, int32_t* q_large,
-                                                      frontier_counters_t* cnt)
+__device__ __forceinline__ unsigned enqueue_with_degree(O const* off, int v, int32_t* q, int32_t* q_deg,
+                                                        frontier_counters_t* cnt)
 {
   const unsigned d = (unsigned)((long long)off[v + 1] - (long long)off[v]);
-  (void)q_large;  // the merge-path advance balances any degree mix: one queue
-  q_small[warp_append(&cnt->n_small)] = v;
+  const int pos    = warp_append(&cnt->n_small);
+  q[pos]           = v;
+  q_deg[pos]       = (int32_t)d;
   return d;
 }
 
@@ -249,7 +251,7 @@ struct bfs_topdown_op {
   int32_t* dist;
   int32_t* pred;  // may be null
   int32_t* next_q;
-  int32_t* next_q_large;  // degrees of the entries of next_q (BFS uses one queue; this buffer carries their degrees)
+  int32_t* next_q_deg;  // degrees of the entries of next_q
   frontier_counters_t* cnt;
   int level;
   __device__ __forceinline__ void edge(int src, long long, int nbr) const
@@ -260,11 +262,7 @@ struct bfs_topdown_op {
     if (old & bit) return;
     dist[nbr] = level + 1;
     if (pred) pred[nbr] = src;
-    // queue entry and its degree side by side: the next level's scan needs no separate degree pass
-    const unsigned d = (unsigned)((long long)off[nbr + 1] - (long long)off[nbr]);
-    const int pos    = warp_append(&cnt->n_small);
-    next_q[pos]      = nbr;
-    next_q_large[pos] = (int32_t)d;
+    const unsigned d = enqueue_with_degree(off, nbr, next_q, next_q_deg, cnt);
     warp_add_u64(&cnt->m_f, d);
   }
 };
@@ -475,7 +473,7 @@ struct sssp_relax_op {
   int32_t* stamp;      // round in which the vertex was last put on a near queue
   int32_t* far_stamp;  // window in which the vertex was last put on the far pile
   int32_t* next_near;
-  int32_t* next_near_large;
+  int32_t* next_near_deg;  // degrees of the entries of next_near
   int32_t* far;
   frontier_counters_t* cnt;
   T threshold;
@@ -490,7 +488,7 @@ struct sssp_relax_op {
     if (!(nd < old)) return;
     if (nd < threshold) {
       if (atomicExch(stamp + nbr, round) != round) {
-        const unsigned d = enqueue_by_degree(off, nbr, next_near, next_near_large, cnt);
+        const unsigned d = enqueue_with_degree(off, nbr, next_near, next_near_deg, cnt);
         warp_add_u64(&cnt->m_f, d);
       }
     } else {
@@ -503,7 +501,7 @@ struct sssp_relax_op {
 template <typename O, typename T>
 __global__ void k_split_far(O const* __restrict__ off, int32_t const* __restrict__ far_in, int n,
                             T const* __restrict__ dist, T lo, T hi, int32_t* stamp, int32_t* far_stamp, int round,
-                            int window, int32_t* near_out, int32_t* near_large_out, int32_t* far_out,
+                            int window, int32_t* near_out, int32_t* near_deg_out, int32_t* far_out,
                             frontier_counters_t* cnt)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -513,7 +511,7 @@ __global__ void k_split_far(O const* __restrict__ off, int32_t const* __restrict
   if (d < lo) return;  // settled through the near pile meanwhile
   if (d < hi) {
     if (atomicExch(stamp + v, round) != round) {
-      const unsigned d = enqueue_by_degree(off, v, near_out, near_large_out, cnt);
+      const unsigned d = enqueue_with_degree(off, v, near_out, near_deg_out, cnt);
       warp_add_u64(&cnt->m_f, d);
     }
   } else {
@@ -640,11 +638,10 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   B200_LAUNCH(h, (k_sssp_seed<T>), 1, 1, 0, dist, stamp.as<int32_t>(), qa.as<int32_t>(), source);
   frontier_counters_t* hc = reinterpret_cast<frontier_counters_t*>(h.pinned);
   int32_t *near = qa.as<int32_t>(), *next_near = qb.as<int32_t>();
-  int32_t *near_l = la.as<int32_t>(), *next_near_l = lb.as<int32_t>();
+  int32_t *near_deg = la.as<int32_t>(), *next_near_deg = lb.as<int32_t>();  // degrees of the queue entries
   int32_t *far = fa.as<int32_t>(), *far2 = fb.as<int32_t>();
-  int n_near = 1, n_near_l = 0, n_far = 0, round = 1, window = 1;
-  bool mixed = true;
-  (void)mixed;
+  int n_near = 1, n_far = 0, round = 1, window = 1;
+  bool deg_ready = false;  // every enqueue writes the degree next to the entry; only the seed does not
   unsigned long long near_edges = (unsigned long long)c.nnz < (1ull << 31) ? (1ull << 31) - 1 : 0;  // seed: unknown -> full grid
   advance_scratch_t adv;
   adv.init(h, nv, (int64_t)c.nnz);
@@ -660,25 +657,24 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   if (const char* e = std::getenv("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) split_min_edges = std::strtoull(e, nullptr, 10);
   while (true) {
     int window_rounds = 0;
-    while (n_near + n_near_l > 0) {
+    while (n_near > 0) {
       ++round;
       ++tr_rounds;
       ++window_rounds;
       if (near_edges < (1ull << 31) - 1) tr_edges += near_edges;
       CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_small, n_large; n_far keeps running
       CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
-      sssp_relax_op<O, T> op{off, w, dist, stamp.as<int32_t>(), far_stamp.as<int32_t>(), next_near, next_near_l, far,
+      sssp_relax_op<O, T> op{off, w, dist, stamp.as<int32_t>(), far_stamp.as<int32_t>(), next_near, next_near_deg, far,
                              dc, hi, cutoff, round, window};
-      advance<O>(h, adv, off, idx, near, n_near, near_edges, op);
+      advance<O>(h, adv, off, idx, near, n_near, near_edges, op, deg_ready ? near_deg : (int32_t const*)nullptr);
+      deg_ready = true;
       CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
       sync(h);
       n_near     = hc->n_small;
-      n_near_l   = hc->n_large;
       n_far      = hc->n_far;
       near_edges = hc->m_f;
-      mixed      = false;
       std::swap(near, next_near);
-      std::swap(near_l, next_near_l);
+      std::swap(near_deg, next_near_deg);
       // A window that is still busy after `split_rounds` rounds is too wide for this stretch of the graph (the hub core
       // of a power-law graph sits in a very narrow distance band): cut it in half now instead of after the damage.  The
       // pending near entries at or beyond the new bound join the far pile (same kernel as the window change, reading
@@ -691,15 +687,14 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
           CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_far keeps running
           CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
           B200_LAUNCH(h, (k_split_far<O, T>), grid_for(n_near), kBlock, 0, off, near, n_near, dist, lo, nhi, stamp.as<int32_t>(),
-                      far_stamp.as<int32_t>(), round, window, next_near, next_near_l, far, dc);
+                      far_stamp.as<int32_t>(), round, window, next_near, next_near_deg, far, dc);
           CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
           sync(h);
           n_near     = hc->n_small;
-          n_near_l   = hc->n_large;
           n_far      = hc->n_far;
           near_edges = hc->m_f;
           std::swap(near, next_near);
-          std::swap(near_l, next_near_l);
+          std::swap(near_deg, next_near_deg);
           hi = nhi;
           if (delta > delta_floor) delta = delta / (T)2;
           window_rounds = 0;
@@ -732,13 +727,13 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
     ++window;
     CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
     B200_LAUNCH(h, (k_split_far<O, T>), grid_for(n_far), kBlock, 0, off, far, n_far, dist, lo, hi, stamp.as<int32_t>(),
-                far_stamp.as<int32_t>(), round, window, near, near_l, far2, dc);
+                far_stamp.as<int32_t>(), round, window, near, near_deg, far2, dc);
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
     sync(h);
     n_near     = hc->n_small;
-    n_near_l   = hc->n_large;
     n_far      = hc->n_far;
     near_edges = hc->m_f;
+    deg_ready  = true;
     std::swap(far, far2);
   }
   if (pred) {
