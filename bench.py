@@ -313,7 +313,7 @@ def _run_side(argv, timeout_s):
 
 
 def _side_measurements(scale, budget_s=None):
-    budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "150")) if budget_s is None else budget_s
+    budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "110")) if budget_s is None else budget_s
     t0 = time.perf_counter()
     side = {"traversal": _run_side(["traversal", scale, 16, 4], 150), "variants": []}
     for cfg in SIDE_VARIANTS:
