@@ -122,8 +122,32 @@ def _cpu_baseline(sample_scale=21, target_s=12.0):
     for _ in range(n):
         x = oracle.spmv_f32(csc, x, ALPHA, 0.15 / V)
     dt = time.perf_counter() - t0
-    return {"value": E * n / dt / 1e6, "unit": "MTEPS", "cores": oracle.num_threads(), "kind": "port",
-            "sample": f"{n} float32 pull-SpMV sweeps (oracle_spmv_f32, OpenMP) over RMAT scale-{sample_scale} ef-16 CSC"}
+    out = {"value": E * n / dt / 1e6, "unit": "MTEPS", "cores": oracle.num_threads(), "kind": "port",
+           "sample": f"{n} float32 pull-SpMV sweeps (oracle_spmv_f32, OpenMP) over RMAT scale-{sample_scale} ef-16 CSC"}
+    out["networkx"] = _networkx_baseline(min(sample_scale, 16))
+    return out
+
+
+def _networkx_baseline(scale):
+    """NetworkX (BASELINE.json's named CPU baseline): nx.pagerank, 100 power iterations (tol = 0 never converges; the
+    PowerIterationFailedConvergence after max_iter marks the end), on a small RMAT sample — building a NetworkX graph at
+    benchmark scale is prohibitive.  Graph construction is not timed."""
+    try:
+        import networkx as nx
+        from oracle.rmat import rmat_edgelist
+        src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
+        G = nx.MultiDiGraph()
+        G.add_edges_from(zip(src.tolist(), dst.tolist()))
+        t0 = time.perf_counter()
+        try:
+            nx.pagerank(G, alpha=ALPHA, tol=0.0, max_iter=ITERS)
+        except nx.PowerIterationFailedConvergence:
+            pass
+        dt = time.perf_counter() - t0
+        return {"value": src.shape[0] * ITERS / dt / 1e6, "unit": "MTEPS", "cores": 1, "version": nx.__version__,
+                "sample": f"nx.pagerank, {ITERS} iterations, RMAT scale-{scale} ef-16 MultiDiGraph (SciPy-backed, single thread)"}
+    except Exception as ex:
+        return {"value": None, "error": f"{type(ex).__name__}: {ex}"[:200]}
 
 
 def run_reference(args):

@@ -91,6 +91,7 @@ def test_bench_single_gpu_arm(surface, monkeypatch, capsys):
     assert out["e2e"]["h2d_bytes_per_step"] == 2 * 4 * (16 << 10)
     assert out["roofline"]["bound"] == "hbm" and out["roofline"]["achieved"] > 0 and 0 < out["roofline"]["frac"]
     assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["value"] > 0
+    assert out["cpu_baseline"]["networkx"]["value"] > 0 and out["cpu_baseline"]["networkx"]["cores"] == 1
     assert out["side"]["traversal"] == {"error": "no GPU in this test"}
     assert all("skipped" in v for v in out["side"]["variants"])
 
