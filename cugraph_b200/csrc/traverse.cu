@@ -405,7 +405,9 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   bool deg_ready = false;  // cur_l holds the degrees of the entries of cur (written by the top-down level that built it)
   int level = 0, prev_n_f = 0;
   // Beamer's switch points (the reference: bfs_impl.cuh:291-297, alpha ~ E/V*0.267, beta = 24)
-  const double alpha = 14.0, beta = 24.0;
+  double alpha = 14.0, beta = 24.0;  // development knobs: only the schedule depends on them, never the result
+  if (const char* e = std::getenv("CUGRAPH_B200_BFS_ALPHA")) alpha = std::atof(e);
+  if (const char* e = std::getenv("CUGRAPH_B200_BFS_BETA")) beta = std::atof(e);
   const bool trace    = std::getenv("CUGRAPH_B200_BFS_TRACE") != nullptr;
   advance_scratch_t adv;
   adv.init(h, nv, (int64_t)c.nnz);

@@ -54,44 +54,71 @@ def traversal(scale, n_bfs, n_sssp):
     n_src = max(n_bfs, n_sssp)
     sources = cand[torch.randperm(cand.numel(), device="cuda")[:n_src + 1]].to(torch.int32)
     out = {"graph": {"scale": scale, "symmetrised_edges": e_sym, "create_s": create_s}}
-    for name, n in (("bfs", n_bfs), ("sssp", n_sssp)):
+
+    def run(name, n, env=None, check=True):
+        """n timed sources after one warm-up source; env = schedule knobs (they never change results)"""
+        env = env or {}
+        os.environ.update(env)
         teps, ms, checked = [], [], None
         l0 = h.launch_count()
-        for i in range(n + 1):  # source 0 is the warm-up
-            s = sources[i:i + 1].contiguous()
-            s_host = int(s.item())
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            if name == "bfs":
-                dist, pred, verts = plc.bfs(h, G, s, True, 0, True, False)
-            else:
-                verts, dist, pred = plc.sssp(h, G, s_host, float("inf"), True, False)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            reached = (dist != 2**31 - 1) if name == "bfs" else (dist < 3e38)
-            ne = int(deg[verts.long()][reached].sum().item()) // 2
-            if i == 0:
-                # property check on the full-size result (external ids)
-                d_ext = torch.empty(V, dtype=dist.dtype, device="cuda")
-                d_ext[verts.long()] = dist
-                has_pred = pred >= 0
-                dp = d_ext[pred[has_pred].long()]
-                dv = dist[has_pred]
-                ok_tree = bool(((dp + 1 == dv) if name == "bfs" else (dp <= dv)).all().item())
-                ok_src = bool((d_ext[s_host] == 0).item())
-                ok_cnt = int(has_pred.sum().item()) == int(reached.sum().item()) - 1
-                checked = {"tree_property": ok_tree, "source_distance_zero": ok_src,
-                           "every_reached_vertex_but_the_source_has_a_predecessor": ok_cnt,
-                           "reached": int(reached.sum().item())}
-            else:
-                teps.append(ne / dt)
-                ms.append(dt * 1e3)
-        out[name] = {"sources": n, "harmonic_mean_mteps": _harmonic(teps) / 1e6 if teps else None,
-                     "mean_mteps": sum(teps) / len(teps) / 1e6 if teps else None,
-                     "mean_ms": sum(ms) / len(ms) if ms else None, "min_ms": min(ms) if ms else None,
-                     "max_ms": max(ms) if ms else None, "launches_per_source": (h.launch_count() - l0) / (n + 1),
-                     "check": checked,
-                     "timing": "wall clock around the synchronous C-ABI call, torch.cuda.synchronize() on both sides"}
+        try:
+            for i in range(n + 1):  # source 0 is the warm-up
+                s = sources[i:i + 1].contiguous()
+                s_host = int(s.item())
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if name == "bfs":
+                    dist, pred, verts = plc.bfs(h, G, s, True, 0, True, False)
+                else:
+                    verts, dist, pred = plc.sssp(h, G, s_host, float("inf"), True, False)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                reached = (dist != 2**31 - 1) if name == "bfs" else (dist < 3e38)
+                ne = int(deg[verts.long()][reached].sum().item()) // 2
+                if i == 0:
+                    if check:  # property check on the full-size result (external ids)
+                        d_ext = torch.empty(V, dtype=dist.dtype, device="cuda")
+                        d_ext[verts.long()] = dist
+                        has_pred = pred >= 0
+                        dp = d_ext[pred[has_pred].long()]
+                        dv = dist[has_pred]
+                        ok_tree = bool(((dp + 1 == dv) if name == "bfs" else (dp <= dv)).all().item())
+                        ok_src = bool((d_ext[s_host] == 0).item())
+                        ok_cnt = int(has_pred.sum().item()) == int(reached.sum().item()) - 1
+                        checked = {"tree_property": ok_tree, "source_distance_zero": ok_src,
+                                   "every_reached_vertex_but_the_source_has_a_predecessor": ok_cnt,
+                                   "reached": int(reached.sum().item())}
+                else:
+                    teps.append(ne / dt)
+                    ms.append(dt * 1e3)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        res = {"sources": n, "harmonic_mean_mteps": _harmonic(teps) / 1e6 if teps else None,
+               "mean_mteps": sum(teps) / len(teps) / 1e6 if teps else None,
+               "mean_ms": sum(ms) / len(ms) if ms else None, "min_ms": min(ms) if ms else None,
+               "max_ms": max(ms) if ms else None, "launches_per_source": (h.launch_count() - l0) / (n + 1)}
+        if check:
+            res["check"] = checked
+            res["timing"] = "wall clock around the synchronous C-ABI call, torch.cuda.synchronize() on both sides"
+        if env:
+            res["env"] = env
+        return res
+
+    out["bfs"] = run("bfs", n_bfs)
+    out["sssp"] = run("sssp", n_sssp)
+    # schedule knobs A/B on the same graph and sources (results are identical by construction; only time differs)
+    ab = []
+    for name, n, env in (("bfs", n_bfs, {"CUGRAPH_B200_BFS_ALPHA": "40"}), ("bfs", n_bfs, {"CUGRAPH_B200_BFS_ALPHA": "120"}),
+                         ("sssp", min(n_sssp, 2), {"CUGRAPH_B200_SSSP_ADAPTIVE": "0"}),
+                         ("sssp", min(n_sssp, 2), {"CUGRAPH_B200_SSSP_SPLIT_ROUNDS": "2"})):
+        try:
+            r = run(name, n, env, check=False)
+            r["algorithm"] = name
+            ab.append(r)
+        except Exception as ex:
+            ab.append({"algorithm": name, "env": env, "error": f"{type(ex).__name__}: {ex}"[:200]})
+    out["schedule_ab"] = ab
     print(json.dumps(out), flush=True)
 
 

@@ -120,6 +120,7 @@ def test_bench_side_traversal(surface, capsys):
     side = _load(os.path.join(ROOT, "scripts", "bench_side.py"), "bench_side_under_test3")
     side.traversal(9, 2, 1)
     out = json.loads(capsys.readouterr().out.splitlines()[-1])
+    assert len(out["schedule_ab"]) == 4 and all(r.get("harmonic_mean_mteps", 0) > 0 for r in out["schedule_ab"]), out["schedule_ab"]
     for name in ("bfs", "sssp"):
         assert out[name]["harmonic_mean_mteps"] > 0
         assert all(out[name]["check"][k] for k in ("tree_property", "source_distance_zero",
