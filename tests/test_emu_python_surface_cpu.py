@@ -103,8 +103,13 @@ def test_bench_side_subprocess_failure_is_contained(monkeypatch):
     assert "error" in res
 
 
-@pytest.mark.parametrize("cfg", ["-", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_LOW_ELL=1"])
+def _side_variants():
+    return _load(os.path.join(ROOT, "bench.py"), "bench_for_variant_list").SIDE_VARIANTS
+
+
+@pytest.mark.parametrize("cfg", _side_variants())
 def test_bench_side_variant(surface, monkeypatch, capsys, cfg):
+    """every switch set bench.py's side run will time on the GPU: parity of the configured sweep against the plain one"""
     monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
     side = _load(os.path.join(ROOT, "scripts", "bench_side.py"), "bench_side_under_test")
     for kv in cfg.split(","):
