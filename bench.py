@@ -310,7 +310,8 @@ def run_single(args):
 # Side measurements (informational; the headline keys above never depend on them).  Each runs in its own process under
 # a timeout: BFS / SSSP of BASELINE.json configs[2] and [3] on the default path, then the experimental sweep variants
 # (off by default, parity-checked against the plain sweep in the same process before they are timed).
-SIDE_VARIANTS = ["-", "CUGRAPH_B200_HOT_X=1", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1", "CUGRAPH_B200_LOW_ELL=1",
+SIDE_VARIANTS = ["-", "CUGRAPH_B200_HOT_X=1", "CUGRAPH_B200_HOT_BANK_ORDER=1", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1",
+                 "CUGRAPH_B200_LOW_ELL=1",
                  "CUGRAPH_B200_LOW_ELL=2", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_LOW_ELL=2",
                  "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=8",
                  "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=1", "CUGRAPH_B200_LOW_ASYNC=1"]

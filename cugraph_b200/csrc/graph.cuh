@@ -47,6 +47,7 @@ struct hot_layout_t {
   int32_t n_hi{0};    // rows covered by the layout: the prefix of degree >= 32 rows (seg_k = 0), or, experimentally,
   int64_t nnz_hi{0};  // the prefix down to a lower degree bound (seg_k > 0: rows [0, seg[seg_k]))
   int seg_k{0};
+  bool bank_order{false};  // experimental: entries inside the lane slots ordered by shared-memory bank, padding on any of the zero columns
   int64_t n_hot_slots{0};
   int64_t n_slots{0};
   // A (row, block) segment is cut into PIECES of <= 64 entries = <= 8 lane slots of 8 entries.  Pieces are

@@ -1160,8 +1160,68 @@ bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int 
   return true;
 }
 
-// one CTA per sub-unit, one warp per group, lane = piece: write the group's slots step-major
+// EXPERIMENTAL (CUGRAPH_B200_HOT_BANK_ORDER=1, 4-byte values): order the entries of the 32 lane slots of one warp step so that
+// the k-th shared-memory gathers of the 32 lanes (one LDS of the sweep kernels) fall into different banks.  Any order
+// inside a slot is a valid layout (hot_slot_sum adds all 8 entries); padding may point at any of the kHotZeroPad zero
+// columns, i.e. at any bank.  Greedy, position by position: the lanes that still hold real entries take turns (lowest
+// lane first) and pick an entry on a bank nobody took at this position; a lane without such an entry waits for a later
+// position while it has spare positions left, else takes a bank used once, else any; all padding of a position shares one
+// zero column on a free bank.  local[k] < 0 marks padding on input; n_real entries come first.
 template <typename T>
+__device__ __forceinline__ void bank_order_slot(int (&local)[kHotSlot], T (&wv)[kHotSlot], int n_real, int W, int lane)
+{
+  unsigned rem = n_real >= kHotSlot ? 0xffu : ((1u << n_real) - 1u);  // real entries not placed yet
+  int out_id[kHotSlot];
+  T out_w[kHotSlot];
+#pragma unroll 1
+  for (int k = 0; k < kHotSlot; ++k) {
+    unsigned taken = 0, taken2 = 0;  // banks used once / twice at this position (the same in every lane)
+    int mine = -1;                   // entry this lane places at position k
+    unsigned turns = __ballot_sync(0xffffffffu, rem != 0);
+    while (turns) {
+      const int l = __ffs(turns) - 1;
+      turns &= turns - 1;
+      int bank = -1;
+      if (lane == l) {
+        const int spare = (kHotSlot - k) - __popc(rem);  // positions left beyond the ones the real entries need
+        for (unsigned r = rem; r; r &= r - 1) {
+          const int e = __ffs(r) - 1;
+          if (!((taken >> (local[e] & 31)) & 1u)) { mine = e; break; }
+        }
+        if (mine < 0 && spare == 0) {
+          for (unsigned r = rem; r; r &= r - 1) {
+            const int e = __ffs(r) - 1;
+            if (!((taken2 >> (local[e] & 31)) & 1u)) { mine = e; break; }
+          }
+          if (mine < 0) mine = __ffs(rem) - 1;
+        }
+        if (mine >= 0) bank = local[mine] & 31;
+      }
+      bank = __shfl_sync(0xffffffffu, bank, l);
+      if (bank >= 0) {
+        taken2 |= taken & (1u << bank);
+        taken |= 1u << bank;
+      }
+    }
+    const int pad_bank = (~taken) ? __ffs(~taken) - 1 : 0;
+    if (mine >= 0) {
+      out_id[k] = local[mine];
+      out_w[k]  = wv[mine];
+      rem &= ~(1u << mine);
+    } else {
+      out_id[k] = W + ((pad_bank - (W & 31)) & 31);  // a zero column on that bank (W .. W + 31)
+      out_w[k]  = (T)0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kHotSlot; ++k) {
+    local[k] = out_id[k];
+    wv[k]    = out_w[k];
+  }
+}
+
+// one CTA per sub-unit, one warp per group, lane = piece: write the group's slots step-major
+template <typename T, bool BANK>
 __global__ void __launch_bounds__(256)
 k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict__ fills, int32_t const* __restrict__ perm,
            int32_t const* __restrict__ piece_start, int32_t const* __restrict__ piece_len,
@@ -1198,6 +1258,27 @@ k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict
     for (int j = 0; j < sb.cls; ++j) {
       const long long slot = (long long)sb.slot_begin + ((long long)q * sb.cls + j) * 32 + lane;
       int col[kHotSlot];
+      if (BANK && hot) {  // the whole warp takes part (lanes without a piece hold padding only)
+        T wv[kHotSlot];
+        int n_real = 0;
+#pragma unroll
+        for (int k = 0; k < kHotSlot; ++k) {
+          const int e   = j * kHotSlot + k;
+          const bool in = e < ln;
+          col[k]        = in ? idx[st + e] - fl.block * W : -1;
+          wv[k]         = (in && w_out) ? w[st + e] : (T)0;
+          n_real += in ? 1 : 0;
+        }
+        bank_order_slot<T>(col, wv, n_real, W, lane);
+        unsigned v[kHotSlot];
+#pragma unroll
+        for (int k = 0; k < kHotSlot; ++k) {
+          v[k] = (unsigned)col[k];
+          if (w_out) w_out[(size_t)slot * kHotSlot + k] = wv[k];
+        }
+        reinterpret_cast<uint4*>(idx16)[slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < kHotSlot; ++k) {
         const int e   = j * kHotSlot + k;
@@ -1382,14 +1463,24 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   if (weighted) L->slot_w = dbuf((size_t)std::max<int64_t>(L->n_slots, 1) * kHotSlot * es, h.stream);
   // padding entries of the cold block read x[n_vertices], which the caller keeps at zero (padded_x_elems)
   if (!subs.empty()) {
-    if (es == 4)
-      B200_LAUNCH(h, (k_hot_fill<float>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+    // experimental: bank-aware entry order inside the lane slots (4-byte values only: a double spans two banks)
+    bool bank_order = false;
+    if (const char* e = std::getenv("CUGRAPH_B200_HOT_BANK_ORDER")) bank_order = std::atoi(e) != 0 && es == 4;
+    L->bank_order = bank_order;
+    if (bank_order)
+      B200_LAUNCH(h, (k_hot_fill<float, true>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+                  perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
+                  c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
+                  L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
+                  L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
+    else if (es == 4)
+      B200_LAUNCH(h, (k_hot_fill<float, false>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
                   c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
                   L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
                   L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
     else
-      B200_LAUNCH(h, (k_hot_fill<double>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+      B200_LAUNCH(h, (k_hot_fill<double, false>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
                   c.weights.as<double>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
                   L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),

@@ -99,7 +99,8 @@ while time.time() < t_end:
     transposed = bool(r.integers(0, 2))
     hot = bool(r.integers(0, 2))
     os.environ["CUGRAPH_B200_HOT_MIN_EDGES"] = "0" if hot else "1000000000"
-    for k, vals in (("CUGRAPH_B200_HOT_X", "01"), ("CUGRAPH_B200_HOT_NARROW", "01"), ("CUGRAPH_B200_LOW_ELL", "012")):
+    for k, vals in (("CUGRAPH_B200_HOT_X", "01"), ("CUGRAPH_B200_HOT_NARROW", "01"), ("CUGRAPH_B200_LOW_ELL", "012"),
+                    ("CUGRAPH_B200_HOT_BANK_ORDER", "01")):
         os.environ[k] = str(r.choice(list(vals)))
     os.environ["CUGRAPH_B200_HOT_UNIT_SLOTS"] = str(r.choice([1024, 8192]))
     os.environ["CUGRAPH_B200_HOT_MIN_DEGREE"] = str(r.choice([32, 32, 8, 1]))

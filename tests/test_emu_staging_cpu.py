@@ -118,8 +118,16 @@ def check_csr(P, src, dst, w):
     assert sorted(set(ext.tolist())) == sorted(set(src.tolist()) | set(dst.tolist()))
 
 
-def hot_pieces(L, g, P):
-    """(row, col[, w]) triples reconstructed from the piece layout + structural checks"""
+def lds_wavefronts(ids):
+    """shared-memory wavefronts of one warp-wide 4-byte gather: max over the 32 banks of the distinct addresses on a bank"""
+    u = np.unique(ids)
+    return int(np.bincount(u & 31, minlength=32).max())
+
+
+def hot_pieces(L, g, P, bank_order=False, stats=None):
+    """(row, col[, w]) triples reconstructed from the piece layout + structural checks.  bank_order: the experimental
+    layout whose slots are ordered by shared-memory bank (padding anywhere in a slot, on any of the 64 zero columns).
+    stats: dict that receives the LDS count and the wavefront count of the 16-bit full-slot classes."""
     ints = (C.c_int64 * 12)()
     ptrs = (C.c_void_p * 10)()
     rc = L.emu_hot_layout(C.c_void_p(L.handle), g, ints, ptrs)
@@ -164,10 +172,17 @@ def hot_pieces(L, g, P):
                     ids = idx16.reshape(-1, 8)[s].astype(np.int64); pad = W
                 else:
                     ids = idx32.reshape(-1, 8)[s - n_hot].astype(np.int64); pad = P["nv"]
-                real = ids != pad
-                # padding only behind the real entries of a slot; unused lanes are all padding
-                assert (real[:, :-1] >= real[:, 1:]).all()
-                assert not real[rows[q] < 0].any()
+                if bank_order and blk < B and code <= 8:
+                    real = ids < W
+                    assert (ids < W + 64).all()             # padding = one of the slice's zero columns
+                else:
+                    real = ids != pad
+                    # padding only behind the real entries of a slot
+                    assert (real[:, :-1] >= real[:, 1:]).all()
+                assert not real[rows[q] < 0].any()          # unused lanes are all padding
+                if stats is not None and blk < B and code <= 8:
+                    stats["lds"] = stats.get("lds", 0) + 8
+                    stats["wavefronts"] = stats.get("wavefronts", 0) + sum(lds_wavefronts(ids[:, k]) for k in range(8))
                 if blk < B:
                     assert (ids[real] < W).all()
                     ids = ids + blk * W
@@ -183,8 +198,8 @@ def hot_pieces(L, g, P):
     return dict(r=r, c=c, w=w, W=W, B=B, subs=subs, units=units, narrow=narrow)
 
 
-def check_hot(L, g, P):
-    H = hot_pieces(L, g, P)
+def check_hot(L, g, P, bank_order=False, stats=None):
+    H = hot_pieces(L, g, P, bank_order, stats)
     n_hi, nnz_hi = P["seg"][0], P["nnz_hi"]
     rows = np.repeat(np.arange(n_hi), np.diff(P["off"][:n_hi + 1]))
     cols = P["idx"][:nnz_hi].astype(np.int64)
@@ -233,6 +248,24 @@ def test_narrow_piece_layout(emu, monkeypatch):
     H = check_hot(emu, g, P)
     assert H["narrow"] and all((H["subs"][:, 3] == code).any() for code in (16, 32, 64))
     emu.cugraph_graph_free(g)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_bank_ordered_piece_layout(emu, monkeypatch, weighted):
+    """CUGRAPH_B200_HOT_BANK_ORDER=1: same (row, source[, weight]) multiset, and fewer shared-memory wavefronts per gather"""
+    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    src, dst, w = make_edges(120_000, 900_000, seed=21 + weighted, weighted=weighted, id_offset=3)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CUGRAPH_B200_HOT_BANK_ORDER", mode)
+        g = create_graph(emu, src, dst, w)
+        P = primary(emu, g)
+        st = {}
+        check_hot(emu, g, P, bank_order=(mode == "1"), stats=st)
+        res[mode] = st["wavefronts"] / st["lds"]
+        emu.cugraph_graph_free(g)
+    print(f"wavefronts per LDS: default order {res['0']:.3f}, bank order {res['1']:.3f}")
+    assert res["1"] < 0.8 * res["0"], res
 
 
 @pytest.mark.parametrize("weighted", [False, True])
