@@ -227,7 +227,9 @@ def run_single(args):
     launches = h.launch_count() - l0
     clocks = sampler.stop()
     dev_s = e0.elapsed_time(e1) * 1e-3  # device time between the two events; wall is the host's view of the same region
-    timed_s = dev_s if dev_s > 0 else wall
+    # the calls are synchronous, so the two clocks must agree; if the events saw something else (wrong stream), fall back
+    events_ok = 0.5 * wall <= dev_s <= 1.05 * wall
+    timed_s = dev_s if events_ok else wall
     ms_step = timed_s / args.steps * 1e3
     value = E * ITERS * args.steps / timed_s / 1e6
 
@@ -300,6 +302,7 @@ def run_single(args):
                       "num_vertices": nv, "num_edges": E, "alpha": ALPHA, "iterations": ITERS, "vertex_type": "int32",
                       "l2": "inputs (1.2 GB/sweep) exceed the 126 MB L2; no explicit flush"},
            "timing": {"device_ms_per_step": dev_s / args.steps * 1e3, "wall_ms_per_step": wall / args.steps * 1e3,
+                      "value_from": "device events" if events_ok else "wall clock (events disagreed)",
                       "how": "CUDA events recorded on the handle's stream around the K synchronous C-ABI calls"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     if side is not None:
