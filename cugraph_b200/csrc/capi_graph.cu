@@ -22,6 +22,58 @@ __global__ void k_offsets_to_rows(O const* offsets, int64_t n_rows, VT* rows)
     for (long long e = (long long)offsets[r] + lane; e < (long long)offsets[r + 1]; e += 32) rows[e] = (VT)r;
 }
 
+// do_expensive_check of the constructors (create_graph_from_edgelist_impl.cuh:803-830: check_symmetric :260-314,
+// check_no_parallel_edge :316-334), evaluated on the staged adjacency instead of on sorted copies of the edge list: rows
+// and neighbours are internal ids of one id space and every row's neighbours are ascending, so a parallel edge is two
+// equal neighbours side by side and (r, c) has its reverse iff r is found in row c.  One warp per row.
+// flags[0]: an edge without its reverse; flags[1]: a parallel edge.
+template <typename O>
+__global__ void k_expensive_check(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t n_rows, int check_sym,
+                                  int check_dup, int* __restrict__ flags)
+{
+  const int lane = threadIdx.x & 31;
+  for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < n_rows;
+       r += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const long long beg = (long long)off[r], end = (long long)off[r + 1];
+    for (long long e = beg + lane; e < end; e += 32) {
+      const int c = idx[e];
+      if (check_dup && e > beg && idx[e - 1] == c) flags[1] = 1;
+      if (check_sym) {
+        long long lo = (long long)off[c], hi = (long long)off[c + 1];  // first position in row c with idx >= r
+        while (lo < hi) {
+          const long long mid = lo + ((hi - lo) >> 1);
+          if (idx[mid] < (int)r) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= (long long)off[c + 1] || idx[lo] != (int)r) flags[0] = 1;
+      }
+    }
+  }
+}
+
+void expensive_check(handle_impl const& h, graph_impl const& g, bool check_sym, bool check_dup)
+{
+  csx_t const& c = *g.primary;
+  if ((!check_sym && !check_dup) || c.nnz == 0) return;
+  dbuf flags = make_dbuf<int>(2, h.stream);
+  CUDA_TRY(cudaMemsetAsync(flags.data(), 0, 2 * sizeof(int), h.stream));
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(((int64_t)c.n_rows * 32 + 255) / 256, 1), (int64_t)h.sm_count * 32);
+  if (c.offs64)
+    B200_LAUNCH(h, (k_expensive_check<int64_t>), grid, 256, 0, c.offsets.as<int64_t>(), c.indices.as<int32_t>(), c.n_rows,
+                check_sym ? 1 : 0, check_dup ? 1 : 0, flags.as<int>());
+  else
+    B200_LAUNCH(h, (k_expensive_check<int32_t>), grid, 256, 0, c.offsets.as<int32_t>(), c.indices.as<int32_t>(), c.n_rows,
+                check_sym ? 1 : 0, check_dup ? 1 : 0, flags.as<int>());
+  int hf[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(hf, flags.data(), sizeof(hf), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  check_last("expensive check");
+  // the reference raises cugraph::logic_error here, which its C layer reports as CUGRAPH_UNKNOWN_ERROR (c_api/utils.hpp:43-46)
+  B200_EXPECTS(hf[0] == 0, CUGRAPH_UNKNOWN_ERROR,
+               "Invalid input arguments: graph_properties.is_symmetric is true but the input edge list is not symmetric.");
+  B200_EXPECTS(hf[1] == 0, CUGRAPH_UNKNOWN_ERROR,
+               "Invalid input arguments: graph_properties.is_multigraph is false but the input edge list has parallel edges.");
+}
+
 bool is_int_type(cugraph_data_type_id_t t) { return t == INT32 || t == INT64; }
 bool is_float_type(cugraph_data_type_id_t t) { return t == FLOAT32 || t == FLOAT64; }
 
@@ -36,7 +88,7 @@ void create_sg_common(const cugraph_resource_handle_t* handle, const cugraph_gra
                       const cugraph_type_erased_device_array_view_t* edge_start_times,
                       const cugraph_type_erased_device_array_view_t* edge_end_times, bool_t store_transposed,
                       bool_t renumber, bool_t drop_self_loops, bool_t drop_multi_edges, bool_t symmetrize,
-                      cugraph_graph_t** graph)
+                      bool_t do_expensive_check, cugraph_graph_t** graph)
 {
   auto const& h = H(handle);
   B200_EXPECTS(graph != nullptr, CUGRAPH_INVALID_INPUT, "graph out-pointer is NULL");
@@ -81,6 +133,10 @@ void create_sg_common(const cugraph_resource_handle_t* handle, const cugraph_gra
   g->device           = h.device;
   stage_graph(h, *g, vx, s, d, w, renumber == TRUE, drop_self_loops == TRUE, drop_multi_edges == TRUE,
               symmetrize == TRUE);
+  // the reference checks the edge list it hands to the graph constructor, i.e. after the drop / symmetrize passes
+  if (do_expensive_check == TRUE)
+    expensive_check(h, *g, properties->is_symmetric == TRUE && symmetrize != TRUE,
+                    properties->is_multigraph != TRUE && drop_multi_edges != TRUE);
   *graph = reinterpret_cast<cugraph_graph_t*>(g.release());
 }
 
@@ -103,10 +159,9 @@ cugraph_error_code_t cugraph_graph_create_sg(const cugraph_resource_handle_t* ha
                                              bool_t drop_multi_edges, bool_t symmetrize, bool_t do_expensive_check,
                                              cugraph_graph_t** graph, cugraph_error_t** error)
 {
-  (void)do_expensive_check;
   return guarded(error, [&] {
     create_sg_common(handle, properties, vertices, src, dst, weights, edge_ids, edge_type_ids, nullptr, nullptr,
-                     store_transposed, renumber, drop_self_loops, drop_multi_edges, symmetrize, graph);
+                     store_transposed, renumber, drop_self_loops, drop_multi_edges, symmetrize, do_expensive_check, graph);
   });
 }
 
@@ -120,11 +175,10 @@ cugraph_error_code_t cugraph_graph_create_with_times_sg(
   bool_t drop_self_loops, bool_t drop_multi_edges, bool_t symmetrize, bool_t do_expensive_check,
   cugraph_graph_t** graph, cugraph_error_t** error)
 {
-  (void)do_expensive_check;
   return guarded(error, [&] {
     create_sg_common(handle, properties, vertices, src, dst, weights, edge_ids, edge_type_ids, edge_start_time_ids,
                      edge_end_time_ids, store_transposed, renumber, drop_self_loops, drop_multi_edges, symmetrize,
-                     graph);
+                     do_expensive_check, graph);
   });
 }
 
@@ -136,7 +190,6 @@ cugraph_error_code_t cugraph_graph_create_sg_from_csr(
   const cugraph_type_erased_device_array_view_t* edge_type_ids, bool_t store_transposed, bool_t renumber,
   bool_t symmetrize, bool_t do_expensive_check, cugraph_graph_t** graph, cugraph_error_t** error)
 {
-  (void)do_expensive_check;
   return guarded(error, [&] {
     auto const& h = H(handle);
     B200_EXPECTS(offsets && indices, CUGRAPH_INVALID_INPUT, "offsets and indices are required");
@@ -175,7 +228,7 @@ cugraph_error_code_t cugraph_graph_create_sg_from_csr(
     create_sg_common(handle, properties, reinterpret_cast<cugraph_type_erased_device_array_view_t const*>(&vview),
                      reinterpret_cast<cugraph_type_erased_device_array_view_t const*>(&src_view), indices, weights,
                      edge_ids, edge_type_ids, nullptr, nullptr, store_transposed, renumber, FALSE, FALSE, symmetrize,
-                     graph);
+                     do_expensive_check, graph);
   });
 }
 

@@ -102,3 +102,40 @@ def test_large_hub_goes_through_large_queue():
     verts, dist, pred = plc.sssp(h, g, 0, float("inf"), True, False)
     rd, _ = oracle.sssp(src, dst, w, n + 1, 0)
     assert np.array_equal(by_vertex(verts, dist, n + 1).astype(np.float64), rd)
+
+
+@pytest.mark.parametrize("store_transposed", [False, True])
+def test_expensive_check_at_graph_creation(store_transposed):
+    """do_expensive_check of the constructors (create_graph_from_edgelist_impl.cuh:803-830); the first case is the
+    reference's test_create_sg_graph_symmetric_error (cpp/tests/c_api/create_graph_test.c:430-535)"""
+    import torch
+    from cugraph_b200 import _capi
+    from cugraph_b200 import pylibcugraph as plc
+    h = plc.ResourceHandle()
+    src, dst = [0, 1, 1, 2, 2, 2, 3, 4], [1, 3, 4, 0, 1, 3, 5, 5]
+
+    def create(s, d, symmetric, multigraph, **kw):
+        return plc.SGGraph(h, plc.GraphProperties(is_symmetric=symmetric, is_multigraph=multigraph),
+                           torch.tensor(s, dtype=torch.int32).cuda(), torch.tensor(d, dtype=torch.int32).cuda(),
+                           store_transposed=store_transposed, renumber=True, do_expensive_check=True, **kw)
+
+    with pytest.raises(_capi.CugraphError) as e:
+        create(src, dst, True, False)
+    assert e.value.code == _capi.UNKNOWN_ERROR and "not symmetric" in str(e.value)
+    create(src, dst, False, False)
+    create(src + dst, dst + src, True, False)
+    create(src, dst, True, False, symmetrize=True)
+    with pytest.raises(_capi.CugraphError) as e:
+        create(src + [2], dst + [3], False, False)
+    assert "parallel edges" in str(e.value)
+    create(src + [2], dst + [3], False, True)
+    create(src + [2], dst + [3], False, False, drop_multi_edges=True)
+    # RMAT-14 symmetrised (multi-edges present): passes as a multigraph, fails once one direction of an edge is removed
+    from oracle.rmat import rmat_edgelist
+    s, d = rmat_edgelist(14, 16 << 14, seed=5)
+    s2, d2 = np.concatenate([s, d]), np.concatenate([d, s])
+    create(s2.tolist(), d2.tolist(), True, True)
+    victim = int(np.nonzero(s2 != d2)[0][0])
+    keep = ~((s2 == s2[victim]) & (d2 == d2[victim]))
+    with pytest.raises(_capi.CugraphError):
+        create(s2[keep].tolist(), d2[keep].tolist(), True, True)

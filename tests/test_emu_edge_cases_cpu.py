@@ -204,3 +204,49 @@ def test_csr_input(emu):  # noqa: F811
     ref, _, _ = oracle.pagerank(s, d, V, w.astype(np.float64), alpha=0.85, epsilon=0.0, max_iterations=15)
     np.testing.assert_allclose(by_vertex(verts, pr, V), ref, rtol=2e-5)
     L.cugraph_graph_free(g)
+
+
+def _create_checked(L, src, dst, symmetric, multigraph, transposed=False, renumber=True, **flags):
+    """cugraph_graph_create_with_times_sg with do_expensive_check = TRUE; returns (code, message)"""
+    a = [np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)]
+    v = [_view(L, x) for x in a]
+    g, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_graph_create_with_times_sg(C.c_void_p(L.handle), C.byref(Props(int(symmetric), int(multigraph))), None, v[0], v[1],
+                                                None, None, None, None, None, int(transposed), int(renumber),
+                                                0, int(flags.get("drop_multi_edges", 0)), int(flags.get("symmetrize", 0)), 1,
+                                                C.byref(g), C.byref(err))
+    msg = L.cugraph_error_message(err).decode() if code != 0 else ""
+    if code == 0:
+        L.cugraph_graph_free(g)
+    else:
+        assert not g.value
+    return code, msg
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("renumber", [False, True])
+def test_expensive_check_at_graph_creation(emu, transposed, renumber):  # noqa: F811
+    """do_expensive_check of the constructors (create_graph_from_edgelist_impl.cuh:803-830); the first case is the
+    reference's test_create_sg_graph_symmetric_error (cpp/tests/c_api/create_graph_test.c:430-535)"""
+    src, dst = [0, 1, 1, 2, 2, 2, 3, 4], [1, 3, 4, 0, 1, 3, 5, 5]
+    kw = dict(transposed=transposed, renumber=renumber)
+    code, msg = _create_checked(emu, src, dst, symmetric=True, multigraph=False, **kw)
+    assert code == 1 and "not symmetric" in msg                      # CUGRAPH_UNKNOWN_ERROR, as the reference's C layer reports it
+    assert _create_checked(emu, src, dst, symmetric=False, multigraph=False, **kw)[0] == 0
+    assert _create_checked(emu, src + dst, dst + src, symmetric=True, multigraph=False, **kw)[0] == 0
+    assert _create_checked(emu, src, dst, symmetric=True, multigraph=False, symmetrize=1, **kw)[0] == 0
+    code, msg = _create_checked(emu, src + [2], dst + [3], symmetric=False, multigraph=False, **kw)
+    assert code == 1 and "parallel edges" in msg
+    assert _create_checked(emu, src + [2], dst + [3], symmetric=False, multigraph=True, **kw)[0] == 0
+    assert _create_checked(emu, src + [2], dst + [3], symmetric=False, multigraph=False, drop_multi_edges=1, **kw)[0] == 0
+    # a larger random case: symmetric with parallel edges declared as a multigraph passes, one missing reverse edge fails
+    r = np.random.default_rng(4)
+    s, d = r.integers(0, 300, 4000), r.integers(0, 300, 4000)
+    s2, d2 = np.concatenate([s, d]), np.concatenate([d, s])
+    assert _create_checked(emu, s2, d2, symmetric=True, multigraph=True, **kw)[0] == 0
+    keep = np.ones(s2.size, bool)
+    victim = int(np.nonzero(s2 != d2)[0][0])
+    keep[(s2 == s2[victim]) & (d2 == d2[victim])] = False                 # every copy of one direction
+    has_reverse = ((s2 == d2[victim]) & (d2 == s2[victim]) & keep).any()
+    code, msg = _create_checked(emu, s2[keep], d2[keep], symmetric=True, multigraph=True, **kw)
+    assert (code == 1 and "not symmetric" in msg) if has_reverse else code == 0
