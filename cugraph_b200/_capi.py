@@ -116,14 +116,42 @@ def lib():
     return L
 
 
-class CugraphError(RuntimeError):
+class CugraphError(Exception):
+    """Base of the errors raised for a non-success C return code.  `code` is the cugraph_error_code_t; the concrete class
+    also derives from the builtin exception the reference raises for that code (utils.pyx:40-83), so callers written
+    against the reference (`except ValueError`, `pytest.raises(RuntimeError)`) keep working."""
+
     def __init__(self, code, message, where):
         self.code = code
-        super().__init__(f"{where} failed (code {code}): {message}")
+        super().__init__(f"non-success value returned from {where}: {_CODE_NAMES.get(code, 'unknown error code')} {message}")
+
+
+class CugraphRuntimeError(CugraphError, RuntimeError):
+    pass
+
+
+class CugraphValueError(CugraphError, ValueError):
+    pass
+
+
+class CugraphMemoryError(CugraphError, MemoryError):
+    pass
+
+
+class CugraphNotImplementedError(CugraphError, NotImplementedError):
+    pass
+
+
+_CODE_NAMES = {UNKNOWN_ERROR: "CUGRAPH_UNKNOWN_ERROR", INVALID_HANDLE: "CUGRAPH_INVALID_HANDLE", ALLOC_ERROR: "CUGRAPH_ALLOC_ERROR",
+               INVALID_INPUT: "CUGRAPH_INVALID_INPUT", NOT_IMPLEMENTED: "CUGRAPH_NOT_IMPLEMENTED",
+               UNSUPPORTED_TYPE_COMBINATION: "CUGRAPH_UNSUPPORTED_TYPE_COMBINATION"}
+_CODE_CLASS = {UNKNOWN_ERROR: CugraphRuntimeError, INVALID_HANDLE: CugraphValueError, ALLOC_ERROR: CugraphMemoryError,
+               INVALID_INPUT: CugraphValueError, NOT_IMPLEMENTED: CugraphNotImplementedError,
+               UNSUPPORTED_TYPE_COMBINATION: CugraphValueError}
 
 
 def check(code, err_ptr, where):
-    """assert_success of python/pylibcugraph/pylibcugraph/utils.pyx:40-83."""
+    """assert_success of python/pylibcugraph/pylibcugraph/utils.pyx:40-83: same exception type per error code."""
     if code == SUCCESS:
         return
     msg = ""
@@ -131,4 +159,4 @@ def check(code, err_ptr, where):
         m = lib().cugraph_error_message(err_ptr)
         msg = m.decode() if m else ""
         lib().cugraph_error_free(err_ptr)
-    raise CugraphError(code, msg, where)
+    raise _CODE_CLASS.get(code, CugraphRuntimeError)(code, msg, where)

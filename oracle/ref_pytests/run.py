@@ -1,0 +1,41 @@
+"""TEST INFRASTRUCTURE: run the reference's OWN pylibcugraph tests for this path —
+python/pylibcugraph/pylibcugraph/tests/{test_pagerank,test_sssp}.py with their conftest.py, unmodified, from where they lie
+under $REF — against this repository's pylibcugraph mirror.  `import pylibcugraph` and `import cupy` resolve to the
+stand-ins in oracle/ref_pytests/shims/.  Without a GPU the library under test is the CPU emulation build
+(tests/emu_py.py); on a box with a GPU and the reference sources it is the CUDA library.
+    python oracle/ref_pytests/run.py [extra pytest args]"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("REF", "/root/reference")
+TESTS = os.path.join(REF, "python", "pylibcugraph", "pylibcugraph", "tests")
+
+
+def main(argv):
+    import contextlib
+    import pytest
+    import torch
+    if not os.path.isdir(TESTS):
+        print(f"reference tests not found under {TESTS}")
+        return 3
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    os.environ.setdefault("RAPIDS_DATASET_ROOT_DIR", os.path.join(REF, "datasets"))
+    if torch.cuda.is_available():
+        cm = contextlib.nullcontext()
+    else:
+        from tests.emu_py import emulated_python_surface
+        cm = emulated_python_surface()
+    with cm:
+        files = [a for a in argv if a.endswith(".py")] or ["test_pagerank.py", "test_sssp.py", "test_graph_sg.py"]
+        argv = [a for a in argv if not a.endswith(".py")]
+        # test_SGGraph_create_from_cudf needs cudf (a DataFrame library outside this path; not installed)
+        argv = argv + ["-k", "not test_SGGraph_create_from_cudf"]
+        return pytest.main([os.path.join(TESTS, f) for f in files] + ["-q",
+                            "-p", "no:cacheprovider", "--rootdir", TESTS, "-c", os.devnull] + argv)
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))

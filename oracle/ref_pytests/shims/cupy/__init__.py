@@ -1,0 +1,19 @@
+"""TEST INFRASTRUCTURE (oracle/ref_pytests): the two things the reference's pylibcugraph tests need from cupy — `asarray`
+for building device arrays and array objects that answer `.dtype`, `.tolist()`, `len()` — served by torch tensors (CUDA
+when a device is present, host memory when the library under test is the CPU emulation build).  cupy is not installed in
+this image; the product never imports this module."""
+import numpy as _np
+import torch as _torch
+
+
+def _device():
+    return "cuda" if _torch.cuda.is_available() else "cpu"
+
+
+def asarray(obj, dtype=None):
+    a = _np.asarray(obj if not isinstance(obj, range) else list(obj), dtype=dtype)
+    return _torch.as_tensor(_np.array(a, copy=True)).to(_device())
+
+
+array = asarray
+float32, float64, int32, int64 = _np.float32, _np.float64, _np.int32, _np.int64
