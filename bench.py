@@ -316,6 +316,7 @@ def run_single(args):
 SIDE_VARIANTS = ["-", "CUGRAPH_B200_HOT_X=1", "CUGRAPH_B200_HOT_BANK_ORDER=1", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1",
                  "CUGRAPH_B200_LOW_ELL=1",
                  "CUGRAPH_B200_LOW_ELL=2", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_LOW_ELL=2",
+                 "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_BANK_ORDER=1,CUGRAPH_B200_LOW_ELL=2",
                  "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=8",
                  "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=1", "CUGRAPH_B200_LOW_ASYNC=1"]
 
@@ -341,7 +342,7 @@ def _run_side(argv, timeout_s):
 
 
 def _side_measurements(scale, budget_s=None):
-    budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "110")) if budget_s is None else budget_s
+    budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "130")) if budget_s is None else budget_s
     t0 = time.perf_counter()
     side = {"traversal": _run_side(["traversal", scale, 16, 4], 150), "variants": []}
     for cfg in SIDE_VARIANTS:
