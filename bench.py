@@ -344,12 +344,12 @@ def _run_side(argv, timeout_s):
 def _side_measurements(scale, budget_s=None):
     budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "130")) if budget_s is None else budget_s
     t0 = time.perf_counter()
-    side = {"traversal": _run_side(["traversal", scale, 16, 4], 150), "variants": []}
+    side = {"traversal": _run_side(["traversal", scale, 16, 4], 120), "variants": []}
     for cfg in SIDE_VARIANTS:
         if time.perf_counter() - t0 > budget_s:
             side["variants"].append({"config": cfg, "skipped": f"side budget of {budget_s:.0f} s spent"})
             continue
-        res = _run_side(["variant", scale, cfg], 75)
+        res = _run_side(["variant", scale, cfg], 50)
         res.setdefault("config", cfg)
         side["variants"].append(res)
     side["seconds"] = time.perf_counter() - t0
