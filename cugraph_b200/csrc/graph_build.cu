@@ -1160,64 +1160,64 @@ bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int 
   return true;
 }
 
-// EXPERIMENTAL (CUGRAPH_B200_HOT_BANK_ORDER=1, 4-byte values): order the entries of the 32 lane slots of one warp step so that
-// the k-th shared-memory gathers of the 32 lanes (one LDS of the sweep kernels) fall into different banks.  Any order
-// inside a slot is a valid layout (hot_slot_sum adds all 8 entries); padding may point at any of the kHotZeroPad zero
-// columns, i.e. at any bank.  Greedy, position by position: the lanes that still hold real entries take turns (lowest
-// lane first) and pick an entry on a bank nobody took at this position; a lane without such an entry waits for a later
-// position while it has spare positions left, else takes a bank used once, else any; all padding of a position shares one
-// zero column on a free bank.  local[k] < 0 marks padding on input; n_real entries come first.
-template <typename T>
-__device__ __forceinline__ void bank_order_slot(int (&local)[kHotSlot], T (&wv)[kHotSlot], int n_real, int W, int lane)
+// EXPERIMENTAL (CUGRAPH_B200_HOT_BANK_ORDER=1, 4-byte values): order the entries of the 32 pieces of a group so that the
+// k-th shared-memory gathers of the 32 lanes in every step (one LDS of the sweep kernels) fall into different banks.  Any
+// assignment of a piece's entries to its (step, position) places is a valid layout (the sweep adds all of them into one
+// sum per piece); padding may point at any of the kHotZeroPad zero columns, i.e. at any bank.  Greedy, place by place:
+// the lanes that still hold entries take turns (lowest lane first) and pick an entry on a bank nobody took at this place;
+// a lane without such an entry waits for a later place while it has spare places left, else takes a bank used once, else
+// any; all padding of a place shares one zero column on a free bank.
+// State per lane: bank_bits[b] = the piece's entries (bit e = entry e, <= 64 per piece) on bank b, `rem` = not placed yet,
+// `have` = banks with an entry left.
+struct bank_piece_t {
+  unsigned long long bank_bits[32];
+  unsigned long long rem;
+  unsigned have;
+  unsigned have2;  // banks with at least two entries left: used first, which keeps the number of distinct banks up
+};
+
+// one place of all 32 lanes: returns this lane's entry index (>= 0) or -1 - pad_bank for padding
+__device__ __forceinline__ int bank_order_place(bank_piece_t& P, int places_left, int lane)
 {
-  unsigned rem = n_real >= kHotSlot ? 0xffu : ((1u << n_real) - 1u);  // real entries not placed yet
-  int out_id[kHotSlot];
-  T out_w[kHotSlot];
-#pragma unroll 1
-  for (int k = 0; k < kHotSlot; ++k) {
-    unsigned taken = 0, taken2 = 0;  // banks used once / twice at this position (the same in every lane)
-    int mine = -1;                   // entry this lane places at position k
-    unsigned turns = __ballot_sync(0xffffffffu, rem != 0);
-    while (turns) {
-      const int l = __ffs(turns) - 1;
-      turns &= turns - 1;
-      int bank = -1;
-      if (lane == l) {
-        const int spare = (kHotSlot - k) - __popc(rem);  // positions left beyond the ones the real entries need
-        for (unsigned r = rem; r; r &= r - 1) {
-          const int e = __ffs(r) - 1;
-          if (!((taken >> (local[e] & 31)) & 1u)) { mine = e; break; }
-        }
-        if (mine < 0 && spare == 0) {
-          for (unsigned r = rem; r; r &= r - 1) {
-            const int e = __ffs(r) - 1;
-            if (!((taken2 >> (local[e] & 31)) & 1u)) { mine = e; break; }
-          }
-          if (mine < 0) mine = __ffs(rem) - 1;
-        }
-        if (mine >= 0) bank = local[mine] & 31;
+  unsigned taken = 0, taken2 = 0;  // banks used once / twice at this place (the same in every lane)
+  int mine       = -1;
+  const unsigned active = __ballot_sync(0xffffffffu, P.rem != 0ull);
+  const int t0          = (11 * places_left) & 31;  // the lane that chooses first changes from place to place
+  unsigned turns        = t0 ? ((active >> t0) | (active << (32 - t0))) : active;
+  while (turns) {
+    const int l = (__ffs(turns) - 1 + t0) & 31;
+    turns &= turns - 1;
+    int bank = -1;
+    if (lane == l) {
+      const int spare = places_left - __popcll(P.rem);  // places beyond the ones the remaining entries need
+      unsigned pick   = P.have2 & ~taken;
+      if (!pick) pick = P.have & ~taken;
+      if (!pick && spare <= 0) {
+        pick = P.have & ~taken2;
+        if (!pick) pick = P.have;
       }
-      bank = __shfl_sync(0xffffffffu, bank, l);
-      if (bank >= 0) {
-        taken2 |= taken & (1u << bank);
-        taken |= 1u << bank;
+      if (pick) {
+        // start the search at a bank that depends on lane and place: always taking the lowest bank would use up every
+        // piece's low banks first and leave the late places with what nobody could use
+        const int r0       = (lane + 5 * places_left) & 31;
+        const unsigned rot = r0 ? ((pick >> r0) | (pick << (32 - r0))) : pick;
+        bank               = (__ffs(rot) - 1 + r0) & 31;
+        mine = __ffsll((long long)(P.bank_bits[bank] & P.rem)) - 1;
+        P.rem &= ~(1ull << mine);
+        const int left = __popcll(P.bank_bits[bank] & P.rem);
+        if (left < 2) P.have2 &= ~(1u << bank);
+        if (left < 1) P.have &= ~(1u << bank);
       }
     }
-    const int pad_bank = (~taken) ? __ffs(~taken) - 1 : 0;
-    if (mine >= 0) {
-      out_id[k] = local[mine];
-      out_w[k]  = wv[mine];
-      rem &= ~(1u << mine);
-    } else {
-      out_id[k] = W + ((pad_bank - (W & 31)) & 31);  // a zero column on that bank (W .. W + 31)
-      out_w[k]  = (T)0;
+    bank = __shfl_sync(0xffffffffu, bank, l);
+    if (bank >= 0) {
+      taken2 |= taken & (1u << bank);
+      taken |= 1u << bank;
     }
   }
-#pragma unroll
-  for (int k = 0; k < kHotSlot; ++k) {
-    local[k] = out_id[k];
-    wv[k]    = out_w[k];
-  }
+  if (mine >= 0) return mine;
+  const int pad_bank = (~taken) ? __ffs(~taken) - 1 : 0;
+  return -1 - pad_bank;
 }
 
 // one CTA per sub-unit, one warp per group, lane = piece: write the group's slots step-major
@@ -1255,26 +1255,28 @@ k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict
       else idx_s[slot] = (uint16_t)v[0];
       continue;
     }
+    bank_piece_t bp;  // only used by the BANK instantiation
     for (int j = 0; j < sb.cls; ++j) {
       const long long slot = (long long)sb.slot_begin + ((long long)q * sb.cls + j) * 32 + lane;
       int col[kHotSlot];
       if (BANK && hot) {  // the whole warp takes part (lanes without a piece hold padding only)
-        T wv[kHotSlot];
-        int n_real = 0;
-#pragma unroll
-        for (int k = 0; k < kHotSlot; ++k) {
-          const int e   = j * kHotSlot + k;
-          const bool in = e < ln;
-          col[k]        = in ? idx[st + e] - fl.block * W : -1;
-          wv[k]         = (in && w_out) ? w[st + e] : (T)0;
-          n_real += in ? 1 : 0;
+        if (j == 0) {
+          for (int b = 0; b < 32; ++b) bp.bank_bits[b] = 0ull;
+          bp.have = bp.have2 = 0u;
+          for (int e = 0; e < ln; ++e) {
+            const int b = (idx[st + e] - fl.block * W) & 31;
+            if (bp.bank_bits[b]) bp.have2 |= 1u << b;
+            bp.bank_bits[b] |= 1ull << e;
+            bp.have |= 1u << b;
+          }
+          bp.rem = ln >= 64 ? ~0ull : ((1ull << ln) - 1ull);
         }
-        bank_order_slot<T>(col, wv, n_real, W, lane);
         unsigned v[kHotSlot];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < kHotSlot; ++k) {
-          v[k] = (unsigned)col[k];
-          if (w_out) w_out[(size_t)slot * kHotSlot + k] = wv[k];
+          const int e = bank_order_place(bp, (sb.cls - j) * kHotSlot - k, lane);
+          v[k]        = e >= 0 ? (unsigned)(idx[st + e] - fl.block * W) : (unsigned)(W + ((-1 - e - (W & 31)) & 31));
+          if (w_out) w_out[(size_t)slot * kHotSlot + k] = e >= 0 ? w[st + e] : (T)0;
         }
         reinterpret_cast<uint4*>(idx16)[slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
         continue;

@@ -319,6 +319,8 @@ inline void __syncthreads()
   emu::yield_to_scheduler();
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
