@@ -71,7 +71,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    _build_cbench(force or bool(jobs))
     return LIB
+
+
+def _build_cbench(force):
+    """scripts/cbench.cu -> cugraph_b200/lib/cbench: the Python-free development probe (travels to the GPU box with the library)"""
+    src = os.path.join(ROOT, "scripts", "cbench.cu")
+    out = os.path.join(LIBDIR, "cbench")
+    if not os.path.exists(src) or not (force or _newer(src, out) or _newer(LIB, out)):
+        return
+    cmd = [NVCC, "-O2", "-std=c++17"] + ARCH + ["-I", os.path.join(ROOT, "include"), src, "-o", out, "-L", LIBDIR,
+                                                 "-l:libcugraph_c.so", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-ccbin", "/usr/bin/g++"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:  # a development tool: report, do not fail the library build
+        sys.stderr.write("cbench not built:\n" + r.stdout + r.stderr)
 
 
 def _find_nccl():

@@ -246,6 +246,7 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
   return cudaSuccess;
 }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 {
   double ta, tb;
