@@ -5,6 +5,8 @@
 mkdir -p gpurun_out
 make -s -C oracle
 timeout 120 python -c "import torch; torch.zeros(1, device='cuda'); print('cuda ok')"          # warms the image
+# 0. the cheap part first: Python-free A/B of every sweep variant and the traversal knobs (seconds each)
+timeout 400 bash scripts/cbench_ab.sh 24 2>&1 | tee gpurun_out/cbench_ab.log | grep -E '^==|sweep_ms|pagerank100|mean_ms'
 # 1. parity: the whole GPU suite (includes the RMAT-24 certificates and the reference's C test programs)
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -5
 # 2. the bench line; its `side` block carries BFS / SSSP TEPS, the schedule A/B and parity + timing of every experimental
