@@ -709,7 +709,7 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
                    window, (double)hi, (double)delta, window_rounds, tr_rounds, tr_edges, n_far, tr_splits);
     if (n_far == 0) break;
     if (adaptive) {
-      if (window_rounds <= 2) delta = delta * (T)2;
+      if (window_rounds <= 2) { if (delta < std::numeric_limits<T>::max() / (T)4) delta = delta * (T)2; }
       else if (window_rounds >= 6 && delta > delta_floor) delta = delta / (T)2;
     }
     // advance the window to the smallest pending distance, then split the far pile
