@@ -24,6 +24,7 @@
 #include <climits>
 #include <cstdlib>
 #include <cmath>
+#include <limits>
 #include <vector>
 
 namespace b200 {
