@@ -292,7 +292,12 @@ def run_single(args):
 
     del h_src, h_dst, h_v, h_p
     torch.cuda.empty_cache()
-    side = _side_measurements(scale) if os.environ.get("CUGRAPH_B200_BENCH_SIDE", "1") != "0" else None
+    side = None
+    if os.environ.get("CUGRAPH_B200_BENCH_SIDE", "1") != "0":
+        try:
+            side = _side_measurements(scale)
+        except Exception as ex:  # informational extras must never cost the main line
+            side = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     cpu = _cpu_baseline(sample_scale=args.cpu_sample_scale)
     out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
