@@ -299,7 +299,10 @@ def run_single(args):
         except Exception as ex:  # informational extras must never cost the main line
             side = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
-    cpu = _cpu_baseline(sample_scale=args.cpu_sample_scale)
+    try:
+        cpu = _cpu_baseline(sample_scale=args.cpu_sample_scale)
+    except Exception as ex:  # the GPU measurements above must still be reported
+        cpu = {"value": None, "unit": "MTEPS", "cores": None, "kind": "port", "error": f"{type(ex).__name__}: {ex}"[:300]}
     out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
