@@ -256,6 +256,11 @@ def run_single(args):
     roofline["iteration"] = {"algorithmic_bytes": b_iter, "ms": ms_iter, "achieved": b_iter / (ms_iter * 1e-3) / 1e9,
                              "frac": b_iter / (ms_iter * 1e-3) / 1e9 / peak}
 
+    # the device-resident numbers go to stderr right away: should anything below take the process down, the log has them
+    sys.stderr.write("[bench provisional] " + json.dumps({"value": value, "unit": "MTEPS", "ms_per_step": ms_step,
+                                                          "gpu_launches": launches, "roofline": roofline}) + "\n")
+    sys.stderr.flush()
+
     # e2e: host edge list -> H2D -> graph create -> pagerank -> D2H
     del G
     torch.cuda.empty_cache()
