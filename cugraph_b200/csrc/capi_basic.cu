@@ -54,6 +54,7 @@ cugraph_resource_handle_t* cugraph_create_resource_handle(void* raft_handle)
 {
   try {
     auto* h = new handle_impl{};
+    h->tune = tuning_t::from_env();
     CUDA_TRY(cudaGetDevice(&h->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));

@@ -5,8 +5,10 @@
 #include <cugraph_c/b200_ext.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -91,9 +93,42 @@ inline size_t dtype_size(cugraph_data_type_id_t t)
 struct comm_impl;
 
 // ---------------------------------------------------------------------------------------------
+// schedule knobs (development / tests): environment variables read ONCE, when a handle is created.  Results never
+// depend on them.
+// ---------------------------------------------------------------------------------------------
+struct tuning_t {
+  long long sweep_min_edges{1ll << 22};  // CUGRAPH_B200_SWEEP_MIN_EDGES: graphs below it use the plain sweep (tests: 0)
+  bool sweep_bank_order{true};           // CUGRAPH_B200_SWEEP_BANK_ORDER
+  double bfs_alpha{14.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer's switch points)
+  bool sssp_adaptive{true};                // CUGRAPH_B200_SSSP_ADAPTIVE
+  double sssp_delta_scale{1.0};            // CUGRAPH_B200_SSSP_DELTA_SCALE
+  int sssp_split_rounds{1};                // CUGRAPH_B200_SSSP_SPLIT_ROUNDS
+  unsigned long long sssp_split_min_edges{1ull << 20};  // CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES
+  bool bfs_trace{false}, sssp_trace{false}, build_trace{false};  // CUGRAPH_B200_{BFS,SSSP,BUILD}_TRACE
+  static tuning_t from_env()
+  {
+    tuning_t t;
+    auto get = [](const char* k) { return std::getenv(k); };
+    if (auto e = get("CUGRAPH_B200_SWEEP_MIN_EDGES")) t.sweep_min_edges = std::atoll(e);
+    if (auto e = get("CUGRAPH_B200_SWEEP_BANK_ORDER")) t.sweep_bank_order = std::atoi(e) != 0;
+    if (auto e = get("CUGRAPH_B200_BFS_ALPHA")) t.bfs_alpha = std::atof(e);
+    if (auto e = get("CUGRAPH_B200_BFS_BETA")) t.bfs_beta = std::atof(e);
+    if (auto e = get("CUGRAPH_B200_SSSP_ADAPTIVE")) t.sssp_adaptive = std::atoi(e) != 0;
+    if (auto e = get("CUGRAPH_B200_SSSP_DELTA_SCALE")) t.sssp_delta_scale = std::atof(e);
+    if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_ROUNDS")) t.sssp_split_rounds = std::max(1, std::atoi(e));
+    if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) t.sssp_split_min_edges = std::strtoull(e, nullptr, 10);
+    t.bfs_trace   = get("CUGRAPH_B200_BFS_TRACE") != nullptr;
+    t.sssp_trace  = get("CUGRAPH_B200_SSSP_TRACE") != nullptr;
+    t.build_trace = get("CUGRAPH_B200_BUILD_TRACE") != nullptr;
+    return t;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // resource handle: one device, one stream, the device's default stream-ordered pool.
 // ---------------------------------------------------------------------------------------------
 struct handle_impl {
+  tuning_t tune{};
   int device{0};
   cudaStream_t stream{nullptr};
   bool borrowed_stream{false};        // stream belongs to the caller (torch): never destroyed here
@@ -283,7 +318,7 @@ struct phase_trace {
   handle_impl const& h;
   bool on;
   cudaEvent_t e0{}, e1{};
-  explicit phase_trace(handle_impl const& hh) : h(hh), on(std::getenv("CUGRAPH_B200_BUILD_TRACE") != nullptr)
+  explicit phase_trace(handle_impl const& hh) : h(hh), on(hh.tune.build_trace)
   {
     if (on) {
       cudaEventCreate(&e0);

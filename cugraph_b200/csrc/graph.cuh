@@ -28,73 +28,65 @@ constexpr int kWarpChunk  = 1024;
 constexpr int kWarpsPerCta = 8;
 
 // ---------------------------------------------------------------------------------------------
-// Column-blocked copy of the degree>=32 prefix for the shared-memory gather kernel (spmv_hot.cuh).
-// The source (column) space is cut into B "hot" blocks of W vertices (W * sizeof(T) = 192 KiB, the
-// slice of x one CTA keeps in shared memory) plus one cold block (everything >= B*W).  Because rows
-// keep their neighbours sorted by source id, a row's adjacency is already partitioned by block; the
-// copy stores the segments block-major: all (row, block 0) segments, then block 1, ...
-// Hot blocks store 16-bit local column ids (halves the index stream), the cold block 32-bit ids.
-// Every (row, block) segment is cut into LANE SLOTS of 8 entries (16 bytes of ids: one 128-bit load per
-// lane); the last slot of a segment is padded with a column that reads 0, so the kernel is predicate-free.
+// Column-blocked "piece stream" of ALL non-empty rows for the shared-memory pull sweep (sweep.cuh).
+// The source (column) space is cut into B blocks of W vertices (W * sizeof(T) = 192 KiB minus 64 zero columns: the slice of
+// x a persistent CTA keeps in shared memory).  Rows keep their neighbours sorted by source id, so a row's adjacency is
+// already partitioned by block; every (row, block) SEGMENT is cut into PIECES of <= 64 entries.  A piece is stored with
+// 16-bit local column ids in one of 11 KINDS: S / Q / H = 1 / 2 / <= 4 entries (2 / 4 / 8 bytes of ids), F1..F8 = 1..8 lane
+// slots of 8 entries (16 bytes each; short pieces are padded with a column that reads 0).  Pieces are ordered by
+// (block, kind).  The unit every kernel step works on is a STEP-ROW = 32 lanes x 16 bytes of ids (one 128-bit load per
+// lane, 512 contiguous bytes per warp): it holds 256 S pieces, 128 Q pieces, 64 H pieces, or one of the c slots of 32 Fc
+// pieces (a GROUP of kind Fc is c consecutive step-rows, lane = piece).  Row ids (int32, -1 = unused piece) are stored per
+// group so that a lane's rows are contiguous: 8 / 4 / 2 / 1 per lane.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHotSliceBytes = 192 * 1024;  // x slice a CTA keeps in shared memory
 constexpr int kHotZeroPad    = 64;          // trailing elements of the slice that hold zeros (padding target)
 constexpr int kHotSlot       = 8;           // entries per lane slot
 
-struct hot_layout_t {
-  int W{0};      // source columns per hot block (= slice elements - kHotZeroPad)
-  int B{0};      // hot blocks; the cold block (sources >= B*W) is block B
-  int32_t n_hi{0};    // rows covered by the layout: the prefix of degree >= 32 rows (seg_k = 0), or, experimentally,
-  int64_t nnz_hi{0};  // the prefix down to a lower degree bound (seg_k > 0: rows [0, seg[seg_k]))
-  int seg_k{0};
-  bool bank_order{false};  // experimental: entries inside the lane slots ordered by shared-memory bank, padding on any of the zero columns
-  int64_t n_hot_slots{0};
-  int64_t n_slots{0};
-  // A (row, block) segment is cut into PIECES of <= 64 entries = <= 8 lane slots of 8 entries.  Pieces are
-  // ordered by (block, slots per piece); 32 consecutive pieces of one class form a GROUP = the work of one
-  // warp (lane = piece).  Slots of a group are stored step-major: slot (step j, lane l) at group_base + 32 j + l.
-  dbuf slot_idx16;   // n_hot_slots x 8 x uint16 : column - block*W, padding -> W (the slice's zero column)
-  dbuf slot_idx32;   // (n_slots - n_hot_slots) x 8 x int32 : cold columns, padding -> n_vertices (x is 0 there)
-  dbuf slot_w;       // n_slots x 8 x T, padding 0; or empty
-  // EXPERIMENTAL narrow classes (CUGRAPH_B200_HOT_NARROW=1, unweighted graphs, hot blocks only; consumed by
-  // k_spmv_blocked_x): pieces of 3-4 entries use an 8-byte slot (class code 16), of 2 entries a 4-byte slot (32), of 1 entry
-  // a 2-byte slot (64)
-  bool narrow{false};
-  dbuf slot_idx_h;   // n_hslots x 4 x uint16
-  dbuf slot_idx_q;   // n_qslots x 2 x uint16
-  dbuf slot_idx_s;   // n_sslots x 1 x uint16 : one-entry pieces (class code 64)
-  dbuf seg_row;      // per (group, lane): row of the piece, -1 for the unused lanes of a class's last group
-  dbuf subs;         // n_subs x hot_sub_t (spmv_hot.cuh): consecutive groups of one class (cls 1..8; 16 / 32 / 64 = narrow)
-  dbuf units;        // n_units x hot_unit_t: consecutive sub-units of one block, about 8192 slots
-  int32_t n_subs{0};
-  int32_t n_units{0};
-  dbuf cta_range;    // (n_cta + 1) x int32 : CTA c owns units [cta_range[c], cta_range[c+1]) (cost-balanced)
-  dbuf unit_counter; // n_cta x int : per-range cursors, also used for stealing (reset by the finish kernel)
-  int n_cta{0};      // CTAs of the persistent kernel = min(SM count, n_units)
-};
-
-// EXPERIMENTAL (CUGRAPH_B200_LOW_ELL=1): exact-degree classes of the degree < 32 rows.  Rows are degree-descending, so
-// the rows of degree d are the contiguous range [row_begin[d], row_begin[d] + n[d]) and their adjacency is a dense
-// n[d] x d matrix starting at indices[off0[d]]; `idx` holds it TRANSPOSED (entry k of row i at off0[d] - off0[31] +
-// k * n[d] + i): a lane per row reads coalesced, needs no offsets, and can own several rows.
-struct low_ell_t {
-  int32_t row_begin[32]{};
-  int32_t n[32]{};
-  long long base[32]{};  // start of class d inside idx / w
-  dbuf idx;              // (nnz - nnz_hi) x int32
-  dbuf w;                // same x T, or empty
-};
-
-// EXPERIMENTAL (CUGRAPH_B200_HOT_MIN_DEGREE = 32 | 16 | 8 | 4 | 2 | 1, default 32): rows down to that degree go through the
-// piece layout of the blocked sweep instead of the gather kernel for low rows.  Returns the index into csx_t::seg.
-inline int hot_seg_index()
+constexpr int kNumKinds = 11;  // S, Q, H, F1..F8
+constexpr int kKindS = 0, kKindQ = 1, kKindH = 2, kKindF1 = 3;
+__host__ __device__ __forceinline__ int kind_steps(int kind) { return kind < kKindF1 ? 1 : kind - 2; }  // step-rows per group
+__host__ __device__ __forceinline__ int kind_pieces(int kind) { return kind == kKindS ? 256 : (kind == kKindQ ? 128 : (kind == kKindH ? 64 : 32)); }
+// groups per chunk (a chunk = consecutive groups of one kind in one block = what a warp loads into its registers at once:
+// at most 8 x 128 bits of ids / rows + 2 row words, chunk_regs_t in sweep.cuh)
+__host__ __device__ __forceinline__ int kind_chunk_groups(int kind)
 {
-  const char* e = std::getenv("CUGRAPH_B200_HOT_MIN_DEGREE");
-  const int d   = e ? std::atoi(e) : 32;
-  for (int k = 0; k < kNumSeg - 1; ++k)
-    if (kSegThreshold[k] == d) return k;
-  return 0;
+  return kind == kKindS ? 2 : (kind == kKindQ ? 4 : (kind == kKindH ? 4 : (kind == kKindF1 ? 6 : (kind == kKindF1 + 1 ? 3 : (kind <= kKindF1 + 3 ? 2 : 1)))));
 }
+
+struct sweep_chunk_t {  // 16 bytes
+  int32_t sr_begin;   // first step-row
+  int32_t row_begin;  // first row slot
+  int32_t n_groups;   // 1 .. kind_chunk_groups(kind)
+  int32_t kind;
+};
+struct sweep_phase_t {  // consecutive chunks of one block inside one CTA's range; its cursor is phase-indexed
+  int32_t block;
+  int32_t chunk_begin;
+  int32_t chunk_end;
+  int32_t pad;
+};
+
+struct sweep_layout_t {
+  int W{0};               // source columns per block (= slice elements - kHotZeroPad)
+  int B{0};               // blocks
+  int32_t n_cov{0};       // rows [0, n_cov) are covered = every non-empty row (rows are degree-descending)
+  int64_t nnz{0};
+  bool bank_order{false};  // entries inside the F slots ordered by shared-memory bank (4-byte values)
+  int64_t n_steprows{0};
+  int64_t n_rowslots{0};
+  int64_t n_pieces{0};
+  dbuf ids;        // n_steprows x 32 x uint4 (8 x uint16: column - block * W; padding -> one of the zero columns)
+  dbuf w;          // n_steprows x 32 x 8 x T, padding 0; or empty
+  dbuf rows;       // n_rowslots x int32
+  dbuf chunks;     // n_chunks x sweep_chunk_t
+  dbuf phases;     // n_phases x sweep_phase_t
+  dbuf cta_phase;  // (n_cta + 1) x int32: CTA c owns phases [cta_phase[c], cta_phase[c+1]) (cost-balanced, contiguous chunks)
+  dbuf cursor;     // n_phases x int: next chunk of the phase (relative); reset by the finish kernel
+  int32_t n_chunks{0};
+  int32_t n_phases{0};
+  int n_cta{0};
+};
 
 // One orientation: compressed rows over `n_rows` physical rows.
 // row_vertex == nullptr  -> physical row r is vertex r (rows are degree-descending by construction)
@@ -117,15 +109,13 @@ struct csx_t {
   int32_t n_split{0};
   dbuf split_rows;  // n_split x int32 : rows that straddle a chunk boundary (each listed once)
   // lazily built column-blocked copies (float / double element width) and cached out-weight sums
-  mutable std::unique_ptr<hot_layout_t> hot4, hot8;
+  mutable std::unique_ptr<sweep_layout_t> hot4, hot8;
   mutable bool hot4_tried{false}, hot8_tried{false};
   mutable dbuf out_w;  // n_vertices x T : per-source sum of edge weights (or out-degree), T = weight type
-  mutable std::unique_ptr<low_ell_t> low_ell;
-  mutable bool low_ell_tried{false};
 };
 
-// rows that may need an fp64 accumulator in a sweep (callers size acc_hi with it)
-inline int32_t acc_rows(csx_t const& c) { return std::max(std::max(c.seg[0], c.seg[hot_seg_index()]), 1); }
+// rows that may need an fp64 accumulator in a sweep (callers size acc_hi with it): the piece stream covers every row
+inline int32_t acc_rows(csx_t const& c) { return std::max(c.n_rows, 1); }
 
 struct graph_impl {
   cugraph_data_type_id_t vertex_type{INT32};
@@ -162,10 +152,8 @@ inline graph_impl* G(cugraph_graph_t* g)
 
 // Accessors that build the missing orientation on demand (graph_build.cu).
 csx_t const& pull_view(handle_impl const& h, graph_impl& g);  // rows = destinations, indices = sources
-// column-blocked copy for elements of `elem_size` bytes, or nullptr when the graph is too small for it
-hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size);
-// exact-degree ELL copy of the degree < 32 rows; nullptr unless CUGRAPH_B200_LOW_ELL=1 (graph_build.cu)
-low_ell_t const* low_ell_layout(handle_impl const& h, csx_t const& c, size_t elem_size);
+// piece stream for elements of `elem_size` bytes, or nullptr when the graph is too small for it
+sweep_layout_t const* sweep_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size);
 csx_t const& push_view(handle_impl const& h, graph_impl& g);  // rows = sources, vertex-indexed offsets
 
 // external <-> internal id helpers (graph_build.cu)

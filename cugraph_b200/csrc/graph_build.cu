@@ -955,46 +955,31 @@ csx_t const& push_view(handle_impl const& h, graph_impl& g)
 }
 
 // ---------------------------------------------------------------------------------------------
-// column-blocked, slotted copy of the degree>=32 prefix (hot_layout_t, consumed by spmv_hot.cuh)
+// piece stream of all non-empty rows (sweep_layout_t, consumed by sweep.cuh)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-// Hot blocks by default: ALL of the source space (a cold block only exists beyond 2048 slices = 100 M
-// float columns).  Measured on RMAT-24 (8.87 M non-isolated vertices = 181 slices) with the piece layout, pull
-// sweep: B = 48 -> 0.535 ms, 96 -> 0.538, 160 -> 0.520, 181 (all) -> 0.456 (profiles/r01_notes.md); since every
-// CTA owns a contiguous range of units, more blocks cost no extra slice fills (1-2 slices per CTA).
-constexpr int kHotMaxBDefault = 2048;
-inline int hot_max_blocks()
-{
-  if (const char* e = std::getenv("CUGRAPH_B200_HOT_BLOCKS")) return std::max(1, std::min(std::atoi(e), 2048));
-  return kHotMaxBDefault;
-}
-
-// ---- staging of the piece layout (hot_layout_t, graph.cuh).  All passes are O(nnz_hi + #segments):
+// ---- staging of the piece stream.  All passes are O(nnz + #segments):
 //   1. head flags: an edge starts a (row, block) segment if it starts its row or its source lies in another
 //      block than its predecessor's (neighbours are sorted by source id)
-//   2. segments = compacted head positions; each is cut into pieces of <= 64 entries (<= 8 lane slots)
-//   3. pieces are ordered (stable radix sort) by (block, slots-per-piece); 32 consecutive pieces of one
-//      class form a GROUP that one warp processes, lane = piece
-//   4. slots are written step-major inside a group, so every warp step is one coalesced 512-byte read
-
-__device__ __forceinline__ int hot_block_of(int col, int W, int B)
-{
-  const int b = col / W;
-  return b < B ? b : B;
-}
+//   2. segments = compacted head positions; each is cut into pieces of <= 64 entries, a piece gets its kind
+//      (S / Q / H = 1 / 2 / <= 4 entries, F1..F8 = that many lane slots of 8 entries)
+//   3. pieces are ordered (stable radix sort) by (block, kind); a run of one (block, kind) is cut into groups of
+//      256 / 128 / 64 / 32 pieces and chunks of a few groups; chunks are dealt to the persistent CTAs as contiguous,
+//      cost-balanced ranges, the part of one block inside a range is a phase
+//   4. one warp per group writes its step-rows (32 lanes x 16 bytes of ids) and row slots
 
 template <typename O>
-__global__ void k_hot_row_starts(O const* __restrict__ off, int32_t n_hi, uint8_t* __restrict__ flag)
+__global__ void k_hot_row_starts(O const* __restrict__ off, int32_t n_cov, uint8_t* __restrict__ flag)
 {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_hi) flag[(size_t)off[r]] = 1;  // degree >= 32 rows are never empty
+  if (r < n_cov) flag[(size_t)off[r]] = 1;  // covered rows are never empty
 }
 
-__global__ void k_hot_heads(int32_t const* __restrict__ idx, long long nnz_hi, int W, int B, uint8_t* __restrict__ flag)
+__global__ void k_hot_heads(int32_t const* __restrict__ idx, long long nnz, int W, uint8_t* __restrict__ flag)
 {
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nnz_hi; e += (long long)gridDim.x * blockDim.x) {
-    if (e > 0 && !flag[e] && hot_block_of(idx[e], W, B) != hot_block_of(idx[e - 1], W, B)) flag[e] = 1;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+    if (e > 0 && !flag[e] && idx[e] / W != idx[e - 1] / W) flag[e] = 1;
   }
 }
 
@@ -1003,8 +988,8 @@ constexpr int kHotPieceEntries = kHotPieceSlots * kHotSlot;  // 64
 
 // per segment: its row (binary search in the offsets) and how many pieces it yields
 template <typename O>
-__global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz_hi,
-                                   O const* __restrict__ off, int32_t n_hi, int32_t* __restrict__ seg_row,
+__global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz,
+                                   O const* __restrict__ off, int32_t n_cov, int32_t* __restrict__ seg_row,
                                    int32_t* __restrict__ seg_pieces)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1014,8 +999,8 @@ __global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t
     return;
   }
   const long long start = head_pos[k];
-  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz_hi;
-  int lo = 0, hi = n_hi;  // last row r with off[r] <= start
+  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz;
+  int lo = 0, hi = n_cov;  // last row r with off[r] <= start
   while (hi - lo > 1) {
     const int mid = lo + ((hi - lo) >> 1);
     if ((long long)off[mid] <= start) lo = mid; else hi = mid;
@@ -1024,29 +1009,28 @@ __global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t
   seg_pieces[k] = (int)((end - start + kHotPieceEntries - 1) / kHotPieceEntries);
 }
 
-// per segment: write its pieces (start edge, entries, row) and their class key = block * 8 + (slots - 1)
-__global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz_hi,
-                                  int32_t const* __restrict__ idx, int W, int B, int32_t const* __restrict__ seg_row,
+__host__ __device__ __forceinline__ int piece_kind(int len)
+{
+  return len == 1 ? kKindS : (len == 2 ? kKindQ : (len <= 4 ? kKindH : kKindF1 + (len + kHotSlot - 1) / kHotSlot - 1));
+}
+
+// per segment: write its pieces (start edge, entries, row) and their key = block * kNumKinds + kind
+__global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz,
+                                  int32_t const* __restrict__ idx, int W, int32_t const* __restrict__ seg_row,
                                   int32_t const* __restrict__ piece_off, uint32_t* __restrict__ piece_key,
                                   int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
-                                  int32_t* __restrict__ piece_row, int narrow, int kinds)
+                                  int32_t* __restrict__ piece_row)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_segs) return;
   const long long start = head_pos[k];
-  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz_hi;
-  const int b           = hot_block_of(idx[start], W, B);
+  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz;
+  const int b           = idx[start] / W;
   const int row         = seg_row[k];
   int p                 = piece_off[k];
   for (long long s = start; s < end; s += kHotPieceEntries, ++p) {
     const int len  = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
-    const int cls  = (len + kHotSlot - 1) / kHotSlot;  // 1..8
-    int code       = cls - 1;
-    if (narrow) {  // kinds: S (1 entry), Q (2), H (<= 4), then 1..8 full slots; the cold block only has full slots
-      code = cls + 2;
-      if (b < B && len <= 4) code = len == 1 ? 0 : (len == 2 ? 1 : 2);
-    }
-    piece_key[p]   = (uint32_t)(b * kinds + code);
+    piece_key[p]   = (uint32_t)(b * kNumKinds + piece_kind(len));
     piece_start[p] = (int32_t)s;
     piece_len[p]   = len;
     piece_row[p]   = row;
@@ -1066,107 +1050,90 @@ __global__ void k_hot_class_starts(uint32_t const* __restrict__ sorted_key, int3
   class_start[key] = lo;
 }
 
-struct hot_sub_host_t {  // mirrors hot_sub_t (spmv_hot.cuh)
-  int32_t slot_begin, row_begin, n_groups, cls;
-};
-struct hot_unit_host_t {  // mirrors hot_unit_t (spmv_hot.cuh)
-  int32_t sub_begin, sub_end, block, pad;
-};
-struct hot_fill_t {  // build-time companion of a sub-unit
+struct sweep_fill_t {  // build-time companion of a chunk: its pieces start at piece_begin, its (block, kind) run ends at piece_end
   int32_t piece_begin, piece_end, block, pad;
 };
 
-// Host-side plan of the blocked sweep's work structure, from the per-class piece counts alone (class_start[key] =
-// first piece of class key = block * kinds + kind, pieces ordered by key; kinds = 8, or 11 for narrow layouts where
-// kinds 0 / 1 / 2 are the one-entry (S), quarter (Q) and half (H) slot classes):
-//   sub-unit = consecutive groups (32 pieces each) of one class, at most `unit_slots` slots;
-//   unit     = consecutive sub-units of one block, closed once it holds >= unit_slots slots (narrow slots count half);
-//   range    = contiguous units per persistent CTA, balanced by slots (cold block weighted by cold_cost).
-// Pure host code: exercised on CPU through cugraph_b200_debug_plan_hot_units (tests/test_hot_plan_cpu.py).
-struct hot_plan_t {
-  std::vector<hot_sub_host_t> subs;
-  std::vector<hot_fill_t> fills;
-  std::vector<hot_unit_host_t> units;
-  std::vector<int32_t> range;
-  int64_t slot_run{0}, row_run{0}, cold_slot0{0}, hslot_run{0}, qslot_run{0}, sslot_run{0};
+// Host-side plan of the sweep's work structure, from the piece counts per (block, kind) alone (class_start[key] = first
+// piece of key = block * kNumKinds + kind, pieces ordered by key):
+//   group = 256 / 128 / 64 / 32 pieces of one kind (S / Q / H / F), 1 or (F kinds) 1..8 step-rows
+//   chunk = consecutive groups of one kind in one block, at most kind_chunk_groups(kind)
+//   range = contiguous chunks per persistent CTA, balanced by an estimate of their load/store-unit time (the sweep is
+//           bound by it: one cycle per 128-byte line of ids, per conflict-free 32 gathers, per sector of atomics)
+//   phase = the chunks of one block inside one range (a CTA loads the block's slice once per phase)
+// Pure host code: exercised on CPU through cugraph_b200_debug_plan_sweep (tests/test_sweep_plan_cpu.py).
+struct sweep_plan_t {
+  std::vector<sweep_chunk_t> chunks;
+  std::vector<sweep_fill_t> fills;
+  std::vector<sweep_phase_t> phases;
+  std::vector<int32_t> cta_phase;
+  int64_t n_steprows{0}, n_rowslots{0};
   int n_cta{1};
 };
 
-bool plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int unit_slots_target, int sm_count,
-                    double cold_cost, hot_plan_t& P)
+inline double sweep_group_cost(int kind)
 {
-  const int kinds         = narrow ? kHotPieceSlots + 3 : kHotPieceSlots;
-  const int kHotUnitSlots = unit_slots_target;
-  auto& subs  = P.subs;
-  auto& fills = P.fills;
-  auto& units = P.units;
-  std::vector<double> unit_cost;
-  int64_t &slot_run = P.slot_run, &row_run = P.row_run, &cold_slot0 = P.cold_slot0, &hslot_run = P.hslot_run,
-          &qslot_run = P.qslot_run, &sslot_run = P.sslot_run;
-  for (int b = 0; b <= B; ++b) {
-    if (b == B) cold_slot0 = slot_run;
-    int64_t unit_slots = 0;
-    int unit_sub0      = (int)subs.size();
-    auto close_unit = [&]() {
-      if ((int)subs.size() > unit_sub0) {
-        units.push_back({unit_sub0, (int32_t)subs.size(), b, 0});
-        unit_cost.push_back((double)unit_slots * (b == B ? cold_cost : 1.0) + 64.0);
-      }
-      unit_sub0  = (int)subs.size();
-      unit_slots = 0;
-    };
-    for (int kind = 0; kind < kinds; ++kind) {
-      // steps per group and the sub-unit's class code: 1..8 = full 8-entry slots; narrow layouts put the
-      // one-step kinds S (code 64: 1 id per slot), Q (code 32: 2 ids) and H (code 16: 4 ids) in front
-      int cls = kind + 1, code = kind + 1;
-      if (narrow) {
-        cls  = kind < 3 ? 1 : kind - 2;
-        code = kind == 0 ? 64 : (kind == 1 ? 32 : (kind == 2 ? 16 : kind - 2));
-      }
-      const bool is_narrow = code > kHotPieceSlots;
-      const int key    = b * kinds + kind;
+  // step-rows: id load (4 lines) + 8 gathers at ~1.5 wavefronts; pieces: one fp64 atomic each (F8 pieces of hub rows are
+  // summed by shuffles first)
+  return kind_steps(kind) * 18.0 + kind_pieces(kind) * (kind == kNumKinds - 1 ? 0.15 : 0.6) + 6.0;
+}
+constexpr double kPhaseCost = 2500.0;  // barrier + 192 KiB slice fill, in the same unit
+
+bool plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, sweep_plan_t& P)
+{
+  std::vector<double> cost;  // per chunk, the phase overhead on the first chunk of every block
+  for (int b = 0; b < B; ++b) {
+    bool first = true;
+    for (int kind = 0; kind < kNumKinds; ++kind) {
+      const int key    = b * kNumKinds + kind;
       int32_t p        = cstart[key];
       const int32_t pe = cstart[key + 1];
-      // narrow slots count half towards the size of a unit
-      const int max_groups = is_narrow ? std::max(1, kHotUnitSlots / 16) : std::max(1, kHotUnitSlots / (32 * cls));
-      int64_t& run         = is_narrow ? (code == 16 ? hslot_run : (code == 32 ? qslot_run : sslot_run)) : slot_run;
+      const int ppg = kind_pieces(kind), steps = kind_steps(kind), gmax = kind_chunk_groups(kind);
       while (p < pe) {
-        const int groups = (int)std::min<int64_t>(max_groups, ((int64_t)(pe - p) + 31) / 32);
-        if (run + (int64_t)groups * 32 * cls >= (1ll << 31) - 64) return false;  // 32-bit slot ids
-        subs.push_back({(int32_t)run, (int32_t)row_run, groups, code});
-        fills.push_back({p, std::min<int32_t>(pe, p + groups * 32), b, 0});
-        run += (int64_t)groups * 32 * cls;
-        row_run += (int64_t)groups * 32;
-        unit_slots += is_narrow ? (int64_t)groups * 16 : (int64_t)groups * 32 * cls;
-        p += groups * 32;
-        if (unit_slots >= kHotUnitSlots) close_unit();
+        const int groups = (int)std::min<int64_t>(gmax, ((int64_t)(pe - p) + ppg - 1) / ppg);
+        if (P.n_steprows + (int64_t)groups * steps >= (1ll << 31) - 64 || P.n_rowslots + (int64_t)groups * ppg >= (1ll << 31) - 64)
+          return false;  // 32-bit step-row / row-slot numbers
+        P.chunks.push_back({(int32_t)P.n_steprows, (int32_t)P.n_rowslots, groups, kind});
+        P.fills.push_back({p, pe, b, 0});
+        cost.push_back(groups * sweep_group_cost(kind) + (first ? kPhaseCost : 0.0));
+        first = false;
+        P.n_steprows += (int64_t)groups * steps;
+        P.n_rowslots += (int64_t)groups * ppg;
+        p += groups * ppg;  // may pass pe inside the last group: the fill pads
       }
     }
-    close_unit();
   }
-  P.n_cta = (int)std::max<size_t>(1, std::min<size_t>((size_t)sm_count, units.size()));
-  P.range.assign(P.n_cta + 1, 0);
-  {
-    std::vector<double> cost(units.size() + 1, 0.0);
-    for (size_t u = 0; u < units.size(); ++u) cost[u + 1] = cost[u] + unit_cost[u];
-    size_t u = 0;
-    for (int cta = 1; cta < P.n_cta; ++cta) {
-      const double target = cost[units.size()] * cta / P.n_cta;
-      while (u < units.size() && cost[u + 1] <= target) ++u;
-      P.range[cta] = (int32_t)u;
+  const size_t n = P.chunks.size();
+  P.n_cta        = (int)std::max<size_t>(1, std::min<size_t>((size_t)sm_count, n));
+  std::vector<double> pre(n + 1, 0.0);
+  for (size_t c = 0; c < n; ++c) pre[c + 1] = pre[c] + cost[c];
+  P.cta_phase.assign(P.n_cta + 1, 0);
+  size_t c = 0;
+  for (int cta = 0; cta < P.n_cta; ++cta) {
+    const double target = pre[n] * (cta + 1) / P.n_cta;
+    const size_t c0     = c;
+    if (cta == P.n_cta - 1) c = n;
+    else while (c < n && pre[c + 1] <= target) ++c;
+    P.cta_phase[cta] = (int32_t)P.phases.size();
+    for (size_t k = c0; k < c;) {  // split the range by block
+      size_t e = k;
+      while (e < c && P.fills[e].block == P.fills[k].block) ++e;
+      P.phases.push_back({P.fills[k].block, (int32_t)k, (int32_t)e, 0});
+      k = e;
     }
-    P.range[P.n_cta] = (int32_t)units.size();
   }
+  P.cta_phase[P.n_cta] = (int32_t)P.phases.size();
   return true;
 }
 
-// EXPERIMENTAL (CUGRAPH_B200_HOT_BANK_ORDER=1, 4-byte values): order the entries of the 32 pieces of a group so that the
-// k-th shared-memory gathers of the 32 lanes in every step (one LDS of the sweep kernels) fall into different banks.  Any
-// assignment of a piece's entries to its (step, position) places is a valid layout (the sweep adds all of them into one
-// sum per piece); padding may point at any of the kHotZeroPad zero columns, i.e. at any bank.  Greedy, place by place:
-// the lanes that still hold entries take turns (lowest lane first) and pick an entry on a bank nobody took at this place;
-// a lane without such an entry waits for a later place while it has spare places left, else takes a bank used once, else
-// any; all padding of a place shares one zero column on a free bank.
+// Bank-aware entry order inside the lane slots of the F kinds (4-byte values): order the entries of the 32 pieces of a group
+// so that the k-th shared-memory gathers of the 32 lanes in every step (one LDS of the sweep kernel) fall into different
+// banks.  Any assignment of a piece's entries to its (step, position) places is a valid layout (the sweep adds all of them
+// into one sum per piece); padding may point at any of the kHotZeroPad zero columns, i.e. at any bank.  Greedy, place by
+// place: the lanes that still hold entries take turns and pick an entry on a bank nobody took at this place; a lane without
+// such an entry waits for a later place while it has spare places left, else takes a bank used once, else any; all padding
+// of a place shares one zero column on a free bank.  Measured (emulated staging, r01_notes.md): 3.1 -> 1.5 wavefronts per
+// LDS on RMAT-20; ncu r02 on RMAT-24: 2.46 -> ~1.7 for the F kinds.
 // State per lane: bank_bits[b] = the piece's entries (bit e = entry e, <= 64 per piece) on bank b, `rem` = not placed yet,
 // `have` = banks with an entry left.
 struct bank_piece_t {
@@ -1220,129 +1187,105 @@ __device__ __forceinline__ int bank_order_place(bank_piece_t& P, int places_left
   return -1 - pad_bank;
 }
 
-// one CTA per sub-unit, one warp per group, lane = piece: write the group's slots step-major
+constexpr int kFillWarps = 6;  // = the largest kind_chunk_groups()
+
+// one CTA per chunk, one warp per group
 template <typename T, bool BANK>
-__global__ void __launch_bounds__(256)
-k_hot_fill(hot_sub_host_t const* __restrict__ subs, hot_fill_t const* __restrict__ fills, int32_t const* __restrict__ perm,
-           int32_t const* __restrict__ piece_start, int32_t const* __restrict__ piece_len,
-           int32_t const* __restrict__ piece_row, int32_t const* __restrict__ idx, T const* __restrict__ w, int W, int B,
-           int zero_col_cold, long long cold_slot0, uint16_t* __restrict__ idx16, int32_t* __restrict__ idx32,
-           T* __restrict__ w_out, int32_t* __restrict__ seg_row_out, uint2* __restrict__ idx_h, uint32_t* __restrict__ idx_q,
-           uint16_t* __restrict__ idx_s)
+__global__ void __launch_bounds__(kFillWarps * 32)
+k_sweep_fill(sweep_chunk_t const* __restrict__ chunks, sweep_fill_t const* __restrict__ fills, int32_t const* __restrict__ perm,
+             int32_t const* __restrict__ piece_start, int32_t const* __restrict__ piece_len,
+             int32_t const* __restrict__ piece_row, int32_t const* __restrict__ idx, T const* __restrict__ w, int W,
+             uint4* __restrict__ ids_out, T* __restrict__ w_out, int32_t* __restrict__ rows_out)
 {
-  const hot_sub_host_t sb = subs[blockIdx.x];
-  const hot_fill_t fl     = fills[blockIdx.x];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool hot = fl.block < B;
-  for (int q = warp; q < sb.n_groups; q += 8) {
-    const int pi     = fl.piece_begin + q * 32 + lane;
-    const bool valid = pi < fl.piece_end;
-    int st = 0, ln = 0, row = -1;
-    if (valid) {
-      const int p = perm[pi];
-      st          = piece_start[p];
-      ln          = piece_len[p];
-      row         = piece_row[p];
-    }
-    seg_row_out[(size_t)sb.row_begin + (size_t)q * 32 + lane] = row;
-    if (sb.cls > kHotPieceSlots) {  // narrow classes: one step, 4 (cls 16), 2 (cls 32) or 1 (cls 64) ids per slot, hot blocks only
-      const size_t slot = (size_t)sb.slot_begin + (size_t)q * 32 + lane;
-      unsigned v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = k < ln ? (unsigned)(idx[st + k] - fl.block * W) : (unsigned)W;
-      if (sb.cls == 16) idx_h[slot] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-      else if (sb.cls == 32) idx_q[slot] = v[0] | (v[1] << 16);
-      else idx_s[slot] = (uint16_t)v[0];
-      continue;
-    }
-    bank_piece_t bp;  // only used by the BANK instantiation
-    for (int j = 0; j < sb.cls; ++j) {
-      const long long slot = (long long)sb.slot_begin + ((long long)q * sb.cls + j) * 32 + lane;
-      int col[kHotSlot];
-      if (BANK && hot) {  // the whole warp takes part (lanes without a piece hold padding only)
-        if (j == 0) {
-          for (int b = 0; b < 32; ++b) bp.bank_bits[b] = 0ull;
-          bp.have = bp.have2 = 0u;
-          for (int e = 0; e < ln; ++e) {
-            const int b = (idx[st + e] - fl.block * W) & 31;
-            if (bp.bank_bits[b]) bp.have2 |= 1u << b;
-            bp.bank_bits[b] |= 1ull << e;
-            bp.have |= 1u << b;
-          }
-          bp.rem = ln >= 64 ? ~0ull : ((1ull << ln) - 1ull);
-        }
-        unsigned v[kHotSlot];
-#pragma unroll 1
-        for (int k = 0; k < kHotSlot; ++k) {
-          const int e = bank_order_place(bp, (sb.cls - j) * kHotSlot - k, lane);
-          v[k]        = e >= 0 ? (unsigned)(idx[st + e] - fl.block * W) : (unsigned)(W + ((-1 - e - (W & 31)) & 31));
-          if (w_out) w_out[(size_t)slot * kHotSlot + k] = e >= 0 ? w[st + e] : (T)0;
-        }
-        reinterpret_cast<uint4*>(idx16)[slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-        continue;
+  const sweep_chunk_t ch = chunks[blockIdx.x];
+  const sweep_fill_t fl  = fills[blockIdx.x];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  if (g >= ch.n_groups) return;
+  const int col0 = fl.block * W;
+  if (ch.kind < kKindF1) {  // S / Q / H: R pieces of E entries per lane; piece k of lane l is piece k * 32 + l of the group
+    const int R = ch.kind == kKindS ? 8 : (ch.kind == kKindQ ? 4 : 2), E = 8 / R;
+    const size_t slot = ((size_t)(unsigned)(ch.sr_begin + g) << 5) + lane;
+    unsigned v[8];
+    for (int k = 0; k < R; ++k) {
+      const long long pi = (long long)fl.piece_begin + ((long long)g * 32 * R) + k * 32 + lane;
+      int st = 0, ln = 0, row = -1;
+      if (pi < fl.piece_end) {
+        const int p = perm[pi];
+        st          = piece_start[p];
+        ln          = piece_len[p];
+        row         = piece_row[p];
       }
+      for (int e = 0; e < E; ++e) {
+        v[k * E + e] = e < ln ? (unsigned)(idx[st + e] - col0) : (unsigned)W;
+        if (w_out) w_out[slot * 8 + k * E + e] = e < ln ? w[st + e] : (T)0;
+      }
+      rows_out[(size_t)(unsigned)ch.row_begin + ((size_t)g * 32 + lane) * R + k] = row;
+    }
+    ids_out[slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+    return;
+  }
+  const int C        = ch.kind - kKindF1 + 1;
+  const long long pi = (long long)fl.piece_begin + (long long)g * 32 + lane;
+  int st = 0, ln = 0, row = -1;
+  if (pi < fl.piece_end) {
+    const int p = perm[pi];
+    st          = piece_start[p];
+    ln          = piece_len[p];
+    row         = piece_row[p];
+  }
+  rows_out[(size_t)(unsigned)ch.row_begin + (size_t)g * 32 + lane] = row;
+  bank_piece_t bp;  // only used by the BANK instantiation
+  if (BANK) {       // the whole warp takes part (lanes without a piece hold padding only)
+    for (int b = 0; b < 32; ++b) bp.bank_bits[b] = 0ull;
+    bp.have = bp.have2 = 0u;
+    for (int e = 0; e < ln; ++e) {
+      const int b = (idx[st + e] - col0) & 31;
+      if (bp.bank_bits[b]) bp.have2 |= 1u << b;
+      bp.bank_bits[b] |= 1ull << e;
+      bp.have |= 1u << b;
+    }
+    bp.rem = ln >= 64 ? ~0ull : ((1ull << ln) - 1ull);
+  }
+  for (int j = 0; j < C; ++j) {
+    const size_t slot = ((size_t)(unsigned)(ch.sr_begin + g * C + j) << 5) + lane;
+    unsigned v[kHotSlot];
+    if (BANK) {
+#pragma unroll 1
+      for (int k = 0; k < kHotSlot; ++k) {
+        const int e = bank_order_place(bp, (C - j) * kHotSlot - k, lane);
+        v[k]        = e >= 0 ? (unsigned)(idx[st + e] - col0) : (unsigned)(W + ((-1 - e - (W & 31)) & 31));
+        if (w_out) w_out[slot * kHotSlot + k] = e >= 0 ? w[st + e] : (T)0;
+      }
+    } else {
 #pragma unroll
       for (int k = 0; k < kHotSlot; ++k) {
         const int e   = j * kHotSlot + k;
         const bool in = e < ln;
-        col[k]        = in ? idx[st + e] : -1;
-        if (w_out) w_out[(size_t)slot * kHotSlot + k] = in ? w[st + e] : (T)0;
-      }
-      if (hot) {
-        unsigned v[kHotSlot];
-#pragma unroll
-        for (int k = 0; k < kHotSlot; ++k) v[k] = col[k] >= 0 ? (unsigned)(col[k] - fl.block * W) : (unsigned)W;
-        uint4 o = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-        reinterpret_cast<uint4*>(idx16)[slot] = o;
-      } else {
-        int v[kHotSlot];
-#pragma unroll
-        for (int k = 0; k < kHotSlot; ++k) v[k] = col[k] >= 0 ? col[k] : zero_col_cold;
-        int4* dst = reinterpret_cast<int4*>(idx32) + (slot - cold_slot0) * 2;
-        dst[0]    = make_int4(v[0], v[1], v[2], v[3]);
-        dst[1]    = make_int4(v[4], v[5], v[6], v[7]);
+        v[k]          = in ? (unsigned)(idx[st + e] - col0) : (unsigned)W;
+        if (w_out) w_out[slot * kHotSlot + k] = in ? w[st + e] : (T)0;
       }
     }
+    ids_out[slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
   }
-}
-
-// slots per work unit, about (a unit is a run of sub-units of one block; sub-units are at most this long)
-inline int hot_unit_slots()
-{
-  if (const char* e = std::getenv("CUGRAPH_B200_HOT_UNIT_SLOTS")) return std::max(1024, std::min(std::atoi(e), 1 << 20));
-  return 8192;
 }
 
 template <typename O>
-std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const& c, int32_t nv, size_t es)
+std::unique_ptr<sweep_layout_t> build_sweep_layout(handle_impl const& h, csx_t const& c, int32_t nv, size_t es)
 {
   phase_trace tr(h);
-  const int W        = (int)(kHotSliceBytes / es) - kHotZeroPad;  // columns per hot block; the pad holds zeros
-  const int seg_k    = hot_seg_index();  // 0 unless CUGRAPH_B200_HOT_MIN_DEGREE lowers the bound (experimental)
-  const int32_t n_hi = c.seg[seg_k];
-  const int B        = (int)std::min<int64_t>(hot_max_blocks(), ((int64_t)nv + W - 1) / W);
-  int64_t nnz        = c.nnz_hi;
-  if (seg_k > 0) {  // entries of the covered rows = offsets[n_hi]
-    O last = 0;
-    CUDA_TRY(cudaMemcpyAsync(&last, c.offsets.as<O>() + n_hi, sizeof(O), cudaMemcpyDeviceToHost, h.stream));
-    sync(h);
-    nnz = (int64_t)last;
-    if (nnz >= (1ll << 31) - 4096) return nullptr;
-  }
-  auto L             = std::make_unique<hot_layout_t>();
-  L->W = W; L->B = B; L->n_hi = n_hi; L->nnz_hi = nnz; L->seg_k = seg_k;
+  const int W         = (int)(kHotSliceBytes / es) - kHotZeroPad;  // columns per block; the pad holds zeros
+  const int32_t n_cov = c.seg[kNumSeg - 2];                         // rows of degree >= 1
+  const int B         = (int)(((int64_t)nv + W - 1) / W);
+  const int64_t nnz   = c.nnz;
+  auto L              = std::make_unique<sweep_layout_t>();
+  L->W = W; L->B = B; L->n_cov = n_cov; L->nnz = nnz;
   int32_t const* idx = c.indices.as<int32_t>();
-  // experimental narrow slots (graph.cuh): unweighted only; needs k_spmv_blocked_x
-  bool narrow = false;
-  if (const char* e = std::getenv("CUGRAPH_B200_HOT_NARROW")) narrow = std::atoi(e) != 0 && c.weights.data() == nullptr;
-  const int kinds = narrow ? kHotPieceSlots + 3 : kHotPieceSlots;
-  L->narrow       = narrow;
 
   // 1. segment heads
   dbuf flag = make_dbuf<uint8_t>(nnz, h.stream);
   CUDA_TRY(cudaMemsetAsync(flag.data(), 0, nnz, h.stream));
-  B200_LAUNCH(h, (k_hot_row_starts<O>), grid_for(n_hi), kBlock, 0, c.offsets.as<O>(), n_hi, flag.as<uint8_t>());
-  B200_LAUNCH(h, k_hot_heads, std::min(grid_for(nnz, 4), 148 * 32), kBlock, 0, idx, (long long)nnz, W, B, flag.as<uint8_t>());
+  B200_LAUNCH(h, (k_hot_row_starts<O>), grid_for(n_cov), kBlock, 0, c.offsets.as<O>(), n_cov, flag.as<uint8_t>());
+  B200_LAUNCH(h, k_hot_heads, std::min(grid_for(nnz, 4), 148 * 32), kBlock, 0, idx, (long long)nnz, W, flag.as<uint8_t>());
   dbuf head_pos = make_dbuf<int32_t>(nnz, h.stream);
   int64_t n_segs64;
   {
@@ -1359,31 +1302,32 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   }
   flag.release();
   const int32_t n_segs = (int32_t)n_segs64;
-  tr.mark("hot: segment heads");
+  tr.mark("sweep layout: segment heads");
 
   // 2. pieces
   dbuf seg_row = make_dbuf<int32_t>(n_segs, h.stream), seg_pieces = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
   dbuf piece_off = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
   B200_LAUNCH(h, (k_hot_segment_info<O>), grid_for((int64_t)n_segs + 1), kBlock, 0, head_pos.as<int32_t>(), n_segs,
-              (long long)nnz, c.offsets.as<O>(), n_hi, seg_row.as<int32_t>(), seg_pieces.as<int32_t>());
+              (long long)nnz, c.offsets.as<O>(), n_cov, seg_row.as<int32_t>(), seg_pieces.as<int32_t>());
   exclusive_scan_i32(h, seg_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_segs + 1);
   int32_t n_pieces = 0;
   CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_segs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
   sync(h);
   seg_pieces.release();
+  L->n_pieces = n_pieces;
   dbuf piece_key = make_dbuf<uint32_t>(n_pieces, h.stream), piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
   dbuf piece_start = make_dbuf<int32_t>(n_pieces, h.stream), piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
   dbuf piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
-  B200_LAUNCH(h, k_hot_emit_pieces, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W, B,
+  B200_LAUNCH(h, k_hot_emit_pieces, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W,
               seg_row.as<int32_t>(), piece_off.as<int32_t>(), piece_key.as<uint32_t>(), piece_start.as<int32_t>(),
-              piece_len.as<int32_t>(), piece_row.as<int32_t>(), narrow ? 1 : 0, kinds);
+              piece_len.as<int32_t>(), piece_row.as<int32_t>());
   head_pos.release();
   seg_row.release();
   piece_off.release();
-  tr.mark("hot: pieces");
+  tr.mark("sweep layout: pieces");
 
-  // 3. order pieces by class
-  const int n_keys = (B + 1) * kinds;
+  // 3. order pieces by (block, kind)
+  const int n_keys = B * kNumKinds;
   dbuf perm = make_dbuf<uint32_t>(n_pieces, h.stream), perm2 = make_dbuf<uint32_t>(n_pieces, h.stream);
   B200_LAUNCH(h, k_iota64, grid_for(n_pieces, 4), kBlock, 0, (int64_t)n_pieces, perm.as<uint32_t>());
   sort_pairs<uint32_t, uint32_t>(h, piece_key.as<uint32_t>(), piece_key2.as<uint32_t>(), perm.as<uint32_t>(),
@@ -1397,219 +1341,103 @@ std::unique_ptr<hot_layout_t> build_hot_layout(handle_impl const& h, csx_t const
   piece_key.release();
   piece_key2.release();
   perm.release();
-  tr.mark("hot: class sort");
-  if (tr.on) {  // layout statistics: pieces by class and by entries, per range of blocks
-    std::vector<int32_t> hlen(n_pieces), hperm(n_pieces);
-    CUDA_TRY(cudaMemcpy(hlen.data(), piece_len.data(), sizeof(int32_t) * n_pieces, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(hperm.data(), perm2.data(), sizeof(int32_t) * n_pieces, cudaMemcpyDeviceToHost));
-    int edges[] = {0, 1, 4, 16, 64, 160, 250, B, B + 1};
-    for (int k = 0; k < 7; ++k) edges[k] = std::min(edges[k], B);  // ranges of hot blocks, then the cold block [B, B+1)
-    std::fprintf(stderr, "[hot] B=%d W=%d n_hi=%d nnz_hi=%lld segments=%d pieces=%d\n", B, W, n_hi, (long long)nnz, n_segs, n_pieces);
-    for (int k = 0; k + 1 < 9; ++k) {
-      const int b0 = std::min(edges[k], B + 1), b1 = std::min(edges[k + 1], B + 1);
+  tr.mark("sweep layout: kind sort");
+  if (tr.on) {  // layout statistics: pieces by kind, per range of blocks
+    int edges[] = {0, 1, 4, 16, 64, 160, B};
+    std::fprintf(stderr, "[sweep] B=%d W=%d rows=%d nnz=%lld segments=%d pieces=%d\n", B, W, n_cov, (long long)nnz, n_segs, n_pieces);
+    for (int k = 0; k + 1 < 7; ++k) {
+      const int b0 = std::min(edges[k], B), b1 = std::min(edges[k + 1], B);
       if (b1 <= b0) continue;
-      long long by_len[9] = {0}, by_cls[9] = {0}, entries = 0;
-      for (int key = b0 * kinds; key < b1 * kinds; ++key)
-        for (int p = cstart[key]; p < cstart[key + 1]; ++p) {
-          const int ln = hlen[hperm[p]];
-          entries += ln;
-          by_cls[(ln + 7) / 8]++;
-          if (ln <= 8) by_len[ln]++;
-        }
-      std::fprintf(stderr, "[hot] blocks [%d,%d)%s entries %lld  pieces by slots:", b0, b1, b1 == B + 1 && b0 == B ? " (cold)" : "", entries);
-      for (int c2 = 1; c2 <= 8; ++c2) std::fprintf(stderr, " %lld", by_cls[c2]);
-      std::fprintf(stderr, "  1-slot pieces by entries:");
-      for (int c2 = 1; c2 <= 8; ++c2) std::fprintf(stderr, " %lld", by_len[c2]);
+      std::fprintf(stderr, "[sweep] blocks [%d,%d) pieces by kind S Q H F1..F8:", b0, b1);
+      for (int kind = 0; kind < kNumKinds; ++kind) {
+        long long np = 0;
+        for (int b = b0; b < b1; ++b) np += cstart[b * kNumKinds + kind + 1] - cstart[b * kNumKinds + kind];
+        std::fprintf(stderr, " %lld", np);
+      }
       std::fprintf(stderr, "\n");
     }
   }
 
-  // 4. sub-units (runs of groups of one class), units (runs of sub-units of one block), CTA ranges
-  double cold_cost = 2.0;
-  if (const char* e = std::getenv("CUGRAPH_B200_HOT_COLD_COST")) cold_cost = std::atof(e);
-  hot_plan_t plan;
-  if (!plan_hot_units(cstart, B, narrow, hot_unit_slots(), h.sm_count, cold_cost, plan)) return nullptr;  // slots overflow 31 bits
-  auto& subs  = plan.subs;
-  auto& fills = plan.fills;
-  auto& units = plan.units;
-  auto& range = plan.range;
-  const int64_t row_run = plan.row_run, hslot_run = plan.hslot_run, qslot_run = plan.qslot_run, sslot_run = plan.sslot_run,
-                cold_slot0 = plan.cold_slot0;
-  L->n_hot_slots = plan.cold_slot0;
-  L->n_slots     = plan.slot_run;
-  L->n_units     = (int32_t)units.size();
-  L->n_subs      = (int32_t)subs.size();
-  L->n_cta       = plan.n_cta;
-  L->units     = make_dbuf<hot_unit_host_t>(std::max<size_t>(units.size(), 1), h.stream);
-  L->subs      = make_dbuf<hot_sub_host_t>(std::max<size_t>(subs.size(), 1), h.stream);
-  L->cta_range = make_dbuf<int32_t>(range.size(), h.stream);
-  dbuf d_fills = make_dbuf<hot_fill_t>(std::max<size_t>(fills.size(), 1), h.stream);
-  if (!units.empty()) {
-    CUDA_TRY(cudaMemcpyAsync(L->units.data(), units.data(), sizeof(hot_unit_host_t) * units.size(), cudaMemcpyHostToDevice, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(L->subs.data(), subs.data(), sizeof(hot_sub_host_t) * subs.size(), cudaMemcpyHostToDevice, h.stream));
-    CUDA_TRY(cudaMemcpyAsync(d_fills.data(), fills.data(), sizeof(hot_fill_t) * fills.size(), cudaMemcpyHostToDevice, h.stream));
+  // 4. chunks, CTA ranges, phases
+  sweep_plan_t plan;
+  if (!plan_sweep(cstart, B, h.sm_count, plan)) return nullptr;  // step-row numbers overflow 31 bits
+  L->n_steprows = plan.n_steprows;
+  L->n_rowslots = plan.n_rowslots;
+  L->n_chunks   = (int32_t)plan.chunks.size();
+  L->n_phases   = (int32_t)plan.phases.size();
+  L->n_cta      = plan.n_cta;
+  L->chunks     = make_dbuf<sweep_chunk_t>(std::max<size_t>(plan.chunks.size(), 1), h.stream);
+  L->phases     = make_dbuf<sweep_phase_t>(std::max<size_t>(plan.phases.size(), 1), h.stream);
+  L->cta_phase  = make_dbuf<int32_t>(plan.cta_phase.size(), h.stream);
+  dbuf d_fills  = make_dbuf<sweep_fill_t>(std::max<size_t>(plan.fills.size(), 1), h.stream);
+  if (!plan.chunks.empty()) {
+    CUDA_TRY(cudaMemcpyAsync(L->chunks.data(), plan.chunks.data(), sizeof(sweep_chunk_t) * plan.chunks.size(), cudaMemcpyHostToDevice, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(L->phases.data(), plan.phases.data(), sizeof(sweep_phase_t) * plan.phases.size(), cudaMemcpyHostToDevice, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_fills.data(), plan.fills.data(), sizeof(sweep_fill_t) * plan.fills.size(), cudaMemcpyHostToDevice, h.stream));
   }
-  CUDA_TRY(cudaMemcpyAsync(L->cta_range.data(), range.data(), sizeof(int32_t) * range.size(), cudaMemcpyHostToDevice, h.stream));
+  CUDA_TRY(cudaMemcpyAsync(L->cta_phase.data(), plan.cta_phase.data(), sizeof(int32_t) * plan.cta_phase.size(), cudaMemcpyHostToDevice, h.stream));
   sync(h);  // the host vectors are pageable
-  L->unit_counter = make_dbuf<int>(L->n_cta, h.stream);
-  CUDA_TRY(cudaMemsetAsync(L->unit_counter.data(), 0, sizeof(int) * L->n_cta, h.stream));
+  L->cursor = make_dbuf<int>(std::max(L->n_phases, 1), h.stream);
+  CUDA_TRY(cudaMemsetAsync(L->cursor.data(), 0, sizeof(int) * std::max(L->n_phases, 1), h.stream));
 
-  // 5. slots
-  L->seg_row    = make_dbuf<int32_t>(std::max<int64_t>(row_run, 1), h.stream);
-  L->slot_idx16 = make_dbuf<uint16_t>(std::max<int64_t>(L->n_hot_slots, 1) * kHotSlot, h.stream);
-  L->slot_idx32 = make_dbuf<int32_t>(std::max<int64_t>(L->n_slots - L->n_hot_slots, 1) * kHotSlot, h.stream);
-  L->slot_idx_h = make_dbuf<uint2>(std::max<int64_t>(hslot_run, 1), h.stream);
-  L->slot_idx_q = make_dbuf<uint32_t>(std::max<int64_t>(qslot_run, 1), h.stream);
-  L->slot_idx_s = make_dbuf<uint16_t>(std::max<int64_t>(sslot_run, 1), h.stream);
+  // 5. step-rows and row slots
+  L->ids  = make_dbuf<uint4>((size_t)std::max<int64_t>(L->n_steprows, 1) * 32, h.stream);
+  L->rows = make_dbuf<int32_t>(std::max<int64_t>(L->n_rowslots, 1), h.stream);
   const bool weighted = c.weights.data() != nullptr;
-  if (weighted) L->slot_w = dbuf((size_t)std::max<int64_t>(L->n_slots, 1) * kHotSlot * es, h.stream);
-  // padding entries of the cold block read x[n_vertices], which the caller keeps at zero (padded_x_elems)
-  if (!subs.empty()) {
-    // experimental: bank-aware entry order inside the lane slots (4-byte values only: a double spans two banks)
-    bool bank_order = false;
-    if (const char* e = std::getenv("CUGRAPH_B200_HOT_BANK_ORDER")) bank_order = std::atoi(e) != 0 && es == 4;
-    L->bank_order = bank_order;
-    if (bank_order)
-      B200_LAUNCH(h, (k_hot_fill<float, true>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+  if (weighted) L->w = dbuf((size_t)std::max<int64_t>(L->n_steprows, 1) * 32 * kHotSlot * es, h.stream);
+  L->bank_order = h.tune.sweep_bank_order && es == 4;  // a double spans two banks
+  if (!plan.chunks.empty()) {
+    const int grid = (int)plan.chunks.size();
+    if (es == 4 && L->bank_order)
+      B200_LAUNCH(h, (k_sweep_fill<float, true>), grid, kFillWarps * 32, 0, L->chunks.as<sweep_chunk_t>(), d_fills.as<sweep_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
-                  c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
-                  L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
-                  L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
+                  c.weights.as<float>(), W, L->ids.as<uint4>(), L->w.as<float>(), L->rows.as<int32_t>());
     else if (es == 4)
-      B200_LAUNCH(h, (k_hot_fill<float, false>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+      B200_LAUNCH(h, (k_sweep_fill<float, false>), grid, kFillWarps * 32, 0, L->chunks.as<sweep_chunk_t>(), d_fills.as<sweep_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
-                  c.weights.as<float>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
-                  L->slot_idx32.as<int32_t>(), L->slot_w.as<float>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
-                  L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
+                  c.weights.as<float>(), W, L->ids.as<uint4>(), L->w.as<float>(), L->rows.as<int32_t>());
     else
-      B200_LAUNCH(h, (k_hot_fill<double, false>), (int)subs.size(), 256, 0, L->subs.as<hot_sub_host_t>(), d_fills.as<hot_fill_t>(),
+      B200_LAUNCH(h, (k_sweep_fill<double, false>), grid, kFillWarps * 32, 0, L->chunks.as<sweep_chunk_t>(), d_fills.as<sweep_fill_t>(),
                   perm2.as<int32_t>(), piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>(), idx,
-                  c.weights.as<double>(), W, B, (int)nv, (long long)cold_slot0, L->slot_idx16.as<uint16_t>(),
-                  L->slot_idx32.as<int32_t>(), L->slot_w.as<double>(), L->seg_row.as<int32_t>(), L->slot_idx_h.as<uint2>(),
-                  L->slot_idx_q.as<uint32_t>(), L->slot_idx_s.as<uint16_t>());
+                  c.weights.as<double>(), W, L->ids.as<uint4>(), L->w.as<double>(), L->rows.as<int32_t>());
   }
-  check_last("hot layout");
+  check_last("sweep layout");
   sync(h);
-  tr.mark("hot: fill slots");
+  tr.mark("sweep layout: fill");
   if (tr.on)
-    std::fprintf(stderr, "[hot] slots %lld (hot %lld) + %lld half + %lld quarter + %lld single = %.1f MB ids, seg rows %lld, units %d, subs %d\n",
-                 (long long)L->n_slots, (long long)L->n_hot_slots, (long long)hslot_run, (long long)qslot_run, (long long)sslot_run,
-                 (double)(L->n_hot_slots * 16 + (L->n_slots - L->n_hot_slots) * 32 + hslot_run * 8 + qslot_run * 4 + sslot_run * 2) / 1e6,
-                 (long long)row_run, L->n_units, L->n_subs);
+    std::fprintf(stderr, "[sweep] %lld step-rows = %.1f MB of ids, %lld row slots = %.1f MB, %d chunks, %d phases, %d CTAs\n",
+                 (long long)L->n_steprows, (double)L->n_steprows * 512 / 1e6, (long long)L->n_rowslots,
+                 (double)L->n_rowslots * 4 / 1e6, L->n_chunks, L->n_phases, L->n_cta);
   return L;
 }
 
 }  // namespace
 
-// flat copy of plan_hot_units' result for the debug C entry (CPU tests)
-bool debug_plan_hot_units(std::vector<int32_t> const& cstart, int B, bool narrow, int unit_slots, int sm_count, double cold_cost,
-                          int64_t totals[7], std::vector<int32_t>& subs4, std::vector<int32_t>& fills4,
-                          std::vector<int32_t>& units4, std::vector<int32_t>& range)
+// flat copy of plan_sweep's result for the debug C entry (CPU tests)
+bool debug_plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, int64_t totals[3], std::vector<int32_t>& chunks4,
+                      std::vector<int32_t>& fills4, std::vector<int32_t>& phases4, std::vector<int32_t>& cta_phase)
 {
-  hot_plan_t P;
-  if (!plan_hot_units(cstart, B, narrow, unit_slots, sm_count, cold_cost, P)) return false;
-  totals[0] = P.slot_run; totals[1] = P.row_run; totals[2] = P.cold_slot0; totals[3] = P.hslot_run; totals[4] = P.qslot_run;
-  totals[5] = P.n_cta;
-  totals[6] = P.sslot_run;
-  for (auto const& x : P.subs) subs4.insert(subs4.end(), {x.slot_begin, x.row_begin, x.n_groups, x.cls});
+  sweep_plan_t P;
+  if (!plan_sweep(cstart, B, sm_count, P)) return false;
+  totals[0] = P.n_steprows; totals[1] = P.n_rowslots; totals[2] = P.n_cta;
+  for (auto const& x : P.chunks) chunks4.insert(chunks4.end(), {x.sr_begin, x.row_begin, x.n_groups, x.kind});
   for (auto const& x : P.fills) fills4.insert(fills4.end(), {x.piece_begin, x.piece_end, x.block, x.pad});
-  for (auto const& x : P.units) units4.insert(units4.end(), {x.sub_begin, x.sub_end, x.block, x.pad});
-  range = P.range;
+  for (auto const& x : P.phases) phases4.insert(phases4.end(), {x.block, x.chunk_begin, x.chunk_end, x.pad});
+  cta_phase = P.cta_phase;
   return true;
 }
 
-hot_layout_t const* hot_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size)
+sweep_layout_t const* sweep_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size)
 {
   auto& slot  = (elem_size == 4) ? c.hot4 : c.hot8;
   auto& tried = (elem_size == 4) ? c.hot4_tried : c.hot8_tried;
   if (tried) return slot.get();
   tried = true;
-  long long min_edges = 1ll << 22;
-  if (const char* e = std::getenv("CUGRAPH_B200_HOT_MIN_EDGES")) min_edges = std::atoll(e);
-  // 32-bit edge positions / slot numbers; build_hot_layout itself gives up (nullptr) if the slots overflow
-  if (!c.degree_sorted || c.seg[0] <= 0 || c.nnz_hi < min_edges || c.offs64 || c.nnz_hi >= (1ll << 31) - 4096) return nullptr;
-  slot = build_hot_layout<int32_t>(h, c, n_vertices, elem_size);
+  // 32-bit edge positions / step-row numbers; build_sweep_layout itself gives up (nullptr) if the step-rows overflow
+  if (!c.degree_sorted || c.seg[kNumSeg - 2] <= 0 || c.nnz < h.tune.sweep_min_edges || c.offs64 || c.nnz >= (1ll << 31) - 4096)
+    return nullptr;
+  slot = build_sweep_layout<int32_t>(h, c, n_vertices, elem_size);
   return slot.get();
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL exact-degree ELL copy of the degree < 32 rows (low_ell_t, consumed by k_spmv_low_ell)
-// ---------------------------------------------------------------------------------------------
-namespace {
-
-// P[d] = number of rows with degree >= d (rows are degree-descending), d = 0..32
-template <typename O>
-__global__ void k_low_class_bounds(O const* __restrict__ off, int32_t n_rows, int32_t* __restrict__ P)
-{
-  const int d = threadIdx.x;
-  if (d > 32) return;
-  int lo = 0, hi = n_rows;  // first row with degree < d
-  while (lo < hi) {
-    const int mid = lo + ((hi - lo) >> 1);
-    if ((long long)(off[mid + 1] - off[mid]) >= d) lo = mid + 1; else hi = mid;
-  }
-  P[d] = lo;
-}
-
-// out[k * n + i] = in[i * d + k]  (one degree class)
-template <typename V>
-__global__ void k_low_transpose(V const* __restrict__ in, V* __restrict__ out, int32_t n, int d)
-{
-  const long long total = (long long)n * d;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(e / n), i = (int)(e - (long long)k * n);
-    out[e]      = in[(long long)i * d + k];
-  }
-}
-
-template <typename O>
-std::unique_ptr<low_ell_t> build_low_ell(handle_impl const& h, csx_t const& c, size_t es)
-{
-  auto L = std::make_unique<low_ell_t>();
-  dbuf dP = make_dbuf<int32_t>(33, h.stream);
-  B200_LAUNCH(h, (k_low_class_bounds<O>), 1, 64, 0, c.offsets.as<O>(), c.n_rows, dP.as<int32_t>());
-  int32_t P[33];
-  CUDA_TRY(cudaMemcpyAsync(P, dP.data(), sizeof(P), cudaMemcpyDeviceToHost, h.stream));
-  sync(h);
-  const int64_t low_nnz = c.nnz - c.nnz_hi;
-  L->idx = make_dbuf<int32_t>(std::max<int64_t>(low_nnz, 1), h.stream);
-  const bool weighted = c.weights.data() != nullptr;
-  if (weighted) L->w = dbuf((size_t)std::max<int64_t>(low_nnz, 1) * es, h.stream);
-  long long run = 0;  // classes in row order: degree 31 first
-  for (int d = 31; d >= 0; --d) {
-    L->row_begin[d] = P[d + 1];
-    L->n[d]         = P[d] - P[d + 1];
-    L->base[d]      = run;
-    if (d == 0 || L->n[d] == 0) continue;
-    // the class's rows are contiguous and all have d entries: a dense n x d matrix at offsets[row_begin]
-    const long long src0 = c.nnz_hi + run;  // = offsets[row_begin[d]]
-    const int grid       = (int)std::min<long long>(((long long)L->n[d] * d + 255) / 256, 148 * 64);
-    B200_LAUNCH(h, (k_low_transpose<int32_t>), grid, 256, 0, c.indices.as<int32_t>() + src0, L->idx.as<int32_t>() + run,
-                L->n[d], d);
-    if (weighted) {
-      if (es == 4)
-        B200_LAUNCH(h, (k_low_transpose<float>), grid, 256, 0, c.weights.as<float>() + src0, L->w.as<float>() + run, L->n[d], d);
-      else
-        B200_LAUNCH(h, (k_low_transpose<double>), grid, 256, 0, c.weights.as<double>() + src0, L->w.as<double>() + run, L->n[d], d);
-    }
-    run += (long long)L->n[d] * d;
-  }
-  B200_EXPECTS(run == low_nnz, CUGRAPH_UNKNOWN_ERROR, "internal: degree classes do not add up");
-  check_last("low ell");
-  sync(h);
-  return L;
-}
-
-}  // namespace
-
-low_ell_t const* low_ell_layout(handle_impl const& h, csx_t const& c, size_t elem_size)
-{
-  if (c.low_ell_tried) return c.low_ell.get();
-  c.low_ell_tried = true;
-  const char* e   = std::getenv("CUGRAPH_B200_LOW_ELL");
-  if (!e || std::atoi(e) == 0 || !c.degree_sorted || c.n_rows <= c.seg[0]) return nullptr;
-  c.low_ell = c.offs64 ? build_low_ell<int64_t>(h, c, elem_size) : build_low_ell<int32_t>(h, c, elem_size);
-  return c.low_ell.get();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1709,30 +1537,30 @@ template dbuf collect_vertex_values<double>(handle_impl const&, graph_impl const
 
 }  // namespace b200
 
-extern "C" cugraph_error_code_t cugraph_b200_debug_plan_hot_units(
-  const int32_t* class_start, int n_hot_blocks, bool_t narrow, int unit_slots, int sm_count, double cold_cost,
-  int64_t* totals, int32_t* subs, int32_t* fills, size_t subs_capacity, size_t* n_subs, int32_t* units,
-  size_t units_capacity, size_t* n_units, int32_t* range, size_t range_capacity, cugraph_error_t** error)
+extern "C" cugraph_error_code_t cugraph_b200_debug_plan_sweep(const int32_t* class_start, int n_blocks, int sm_count,
+                                                              int64_t* totals, int32_t* chunks, int32_t* fills,
+                                                              size_t chunks_capacity, size_t* n_chunks, int32_t* phases,
+                                                              size_t phases_capacity, size_t* n_phases, int32_t* cta_phase,
+                                                              size_t cta_capacity, cugraph_error_t** error)
 {
   using namespace b200;
   return guarded(error, [&] {
-    B200_EXPECTS(class_start && totals && subs && fills && units && range && n_subs && n_units, CUGRAPH_INVALID_INPUT,
+    B200_EXPECTS(class_start && totals && chunks && fills && phases && cta_phase && n_chunks && n_phases, CUGRAPH_INVALID_INPUT,
                  "null argument");
-    B200_EXPECTS(n_hot_blocks >= 0 && unit_slots >= 32 && sm_count >= 1, CUGRAPH_INVALID_INPUT, "bad parameter");
-    const int kinds = narrow == TRUE ? 11 : 8;
-    std::vector<int32_t> cstart(class_start, class_start + (size_t)(n_hot_blocks + 1) * kinds + 1);
-    std::vector<int32_t> s4, f4, u4, r;
-    int64_t t[7];
-    B200_EXPECTS(debug_plan_hot_units(cstart, n_hot_blocks, narrow == TRUE, unit_slots, sm_count, cold_cost, t, s4, f4, u4, r),
-                 CUGRAPH_INVALID_INPUT, "slot numbers overflow 31 bits");
-    B200_EXPECTS(s4.size() / 4 <= subs_capacity && u4.size() / 4 <= units_capacity && r.size() <= range_capacity,
+    B200_EXPECTS(n_blocks >= 0 && sm_count >= 1, CUGRAPH_INVALID_INPUT, "bad parameter");
+    std::vector<int32_t> cstart(class_start, class_start + (size_t)n_blocks * kNumKinds + 1);
+    std::vector<int32_t> c4, f4, p4, r;
+    int64_t t[3];
+    B200_EXPECTS(debug_plan_sweep(cstart, n_blocks, sm_count, t, c4, f4, p4, r), CUGRAPH_INVALID_INPUT,
+                 "step-row numbers overflow 31 bits");
+    B200_EXPECTS(c4.size() / 4 <= chunks_capacity && p4.size() / 4 <= phases_capacity && r.size() <= cta_capacity,
                  CUGRAPH_INVALID_INPUT, "output capacity too small");
-    std::copy(t, t + 7, totals);
-    std::copy(s4.begin(), s4.end(), subs);
+    std::copy(t, t + 3, totals);
+    std::copy(c4.begin(), c4.end(), chunks);
     std::copy(f4.begin(), f4.end(), fills);
-    std::copy(u4.begin(), u4.end(), units);
-    std::copy(r.begin(), r.end(), range);
-    *n_subs  = s4.size() / 4;
-    *n_units = u4.size() / 4;
+    std::copy(p4.begin(), p4.end(), phases);
+    std::copy(r.begin(), r.end(), cta_phase);
+    *n_chunks = c4.size() / 4;
+    *n_phases = p4.size() / 4;
   });
 }

@@ -7,7 +7,7 @@
 // the C ABI: a resource handle bound to the caller's CUDA stream, rectangular edge blocks with the
 // same binned / column-blocked layout as the single-GPU graph, the block pull sweep and the fused
 // per-iteration vertex step.  All calls only ENQUEUE work on the handle's stream.
-#include "spmv_hot_x.cuh"
+#include "sweep.cuh"
 
 #include <algorithm>
 
@@ -92,6 +92,7 @@ cugraph_resource_handle_t* cugraph_b200_create_resource_handle_on_stream(void* c
 {
   try {
     auto* h = new handle_impl{};
+    h->tune = tuning_t::from_env();
     CUDA_TRY(cudaGetDevice(&h->device));
     h->stream         = reinterpret_cast<cudaStream_t>(cuda_stream);
     h->borrowed_stream = true;
@@ -147,7 +148,7 @@ cugraph_error_code_t cugraph_b200_block_create(const cugraph_resource_handle_t* 
     b->state = make_dbuf<pr_state_t>(1, h.stream);
     CUDA_TRY(cudaMemsetAsync(b->state.data(), 0, sizeof(pr_state_t), h.stream));
     // build the column-blocked copy now (it is lazily created otherwise, inside the first timed sweep)
-    if (!b->csx->offs64) (void)hot_layout(h, *b->csx, b->n_span, b->wtype == FLOAT64 ? 8 : 4);
+    if (!b->csx->offs64) (void)sweep_layout(h, *b->csx, b->n_span, b->wtype == FLOAT64 ? 8 : 4);
     sync(h);
     *block = reinterpret_cast<cugraph_b200_block_t*>(b.release());
   });

@@ -7,7 +7,7 @@
 // advances the device-resident loop state.  The host enqueues iterations in batches and only reads the
 // `done` flag between batches; kernels of iterations past convergence are no-ops, so the iteration
 // count and result are exactly those of a check-every-iteration loop.
-#include "spmv_hot_x.cuh"
+#include "sweep.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -513,8 +513,8 @@ cugraph_error_code_t cugraph_b200_time_pull_spmv(const cugraph_resource_handle_t
   });
 }
 
-// Debug hook for the experimental sweep variants: y of the configured sweep (environment switches as they are) against
-// the plain reference sweep (k_spmv_hi + k_spmv_low) on the same pseudo-random x.  out[0..3] = degree >= 32 rows:
+// Debug hook: y of the sweep PageRank would use on this graph (the shared-memory piece stream when the graph has one)
+// against the plain sweep (k_spmv_hi + k_spmv_low, an independent implementation) on the same pseudo-random x.  out[0..3] = degree >= 32 rows:
 // max relative difference, its row, that row's degree, rows above 1e-5; out[4..7] = the same for the degree < 32 rows.
 cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph,
                                                        double* out, cugraph_error_t** error)
@@ -535,9 +535,7 @@ cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugraph_resource_ha
     CUDA_TRY(cudaMemsetAsync(acc.data(), 0, sizeof(double) * acc_rows(c), h.stream));
     dbuf state = make_dbuf<pr_state_t>(1, h.stream);
     CUDA_TRY(cudaMemsetAsync(state.data(), 0, sizeof(pr_state_t), h.stream));
-    reference_sweep_only() = true;
     launch_pull_sweep<int32_t, float>(h, c, x.as<float>(), y0.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
-    reference_sweep_only() = false;
     launch_pull_sweep_auto<int32_t, float>(h, c, nv, x.as<float>(), y1.as<float>(), acc.as<double>(), 0.85, state.as<pr_state_t>());
     dbuf res = make_dbuf<unsigned long long>(4, h.stream);
     CUDA_TRY(cudaMemsetAsync(res.data(), 0, 4 * sizeof(unsigned long long), h.stream));

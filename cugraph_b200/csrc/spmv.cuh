@@ -8,8 +8,10 @@
 //     (edge-balanced, merge-path style: a hub row is spread over as many warps as it needs, a chunk
 //     holds up to 32 whole rows).  Only row pieces that straddle a chunk boundary use atomics
 //     (double, into acc_hi[row]); whole rows are stored directly.
-//   * rows with degree < 32 use vertex-group-per-warp: 16/8/4/2/1 lanes per row chosen by the bin,
+//   * rows with degree < 32 use vertex-group-per-warp: 4/2/1 lanes per row chosen by the bin,
 //     sub-warp shuffle reductions, contiguous rows => contiguous index reads.
+// This is the sweep of graphs too small for the shared-memory piece stream (sweep.cuh) and of 64-bit-offset graphs, and
+// the independent implementation the piece stream is compared with (cugraph_b200_debug_compare_sweeps).
 //   * index / weight streams are read once with L1 no-allocate loads so that L1 keeps x[] lines;
 //     row sums are accumulated in fp64 and rounded once (keeps 100-iteration PageRank within 1e-6
 //     of an fp64 oracle).
@@ -157,7 +159,7 @@ template <typename O, typename T, bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 k_spmv_low(O const* __restrict__ offsets, int32_t const* __restrict__ indices, T const* __restrict__ weights,
            T const* __restrict__ x, T* __restrict__ y, int32_t const* __restrict__ row_vertex, low_bins_t bins,
-           double alpha, pr_state_t const* __restrict__ st, int mode)
+           double alpha, pr_state_t const* __restrict__ st)
 {
   if (st->done) return;
   int b = 0;
@@ -187,8 +189,10 @@ k_spmv_low(O const* __restrict__ offsets, int32_t const* __restrict__ indices, T
       c[k]              = 0;
       wv[k]             = (T)0;
       if (e < hi) {
-        c[k]  = mode ? __ldg(indices + e) : ld_stream(indices + e);
-        wv[k] = WEIGHTED ? (mode ? __ldg(weights + e) : ld_stream(weights + e)) : (T)1;
+        // these loads allocate in L1: a lane walks 4..32 consecutive bytes of its row, so the sectors are re-used by its
+        // next loads (measured: sweep 0.470 -> 0.456 ms on RMAT-24 against streaming loads)
+        c[k]  = __ldg(indices + e);
+        wv[k] = WEIGHTED ? __ldg(weights + e) : (T)1;
       }
     }
     T v[kR];
@@ -202,203 +206,16 @@ k_spmv_low(O const* __restrict__ offsets, int32_t const* __restrict__ indices, T
 }
 
 // ------------------------------------------------------------------------------------------
-// EXPERIMENTAL (CUGRAPH_B200_LOW_ELL=1): degree < 32 rows from the exact-degree ELL copy (low_ell_t).  One lane per
-// row, no offsets load, coalesced index reads; a thread owns R rows of its class (R = 4 for degree <= 4, 2 for <= 8)
-// so that 8..16 independent index loads, then as many gathers, are in flight per lane.
-// ------------------------------------------------------------------------------------------
-struct low_ell_args_t {
-  int32_t row_begin[32];
-  int32_t n[32];
-  long long base[32];
-  int32_t block_begin[33];  // in class order 31, 30, ..., 0; [32] = total
-};
-
-__host__ __device__ __forceinline__ int low_ell_rows_per_thread(int d) { return d <= 4 ? 4 : (d <= 8 ? 2 : 1); }
-
-// how a kernel reads x[c]: straight from global memory, or (hot variant) from a shared-memory copy of the first
-// `w_hot` entries — the sources with the largest in-degree, which in power-law graphs are also gathered most often
-template <typename T>
-struct gather_global_t {
-  T const* __restrict__ x;
-  __device__ __forceinline__ T operator()(int c) const { return x[c]; }
-};
-template <typename T>
-struct gather_hot_t {
-  T const* __restrict__ x;
-  T const* __restrict__ sx;
-  int w_hot;
-  __device__ __forceinline__ T operator()(int c) const { return c < w_hot ? sx[c] : x[c]; }
-};
-
-// D entries of R rows per thread, fully unrolled
-template <typename T, bool WEIGHTED, int D, int R, typename G>
-__device__ __forceinline__ void low_ell_rows(int32_t const* __restrict__ ell, T const* __restrict__ ellw, int n, int i0,
-                                             G const& gather, double (&acc)[4])
-{
-  int c[R][D];
-  T wv[R][D];
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    const int i = i0 + j * 256;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      c[j][k]  = -1;
-      wv[j][k] = (T)1;
-      if (i < n) {
-        c[j][k] = ld_stream(ell + (long long)k * n + i);
-        if (WEIGHTED) wv[j][k] = ld_stream(ellw + (long long)k * n + i);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    double a = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; ++k)
-      if (c[j][k] >= 0) a += (double)(gather(c[j][k]) * wv[j][k]);
-    acc[j] = a;
-  }
-}
-
-// one virtual block (256 threads, `vblock` in the block numbering of make_low_ell_args) of the ELL sweep
-template <typename T, bool WEIGHTED, typename G>
-__device__ __forceinline__ void low_ell_block(int vblock, int vtid, int32_t const* __restrict__ ell, T const* __restrict__ ellw,
-                                              G const& gather, T* __restrict__ y, int32_t const* __restrict__ row_vertex,
-                                              low_ell_args_t const& L, double alpha, double init)
-{
-  int d = 31;  // class of this block
-#pragma unroll 1
-  for (int k = 1; k < 32; ++k)
-    if (vblock >= L.block_begin[k]) d = 31 - k;
-  const int blk = vblock - L.block_begin[31 - d];
-  const int n   = L.n[d];
-  const int R   = low_ell_rows_per_thread(d);
-  const int i0  = blk * 256 * R + vtid;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  if (d > 0) {
-    int32_t const* e = ell + L.base[d];
-    T const* ew      = WEIGHTED ? ellw + L.base[d] : nullptr;
-    switch (d) {
-      case 1: low_ell_rows<T, WEIGHTED, 1, 4>(e, ew, n, i0, gather, acc); break;
-      case 2: low_ell_rows<T, WEIGHTED, 2, 4>(e, ew, n, i0, gather, acc); break;
-      case 3: low_ell_rows<T, WEIGHTED, 3, 4>(e, ew, n, i0, gather, acc); break;
-      case 4: low_ell_rows<T, WEIGHTED, 4, 4>(e, ew, n, i0, gather, acc); break;
-      case 5: low_ell_rows<T, WEIGHTED, 5, 2>(e, ew, n, i0, gather, acc); break;
-      case 6: low_ell_rows<T, WEIGHTED, 6, 2>(e, ew, n, i0, gather, acc); break;
-      case 7: low_ell_rows<T, WEIGHTED, 7, 2>(e, ew, n, i0, gather, acc); break;
-      case 8: low_ell_rows<T, WEIGHTED, 8, 2>(e, ew, n, i0, gather, acc); break;
-      default: {  // 9..31: eight entries at a time
-        if (i0 < n) {
-          double a = 0.0;
-          for (int k0 = 0; k0 < d; k0 += 8) {
-            int c[8];
-            T wv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              c[k]  = -1;
-              wv[k] = (T)1;
-              if (k0 + k < d) {
-                c[k] = ld_stream(e + (long long)(k0 + k) * n + i0);
-                if (WEIGHTED) wv[k] = ld_stream(ew + (long long)(k0 + k) * n + i0);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (c[k] >= 0) a += (double)(gather(c[k]) * wv[k]);
-          }
-          acc[0] = a;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int i = i0 + j * 256;
-    if (j < R && i < n) {
-      const int r                       = L.row_begin[d] + i;
-      y[row_vertex ? row_vertex[r] : r] = (T)(acc[j] * alpha + init);
-    }
-  }
-}
-
-template <typename T, bool WEIGHTED>
-__global__ void __launch_bounds__(256)
-k_spmv_low_ell(int32_t const* __restrict__ ell, T const* __restrict__ ellw, T const* __restrict__ x, T* __restrict__ y,
-               int32_t const* __restrict__ row_vertex, low_ell_args_t L, double alpha, pr_state_t const* __restrict__ st)
-{
-  if (st->done) return;
-  gather_global_t<T> g{x};
-  low_ell_block<T, WEIGHTED>((int)blockIdx.x, (int)threadIdx.x, ell, ellw, g, y, row_vertex, L, alpha, st->init);
-}
-
-// set by cugraph_b200_debug_compare_sweeps while it computes the reference result: launch_pull_sweep then uses
-// k_spmv_hi + k_spmv_low only, whatever experimental switches are on
-inline bool& reference_sweep_only()
-{
-  static thread_local bool v = false;
-  return v;
-}
-
-inline int low_ell_mode()
-{
-  const char* e = std::getenv("CUGRAPH_B200_LOW_ELL");
-  return e ? std::atoi(e) : 0;
-}
-
-// min_degree_covered: rows of degree >= that are handled by the blocked sweep's piece layout (32 = none of the classes)
-inline low_ell_args_t make_low_ell_args(low_ell_t const& E, int min_degree_covered = 32)
-{
-  low_ell_args_t a{};
-  int blocks = 0;
-  for (int k = 0; k < 32; ++k) {
-    const int d      = 31 - k;
-    a.row_begin[d]   = E.row_begin[d];
-    a.n[d]           = d >= min_degree_covered ? 0 : E.n[d];
-    a.base[d]        = E.base[d];
-    a.block_begin[k] = blocks;
-    const int per    = 256 * low_ell_rows_per_thread(d);
-    blocks += (a.n[d] + per - 1) / per;
-  }
-  a.block_begin[32] = blocks;
-  return a;
-}
-
-template <typename T>
-void launch_low_rows_ell(handle_impl const& h, csx_t const& c, low_ell_t const& E, T const* x, T* y, double alpha,
-                         pr_state_t const* st, int min_degree_covered = 32)
-{
-  low_ell_args_t a = make_low_ell_args(E, min_degree_covered);
-  const int blocks = a.block_begin[32];
-  if (blocks <= 0) return;
-  if (E.w.data())
-    B200_LAUNCH(h, (k_spmv_low_ell<T, true>), blocks, 256, 0, E.idx.as<int32_t>(), E.w.as<T>(), x, y,
-                c.row_vertex.as<int32_t>(), a, alpha, st);
-  else
-    B200_LAUNCH(h, (k_spmv_low_ell<T, false>), blocks, 256, 0, E.idx.as<int32_t>(), E.w.as<T>(), x, y,
-                c.row_vertex.as<int32_t>(), a, alpha, st);
-}
-
-// ------------------------------------------------------------------------------------------
 // host-side launcher of one full sweep
 // ------------------------------------------------------------------------------------------
-// 1 (default): index / weight loads of the low rows allocate in L1 — a lane walks 4..32 consecutive bytes of
-// its row, so the sectors are re-used by its next loads (measured: sweep 0.470 -> 0.456 ms on RMAT-24);
-// 0: streaming (L1::no_allocate) loads
-inline int low_mode()
-{
-  const char* e = std::getenv("CUGRAPH_B200_LOW_MODE");
-  return e ? std::atoi(e) : 1;
-}
-
-// first_bin > 0: bins below it (rows [0, seg[first_bin])) are handled by the blocked sweep's piece layout
-inline low_bins_t make_low_bins(csx_t const& c, int first_bin = 0)
+inline low_bins_t make_low_bins(csx_t const& c)
 {
   low_bins_t b{};
   int blocks = 0;
   for (int k = 0; k < kNumSeg - 1; ++k) {
     b.row_begin[k]   = c.seg[k];
     b.block_begin[k] = blocks;
-    int rows         = k < first_bin ? 0 : c.seg[k + 1] - c.seg[k];
+    int rows         = c.seg[k + 1] - c.seg[k];
     int per_block    = (k == kNumSeg - 2) ? 256 : 256 / low_bin_lanes(k);
     blocks += (rows + per_block - 1) / per_block;
   }
@@ -428,17 +245,13 @@ void launch_pull_sweep(handle_impl const& h, csx_t const& c, T const* x, T* y, d
       B200_LAUNCH(h, (k_spmv_hi_finish<T>), (c.n_split + 255) / 256, 256, 0, c.split_rows.as<int32_t>(), c.n_split,
                   acc_hi, y, rv, alpha, st);
   }
-  if (low_ell_t const* E = reference_sweep_only() ? nullptr : low_ell_layout(h, c, sizeof(T))) {
-    launch_low_rows_ell<T>(h, c, *E, x, y, alpha, st);
-    return;
-  }
   low_bins_t bins = make_low_bins(c);
   int lblocks     = bins.block_begin[kNumSeg - 1];
   if (lblocks > 0) {
     if (weighted)
-      B200_LAUNCH(h, (k_spmv_low<O, T, true>), lblocks, 256, 0, off, idx, w, x, y, rv, bins, alpha, st, low_mode());
+      B200_LAUNCH(h, (k_spmv_low<O, T, true>), lblocks, 256, 0, off, idx, w, x, y, rv, bins, alpha, st);
     else
-      B200_LAUNCH(h, (k_spmv_low<O, T, false>), lblocks, 256, 0, off, idx, w, x, y, rv, bins, alpha, st, low_mode());
+      B200_LAUNCH(h, (k_spmv_low<O, T, false>), lblocks, 256, 0, off, idx, w, x, y, rv, bins, alpha, st);
   }
 }
 

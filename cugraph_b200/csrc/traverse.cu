@@ -406,10 +406,8 @@ void run_bfs(handle_impl const& h, csx_t const& c, int32_t nv, int32_t const* so
   bool deg_ready = false;  // cur_l holds the degrees of the entries of cur (written by the top-down level that built it)
   int level = 0, prev_n_f = 0;
   // Beamer's switch points (the reference: bfs_impl.cuh:291-297, alpha ~ E/V*0.267, beta = 24)
-  double alpha = 14.0, beta = 24.0;  // development knobs: only the schedule depends on them, never the result
-  if (const char* e = std::getenv("CUGRAPH_B200_BFS_ALPHA")) alpha = std::atof(e);
-  if (const char* e = std::getenv("CUGRAPH_B200_BFS_BETA")) beta = std::atof(e);
-  const bool trace    = std::getenv("CUGRAPH_B200_BFS_TRACE") != nullptr;
+  const double alpha = h.tune.bfs_alpha, beta = h.tune.bfs_beta;  // only the schedule depends on them, never the result
+  const bool trace   = h.tune.bfs_trace;
   advance_scratch_t adv;
   adv.init(h, nv, (int64_t)c.nnz);
   while (n_f > 0 && level < depth_limit) {
@@ -611,8 +609,7 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   sync(h);
   const double avg_w   = hsum / (double)c.nnz;
   const double avg_deg = (double)c.nnz / (double)nv;
-  double delta_scale = 1.0;  // tuning knob (results do not depend on it)
-  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_DELTA_SCALE")) delta_scale = std::atof(e);
+  const double delta_scale = h.tune.sssp_delta_scale;  // tuning knob (results do not depend on it)
   T delta = (T)(32.0 * avg_w / std::max(avg_deg, 1e-30) * delta_scale);
   if (!(delta > (T)0)) delta = (T)1;
   // Window width control (results do not depend on it; CUGRAPH_B200_SSSP_ADAPTIVE=0 keeps the fixed reference width).
@@ -622,8 +619,7 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   // the traversal relaxes 6 x E edges in 30 rounds.  The controller starts 64 times narrower and steers the width by
   // the number of rounds the last window took: <= 2 rounds: twice as wide (sparse stretches cost one cheap window per
   // doubling), >= 6 rounds: half as wide.
-  bool adaptive = true;
-  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_ADAPTIVE")) adaptive = std::atoi(e) != 0;
+  const bool adaptive = h.tune.sssp_adaptive;
   const T delta_floor = delta / (T)4096;
   if (adaptive) delta = delta / (T)64;
 
@@ -650,14 +646,12 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   adv.init(h, nv, (int64_t)c.nnz);
   T lo = (T)0, hi = delta;
   const int full_grid = h.sm_count * 8;
-  const bool trace    = std::getenv("CUGRAPH_B200_SSSP_TRACE") != nullptr;
+  const bool trace    = h.tune.sssp_trace;
   unsigned long long tr_edges = 0;
   int tr_rounds = 0, tr_splits = 0;
-  int split_rounds = 1;
-  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_SPLIT_ROUNDS")) split_rounds = std::max(1, std::atoi(e));
+  const int split_rounds = h.tune.sssp_split_rounds;
   // a split costs about one round (a kernel + a read-back): only worth it when the pending round is real work
-  unsigned long long split_min_edges = 1ull << 20;
-  if (const char* e = std::getenv("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) split_min_edges = std::strtoull(e, nullptr, 10);
+  const unsigned long long split_min_edges = h.tune.sssp_split_min_edges;
   while (true) {
     int window_rounds = 0;
     while (n_near > 0) {

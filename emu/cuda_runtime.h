@@ -32,6 +32,10 @@ struct int2 { int x, y; };
 inline int2 make_int2(int a, int b) { return {a, b}; }
 struct uint4 { unsigned x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct double2 { double x, y; };
+struct float4 { float x, y, z, w; };
+inline double2 make_double2(double a, double b) { return {a, b}; }
+inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
 inline int4 make_int4(int a, int b, int c, int d) { return {a, b, c, d}; }

@@ -98,7 +98,7 @@ while time.time() < t_end:
     renumber = bool(r.integers(0, 2))
     transposed = bool(r.integers(0, 2))
     hot = bool(r.integers(0, 2))
-    os.environ["CUGRAPH_B200_HOT_MIN_EDGES"] = "0" if hot else "1000000000"
+    os.environ["CUGRAPH_B200_SWEEP_MIN_EDGES"] = "0" if hot else "1000000000"
     for k, vals in (("CUGRAPH_B200_HOT_X", "01"), ("CUGRAPH_B200_HOT_NARROW", "01"), ("CUGRAPH_B200_LOW_ELL", "012"),
                     ("CUGRAPH_B200_HOT_BANK_ORDER", "01")):
         os.environ[k] = str(r.choice(list(vals)))

@@ -64,7 +64,7 @@ for k in (1, 2, 4, 16, 64):
 hi_idx = idx[:off[n_hi]]
 for k in (1, 2, 4, 16, 64):
     print(f"  sources of degree>=32 rows inside the first {k} column block(s): {100.0 * (hi_idx < k * W).mean():.1f} %", flush=True)
-os.environ["CUGRAPH_B200_HOT_MIN_EDGES"] = "0"
+os.environ["CUGRAPH_B200_SWEEP_MIN_EDGES"] = "0"
 os.environ["CUGRAPH_B200_BUILD_TRACE"] = "1"
 configs = sys.argv[2:] or ["CUGRAPH_B200_HOT_NARROW=0", "CUGRAPH_B200_HOT_NARROW=1"]
 for cfg in configs:

@@ -70,23 +70,24 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_pagerank_vertex_step(
   cugraph_type_erased_device_array_view_t* x, size_t n_local, double alpha, double n_vertices_global, bool_t first,
   const double* totals_prev_device, double* partial_out_device, cugraph_error_t** error);
 
-/* Debug hook for the experimental sweep variants: one sweep as configured by the CUGRAPH_B200_* switches against the plain
- * reference sweep on the same pseudo-random x.  out[0..3] = degree >= 32 rows {max relative difference, its row, that
- * row's degree, rows above 1e-5}; out[4..7] = the same for the degree < 32 rows.  (scripts/debug_variant.py) */
+/* Debug hook: one sweep as PageRank would run it on this graph (the shared-memory piece stream when the graph has one)
+ * against the plain sweep (an independent implementation) on the same pseudo-random x.  out[0..3] = degree >= 32 rows
+ * {max relative difference, its row, that row's degree, rows above 1e-5}; out[4..7] = the same for the degree < 32 rows. */
 CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_compare_sweeps(const cugraph_resource_handle_t* handle,
                                                                      cugraph_graph_t* graph, double* out,
                                                                      cugraph_error_t** error);
 
-/* Host-only planner of the blocked sweep's work structure (sub-units, units, per-CTA unit ranges) from the per-class
- * piece counts; the function graph staging itself uses.  Needs no GPU: exposed so that the host logic is testable on
- * CPU (tests/test_hot_plan_cpu.py).  class_start has (n_hot_blocks + 1) * kinds + 1 entries (kinds = 8, narrow: 11).
- * Outputs: totals[7] = {slots, seg rows, first cold slot, half slots, quarter slots, CTAs, single slots}; subs / fills / units are
- * 4 x int32 records ({slot_begin,row_begin,n_groups,class}, {piece_begin,piece_end,block,0}, {sub_begin,sub_end,block,0});
- * range has totals[5] + 1 entries.  Returns CUGRAPH_INVALID_INPUT when a capacity is too small. */
-CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_plan_hot_units(
-  const int32_t* class_start, int n_hot_blocks, bool_t narrow, int unit_slots, int sm_count, double cold_cost,
-  int64_t* totals, int32_t* subs, int32_t* fills, size_t subs_capacity, size_t* n_subs, int32_t* units,
-  size_t units_capacity, size_t* n_units, int32_t* range, size_t range_capacity, cugraph_error_t** error);
+/* Host-only planner of the sweep's work structure (chunks, phases, per-CTA phase ranges) from the piece counts per
+ * (block, kind); the function graph staging itself uses.  Needs no GPU: exposed so that the host logic is testable on CPU
+ * (tests/test_sweep_plan_cpu.py).  class_start has n_blocks * 11 + 1 entries (kinds S, Q, H, F1..F8).
+ * Outputs: totals[3] = {step-rows, row slots, CTAs}; chunks / fills / phases are 4 x int32 records
+ * ({sr_begin,row_begin,n_groups,kind}, {piece_begin,piece_end,block,0}, {block,chunk_begin,chunk_end,0});
+ * cta_phase has totals[2] + 1 entries.  Returns CUGRAPH_INVALID_INPUT when a capacity is too small. */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_debug_plan_sweep(const int32_t* class_start, int n_blocks, int sm_count,
+                                                                 int64_t* totals, int32_t* chunks, int32_t* fills,
+                                                                 size_t chunks_capacity, size_t* n_chunks, int32_t* phases,
+                                                                 size_t phases_capacity, size_t* n_phases, int32_t* cta_phase,
+                                                                 size_t cta_capacity, cugraph_error_t** error);
 
 #ifdef __cplusplus
 }

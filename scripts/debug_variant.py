@@ -11,7 +11,7 @@ from cugraph_b200 import pylibcugraph as plc  # noqa: E402
 from cugraph_b200.generators import rmat_edgelist  # noqa: E402
 
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-os.environ.setdefault("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+os.environ.setdefault("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
 src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
 h = plc.ResourceHandle()
 g = plc.SGGraph(h, plc.GraphProperties(is_multigraph=True), src, dst, store_transposed=True, renumber=True)

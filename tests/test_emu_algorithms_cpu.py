@@ -56,7 +56,7 @@ PR_CASES = [("plain sweep", "1000000000", False), ("blocked sweep", "0", False),
 
 @pytest.mark.parametrize("name,min_edges,weighted", PR_CASES, ids=[c[0] for c in PR_CASES])
 def test_pagerank_emulated(emu, monkeypatch, name, min_edges, weighted):  # noqa: F811
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", min_edges)
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", min_edges)
     src, dst, w = make_edges(60_000, 250_000, seed=41, weighted=weighted, id_offset=5)
     g = create_graph(emu, src, dst, w)
     verts, pr, it = run_pagerank(emu, g, 0.85, 0.0, 20)             # equal iteration counts: the parity protocol
@@ -73,7 +73,7 @@ def test_pagerank_emulated(emu, monkeypatch, name, min_edges, weighted):  # noqa
 
 def test_pagerank_emulated_experimental_kernel(emu, monkeypatch):  # noqa: F811
     """k_spmv_blocked_x with multi-unit claims and tiny units: own range, then stealing (CTA 0 drains every range)"""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.setenv("CUGRAPH_B200_HOT_X", "1")
     monkeypatch.setenv("CUGRAPH_B200_HOT_NARROW", "1")
     monkeypatch.setenv("CUGRAPH_B200_HOT_CLAIM", "3")
@@ -95,7 +95,7 @@ def test_pagerank_emulated_experimental_kernel(emu, monkeypatch):  # noqa: F811
 def test_pagerank_emulated_double_weights(emu, monkeypatch, hot_x):  # noqa: F811
     """fp64 graphs: 24,512 columns per shared-memory slice, several blocks, base and experimental kernel"""
     from tests.test_emu_staging_cpu import FLOAT64
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.setenv("CUGRAPH_B200_HOT_X", hot_x)
     src, dst, w32 = make_edges(80_000, 300_000, seed=47, weighted=True)
     w = w32.astype(np.float64) * 1.000000123
@@ -120,7 +120,7 @@ def test_pagerank_emulated_double_weights(emu, monkeypatch, hot_x):  # noqa: F81
                                               ("16", {"CUGRAPH_B200_LOW_ELL": "1"}), ("2", {"CUGRAPH_B200_LOW_ELL": "2"})])
 def test_pagerank_emulated_lower_degree_bound(emu, monkeypatch, min_degree, extra):  # noqa: F811
     """CUGRAPH_B200_HOT_MIN_DEGREE: rows down to that degree go through the piece layout, the rest through the low-row kernels"""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_DEGREE", min_degree)
     for k, v in extra.items():
         monkeypatch.setenv(k, v)

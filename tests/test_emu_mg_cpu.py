@@ -34,7 +34,7 @@ def view(L, a):
                                                             (2, 2, False, "1000000000", False), (2, 4, False, "0", True)])
 def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, min_edges, split):  # noqa: F811
     """split: one block per destination partition of the row group (the structure of mg.py's CUGRAPH_B200_MG_SPLIT path)"""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", min_edges)
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", min_edges)
     L = emu
     _api(L)
     P = R * Cc

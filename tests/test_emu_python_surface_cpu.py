@@ -74,7 +74,7 @@ def test_wrappers_match_oracle(surface):
 def test_bench_single_gpu_arm(surface, monkeypatch, capsys):
     """bench.run_single end to end at a toy scale: one JSON line with every key of the contract; the side processes
     (which need a real GPU) fail here and must not take the main line with them."""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.setenv("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "0")   # traversal process only; variants are skipped
     bench = _load(os.path.join(ROOT, "bench.py"), "bench_under_test")
     monkeypatch.setattr(bench, "_run_side", lambda argv, timeout_s: {"error": "no GPU in this test"})
@@ -110,7 +110,7 @@ def _side_variants():
 @pytest.mark.parametrize("cfg", _side_variants())
 def test_bench_side_variant(surface, monkeypatch, capsys, cfg):
     """every switch set bench.py's side run will time on the GPU: parity of the configured sweep against the plain one"""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     side = _load(os.path.join(ROOT, "scripts", "bench_side.py"), "bench_side_under_test")
     for kv in cfg.split(","):
         if "=" in kv:

@@ -37,8 +37,8 @@ def emu():
     L.cugraph_error_message.argtypes = [C.c_void_p]
     L.cugraph_graph_free.argtypes = [C.c_void_p]
     L.emu_graph_primary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.emu_hot_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.emu_low_ell_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+    L.emu_sweep_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emu_reload_tuning.argtypes = [C.c_void_p]
     L.handle = L.cugraph_create_resource_handle(None)
     assert L.handle
     return L
@@ -60,6 +60,7 @@ def make_edges(V, E, seed, weighted=False, id_offset=0):
 
 
 def create_graph(L, src, dst, w, **flags):
+    L.emu_reload_tuning(C.c_void_p(L.handle))   # the knobs are read from the environment per handle; tests change it per case
     views = [L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, t) if a is not None else None
              for a, t in ((src, INT32), (dst, INT32), (w, FLOAT32))]
     g, err = C.c_void_p(), C.c_void_p()
@@ -215,7 +216,7 @@ def check_hot(L, g, P, bank_order=False, stats=None):
 
 @pytest.mark.parametrize("weighted", [False, True])
 def test_staging_and_piece_layout(emu, monkeypatch, weighted):
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.delenv("CUGRAPH_B200_HOT_NARROW", raising=False)
     src, dst, w = make_edges(120_000, 900_000, seed=3 + weighted, weighted=weighted, id_offset=17)
     g = create_graph(emu, src, dst, w)
@@ -228,7 +229,7 @@ def test_staging_and_piece_layout(emu, monkeypatch, weighted):
 
 
 def test_piece_layout_with_cold_block_and_small_units(emu, monkeypatch):
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.setenv("CUGRAPH_B200_HOT_BLOCKS", "1")          # one hot block, the rest of the columns cold (32-bit ids)
     monkeypatch.setenv("CUGRAPH_B200_HOT_UNIT_SLOTS", "1024")
     src, dst, w = make_edges(120_000, 600_000, seed=11)
@@ -240,7 +241,7 @@ def test_piece_layout_with_cold_block_and_small_units(emu, monkeypatch):
 
 
 def test_narrow_piece_layout(emu, monkeypatch):
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     monkeypatch.setenv("CUGRAPH_B200_HOT_NARROW", "1")
     src, dst, w = make_edges(160_000, 700_000, seed=5)
     g = create_graph(emu, src, dst, w)
@@ -253,7 +254,7 @@ def test_narrow_piece_layout(emu, monkeypatch):
 @pytest.mark.parametrize("weighted", [False, True])
 def test_bank_ordered_piece_layout(emu, monkeypatch, weighted):
     """CUGRAPH_B200_HOT_BANK_ORDER=1: same (row, source[, weight]) multiset, and fewer shared-memory wavefronts per gather"""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     src, dst, w = make_edges(120_000, 900_000, seed=21 + weighted, weighted=weighted, id_offset=3)
     res = {}
     for mode in ("0", "1"):
@@ -293,7 +294,7 @@ def test_low_ell_sweep(emu, monkeypatch, weighted):
 
 def test_staging_options(emu, monkeypatch):
     """self-loop / multi-edge removal and symmetrisation against numpy"""
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "1000000000")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "1000000000")
     src, dst, _ = make_edges(3_000, 40_000, seed=9)
     g = create_graph(emu, src, dst, None, drop_self_loops=1, drop_multi_edges=1)
     P = primary(emu, g)

@@ -46,7 +46,7 @@ CASES = [
 
 @pytest.mark.parametrize("name,env,weighted,mode", CASES, ids=[c[0] for c in CASES])
 def test_blocked_sweep_model(emu, monkeypatch, name, env, weighted, mode):  # noqa: F811
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_EDGES", "0")
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     for k in ("CUGRAPH_B200_HOT_BLOCKS", "CUGRAPH_B200_HOT_NARROW", "CUGRAPH_B200_HOT_UNIT_SLOTS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
