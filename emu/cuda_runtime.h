@@ -34,6 +34,8 @@ struct uint4 { unsigned x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct double2 { double x, y; };
 struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+inline float2 make_float2(float a, float b) { return {a, b}; }
 inline double2 make_double2(double a, double b) { return {a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
