@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libcugraph_c.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-ccbin", "/usr/bin/g++"]
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-ccbin", "/usr/bin/g++"] + os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _newer(a, b):

@@ -102,6 +102,7 @@ struct tuning_t {
   double bfs_alpha{14.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer's switch points)
   bool sssp_adaptive{true};                // CUGRAPH_B200_SSSP_ADAPTIVE
   double sssp_delta_scale{1.0};            // CUGRAPH_B200_SSSP_DELTA_SCALE
+  double sssp_start_div{64.0};             // CUGRAPH_B200_SSSP_START_DIV: the controller starts with delta / this
   int sssp_split_rounds{1};                // CUGRAPH_B200_SSSP_SPLIT_ROUNDS
   unsigned long long sssp_split_min_edges{1ull << 20};  // CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES
   bool bfs_trace{false}, sssp_trace{false}, build_trace{false};  // CUGRAPH_B200_{BFS,SSSP,BUILD}_TRACE
@@ -115,6 +116,7 @@ struct tuning_t {
     if (auto e = get("CUGRAPH_B200_BFS_BETA")) t.bfs_beta = std::atof(e);
     if (auto e = get("CUGRAPH_B200_SSSP_ADAPTIVE")) t.sssp_adaptive = std::atoi(e) != 0;
     if (auto e = get("CUGRAPH_B200_SSSP_DELTA_SCALE")) t.sssp_delta_scale = std::atof(e);
+    if (auto e = get("CUGRAPH_B200_SSSP_START_DIV")) t.sssp_start_div = std::max(1.0, std::atof(e));
     if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_ROUNDS")) t.sssp_split_rounds = std::max(1, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) t.sssp_split_min_edges = std::strtoull(e, nullptr, 10);
     t.bfs_trace   = get("CUGRAPH_B200_BFS_TRACE") != nullptr;

@@ -1073,9 +1073,11 @@ struct sweep_plan_t {
 
 inline double sweep_group_cost(int kind)
 {
-  // step-rows: id load (4 lines) + 8 gathers at ~1.5 wavefronts; pieces: one fp64 atomic each (F8 pieces of hub rows are
-  // summed by shuffles first)
-  return kind_steps(kind) * 18.0 + kind_pieces(kind) * (kind == kNumKinds - 1 ? 0.15 : 0.6) + 6.0;
+  // Load/store-unit cycles.  The atomics dominate: a scattered 64-bit RED costs about one cycle PER LANE whatever its
+  // sectors (measured, profiles/r02_notes.md: no atomics -0.106 ms, plain stores or one sector per warp: no change), i.e.
+  // ~1.2 cycles per piece; a step-row costs 4 lines of ids + 8 gathers at ~1.5 wavefronts.  The F8 pieces of hub rows are
+  // summed by shuffles first (one RED per 32 pieces).
+  return kind_steps(kind) * 14.0 + kind_pieces(kind) * (kind == kNumKinds - 1 ? 0.1 : 1.2) + 4.0;
 }
 constexpr double kPhaseCost = 2500.0;  // barrier + 192 KiB slice fill, in the same unit
 

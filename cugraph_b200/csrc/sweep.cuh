@@ -25,11 +25,13 @@
 
 namespace b200 {
 
-constexpr int kSweepThreads = 512;
+
+
+constexpr int kSweepThreads = 512;  // 16 warps x 128 registers, two chunk buffers per warp (384 threads x 3 buffers: no faster)
 constexpr int kSweepWarps   = kSweepThreads / 32;
 constexpr int kSweepDynSmem = kHotSliceBytes;
 constexpr int kTmaPiece     = 16 * 1024;  // bytes per bulk copy of the slice
-constexpr int kStealMin     = 24;         // chunks a phase must have left for another CTA to load its slice and join
+constexpr int kStealMin     = 12;         // chunks a phase must have left for another CTA to load its slice and join
 
 #ifndef B200_HOST_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -37,7 +37,7 @@ inline int grid_for(int64_t n) { return (int)std::min<int64_t>(std::max<int64_t>
 struct frontier_counters_t {
   int n_small;              // entries appended to the next queue
   int n_large;              // unused (kept for the layout of the 2-int reset)
-  int n_far;                // SSSP: entries appended to the far pile
+  int n_far;                // unused (kept for the layout)
   int n_conv;               // bitmap -> queue conversion cursor
   unsigned long long m_f;   // sum of degrees of the vertices appended (direction-optimising heuristic)
 };
@@ -466,67 +466,100 @@ __device__ __forceinline__ double atomic_min_nonneg(double* addr, double v)
   return __longlong_as_double(atomicMin(reinterpret_cast<long long*>(addr), __double_as_longlong(v)));
 }
 
-template <typename O, typename T>
+// There is no far PILE: the vertices a window [lo, hi) has to relax are exactly those whose tentative distance lies in
+// it (a vertex enters a near queue only when its distance drops below the current bound, so anything at or beyond the
+// bound has never been relaxed at its current distance).  The next window's queue is therefore selected by ONE dense,
+// coalesced pass over the distance array (35 MB at RMAT-24, ~10 us) instead of splitting a queue of up to 7.6 M far
+// vertices with three random accesses each at every window change (ncu r02_trav_launches: k_split_far 502 us x 72
+// windows = 36 of the 61 ms of a traversal).
+// Where the tentative distances live.  dist_plain: one word per vertex, lowered with an atomic min (non-negative floats
+// order as integers); predecessors, if wanted, come from a pass over the distance fixpoint afterwards.  dist_packed (float
+// with predecessors): (distance bits << 32 | predecessor) in one 64-bit word lowered with ONE atomic min, i.e. the
+// predecessor is recorded by the relaxation that set the distance, as in the reference (sssp_impl.cuh:43-73,
+// reduce_op::minimum over (distance, predecessor) tuples): always a tree, ties go to the smaller vertex id, and no
+// predecessor pass.  A relaxation is only attempted when it strictly improves the distance read before it, so a vertex's
+// parent attained its distance before the vertex did: no cycles through zero-weight or absorbed edges.
+template <typename T>
+struct dist_plain {
+  T* d;
+  __device__ __forceinline__ T get(int v) const { return d[v]; }
+  __device__ __forceinline__ bool improve(int v, T nd, int) const { return nd < atomic_min_nonneg(d + v, nd); }
+  __device__ __forceinline__ void set_source(int v) const { d[v] = (T)0; }
+};
+struct dist_packed {
+  unsigned long long* p;
+  static __host__ __device__ __forceinline__ unsigned long long pack(unsigned dist_bits, int pred)
+  {
+    return ((unsigned long long)dist_bits << 32) | (unsigned)pred;
+  }
+  __device__ __forceinline__ float get(int v) const { return __uint_as_float((unsigned)(p[v] >> 32)); }
+  __device__ __forceinline__ bool improve(int v, float nd, int src) const
+  {
+    const unsigned long long old = atomicMin(p + v, pack(__float_as_uint(nd), src));
+    return nd < __uint_as_float((unsigned)(old >> 32));
+  }
+  __device__ __forceinline__ void set_source(int v) const { p[v] = pack(0u, -1); }
+};
+
+__global__ void k_unpack_dist(unsigned long long const* __restrict__ p, int n, float* __restrict__ dist, int32_t* __restrict__ pred)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const unsigned long long x = p[v];
+  dist[v]                    = __uint_as_float((unsigned)(x >> 32));
+  pred[v]                    = (int32_t)(unsigned)(x & 0xffffffffu);
+}
+
+template <typename O, typename T, typename DA>
 struct sssp_relax_op {
   O const* off;
   T const* w;
-  T* dist;
-  int32_t* stamp;      // round in which the vertex was last put on a near queue
-  int32_t* far_stamp;  // window in which the vertex was last put on the far pile
+  DA dist;
+  int32_t* stamp;  // round in which the vertex was last put on a near queue
   int32_t* next_near;
   int32_t* next_near_deg;  // degrees of the entries of next_near
-  int32_t* far;
   frontier_counters_t* cnt;
   T threshold;
   T cutoff;
   int round;
-  int window;
   __device__ __forceinline__ void edge(int src, long long e, int nbr) const
   {
-    const T nd = dist[src] + w[e];
-    if (!(nd < dist[nbr]) || !(nd < cutoff)) return;
-    const T old = atomic_min_nonneg(dist + nbr, nd);
-    if (!(nd < old)) return;
+    const T nd = dist.get(src) + w[e];
+    if (!(nd < dist.get(nbr)) || !(nd < cutoff)) return;
+    if (!dist.improve(nbr, nd, src)) return;
     if (nd < threshold) {
       if (atomicExch(stamp + nbr, round) != round) {
         const unsigned d = enqueue_with_degree(off, nbr, next_near, next_near_deg, cnt);
         warp_add_u64(&cnt->m_f, d);
       }
-    } else {
-      if (atomicExch(far_stamp + nbr, window) != window) far[warp_append(&cnt->n_far)] = nbr;
     }
   }
 };
 
-// split the far pile against the new threshold window [lo, hi)
-template <typename O, typename T>
-__global__ void k_split_far(O const* __restrict__ off, int32_t const* __restrict__ far_in, int n,
-                            T const* __restrict__ dist, T lo, T hi, int32_t* stamp, int32_t* far_stamp, int round,
-                            int window, int32_t* near_out, int32_t* near_deg_out, int32_t* far_out,
-                            frontier_counters_t* cnt)
+// mid-window split: keep the queue entries below the new bound (the others are found again by the window selection)
+template <typename O, typename T, typename DA>
+__global__ void k_split_near(O const* __restrict__ off, int32_t const* __restrict__ q_in, int n, DA dist,
+                             T hi, int32_t* stamp, int round, int32_t* near_out, int32_t* near_deg_out,
+                             frontier_counters_t* cnt)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int v = far_in[i];
-  T d   = dist[v];
-  if (d < lo) return;  // settled through the near pile meanwhile
-  if (d < hi) {
-    if (atomicExch(stamp + v, round) != round) {
-      const unsigned d = enqueue_with_degree(off, v, near_out, near_deg_out, cnt);
-      warp_add_u64(&cnt->m_f, d);
-    }
-  } else {
-    if (atomicExch(far_stamp + v, window) != window) far_out[warp_append(&cnt->n_far)] = v;
+  const int v = q_in[i];
+  if (dist.get(v) < hi) {
+    stamp[v]         = round;
+    const unsigned d = enqueue_with_degree(off, v, near_out, near_deg_out, cnt);
+    warp_add_u64(&cnt->m_f, d);
   }
 }
 
-template <typename T>
-__global__ void k_min_far(int32_t const* __restrict__ far, int n, T const* __restrict__ dist, T lo, T* out_min)
+// dense pass 1: smallest tentative distance at or beyond `hi` (reached vertices only)
+template <typename T, typename DA>
+__global__ void k_min_beyond(DA dist, int n, T hi, T unreached, T* out_min)
 {
   T m = (T)INFINITY;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    T d = dist[far[i]];
-    if (d >= lo && d < m) m = d;
+    const T d = dist.get(i);
+    if (d >= hi && d < unreached && d < m) m = d;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -536,7 +569,30 @@ __global__ void k_min_far(int32_t const* __restrict__ far, int n, T const* __res
   if ((threadIdx.x & 31) == 0 && m < (T)INFINITY) atomic_min_nonneg(out_min, m);
 }
 
-// predecessors from the distance fixpoint: dist[v] == fl(dist[u] + w(u,v)) for a tree parent u
+// dense pass 2: the vertices of the window [lo, hi) form the next near queue
+template <typename O, typename T, typename DA>
+__global__ void k_select_window(O const* __restrict__ off, DA dist, int n, T lo, T hi, int32_t* stamp,
+                                int round, int32_t* near_out, int32_t* near_deg_out, frontier_counters_t* cnt)
+{
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const T d = dist.get(v);
+    if (d >= lo && d < hi) {
+      stamp[v]          = round;
+      const unsigned dg = enqueue_with_degree(off, v, near_out, near_deg_out, cnt);
+      warp_add_u64(&cnt->m_f, dg);
+    }
+  }
+}
+
+// Predecessors from the distance fixpoint.  A tree parent u of v has dist[v] == fl(dist[u] + w(u,v)); with dist[u] <
+// dist[v] any such u is valid and the parent pointers cannot form a cycle (distances strictly decrease along them).  Tight edges
+// between vertices at the SAME distance (zero-weight edges, or a weight absorbed by float rounding) are tight in both
+// directions: taking any of them could pair two vertices as each other's parents.  Inside such a plateau pass 1 only accepts
+// a parent with a smaller vertex id ((distance, id) decreases along every parent pointer: still no cycle); vertices that are
+// left without a parent (their only tight edges come from larger ids) are attached in extra passes, each to a tight
+// neighbour that already has a parent (or is the source), with a compare-and-swap from "none" — a vertex only ever gets a
+// parent that was attached before it, so the result is a tree (the reference records the predecessor at the relaxation that
+// set the distance, sssp_impl.cuh:43-73: also a tree).
 template <typename O, typename T>
 __global__ void k_sssp_pred(O const* __restrict__ off, int32_t const* __restrict__ idx, T const* __restrict__ w,
                             T const* __restrict__ dist, int32_t n_vertices, int32_t source, T unreached,
@@ -549,7 +605,8 @@ __global__ void k_sssp_pred(O const* __restrict__ off, int32_t const* __restrict
     if (du == unreached) continue;
     for (long long e = (long long)off[u] + lane; e < (long long)off[u + 1]; e += 32) {
       const int v = idx[e];
-      if (v != source && v != (int)u && du + w[e] == dist[v]) pred[v] = (int32_t)u;
+      const T dv  = dist[v];
+      if (v != source && v != (int)u && (du < dv || (du == dv && (int)u < v)) && du + w[e] == dv) pred[v] = (int32_t)u;
     }
   }
 }
@@ -563,10 +620,62 @@ struct sssp_pred_op {
   T unreached;
   __device__ __forceinline__ void edge(int src, long long e, int nbr) const
   {
-    const T du = dist[src];
-    if (du != unreached && nbr != source && nbr != src && du + w[e] == dist[nbr]) pred[nbr] = src;
+    const T du = dist[src], dv = dist[nbr];
+    if (du != unreached && nbr != source && nbr != src && (du < dv || (du == dv && src < nbr)) && du + w[e] == dv) pred[nbr] = src;
   }
 };
+
+// one pass of the equal-distance attachment, edge-balanced (advance_all_edges)
+template <typename T>
+struct sssp_tie_op {
+  T const* w;
+  T const* dist;
+  int32_t* pred;
+  int32_t source;
+  T unreached;
+  int* changed;
+  __device__ __forceinline__ void edge(int src, long long e, int nbr) const
+  {
+    const T du = dist[src];
+    if (du == unreached || nbr == source || nbr == src || dist[nbr] != du || du + w[e] != du) return;
+    if (src != source && ((volatile int32_t*)pred)[src] < 0) return;  // src itself is not attached yet
+    if (((volatile int32_t*)pred)[nbr] >= 0) return;
+    if (atomicCAS(pred + nbr, -1, (int32_t)src) == -1) *changed = 1;
+  }
+};
+
+// reached vertices other than the source that still have no parent
+template <typename T>
+__global__ void k_sssp_count_orphans(T const* __restrict__ dist, int32_t const* __restrict__ pred, int32_t n, int32_t source,
+                                     T unreached, int* __restrict__ out)
+{
+  int c = 0;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+    c += (v != source && dist[v] != unreached && pred[v] < 0) ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// one pass of the equal-distance attachment: v (no parent yet) takes a tight neighbour u at the same distance that
+// already has a parent or is the source
+template <typename O, typename T>
+__global__ void k_sssp_pred_ties(O const* __restrict__ off, int32_t const* __restrict__ idx, T const* __restrict__ w,
+                                 T const* __restrict__ dist, int32_t n_vertices, int32_t source, T unreached,
+                                 int32_t* __restrict__ pred, int* __restrict__ changed)
+{
+  const int lane = threadIdx.x & 31;
+  for (long long u = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; u < n_vertices;
+       u += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const T du = dist[u];
+    if (du == unreached) continue;
+    if ((int)u != source && ((volatile int32_t*)pred)[u] < 0) continue;  // u itself is not attached yet
+    for (long long e = (long long)off[u] + lane; e < (long long)off[u + 1]; e += 32) {
+      const int v = idx[e];
+      if (v == source || v == (int)u || dist[v] != du || du + w[e] != du) continue;
+      if (atomicCAS(pred + v, -1, (int32_t)u) == -1) *changed = 1;
+    }
+  }
+}
 
 template <typename T>
 __global__ void k_sum_weights(T const* __restrict__ w, long long n, double* out)
@@ -578,28 +687,24 @@ __global__ void k_sum_weights(T const* __restrict__ w, long long n, double* out)
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
-template <typename T>
-__global__ void k_sssp_seed(T* dist, int32_t* stamp, int32_t* q, int32_t source)
+template <typename O, typename DA>
+__global__ void k_sssp_seed(DA dist, int32_t* stamp, int32_t* q, int32_t* q_deg, O const* off, int32_t source)
 {
-  dist[source]  = (T)0;
+  dist.set_source(source);
   stamp[source] = 1;
   q[0]          = source;
+  q_deg[0]      = (int32_t)((long long)off[source + 1] - (long long)off[source]);
 }
 
-template <typename O, typename T>
-void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, double cutoff_d, T* dist, int32_t* pred)
+// the window loop; the distances are initialised (unreached everywhere) by the caller
+template <typename O, typename T, typename DA>
+void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, double cutoff_d, DA dist)
 {
   O const* off       = c.offsets.as<O>();
   int32_t const* idx = c.indices.as<int32_t>();
   T const* w         = c.weights.as<T>();
   const T unreached  = std::numeric_limits<T>::max();
   const T cutoff     = cutoff_d >= (double)unreached ? unreached : (T)cutoff_d;
-  B200_LAUNCH(h, (k_fill<T>), std::min(grid_for(nv), 148 * 32), kBlock, 0, dist, (int64_t)nv, unreached);
-  if (pred) B200_LAUNCH(h, (k_fill<int32_t>), std::min(grid_for(nv), 148 * 32), kBlock, 0, pred, (int64_t)nv, -1);
-  if (c.nnz == 0) {
-    B200_LAUNCH(h, (k_fill<T>), 1, 1, 0, dist + source, (int64_t)1, (T)0);
-    return;
-  }
   // delta = warp_size * average weight / average degree  (sssp_impl.cuh:233-247)
   dbuf wsum = make_dbuf<double>(2, h.stream);
   CUDA_TRY(cudaMemsetAsync(wsum.data(), 0, 2 * sizeof(double), h.stream));
@@ -621,27 +726,28 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
   // doubling), >= 6 rounds: half as wide.
   const bool adaptive = h.tune.sssp_adaptive;
   const T delta_floor = delta / (T)4096;
-  if (adaptive) delta = delta / (T)64;
+  if (adaptive) delta = delta / (T)h.tune.sssp_start_div;
 
-  dbuf stamp = make_dbuf<int32_t>(nv, h.stream), far_stamp = make_dbuf<int32_t>(nv, h.stream);
+  dbuf stamp = make_dbuf<int32_t>(nv, h.stream);
   CUDA_TRY(cudaMemsetAsync(stamp.data(), 0, sizeof(int32_t) * nv, h.stream));
-  CUDA_TRY(cudaMemsetAsync(far_stamp.data(), 0, sizeof(int32_t) * nv, h.stream));
-  // every queue holds a vertex at most once per round / window (stamps), so V entries suffice
+  // every queue holds a vertex at most once per round (stamps), so V entries suffice
   dbuf qa = make_dbuf<int32_t>(nv, h.stream), qb = make_dbuf<int32_t>(nv, h.stream);
   dbuf la = make_dbuf<int32_t>((size_t)nv + 1, h.stream), lb = make_dbuf<int32_t>((size_t)nv + 1, h.stream);  // queue degrees
-  dbuf fa = make_dbuf<int32_t>(nv, h.stream), fb = make_dbuf<int32_t>(nv, h.stream);
   dbuf cnt = make_dbuf<frontier_counters_t>(1, h.stream);
   frontier_counters_t* dc = cnt.as<frontier_counters_t>();
   CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
   dbuf dmin = make_dbuf<T>(1, h.stream);
-  B200_LAUNCH(h, (k_sssp_seed<T>), 1, 1, 0, dist, stamp.as<int32_t>(), qa.as<int32_t>(), source);
+  B200_LAUNCH(h, (k_sssp_seed<O, DA>), 1, 1, 0, dist, stamp.as<int32_t>(), qa.as<int32_t>(), la.as<int32_t>(), off, source);
   frontier_counters_t* hc = reinterpret_cast<frontier_counters_t*>(h.pinned);
+  T* hmin_pinned          = reinterpret_cast<T*>(reinterpret_cast<char*>(h.pinned) + 256);
   int32_t *near = qa.as<int32_t>(), *next_near = qb.as<int32_t>();
   int32_t *near_deg = la.as<int32_t>(), *next_near_deg = lb.as<int32_t>();  // degrees of the queue entries
-  int32_t *far = fa.as<int32_t>(), *far2 = fb.as<int32_t>();
-  int n_near = 1, n_far = 0, round = 1, window = 1;
-  bool deg_ready = false;  // every enqueue writes the degree next to the entry; only the seed does not
-  unsigned long long near_edges = (unsigned long long)c.nnz < (1ull << 31) ? (1ull << 31) - 1 : 0;  // seed: unknown -> full grid
+  int n_near = 1, round = 1, window = 1;
+  // the seed kernel wrote the source's degree next to it: read it back (the first advance needs the edge count)
+  int32_t seed_deg = 0;
+  CUDA_TRY(cudaMemcpyAsync(&seed_deg, near_deg, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
+  sync(h);
+  unsigned long long near_edges = (unsigned long long)(unsigned)seed_deg;
   advance_scratch_t adv;
   adv.init(h, nv, (int64_t)c.nnz);
   T lo = (T)0, hi = delta;
@@ -658,37 +764,31 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
       ++round;
       ++tr_rounds;
       ++window_rounds;
-      if (near_edges < (1ull << 31) - 1) tr_edges += near_edges;
-      CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_small, n_large; n_far keeps running
-      CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
-      sssp_relax_op<O, T> op{off, w, dist, stamp.as<int32_t>(), far_stamp.as<int32_t>(), next_near, next_near_deg, far,
-                             dc, hi, cutoff, round, window};
-      advance<O>(h, adv, off, idx, near, n_near, near_edges, op, deg_ready ? near_deg : (int32_t const*)nullptr);
-      deg_ready = true;
+      tr_edges += near_edges;
+      CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
+      sssp_relax_op<O, T, DA> op{off, w, dist, stamp.as<int32_t>(), next_near, next_near_deg, dc, hi, cutoff, round};
+      advance<O>(h, adv, off, idx, near, n_near, near_edges, op, near_deg);
       CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
       sync(h);
       n_near     = hc->n_small;
-      n_far      = hc->n_far;
       near_edges = hc->m_f;
       std::swap(near, next_near);
       std::swap(near_deg, next_near_deg);
       // A window that is still busy after `split_rounds` rounds is too wide for this stretch of the graph (the hub core
       // of a power-law graph sits in a very narrow distance band): cut it in half now instead of after the damage.  The
-      // pending near entries at or beyond the new bound join the far pile (same kernel as the window change, reading
-      // the near queue; the far pile keeps growing in place), the rest form the next round's queue.
+      // pending near entries at or beyond the new bound are dropped from the queue (the window selection finds them again
+      // when their turn comes), the rest form the next round's queue.
       if (adaptive && window_rounds >= split_rounds && n_near > 0 && near_edges >= split_min_edges &&
           near_edges * 128ull >= (unsigned long long)c.nnz) {
         const T nhi = lo + (hi - lo) * (T)0.5;
         if (nhi > lo && nhi < hi) {
           ++round;
-          CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, 2 * sizeof(int), h.stream));  // n_far keeps running
-          CUDA_TRY(cudaMemsetAsync(&dc->m_f, 0, sizeof(unsigned long long), h.stream));
-          B200_LAUNCH(h, (k_split_far<O, T>), grid_for(n_near), kBlock, 0, off, near, n_near, dist, lo, nhi, stamp.as<int32_t>(),
-                      far_stamp.as<int32_t>(), round, window, next_near, next_near_deg, far, dc);
+          CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
+          B200_LAUNCH(h, (k_split_near<O, T, DA>), grid_for(n_near), kBlock, 0, off, near, n_near, dist, nhi, stamp.as<int32_t>(),
+                      round, next_near, next_near_deg, dc);
           CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
           sync(h);
           n_near     = hc->n_small;
-          n_far      = hc->n_far;
           near_edges = hc->m_f;
           std::swap(near, next_near);
           std::swap(near_deg, next_near_deg);
@@ -700,21 +800,21 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
       }
     }
     if (trace)
-      std::fprintf(stderr, "sssp window %d hi=%g width %g: %d rounds, rounds so far %d, edges relaxed so far %llu, far pile %d, splits so far %d\n",
-                   window, (double)hi, (double)delta, window_rounds, tr_rounds, tr_edges, n_far, tr_splits);
-    if (n_far == 0) break;
+      std::fprintf(stderr, "sssp window %d hi=%g width %g: %d rounds, rounds so far %d, edges relaxed so far %llu, splits so far %d\n",
+                   window, (double)hi, (double)delta, window_rounds, tr_rounds, tr_edges, tr_splits);
     if (adaptive) {
       if (window_rounds <= 2) { if (delta < std::numeric_limits<T>::max() / (T)4) delta = delta * (T)2; }
       else if (window_rounds >= 6 && delta > delta_floor) delta = delta / (T)2;
     }
-    // advance the window to the smallest pending distance, then split the far pile
-    T inf = (T)INFINITY;
-    CUDA_TRY(cudaMemcpyAsync(dmin.data(), &inf, sizeof(T), cudaMemcpyHostToDevice, h.stream));
-    B200_LAUNCH(h, (k_min_far<T>), std::min(grid_for(n_far), full_grid), kBlock, 0, far, n_far, dist, hi, dmin.as<T>());
-    T hmin;
-    CUDA_TRY(cudaMemcpyAsync(&hmin, dmin.data(), sizeof(T), cudaMemcpyDeviceToHost, h.stream));
+    // advance the window to the smallest pending distance (dense pass 1), then select its vertices (dense pass 2)
+    const T inf = (T)INFINITY;
+    *hmin_pinned = inf;
+    CUDA_TRY(cudaMemcpyAsync(dmin.data(), hmin_pinned, sizeof(T), cudaMemcpyHostToDevice, h.stream));
+    B200_LAUNCH(h, (k_min_beyond<T, DA>), std::min(grid_for(nv), h.sm_count * 64), kBlock, 0, dist, nv, hi, unreached, dmin.as<T>());
+    CUDA_TRY(cudaMemcpyAsync(hmin_pinned, dmin.data(), sizeof(T), cudaMemcpyDeviceToHost, h.stream));
     sync(h);
-    if (!(hmin < inf)) break;  // everything left in the pile was settled earlier
+    const T hmin = *hmin_pinned;
+    if (!(hmin < inf)) break;  // nothing pending: done
     lo      = hi;
     T steps = std::floor((hmin - hi) / delta);
     T nhi   = hi + (steps > (T)0 ? steps : (T)0) * delta + delta;
@@ -723,22 +823,68 @@ void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, 
     ++round;
     ++window;
     CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
-    B200_LAUNCH(h, (k_split_far<O, T>), grid_for(n_far), kBlock, 0, off, far, n_far, dist, lo, hi, stamp.as<int32_t>(),
-                far_stamp.as<int32_t>(), round, window, near, near_deg, far2, dc);
+    B200_LAUNCH(h, (k_select_window<O, T, DA>), grid_for(nv), kBlock, 0, off, dist, nv, lo, hi,
+                stamp.as<int32_t>(), round, near, near_deg, dc);
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
     sync(h);
     n_near     = hc->n_small;
-    n_far      = hc->n_far;
     near_edges = hc->m_f;
-    deg_ready  = true;
-    std::swap(far, far2);
   }
+  check_last("sssp");
+}
+
+template <typename O, typename T>
+void run_sssp(handle_impl const& h, csx_t const& c, int32_t nv, int32_t source, double cutoff_d, T* dist, int32_t* pred)
+{
+  O const* off       = c.offsets.as<O>();
+  int32_t const* idx = c.indices.as<int32_t>();
+  T const* w         = c.weights.as<T>();
+  const T unreached  = std::numeric_limits<T>::max();
+  const int full_grid = h.sm_count * 8;
+  if (pred) B200_LAUNCH(h, (k_fill<int32_t>), std::min(grid_for(nv), 148 * 32), kBlock, 0, pred, (int64_t)nv, -1);
+  if (c.nnz == 0) {
+    B200_LAUNCH(h, (k_fill<T>), std::min(grid_for(nv), 148 * 32), kBlock, 0, dist, (int64_t)nv, unreached);
+    B200_LAUNCH(h, (k_fill<T>), 1, 1, 0, dist + source, (int64_t)1, (T)0);
+    return;
+  }
+  if (pred && std::is_same<T, float>::value) {  // float with predecessors: (distance, predecessor) in one word
+    dbuf packed = make_dbuf<unsigned long long>(nv, h.stream);
+    B200_LAUNCH(h, (k_fill<unsigned long long>), std::min(grid_for(nv), 148 * 32), kBlock, 0, packed.as<unsigned long long>(),
+                (int64_t)nv, dist_packed::pack(0x7f7fffffu, -1));
+    sssp_windows<O, float, dist_packed>(h, c, nv, source, cutoff_d, dist_packed{packed.as<unsigned long long>()});
+    B200_LAUNCH(h, k_unpack_dist, grid_for(nv), kBlock, 0, packed.as<unsigned long long>(), nv, reinterpret_cast<float*>(dist), pred);
+    check_last("sssp");
+    return;
+  }
+  B200_LAUNCH(h, (k_fill<T>), std::min(grid_for(nv), 148 * 32), kBlock, 0, dist, (int64_t)nv, unreached);
+  sssp_windows<O, T, dist_plain<T>>(h, c, nv, source, cutoff_d, dist_plain<T>{dist});
   if (pred) {
     if (sizeof(O) == 4) {
       sssp_pred_op<T> pop{w, dist, pred, source, unreached};
       advance_all_edges(h, (int32_t const*)off, idx, nv, (long long)c.nnz, pop);
     } else {
       B200_LAUNCH(h, (k_sssp_pred<O, T>), h.sm_count * 16, kBlock, 0, off, idx, w, dist, nv, source, unreached, pred);
+    }
+    // vertices whose tight edges all come from their own distance level (zero-weight / absorbed edges): rare
+    dbuf flags = make_dbuf<int>(2, h.stream);
+    int* hflags = reinterpret_cast<int*>(reinterpret_cast<char*>(h.pinned) + 512);
+    CUDA_TRY(cudaMemsetAsync(flags.data(), 0, 2 * sizeof(int), h.stream));
+    B200_LAUNCH(h, (k_sssp_count_orphans<T>), std::min(grid_for(nv), full_grid), kBlock, 0, dist, pred, nv, source, unreached,
+                flags.as<int>());
+    CUDA_TRY(cudaMemcpyAsync(hflags, flags.data(), 2 * sizeof(int), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    for (int pass = 0; hflags[0] > 0 && pass < nv; ++pass) {
+      CUDA_TRY(cudaMemsetAsync(flags.as<int>() + 1, 0, sizeof(int), h.stream));
+      if (sizeof(O) == 4) {
+        sssp_tie_op<T> top{w, dist, pred, source, unreached, flags.as<int>() + 1};
+        advance_all_edges(h, (int32_t const*)off, idx, nv, (long long)c.nnz, top);
+      } else {
+        B200_LAUNCH(h, (k_sssp_pred_ties<O, T>), h.sm_count * 16, kBlock, 0, off, idx, w, dist, nv, source, unreached, pred,
+                    flags.as<int>() + 1);
+      }
+      CUDA_TRY(cudaMemcpyAsync(hflags, flags.data(), 2 * sizeof(int), cudaMemcpyDeviceToHost, h.stream));
+      sync(h);
+      if (hflags[1] == 0) break;
     }
   }
   check_last("sssp");

@@ -269,6 +269,7 @@ template <typename T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = 
 template <typename T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline long long __double_as_longlong(double d) { long long u; std::memcpy(&u, &d, 8); return u; }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline unsigned long long emu_bits(T v) { unsigned long long b = 0; static_assert(sizeof(T) <= 8, "shuffle width"); std::memcpy(&b, &v, sizeof(T)); return b; }

@@ -99,11 +99,8 @@ while time.time() < t_end:
     transposed = bool(r.integers(0, 2))
     hot = bool(r.integers(0, 2))
     os.environ["CUGRAPH_B200_SWEEP_MIN_EDGES"] = "0" if hot else "1000000000"
-    for k, vals in (("CUGRAPH_B200_HOT_X", "01"), ("CUGRAPH_B200_HOT_NARROW", "01"), ("CUGRAPH_B200_LOW_ELL", "012"),
-                    ("CUGRAPH_B200_HOT_BANK_ORDER", "01")):
-        os.environ[k] = str(r.choice(list(vals)))
-    os.environ["CUGRAPH_B200_HOT_UNIT_SLOTS"] = str(r.choice([1024, 8192]))
-    os.environ["CUGRAPH_B200_HOT_MIN_DEGREE"] = str(r.choice([32, 32, 8, 1]))
+    os.environ["CUGRAPH_B200_SWEEP_BANK_ORDER"] = str(r.choice(["0", "1"]))
+    L.emu_reload_tuning(H)   # the knobs are read per handle
     skew = float(r.choice([1.0, 2.5])) if not os.environ.get("FUZZ_BIG") else float(r.choice([2.0, 3.0]))
     src = np.minimum((V * r.random(E) ** skew).astype(np.int64), V - 1).astype(idt)
     dst = np.minimum((V * r.random(E) ** skew).astype(np.int64), V - 1).astype(idt)

@@ -22,8 +22,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "bench_ref.c")]
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(_LIB_PATH) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -143,6 +143,48 @@ def spmv_f32(csc, x, alpha, init):
                           _p(w32, ctypes.c_float), ctypes.c_int32(V), _p(x, ctypes.c_float),
                           ctypes.c_float(alpha), ctypes.c_float(init), _p(y, ctypes.c_float))
     return y
+
+
+# ---- the CPU arm of bench.py (bench_ref.c): RMAT on the host, parallel CSC, float32 PageRank on all cores -----------------
+
+def bench_rmat_edges(scale, num_edges, seed=0, a=0.57, b=0.19, c=0.19):
+    src = np.empty(num_edges, dtype=np.int32)
+    dst = np.empty(num_edges, dtype=np.int32)
+    lib().bench_rmat_edges(ctypes.c_int(scale), ctypes.c_int64(num_edges), ctypes.c_uint64(seed), ctypes.c_double(a),
+                           ctypes.c_double(b), ctypes.c_double(c), _p(src, ctypes.c_int32), _p(dst, ctypes.c_int32))
+    return src, dst
+
+
+def bench_build_csc(src, dst, num_vertices):
+    E = src.shape[0]
+    offsets = np.empty(num_vertices + 1, dtype=np.int64)
+    indices = np.empty(E, dtype=np.int32)
+    out_degree = np.empty(num_vertices, dtype=np.int32)
+    rc = lib().bench_build_csc(ctypes.c_int64(E), ctypes.c_int32(num_vertices), _p(src, ctypes.c_int32), _p(dst, ctypes.c_int32),
+                               _p(offsets, ctypes.c_int64), _p(indices, ctypes.c_int32), _p(out_degree, ctypes.c_int32))
+    if rc != 0:
+        raise ValueError(f"bench_build_csc failed rc={rc}")
+    return offsets, indices, out_degree
+
+
+class BenchPageRank:
+    """float32 PageRank (bench_ref.c: bench_pagerank_f32) on a prebuilt CSC; run(k) = k more power iterations"""
+
+    def __init__(self, offsets, indices, out_degree, alpha=0.85):
+        self.off, self.idx, self.deg, self.alpha = offsets, indices, out_degree, alpha
+        self.V = out_degree.shape[0]
+        self.pr = np.full(self.V, 1.0 / self.V, dtype=np.float32)
+        self.x = np.empty(self.V, dtype=np.float32)
+        self.y = np.empty(self.V, dtype=np.float32)
+
+    def reset(self):
+        self.pr[:] = 1.0 / self.V
+
+    def run(self, iterations):
+        lib().bench_pagerank_f32(_p(self.off, ctypes.c_int64), _p(self.idx, ctypes.c_int32), _p(self.deg, ctypes.c_int32),
+                                 ctypes.c_int32(self.V), ctypes.c_double(self.alpha), ctypes.c_int(iterations),
+                                 _p(self.pr, ctypes.c_float), _p(self.x, ctypes.c_float), _p(self.y, ctypes.c_float))
+        return self.pr
 
 
 # ---- validity predicates the reference's own tests use -----------------------------------------

@@ -24,7 +24,7 @@ def test_cbench_under_emulation(tmp_path):
            "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    env = dict(os.environ, CUGRAPH_B200_SWEEP_MIN_EDGES="0", CUGRAPH_B200_HOT_X="1", CUGRAPH_B200_HOT_NARROW="1")
+    env = dict(os.environ, CUGRAPH_B200_SWEEP_MIN_EDGES="0")
     r = subprocess.run([exe, "8", "all", "1"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = {}

@@ -51,7 +51,7 @@ def dense_ids(src, dst):
     return ids, inv[:src.size].astype(np.int32), inv[src.size:].astype(np.int32)
 
 
-PR_CASES = [("plain sweep", "1000000000", False), ("blocked sweep", "0", False), ("blocked sweep weighted", "0", True)]
+PR_CASES = [("plain sweep", "1000000000", False), ("piece-stream sweep", "0", False), ("piece-stream sweep weighted", "0", True)]
 
 
 @pytest.mark.parametrize("name,min_edges,weighted", PR_CASES, ids=[c[0] for c in PR_CASES])
@@ -71,15 +71,11 @@ def test_pagerank_emulated(emu, monkeypatch, name, min_edges, weighted):  # noqa
     emu.cugraph_graph_free(g)
 
 
-def test_pagerank_emulated_experimental_kernel(emu, monkeypatch):  # noqa: F811
-    """k_spmv_blocked_x with multi-unit claims and tiny units: own range, then stealing (CTA 0 drains every range)"""
+def test_pagerank_emulated_stealing_and_tiny_phases(emu, monkeypatch):  # noqa: F811
+    """sources spread over many column blocks with few chunks each: under emulation CTA 0 runs its own phases and then
+    drains every other CTA's phases through the stealing path (CTAs run one after the other)"""
     monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_X", "1")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_NARROW", "1")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_CLAIM", "3")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_UNIT_SLOTS", "1024")
-    monkeypatch.setenv("CUGRAPH_B200_LOW_ELL", "2")
-    src, dst, w = make_edges(70_000, 250_000, seed=43)
+    src, dst, w = make_edges(400_000, 500_000, seed=43)
     g = create_graph(emu, src, dst, w)
     verts, pr, it = run_pagerank(emu, g, 0.85, 0.0, 6)
     ids, s, d = dense_ids(src, dst)
@@ -91,12 +87,24 @@ def test_pagerank_emulated_experimental_kernel(emu, monkeypatch):  # noqa: F811
     emu.cugraph_graph_free(g)
 
 
-@pytest.mark.parametrize("hot_x", ["0", "1"])
-def test_pagerank_emulated_double_weights(emu, monkeypatch, hot_x):  # noqa: F811
-    """fp64 graphs: 24,512 columns per shared-memory slice, several blocks, base and experimental kernel"""
+@pytest.mark.parametrize("weighted", [False, True])
+def test_sweep_against_plain_sweep_emulated(emu, monkeypatch, weighted):  # noqa: F811
+    """cugraph_b200_debug_compare_sweeps: the piece-stream sweep against the plain sweep (independent kernels) row by row"""
+    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
+    src, dst, w = make_edges(150_000, 700_000, seed=61 + weighted, weighted=weighted)
+    g = create_graph(emu, src, dst, w)
+    out = (C.c_double * 8)()
+    err = C.c_void_p()
+    code = emu.cugraph_b200_debug_compare_sweeps(C.c_void_p(emu.handle), g, out, C.byref(err))
+    assert code == 0, emu.cugraph_error_message(err)
+    assert out[0] < 2e-6 and out[4] < 2e-6 and out[3] == 0 and out[7] == 0, list(out)
+    emu.cugraph_graph_free(g)
+
+
+def test_pagerank_emulated_double_weights(emu, monkeypatch):  # noqa: F811
+    """fp64 graphs: 24,512 columns per shared-memory slice, several blocks"""
     from tests.test_emu_staging_cpu import FLOAT64
     monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_X", hot_x)
     src, dst, w32 = make_edges(80_000, 300_000, seed=47, weighted=True)
     w = w32.astype(np.float64) * 1.000000123
     L = emu
@@ -114,25 +122,6 @@ def test_pagerank_emulated_double_weights(emu, monkeypatch, hot_x):  # noqa: F81
     got[np.searchsorted(ids, verts)] = pr
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
     L.cugraph_graph_free(g)
-
-
-@pytest.mark.parametrize("min_degree,extra", [("8", {}), ("1", {}), ("4", {"CUGRAPH_B200_HOT_X": "1", "CUGRAPH_B200_HOT_NARROW": "1"}),
-                                              ("16", {"CUGRAPH_B200_LOW_ELL": "1"}), ("2", {"CUGRAPH_B200_LOW_ELL": "2"})])
-def test_pagerank_emulated_lower_degree_bound(emu, monkeypatch, min_degree, extra):  # noqa: F811
-    """CUGRAPH_B200_HOT_MIN_DEGREE: rows down to that degree go through the piece layout, the rest through the low-row kernels"""
-    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_MIN_DEGREE", min_degree)
-    for k, v in extra.items():
-        monkeypatch.setenv(k, v)
-    src, dst, w = make_edges(70_000, 260_000, seed=53 + int(min_degree))
-    g = create_graph(emu, src, dst, w)
-    verts, pr, it = run_pagerank(emu, g, 0.85, 0.0, 8)
-    ids, s, d = dense_ids(src, dst)
-    ref, _, _ = oracle.pagerank(s, d, ids.size, None, alpha=0.85, epsilon=0.0, max_iterations=8)
-    got = np.zeros(ids.size)
-    got[np.searchsorted(ids, verts)] = pr
-    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=0)
-    emu.cugraph_graph_free(g)
 
 
 def _paths(L, res):
@@ -224,6 +213,59 @@ def _sssp_dist(emu, g, source):  # noqa: F811
     return _paths(emu, res)
 
 
+def follow_to_source(verts, dist, pred, source, unreached):
+    """every reached vertex's predecessor chain must end at the source (no cycles), distances never increasing along it"""
+    pos = {int(v): i for i, v in enumerate(verts)}
+    for i, v in enumerate(verts):
+        if dist[i] == unreached:
+            assert pred[i] == -1
+            continue
+        cur, steps = int(v), 0
+        while cur != source:
+            j = pos[cur]
+            p = int(pred[j])
+            assert p >= 0, f"vertex {cur} (reached from {int(v)}) has no predecessor"
+            assert dist[pos[p]] <= dist[j]
+            cur = p
+            steps += 1
+            assert steps <= len(verts), f"predecessor cycle reached from vertex {int(v)}"
+
+
+def test_sssp_zero_weight_predecessors_emulated(emu):  # noqa: F811
+    """symmetric zero-weight edges and zero-weight cycles: the distance fixpoint alone cannot orient them (both directions of
+    the edge are tight), the predecessors must still form a tree rooted at the source"""
+    r = np.random.default_rng(3)
+    V = 400
+    half_s = r.integers(0, V, 1600).astype(np.int32)
+    half_d = r.integers(0, V, 1600).astype(np.int32)
+    wh = np.where(r.random(1600) < 0.5, 0.0, r.random(1600)).astype(np.float32)      # half of the edges weigh nothing
+    # a zero-weight cycle 7 - 8 - 9 - 7 hanging off vertex 6, and a float-absorbed edge (1e8 + 1 == 1e8)
+    extra = [(6, 7, 0.0), (7, 8, 0.0), (8, 9, 0.0), (9, 7, 0.0), (0, 390, 1e8), (390, 391, 1.0), (391, 392, 1.0)]
+    half_s = np.concatenate([half_s, np.array([e[0] for e in extra], np.int32)])
+    half_d = np.concatenate([half_d, np.array([e[1] for e in extra], np.int32)])
+    wh = np.concatenate([wh, np.array([e[2] for e in extra], np.float32)])
+    s, d, w = np.concatenate([half_s, half_d]), np.concatenate([half_d, half_s]), np.concatenate([wh, wh])
+    g = create_sym_graph(emu, s, d, w)
+    ids, ss, dd = dense_ids(s, d)
+    for source in (int(ids[0]), int(ids[7])):
+        verts, dist, pred = _sssp_dist(emu, g, source)
+        ref_d, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=True)
+        got = np.zeros(ids.size, dtype=np.float32)
+        got[np.searchsorted(ids, verts)] = dist
+        assert (got == ref_d.astype(np.float32)).all()
+        follow_to_source(verts, dist, pred, source, np.finfo(np.float32).max)
+        assert oracle.check_sssp_predecessors(ss, dd, w, ids.size, ref_d, _scatter(ids, verts, pred), int(np.searchsorted(ids, source)))
+    emu.cugraph_graph_free(g)
+
+
+def _scatter(ids, verts, pred):
+    """predecessors (external ids, -1 = none) as an array over dense vertex numbers holding dense predecessor numbers"""
+    out = np.full(ids.size, -1, dtype=np.int32)
+    has = pred >= 0
+    out[np.searchsorted(ids, verts[has])] = np.searchsorted(ids, pred[has])
+    return out
+
+
 @pytest.mark.parametrize("weights", ["uniform", "tiny-and-huge", "constant"])
 def test_sssp_window_control_emulated(emu, monkeypatch, capfd, weights):  # noqa: F811
     """The window-width controller (64x narrower start, doubling / halving by rounds, mid-window split of a busy window)
@@ -248,6 +290,7 @@ def test_sssp_window_control_emulated(emu, monkeypatch, capfd, weights):  # noqa
         monkeypatch.setenv("CUGRAPH_B200_SSSP_ADAPTIVE", mode)
         monkeypatch.setenv("CUGRAPH_B200_SSSP_TRACE", "1")
         monkeypatch.setenv("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES", "0")   # the default only splits rounds of >= 2^20 edges
+        emu.emu_reload_tuning(C.c_void_p(emu.handle))                   # knobs are read per handle
         capfd.readouterr()
         verts, dist, pred = _sssp_dist(emu, g, source)
         trace = capfd.readouterr().err

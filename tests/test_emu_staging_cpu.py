@@ -1,11 +1,11 @@
 """Graph staging on the CPU: the real staging code (capi_graph.cu, graph_build.cu — renumbering, the packed-key sort,
-binning, the piece layout of the blocked sweep, the experimental narrow and ELL layouts) compiled as plain C++ against
+binning, the piece stream of the shared-memory sweep) compiled as plain C++ against
 the host emulation shim in emu/ and driven through the real C ABI with numpy arrays.  The staging kernels are
 data-parallel loops without intra-block communication, so executing every "thread" of a launch in turn is exact.
 
 Checked against numpy: the stored graph is the input multigraph (external ids), rows are degree-descending with sorted
-neighbours and correct segment bounds; the piece layout reproduces every (row, source[, weight]) of the degree >= 32
-rows exactly once, padding only where allowed; the ELL copy + k_spmv_low_ell reproduce the SpMV of the degree < 32 rows.
+neighbours and correct segment bounds; the piece stream reproduces every (row, source[, weight]) of every non-empty row
+exactly once, padding only where allowed.
 """
 import ctypes as C
 import os
@@ -125,171 +125,131 @@ def lds_wavefronts(ids):
     return int(np.bincount(u & 31, minlength=32).max())
 
 
-def hot_pieces(L, g, P, bank_order=False, stats=None):
-    """(row, col[, w]) triples reconstructed from the piece layout + structural checks.  bank_order: the experimental
-    layout whose slots are ordered by shared-memory bank (padding anywhere in a slot, on any of the 64 zero columns).
-    stats: dict that receives the LDS count and the wavefront count of the 16-bit full-slot classes."""
+KIND_PIECES = [256, 128, 64] + [32] * 8     # pieces per group: S, Q, H, F1..F8
+KIND_STEPS = [1, 1, 1] + list(range(1, 9))  # step-rows per group
+
+
+def sweep_pieces(L, g, P, stats=None):
+    """(row, col[, w]) triples reconstructed from the piece stream + structural checks.
+    stats: dict that receives the LDS count and the wavefront count of the F kinds (bank order)."""
     ints = (C.c_int64 * 12)()
-    ptrs = (C.c_void_p * 10)()
-    rc = L.emu_hot_layout(C.c_void_p(L.handle), g, ints, ptrs)
-    assert rc == 0, f"emu_hot_layout returned {rc}"
-    W, B, n_hi, nnz_hi, n_hot, n_slots, n_subs, n_units, n_cta, narrow, es = [int(x) for x in ints[:11]]
-    assert n_hi == P["seg"][0] and nnz_hi == P["nnz_hi"]
-    subs = as_np(ptrs[4], 4 * n_subs, np.int32).reshape(-1, 4)
-    units = as_np(ptrs[5], 4 * n_units, np.int32).reshape(-1, 4)
-    rng = as_np(ptrs[6], n_cta + 1, np.int32)
-    assert rng[0] == 0 and rng[-1] == n_units and (np.diff(rng) >= 0).all()
-    n_rows_seg = int(subs[:, 2].sum()) * 32
-    seg_row = as_np(ptrs[3], n_rows_seg, np.int32)
-    idx16 = as_np(ptrs[0], n_hot * 8, np.uint16)
-    idx32 = as_np(ptrs[1], (n_slots - n_hot) * 8, np.int32)
-    sw = as_np(ptrs[2], n_slots * 8, np.float32) if P["w"] is not None else None
-    n_h = int(sum(32 * s[2] for s in subs if s[3] == 16))
-    n_q = int(sum(32 * s[2] for s in subs if s[3] == 32))
-    n_s = int(sum(32 * s[2] for s in subs if s[3] == 64))
-    idx_h = as_np(ptrs[7], n_h * 4, np.uint16)
-    idx_q = as_np(ptrs[8], n_q * 2, np.uint16)
-    idx_s = as_np(ptrs[9], n_s, np.uint16)
-    sub_block = np.zeros(n_subs, dtype=np.int64)
-    for s0, s1, blk, _ in units:
-        sub_block[s0:s1] = blk
+    ptrs = (C.c_void_p * 6)()
+    rc = L.emu_sweep_layout(C.c_void_p(L.handle), g, ints, ptrs)
+    assert rc == 0, f"emu_sweep_layout returned {rc}"
+    W, B, n_cov, nnz, n_sr, n_rs, n_chunks, n_phases, n_cta, bank, es, n_pieces = [int(x) for x in ints[:12]]
+    assert n_cov == P["seg"][5] and nnz == P["nnz"]          # every non-empty row, every edge
+    ids = as_np(ptrs[0], n_sr * 32 * 8, np.uint16).reshape(n_sr, 32, 8)
+    sw = as_np(ptrs[1], n_sr * 32 * 8, np.float32).reshape(n_sr, 32, 8) if P["w"] is not None else None
+    rows = as_np(ptrs[2], n_rs, np.int32)
+    chunks = as_np(ptrs[3], 4 * n_chunks, np.int32).reshape(-1, 4)
+    phases = as_np(ptrs[4], 4 * n_phases, np.int32).reshape(-1, 4)
+    cta = as_np(ptrs[5], n_cta + 1, np.int32)
+    assert cta[0] == 0 and cta[-1] == n_phases and (np.diff(cta) >= 0).all()
+    blk_of_chunk = np.zeros(n_chunks, dtype=np.int64)
+    at = 0
+    for blk, c0, c1, _ in phases:
+        assert c0 == at and c1 > c0
+        blk_of_chunk[c0:c1] = blk
+        at = c1
+    assert at == n_chunks
     out_r, out_c, out_w = [], [], []
-    for si, (slot_begin, row_begin, n_groups, code) in enumerate(subs):
-        blk = int(sub_block[si])
-        steps, width = {16: (1, 4), 32: (1, 2), 64: (1, 1)}.get(int(code), (int(code), 8))
-        assert narrow or code <= 8
-        rows = seg_row[row_begin:row_begin + 32 * n_groups].reshape(n_groups, 32)
+    n_real_pieces = 0
+    for ci, (sr0, row0, n_groups, kind) in enumerate(chunks):
+        blk = int(blk_of_chunk[ci])
+        steps, ppg = KIND_STEPS[kind], KIND_PIECES[kind]
         for q in range(n_groups):
-            base = slot_begin + q * 32 * steps
-            for j in range(steps):
-                s = base + j * 32 + np.arange(32)
-                if code == 16:
-                    ids = idx_h.reshape(-1, 4)[s].astype(np.int64); pad = W
-                elif code == 32:
-                    ids = idx_q.reshape(-1, 2)[s].astype(np.int64); pad = W
-                elif code == 64:
-                    ids = idx_s.reshape(-1, 1)[s].astype(np.int64); pad = W
-                elif blk < B:
-                    ids = idx16.reshape(-1, 8)[s].astype(np.int64); pad = W
-                else:
-                    ids = idx32.reshape(-1, 8)[s - n_hot].astype(np.int64); pad = P["nv"]
-                if bank_order and blk < B and code <= 8:
-                    real = ids < W
-                    assert (ids < W + 64).all()             # padding = one of the slice's zero columns
-                else:
-                    real = ids != pad
-                    # padding only behind the real entries of a slot
-                    assert (real[:, :-1] >= real[:, 1:]).all()
-                assert not real[rows[q] < 0].any()          # unused lanes are all padding
-                if stats is not None and blk < B and code <= 8:
-                    stats["lds"] = stats.get("lds", 0) + 8
-                    stats["wavefronts"] = stats.get("wavefronts", 0) + sum(lds_wavefronts(ids[:, k]) for k in range(8))
-                if blk < B:
-                    assert (ids[real] < W).all()
-                    ids = ids + blk * W
-                rr = np.repeat(rows[q][:, None], width, 1)
-                out_r.append(rr[real]); out_c.append(ids[real])
-                if sw is not None and code <= 8:
-                    ww = sw.reshape(-1, 8)[s]
+            if kind < 3:      # S / Q / H: R pieces of E entries per lane
+                R = ppg // 32
+                E = 8 // R
+                sl = ids[sr0 + q].astype(np.int64).reshape(32, R, E)
+                rr = rows[row0 + q * ppg: row0 + (q + 1) * ppg].reshape(32, R)
+                real = sl < W
+                assert (sl <= W).all()                              # narrow kinds pad with column W only
+                assert (real[:, :, :-1] >= real[:, :, 1:]).all()    # padding behind the real entries of a piece
+                assert not real[rr < 0].any()                       # unused pieces are all padding
+                assert (real.sum(2)[rr >= 0] >= 1).all()
+                n_real_pieces += int((rr >= 0).sum())
+                cols = sl + blk * W
+                out_r.append(np.repeat(rr[:, :, None], E, 2)[real]); out_c.append(cols[real])
+                if sw is not None:
+                    ww = sw[sr0 + q].reshape(32, R, E)
                     assert (ww[~real] == 0).all()
                     out_w.append(ww[real])
+            else:
+                sl = ids[sr0 + q * steps: sr0 + (q + 1) * steps].astype(np.int64)   # [steps, 32 lanes, 8]
+                rr = rows[row0 + q * 32: row0 + (q + 1) * 32]
+                assert (sl < W + 64).all()                          # padding = one of the slice's zero columns
+                real = sl < W
+                assert not real[:, rr < 0, :].any()
+                per_piece = real.sum((0, 2))
+                assert (per_piece[rr >= 0] > (steps - 1) * 8).all() and (per_piece[rr >= 0] <= steps * 8).all()   # the kind fits
+                if not bank:
+                    flat = real.transpose(1, 0, 2).reshape(32, -1)
+                    assert (flat[:, :-1] >= flat[:, 1:]).all()
+                n_real_pieces += int((rr >= 0).sum())
+                if stats is not None:
+                    stats["lds"] = stats.get("lds", 0) + 8 * steps
+                    stats["wavefronts"] = stats.get("wavefronts", 0) + sum(lds_wavefronts(sl[j, :, k]) for j in range(steps) for k in range(8))
+                cols = sl + blk * W
+                r3 = np.broadcast_to(rr[None, :, None], sl.shape)
+                out_r.append(r3[real]); out_c.append(cols[real])
+                if sw is not None:
+                    ww = sw[sr0 + q * steps: sr0 + (q + 1) * steps]
+                    assert (ww[~real] == 0).all()
+                    out_w.append(ww[real])
+    assert n_real_pieces == n_pieces
     r = np.concatenate(out_r) if out_r else np.zeros(0, np.int64)
     c = np.concatenate(out_c) if out_c else np.zeros(0, np.int64)
     w = np.concatenate(out_w) if out_w else None
-    return dict(r=r, c=c, w=w, W=W, B=B, subs=subs, units=units, narrow=narrow)
+    return dict(r=r, c=c, w=w, W=W, B=B, chunks=chunks, phases=phases, bank=bank)
 
 
-def check_hot(L, g, P, bank_order=False, stats=None):
-    H = hot_pieces(L, g, P, bank_order, stats)
-    n_hi, nnz_hi = P["seg"][0], P["nnz_hi"]
-    rows = np.repeat(np.arange(n_hi), np.diff(P["off"][:n_hi + 1]))
-    cols = P["idx"][:nnz_hi].astype(np.int64)
-    assert H["r"].size == nnz_hi
+def check_sweep_layout(L, g, P, stats=None):
+    H = sweep_pieces(L, g, P, stats)
+    n_cov, nnz = P["seg"][5], P["nnz"]
+    rows = np.repeat(np.arange(n_cov), np.diff(P["off"][:n_cov + 1]))
+    cols = P["idx"][:nnz].astype(np.int64)
+    assert H["r"].size == nnz
     if P["w"] is None:
         o1, o2 = np.lexsort((H["c"], H["r"])), np.lexsort((cols, rows))
         assert (H["r"][o1] == rows[o2]).all() and (H["c"][o1] == cols[o2]).all()
     else:
-        o1, o2 = np.lexsort((H["w"], H["c"], H["r"])), np.lexsort((P["w"][:nnz_hi], cols, rows))
-        assert (H["r"][o1] == rows[o2]).all() and (H["c"][o1] == cols[o2]).all() and (H["w"][o1] == P["w"][:nnz_hi][o2]).all()
+        o1, o2 = np.lexsort((H["w"], H["c"], H["r"])), np.lexsort((P["w"][:nnz], cols, rows))
+        assert (H["r"][o1] == rows[o2]).all() and (H["c"][o1] == cols[o2]).all() and (H["w"][o1] == P["w"][:nnz][o2]).all()
     return H
 
 
 @pytest.mark.parametrize("weighted", [False, True])
-def test_staging_and_piece_layout(emu, monkeypatch, weighted):
+def test_staging_and_piece_stream(emu, monkeypatch, weighted):
     monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.delenv("CUGRAPH_B200_HOT_NARROW", raising=False)
     src, dst, w = make_edges(120_000, 900_000, seed=3 + weighted, weighted=weighted, id_offset=17)
     g = create_graph(emu, src, dst, w)
     P = primary(emu, g)
     check_csr(P, src, dst, w)
     assert P["seg"][0] > 500                      # there are degree >= 32 rows, and several column blocks
-    H = check_hot(emu, g, P)
-    assert H["B"] >= 2 and not H["narrow"]
-    emu.cugraph_graph_free(g)
-
-
-def test_piece_layout_with_cold_block_and_small_units(emu, monkeypatch):
-    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_BLOCKS", "1")          # one hot block, the rest of the columns cold (32-bit ids)
-    monkeypatch.setenv("CUGRAPH_B200_HOT_UNIT_SLOTS", "1024")
-    src, dst, w = make_edges(120_000, 600_000, seed=11)
-    g = create_graph(emu, src, dst, w)
-    P = primary(emu, g)
-    H = check_hot(emu, g, P)
-    assert H["B"] == 1 and (H["units"][:, 2] == 1).any()        # cold units exist
-    emu.cugraph_graph_free(g)
-
-
-def test_narrow_piece_layout(emu, monkeypatch):
-    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.setenv("CUGRAPH_B200_HOT_NARROW", "1")
-    src, dst, w = make_edges(160_000, 700_000, seed=5)
-    g = create_graph(emu, src, dst, w)
-    P = primary(emu, g)
-    H = check_hot(emu, g, P)
-    assert H["narrow"] and all((H["subs"][:, 3] == code).any() for code in (16, 32, 64))
+    H = check_sweep_layout(emu, g, P)
+    assert H["B"] >= 2 and all((H["chunks"][:, 3] == k).any() for k in (0, 1, 2, 3, 10))   # S, Q, H, F1 and F8 pieces exist
     emu.cugraph_graph_free(g)
 
 
 @pytest.mark.parametrize("weighted", [False, True])
-def test_bank_ordered_piece_layout(emu, monkeypatch, weighted):
-    """CUGRAPH_B200_HOT_BANK_ORDER=1: same (row, source[, weight]) multiset, and fewer shared-memory wavefronts per gather"""
+def test_bank_ordered_slots(emu, monkeypatch, weighted):
+    """the F kinds' entries are ordered by shared-memory bank (default for 4-byte values): same (row, source[, weight])
+    multiset, and fewer shared-memory wavefronts per gather than the natural order"""
     monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
     src, dst, w = make_edges(120_000, 900_000, seed=21 + weighted, weighted=weighted, id_offset=3)
     res = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("CUGRAPH_B200_HOT_BANK_ORDER", mode)
+        monkeypatch.setenv("CUGRAPH_B200_SWEEP_BANK_ORDER", mode)
         g = create_graph(emu, src, dst, w)
         P = primary(emu, g)
         st = {}
-        check_hot(emu, g, P, bank_order=(mode == "1"), stats=st)
+        H = check_sweep_layout(emu, g, P, stats=st)
+        assert H["bank"] == int(mode)
         res[mode] = st["wavefronts"] / st["lds"]
         emu.cugraph_graph_free(g)
-    print(f"wavefronts per LDS: default order {res['0']:.3f}, bank order {res['1']:.3f}")
-    assert res["1"] < 0.6 * res["0"], res
-
-
-@pytest.mark.parametrize("weighted", [False, True])
-def test_low_ell_sweep(emu, monkeypatch, weighted):
-    monkeypatch.setenv("CUGRAPH_B200_LOW_ELL", "1")
-    src, dst, w = make_edges(60_000, 400_000, seed=21 + weighted, weighted=weighted)
-    g = create_graph(emu, src, dst, w)
-    P = primary(emu, g)
-    nv, n_hi = P["nv"], P["seg"][0]
-    r = np.random.default_rng(1)
-    x = r.random(nv).astype(np.float32)
-    y = np.full(nv, -7.0, dtype=np.float32)
-    alpha, init = 0.85, 0.125
-    rc = emu.emu_low_ell_sweep(C.c_void_p(emu.handle), g, x.ctypes.data, y.ctypes.data, alpha, init)
-    assert rc == 0
-    deg = np.diff(P["off"])
-    rows = np.repeat(np.arange(P["n_rows"]), deg)
-    vals = x[P["idx"]].astype(np.float64) * (P["w"].astype(np.float64) if weighted else 1.0)
-    exp = np.bincount(rows, weights=vals, minlength=P["n_rows"]) * alpha + init
-    assert (y[:n_hi] == -7.0).all()                              # the degree >= 32 rows belong to the other kernel
-    np.testing.assert_allclose(y[n_hi:], exp[n_hi:].astype(np.float32), rtol=2e-6, atol=0)
-    assert (deg[n_hi:] < 32).all() and len(set(deg[n_hi:].tolist())) > 10
-    emu.cugraph_graph_free(g)
+    print(f"wavefronts per LDS (F kinds): natural order {res['0']:.3f}, bank order {res['1']:.3f}")
+    assert res["1"] < 0.7 * res["0"], res
 
 
 def test_staging_options(emu, monkeypatch):

@@ -178,6 +178,39 @@ def test_sssp_random_vs_oracle(V, E, use_float):
     assert oracle.check_sssp_predecessors(s, d, w, V, got_d, by_vertex(verts, pred, V), 1)
 
 
+def test_sssp_zero_weight_predecessors_form_a_tree():
+    """symmetric zero-weight edges, a zero-weight cycle and a weight absorbed by float rounding: both directions of such
+    an edge are tight, the predecessors must still lead every reached vertex back to the source"""
+    r = np.random.default_rng(3)
+    V = 4000
+    hs = r.integers(0, V, 16000).astype(np.int32)
+    hd = r.integers(0, V, 16000).astype(np.int32)
+    hw = np.where(r.random(16000) < 0.5, 0.0, r.random(16000)).astype(np.float32)
+    extra = [(6, 7, 0.0), (7, 8, 0.0), (8, 9, 0.0), (9, 7, 0.0), (0, 3990, 1e8), (3990, 3991, 1.0), (3991, 3992, 1.0)]
+    hs = np.concatenate([hs, np.array([e[0] for e in extra], np.int32)])
+    hd = np.concatenate([hd, np.array([e[1] for e in extra], np.int32)])
+    hw = np.concatenate([hw, np.array([e[2] for e in extra], np.float32)])
+    s, d, w = np.concatenate([hs, hd]), np.concatenate([hd, hs]), np.concatenate([hw, hw])
+    h, g = make_graph(s, d, w, symmetric=True, vertices=np.arange(V, dtype=np.int32))
+    for source in (0, 7):
+        verts, dist, pred = _sssp(h, g, source)
+        ref_d, _ = oracle.sssp(s, d, w, V, source, use_float=True)
+        got_d, got_p = by_vertex(verts, dist, V), by_vertex(verts, pred, V)
+        assert np.array_equal(got_d.astype(np.float64), ref_d)
+        assert oracle.check_sssp_predecessors(s, d, w, V, got_d.astype(np.float64), got_p, source)
+        unreached = np.finfo(np.float32).max
+        for v in range(V):
+            if got_d[v] == unreached:
+                assert got_p[v] == -1
+                continue
+            cur, steps = v, 0
+            while cur != source:
+                p = int(got_p[cur])
+                assert p >= 0 and got_d[p] <= got_d[cur], (v, cur, p)
+                cur, steps = p, steps + 1
+                assert steps <= V, f"predecessor cycle reached from {v}"
+
+
 def test_sssp_cutoff():
     rng = np.random.default_rng(4)
     V, E = 2000, 16000
