@@ -476,9 +476,9 @@ __device__ __forceinline__ double atomic_min_nonneg(double* addr, double v)
 // order as integers); predecessors, if wanted, come from a pass over the distance fixpoint afterwards.  dist_packed (float
 // with predecessors): (distance bits << 32 | predecessor) in one 64-bit word lowered with ONE atomic min, i.e. the
 // predecessor is recorded by the relaxation that set the distance, as in the reference (sssp_impl.cuh:43-73,
-// reduce_op::minimum over (distance, predecessor) tuples): always a tree, ties go to the smaller vertex id, and no
-// predecessor pass.  A relaxation is only attempted when it strictly improves the distance read before it, so a vertex's
-// parent attained its distance before the vertex did: no cycles through zero-weight or absorbed edges.
+// reduce_op::minimum over (distance, predecessor) tuples): always a tree and no predecessor pass.  The word only changes on a
+// STRICT improvement of the distance, so a vertex's parent attained its distance before the vertex did: no cycles through
+// zero-weight or absorbed edges.
 template <typename T>
 struct dist_plain {
   T* d;
@@ -493,10 +493,20 @@ struct dist_packed {
     return ((unsigned long long)dist_bits << 32) | (unsigned)pred;
   }
   __device__ __forceinline__ float get(int v) const { return __uint_as_float((unsigned)(p[v] >> 32)); }
+  // STRICT improvement only (compare-and-swap loop): with a plain 64-bit atomicMin a relaxation at an EQUAL distance and a
+  // smaller source id would replace the predecessor; the pre-check that should prevent it reads through L1, which is not
+  // coherent with the other SMs' atomics, and on hardware that produced predecessor cycles inside zero-weight cycles.
+  // With strict improvements every vertex's parent attained its value before the vertex did: always a tree.
   __device__ __forceinline__ bool improve(int v, float nd, int src) const
   {
-    const unsigned long long old = atomicMin(p + v, pack(__float_as_uint(nd), src));
-    return nd < __uint_as_float((unsigned)(old >> 32));
+    const unsigned long long want = pack(__float_as_uint(nd), src);
+    unsigned long long cur        = *reinterpret_cast<volatile unsigned long long*>(p + v);
+    while (nd < __uint_as_float((unsigned)(cur >> 32))) {
+      const unsigned long long prev = atomicCAS(p + v, cur, want);
+      if (prev == cur) return true;
+      cur = prev;
+    }
+    return false;
   }
   __device__ __forceinline__ void set_source(int v) const { p[v] = pack(0u, -1); }
 };
