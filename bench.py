@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --gpus 1 --scale 27                      (the single-GPU denominator of the scale-27 configuration)
 
 Workload (BASELINE.json configs[1]): PageRank on RMAT scale-24 edge-factor-16 (Graph500 a,b,c,
 multi-edges and self-loops kept, scrambled ids, unweighted, int32 ids / float32 scores), alpha 0.85,
@@ -15,16 +16,17 @@ A STEP is one call of `cugraph_pagerank_allow_nonconvergence` (100 iterations) t
   e2e    = the same metric for the whole reference-facing call sequence with HOST buffers inside the
            timed region: pinned edge list -> H2D -> cugraph_graph_create_with_times_sg -> pagerank ->
            D2H of (vertices, scores)
-  roofline = the pull-SpMV sweep (kernels k_spmv_blocked + k_spmv_blocked_finish + k_spmv_low = one
-           per_v_transform_reduce_incoming_e) timed alone with CUDA events on the handle's stream;
-           algorithmic bytes per sweep = 4E + 4(V+1) + 4V + 4V; traffic = DRAM bytes of
-           the three kernels from the ncu launch list (profiles/spmv_traffic.json)
-  cpu_baseline = oracle port (oracle/oracle.c, OpenMP) on a bounded sample, host cores stated
+  roofline = the pull-SpMV sweep (kernels k_sweep + k_sweep_finish = one per_v_transform_reduce_incoming_e)
+           timed alone with CUDA events on the handle's stream; algorithmic bytes per sweep =
+           4E + 4(V+1) + 4V + 4V; traffic = DRAM bytes of the two kernels from the ncu capture
+           of the same kernels on the same workload (profiles/spmv_traffic.json names the capture)
+  config.bfs_* / config.sssp_* = BASELINE.json configs[2], [3]: BFS (direction-optimising, 64 random sources) and SSSP
+           (8 sources) on the symmetrised RMAT-24 graph, Graph500 TEPS (undirected edges of the source's component /
+           time of the C-ABI call), harmonic + arithmetic mean, with size-independent result checks
+  cpu_baseline = the CPU port of the same algorithm (oracle/bench_ref.c, float32, OpenMP on the physical cores) on a
+           bounded sample; cpu_baseline.networkx_mteps = nx.pagerank (BASELINE's named baseline) on a small sample
   timing = CUDA events recorded on the handle's stream (the stream the library launches on) around the K calls;
            the wall-clock time of the same region is reported next to it
-  side   = informational extras measured in separate processes under timeouts (scripts/bench_side.py): BFS / SSSP
-           TEPS on the symmetrised RMAT-24 graph (BASELINE.json configs[2], [3]) and the experimental sweep
-           variants; CUGRAPH_B200_BENCH_SIDE=0 skips them
 Synthetic data, random seed 0.  Inputs (1.2 GB per sweep) exceed the 126 MB L2, so no explicit L2 flush
 is needed between timed iterations (stated in config.l2).
 """
@@ -43,7 +45,39 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALPHA, ITERS = 0.85, 100
-METRIC = "MTEPS (million traversed edges/sec) PageRank RMAT-24 ef-16, 100 iterations"
+
+
+def metric_name(scale, n_gpus=1):
+    m = f"MTEPS (million traversed edges/sec) PageRank RMAT-{scale} ef-16, 100 iterations"
+    return m if n_gpus == 1 else m + f", {n_gpus} GPUs (2D edge partition)"
+
+
+def physical_cores():
+    """physical cores this process may run on (cgroup / affinity aware)"""
+    try:
+        allowed = os.sched_getaffinity(0)
+    except Exception:
+        allowed = set(range(os.cpu_count() or 1))
+    cores = set()
+    try:
+        for cpu in allowed:
+            with open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list") as f:
+                cores.add(f.read().strip())
+        return max(1, len(cores))
+    except Exception:
+        return max(1, len(allowed))
+
+
+def pin_host_threads():
+    """OpenMP settings of the CPU arms, fixed BEFORE any OpenMP runtime is loaded: one thread per physical core, bound.
+    (torchrun exports OMP_NUM_THREADS=1 and an unpinned 128-thread run once performed like a single thread: the CPU arm
+    wandered 6.5x between boxes)"""
+    n = physical_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["OMP_PROC_BIND"] = "close"
+    os.environ["OMP_PLACES"] = "cores"
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    return n
 
 
 def _peaks():
@@ -104,27 +138,46 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _cpu_baseline(sample_scale=21, target_s=12.0):
-    """Oracle port on the host cores: float32 pull-SpMV sweeps over a smaller RMAT CSC."""
-    import numpy as np
+def _cpu_port_pagerank(scale, budget_s, steps=1, warmup=0):
+    """The CPU port (oracle/bench_ref.c: float32 PageRank, OpenMP) on RMAT-`scale` ef-16: `steps` timed steps after
+    `warmup` untimed ones.  A step is 100 iterations unless that cannot fit the time budget, then fewer (said so)."""
     import oracle
-    from oracle.rmat import rmat_edgelist
-    src, dst = rmat_edgelist(sample_scale, 16 << sample_scale, seed=0)
-    V = 1 << sample_scale
-    csc = oracle.coo_to_csx(dst, src, V)
-    x = np.full(V, 1.0 / V, dtype=np.float32)
-    E = src.shape[0]
+    V, E = 1 << scale, 16 << scale
     t0 = time.perf_counter()
-    oracle.spmv_f32(csc, x, ALPHA, 0.0)
-    one = time.perf_counter() - t0
-    n = max(1, min(50, int(target_s / max(one, 1e-3))))
+    src, dst = oracle.bench_rmat_edges(scale, E, seed=0)
+    off, idx, deg = oracle.bench_build_csc(src, dst, V)
+    del src, dst
+    setup_s = time.perf_counter() - t0
+    pr = oracle.BenchPageRank(off, idx, deg, ALPHA)
+    pr.run(1)                                   # page in, warm the caches
     t0 = time.perf_counter()
-    for _ in range(n):
-        x = oracle.spmv_f32(csc, x, ALPHA, 0.15 / V)
+    pr.run(2)
+    per_it = (time.perf_counter() - t0) / 2
+    its = ITERS
+    total = (steps + warmup) * ITERS * per_it
+    if total > budget_s:
+        its = max(2, int(budget_s / ((steps + warmup) * per_it)))
+    for _ in range(warmup):
+        pr.reset()
+        pr.run(its)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pr.reset()
+        pr.run(its)
     dt = time.perf_counter() - t0
-    out = {"value": E * n / dt / 1e6, "unit": "MTEPS", "cores": oracle.num_threads(), "kind": "port",
-           "sample": f"{n} float32 pull-SpMV sweeps (oracle_spmv_f32, OpenMP) over RMAT scale-{sample_scale} ef-16 CSC"}
-    out["networkx"] = _networkx_baseline(min(sample_scale, 16))
+    return {"value": E * its * steps / dt / 1e6, "ms_per_step": dt / steps * 1e3, "iterations_per_step": its,
+            "cores": oracle.num_threads(), "setup_s": setup_s, "scale": scale, "edges": E}
+
+
+def _cpu_baseline(sample_scale=22, target_s=12.0):
+    """cpu_baseline of the GPU arm: the same port as `--impl reference` on a bounded sample (rank 0, N = 1 only)."""
+    r = _cpu_port_pagerank(sample_scale, target_s, steps=1, warmup=0)
+    out = {"value": r["value"], "unit": "MTEPS", "cores": r["cores"], "kind": "port",
+           "sample": f"{r['iterations_per_step']} float32 PageRank iterations (oracle/bench_ref.c, OpenMP, threads bound to "
+                     f"physical cores) on RMAT scale-{sample_scale} ef-16; graph set-up ({r['setup_s']:.1f} s) not timed"}
+    nx = _networkx_baseline(16)
+    out["networkx_mteps"] = nx.get("value")
+    out["networkx_sample"] = nx.get("sample") or nx.get("error")
     return out
 
 
@@ -134,8 +187,8 @@ def _networkx_baseline(scale):
     benchmark scale is prohibitive.  Graph construction is not timed."""
     try:
         import networkx as nx
-        from oracle.rmat import rmat_edgelist
-        src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
+        import oracle
+        src, dst = oracle.bench_rmat_edges(scale, 16 << scale, seed=0)
         G = nx.MultiDiGraph()
         G.add_edges_from(zip(src.tolist(), dst.tolist()))
         t0 = time.perf_counter()
@@ -145,41 +198,31 @@ def _networkx_baseline(scale):
             pass
         dt = time.perf_counter() - t0
         return {"value": src.shape[0] * ITERS / dt / 1e6, "unit": "MTEPS", "cores": 1, "version": nx.__version__,
-                "sample": f"nx.pagerank, {ITERS} iterations, RMAT scale-{scale} ef-16 MultiDiGraph (SciPy-backed, single thread)"}
+                "sample": f"nx.pagerank {nx.__version__}, {ITERS} iterations, RMAT scale-{scale} ef-16 MultiDiGraph (SciPy-backed, 1 thread)"}
     except Exception as ex:
         return {"value": None, "error": f"{type(ex).__name__}: {ex}"[:200]}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port
-    (libcugraph itself is not buildable here).  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path.  libcugraph cannot be built here, so
+    this is the port of its algorithm (oracle/bench_ref.c) — on the BENCHMARK configuration itself: RMAT scale-24 ef-16,
+    float32, 100 iterations per step, all physical cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import numpy as np
-    import oracle
-    from oracle.rmat import rmat_edgelist
-    scale = 20
-    src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
-    V, E = 1 << scale, src.shape[0]
-    csc = oracle.coo_to_csx(dst, src, V)
-
-    def step():
-        oracle.pagerank(src, dst, V, None, alpha=ALPHA, epsilon=0.0, max_iterations=ITERS, csc=csc)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    val = E * ITERS * args.steps / dt / 1e6
-    sample = f"PageRank {ITERS} iterations on RMAT scale-{scale} ef-16 per step (oracle_pagerank, fp64, OpenMP)"
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MTEPS", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "pagerank_rmat24_ef16_100it", "sample_scale": scale},
-           "cpu_baseline": {"value": val, "unit": "MTEPS", "cores": oracle.num_threads(), "kind": "port", "sample": sample},
-           "e2e": {"value": val, "unit": "MTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    scale = args.scale or 24
+    r = _cpu_port_pagerank(scale, budget_s=float(os.environ.get("CUGRAPH_B200_REF_BUDGET_S", "150")), steps=args.steps,
+                           warmup=args.warmup)
+    its = r["iterations_per_step"]
+    sample = (f"PageRank on RMAT scale-{scale} ef-16, float32, {its} iterations per step"
+              + ("" if its == ITERS else f" (of the {ITERS} of a full step: time-bounded sample, MTEPS is per iteration)")
+              + f", oracle/bench_ref.c, OpenMP {r['cores']} threads bound to physical cores")
+    out = {"impl": "reference", "metric": metric_name(scale), "value": r["value"], "unit": "MTEPS", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"pagerank_rmat{scale}_ef16_100it", "scale": scale, "edge_factor": 16, "num_edges": r["edges"],
+                      "alpha": ALPHA, "iterations": ITERS, "iterations_timed_per_step": its, "vertex_type": "int32"},
+           "cpu_baseline": {"value": r["value"], "unit": "MTEPS", "cores": r["cores"], "kind": "port", "sample": sample},
+           "e2e": {"value": r["value"], "unit": "MTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
@@ -239,15 +282,17 @@ def run_single(args):
     _capi.check(code, err, "cugraph_b200_time_pull_spmv")
     peak, peak_src = _peaks()
     achieved = by.value / (ms.value * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and scale == 24:
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_sweep")
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("dram_bytes_per_sweep"), tj.get("source")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "pull sweep: k_spmv_blocked+k_spmv_blocked_finish+k_spmv_low",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "pull sweep: k_sweep + k_sweep_finish",
                 "ms_per_sweep": ms.value, "algorithmic_bytes_per_sweep": by.value,
                 "sweep_mteps": E / (ms.value * 1e-3) / 1e6}
     # the same ratio for a whole PageRank iteration (B_iter = B_spmv + 4 V-sized streams of the vertex pass)
@@ -297,83 +342,126 @@ def run_single(args):
 
     del h_src, h_dst, h_v, h_p
     torch.cuda.empty_cache()
-    side = None
-    if os.environ.get("CUGRAPH_B200_BENCH_SIDE", "1") != "0":
+    trav = {}
+    if os.environ.get("CUGRAPH_B200_BENCH_TRAVERSAL", "1") != "0":
         try:
-            side = _side_measurements(scale)
-        except Exception as ex:  # informational extras must never cost the main line
-            side = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+            trav = _traversal(scale, int(os.environ.get("CUGRAPH_B200_BENCH_BFS_SOURCES", "64")),
+                              int(os.environ.get("CUGRAPH_B200_BENCH_SSSP_SOURCES", "8")))
+        except Exception as ex:  # the PageRank line must survive a failure here
+            trav = {"traversal_error": f"{type(ex).__name__}: {ex}"[:300]}
+        torch.cuda.empty_cache()
 
     try:
         cpu = _cpu_baseline(sample_scale=args.cpu_sample_scale)
     except Exception as ex:  # the GPU measurements above must still be reported
         cpu = {"value": None, "unit": "MTEPS", "cores": None, "kind": "port", "error": f"{type(ex).__name__}: {ex}"[:300]}
-    out = {"metric": METRIC, "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    config = {"workload": f"pagerank_rmat{scale}_ef16_100it", "scale": scale, "edge_factor": 16,
+              "num_vertices": nv, "num_edges": E, "alpha": ALPHA, "iterations": ITERS, "vertex_type": "int32",
+              "l2": "inputs (1.2 GB/sweep) exceed the 126 MB L2; no explicit flush"}
+    config.update(trav)
+    config["networkx_mteps"] = cpu.get("networkx_mteps")
+    out = {"metric": metric_name(scale), "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic",
-           "config": {"workload": f"pagerank_rmat{scale}_ef16_100it", "scale": scale, "edge_factor": 16,
-                      "num_vertices": nv, "num_edges": E, "alpha": ALPHA, "iterations": ITERS, "vertex_type": "int32",
-                      "l2": "inputs (1.2 GB/sweep) exceed the 126 MB L2; no explicit flush"},
+           "data": "synthetic", "config": config,
            "timing": {"device_ms_per_step": dev_s / args.steps * 1e3, "wall_ms_per_step": wall / args.steps * 1e3,
                       "value_from": "device events" if events_ok else "wall clock (events disagreed)",
                       "how": "CUDA events recorded on the handle's stream around the K synchronous C-ABI calls"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    if side is not None:
-        out["side"] = side
     print(json.dumps(out), flush=True)
 
 
-# Side measurements (informational; the headline keys above never depend on them).  Each runs in its own process under
-# a timeout: BFS / SSSP of BASELINE.json configs[2] and [3] on the default path, then the experimental sweep variants
-# (off by default, parity-checked against the plain sweep in the same process before they are timed).
-SIDE_VARIANTS = ["-", "CUGRAPH_B200_HOT_X=1", "CUGRAPH_B200_HOT_BANK_ORDER=1", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1",
-                 "CUGRAPH_B200_LOW_ELL=1",
-                 "CUGRAPH_B200_LOW_ELL=2", "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_LOW_ELL=2",
-                 "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_BANK_ORDER=1,CUGRAPH_B200_LOW_ELL=2",
-                 "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=8",
-                 "CUGRAPH_B200_HOT_X=1,CUGRAPH_B200_HOT_NARROW=1,CUGRAPH_B200_HOT_MIN_DEGREE=1", "CUGRAPH_B200_LOW_ASYNC=1"]
+def _harmonic(xs):
+    return len(xs) / sum(1.0 / x for x in xs) if xs else None
 
 
-def _run_side(argv, timeout_s):
-    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_side.py")] + [str(a) for a in argv]
-    t0 = time.perf_counter()
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
-    except subprocess.TimeoutExpired:
-        return {"error": f"timeout after {timeout_s} s"}
-    except Exception as ex:
-        return {"error": f"{type(ex).__name__}: {ex}"[:300]}
-    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-    if r.returncode != 0 or not lines:
-        return {"error": f"exit code {r.returncode}", "stderr_tail": r.stderr[-400:]}
-    try:
-        res = json.loads(lines[-1])
-    except Exception as ex:
-        return {"error": f"unparsable output: {ex}"[:200]}
-    res["process_s"] = time.perf_counter() - t0
-    return res
+def _traversal(scale, n_bfs, n_sssp):
+    """BASELINE.json configs[2] and [3] on the symmetrised RMAT graph (weights U[0,1) for SSSP, symmetric): one warm-up +
+    n timed random sources each (Graph500 protocol, mg_graph500_bfs_test.cu:113-114, 757-764).  TEPS per source = undirected
+    edges of the source's component / time of the C-ABI call (wall clock, device synchronised on both sides, view creation
+    and result read-back outside).  Returns FLAT keys (they go into `config`, which the driver keeps)."""
+    import torch
+    from cugraph_b200 import _capi
+    from cugraph_b200 import pylibcugraph as plc
+    from cugraph_b200.generators import rmat_edgelist
+    from cugraph_b200.pylibcugraph.utils import View
+    L = _capi.lib()
+    V = 1 << scale
+    src, dst = rmat_edgelist(scale, 16 << scale, seed=0)
+    s2, d2 = torch.cat([src, dst]), torch.cat([dst, src])
+    del src, dst
+    g = torch.Generator(device="cuda")
+    g.manual_seed(2)
+    w = torch.rand(s2.numel() // 2, device="cuda", generator=g)
+    w2 = torch.cat([w, w])
+    del w
+    h = plc.ResourceHandle()
+    G = plc.SGGraph(h, plc.GraphProperties(is_symmetric=True, is_multigraph=True), s2, d2, weight_array=w2,
+                    store_transposed=False, renumber=True)
+    deg = torch.bincount(s2.long(), minlength=V)
+    e_sym = int(s2.numel())
+    del s2, d2, w2
+    cand = torch.nonzero(deg > 0).flatten()
+    torch.manual_seed(1)
+    sources = cand[torch.randperm(cand.numel(), device="cuda")[:max(n_bfs, n_sssp) + 1]].to(torch.int32)
+    out = {"traversal_graph": f"RMAT-{scale} ef-16 symmetrised, {e_sym} directed edges, weights U[0,1) symmetric"}
+    INT_MAX, FLT_MAX = 2**31 - 1, 3.0e38
 
+    def c_call(name, s_t):
+        res, err = C.c_void_p(), C.c_void_p()
+        if name == "bfs":
+            sv = View(s_t)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            code = L.cugraph_bfs(h.ptr, G.ptr, sv.ptr, 1, INT_MAX - 1, 1, 0, C.byref(res), C.byref(err))
+            dt = time.perf_counter() - t0      # the C-ABI call is synchronous: the result is complete on return
+            sv.free()
+        else:
+            s_host = int(s_t.item())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            code = L.cugraph_sssp(h.ptr, G.ptr, s_host, float("inf"), 1, 0, C.byref(res), C.byref(err))
+            dt = time.perf_counter() - t0
+        _capi.check(code, err, f"cugraph_{name}")
+        from cugraph_b200.pylibcugraph.utils import copy_to_torch
+        verts = copy_to_torch(h, L.cugraph_paths_result_get_vertices(res))
+        dist = copy_to_torch(h, L.cugraph_paths_result_get_distances(res))
+        pred = copy_to_torch(h, L.cugraph_paths_result_get_predecessors(res))
+        L.cugraph_paths_result_free(res)
+        return dt, verts, dist, pred
 
-def _side_measurements(scale, budget_s=None):
-    budget_s = float(os.environ.get("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "130")) if budget_s is None else budget_s
-    t0 = time.perf_counter()
-    side = {"traversal": _run_side(["traversal", scale, 16, 4], 120), "variants": []}
-    for cfg in SIDE_VARIANTS:
-        if time.perf_counter() - t0 > budget_s:
-            side["variants"].append({"config": cfg, "skipped": f"side budget of {budget_s:.0f} s spent"})
-            continue
-        res = _run_side(["variant", scale, cfg], 50)
-        res.setdefault("config", cfg)
-        side["variants"].append(res)
-    side["seconds"] = time.perf_counter() - t0
-    side["note"] = ("informational: default-path BFS/SSSP (Graph500 TEPS, random sources) and experimental sweep variants "
-                    "(each parity-checked against the plain sweep, then timed); the headline keys use the default path only")
-    return side
+    ok_all = True
+    for name, n in (("bfs", n_bfs), ("sssp", n_sssp)):
+        teps, ms = [], []
+        for i in range(n + 1):  # source 0 is the warm-up (and the checked one)
+            s_t = sources[i:i + 1].contiguous()
+            dt, verts, dist, pred = c_call(name, s_t)
+            reached = (dist != INT_MAX) if name == "bfs" else (dist < FLT_MAX)
+            ne = int(deg[verts.long()][reached].sum().item()) // 2
+            if i == 0:  # size-independent properties of the full-size result (external ids)
+                d_ext = torch.empty(V, dtype=dist.dtype, device="cuda")
+                d_ext[verts.long()] = dist
+                has_pred = pred >= 0
+                dp, dv = d_ext[pred[has_pred].long()], dist[has_pred]
+                ok = bool(((dp + 1 == dv) if name == "bfs" else (dp <= dv)).all().item())
+                ok = ok and bool((d_ext[int(s_t.item())] == 0).item())
+                ok = ok and int(has_pred.sum().item()) == int(reached.sum().item()) - 1
+                ok_all = ok_all and ok
+            else:
+                teps.append(ne / dt)
+                ms.append(dt * 1e3)
+        out[f"{name}_sources"] = n
+        out[f"{name}_harmonic_mteps"] = _harmonic(teps) / 1e6 if teps else None
+        out[f"{name}_mean_mteps"] = sum(teps) / len(teps) / 1e6 if teps else None
+        out[f"{name}_ms_per_source"] = sum(ms) / len(ms) if ms else None
+        out[f"{name}_ms_min_max"] = [min(ms), max(ms)] if ms else None
+    out["traversal_checks_ok"] = ok_all
+    out["traversal_timing"] = "wall clock around the synchronous C-ABI call (cugraph_bfs / cugraph_sssp), device synchronised before"
+    return out
 
 
 def run_multi(args):
     from cugraph_b200.mg_bench import run_mg_pagerank
-    run_mg_pagerank(args, METRIC, ALPHA, ITERS, ClockSampler, _peaks)
+    run_mg_pagerank(args, metric_name, ALPHA, ITERS, ClockSampler, _peaks)
 
 
 def _protect_stdout():
@@ -387,13 +475,14 @@ def _protect_stdout():
 
 def main():
     _protect_stdout()
+    pin_host_threads()  # before numpy / torch / the oracle load an OpenMP runtime
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=int, default=None, help="override RMAT scale (development only)")
-    ap.add_argument("--cpu-sample-scale", type=int, default=21, help="RMAT scale of the cpu_baseline sample")
+    ap.add_argument("--cpu-sample-scale", type=int, default=22, help="RMAT scale of the cpu_baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

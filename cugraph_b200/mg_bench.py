@@ -9,7 +9,42 @@ import torch
 import torch.distributed as dist
 
 
-def run_mg_pagerank(args, metric, alpha, iters, ClockSampler, peaks):
+def mg_parity(groups, alpha, scale=16, iters=30):
+    """MG = SG on a small graph (the protocol of cpp/tests/link_analysis/mg_pagerank_test.cpp:158-248): RMAT-`scale` through
+    MGGraph.pagerank on all ranks, the same edge list through the single-GPU C-ABI on rank 0; every vertex within 1e-6
+    relative.  Returns {max_rel, ok, vertices} on rank 0 (None elsewhere).  The driver's GPU box for the test suite has one
+    GPU, so this is where the NCCL path's correctness becomes visible to it."""
+    from cugraph_b200 import mg
+    from cugraph_b200.generators import rmat_edgelist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    E_local = (16 << scale) // world
+    src, dst = rmat_edgelist(scale, E_local, seed=77 + rank)
+    G = mg.MGGraph(src, dst, None, groups)
+    verts, pr, _, _ = G.pagerank(alpha, 0.0, iters)
+    parts = [None] * world
+    dist.all_gather_object(parts, (src.cpu(), dst.cpu(), verts.cpu(), pr.cpu()))
+    del G
+    if rank != 0:
+        return None
+    from cugraph_b200 import pylibcugraph as plc
+    s_all = torch.cat([p[0] for p in parts]).cuda()
+    d_all = torch.cat([p[1] for p in parts]).cuda()
+    v_mg = torch.cat([p[2] for p in parts]).long()
+    p_mg = torch.cat([p[3] for p in parts]).double()
+    h = plc.ResourceHandle()
+    g1 = plc.SGGraph(h, plc.GraphProperties(is_multigraph=True), s_all, d_all, store_transposed=True, renumber=True)
+    v1, p1, _ = plc.pagerank(h, g1, None, None, None, None, alpha, 0.0, iters, False, fail_on_nonconvergence=False)
+    n = 1 << scale
+    a = torch.zeros(n, dtype=torch.float64)
+    b = torch.zeros(n, dtype=torch.float64)
+    a[v_mg] = p_mg
+    b[v1.cpu().long()] = p1.cpu().double()
+    same_set = bool(((a > 0) == (b > 0)).all())
+    rel = ((a - b).abs() / b.clamp_min(1e-300))[b > 0].max().item() if bool((b > 0).any()) else 0.0
+    return {"max_rel": rel, "ok": bool(same_set and rel < 1e-6), "vertices": int((b > 0).sum()), "scale": scale, "iterations": iters}
+
+
+def run_mg_pagerank(args, metric_name, alpha, iters, ClockSampler, peaks):
     from cugraph_b200 import mg
     from cugraph_b200.generators import rmat_edgelist
     rank = int(os.environ.get("RANK", "0"))
@@ -20,6 +55,11 @@ def run_mg_pagerank(args, metric, alpha, iters, ClockSampler, peaks):
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     groups = mg.make_groups()
+    parity = mg_parity(groups, alpha)
+    ok = torch.tensor([1 if (rank != 0 or parity["ok"]) else 0], dtype=torch.int32, device="cuda")
+    dist.broadcast(ok, src=0)
+    if int(ok.item()) == 0:  # every rank leaves: a wrong multi-GPU result must not produce a bench line
+        raise SystemExit(f"multi-GPU PageRank does not match the single-GPU result: {parity}")
     # weak scaling: 2^28 edge draws per GPU (= the N=1 workload); N=8 is BASELINE's scale-27 configuration
     scale = args.scale if args.scale else 24 + max(0, (world - 1).bit_length())
     E_total = 16 << scale
@@ -107,13 +147,15 @@ def run_mg_pagerank(args, metric, alpha, iters, ClockSampler, peaks):
                "includes": "pinned H2D of the edge list, 2D partition + block staging, 100 iterations, D2H of results"}
     if rank == 0:
         R, Cc = groups.R, groups.C
-        out = {"metric": metric, "value": value, "unit": "MTEPS", "n_gpus": world, "steps": args.steps,
+        out = {"metric": metric_name(scale, world), "value": value, "unit": "MTEPS", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"pagerank_rmat{scale}_ef16_100it_2d{R}x{Cc}", "scale": scale, "edge_factor": 16,
                           "num_edges": E_total, "edges_per_gpu": E_local, "alpha": alpha, "iterations": iters,
                           "partition": f"2D {R}x{Cc} (all-gather group {R}, reduce-scatter group {Cc})",
                           "mass": float(mass.item()),
+                          "mg_parity_ok": parity["ok"], "mg_parity_max_rel": parity["max_rel"],
+                          "mg_parity_sample": f"RMAT-{parity['scale']} ef-16, {parity['iterations']} iterations, MG on {world} GPUs vs the single-GPU C-ABI on rank 0, {parity['vertices']} vertices",
                           "mg_split": os.environ.get("CUGRAPH_B200_MG_SPLIT", "0") == "1",
                           "l2": "inputs per sweep exceed the 126 MB L2; no explicit flush"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None}

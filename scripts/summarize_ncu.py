@@ -54,12 +54,13 @@ if os.path.exists(lpath):
     print(f"{'kernel':34s} {'n':>5s} {'total us':>10s} {'avg us':>9s} {'share':>6s} {'DRAM MB/launch':>15s}")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:34s} {a[0]:5d} {a[1]:10.1f} {a[1] / a[0]:9.1f} {100 * a[1] / total:5.1f}% {a[2] / a[0] / 1e6:15.1f}")
-    sweep = {k: a for k, a in agg.items() if k.startswith("k_spmv")}
+    sweep = {k: a for k, a in agg.items() if k.startswith("k_sweep")}
     if sweep:
-        js = {"dram_bytes_per_sweep": sum(a[2] / a[0] for a in sweep.values()),
+        js = {"dram_bytes_per_sweep": sum(a[2] / a[0] for a in sweep.values()),  # k_sweep + k_sweep_finish, per launch
               "per_kernel": {k: {"dram_bytes": a[2] / a[0], "time_us_under_ncu": a[1] / a[0], "launches_averaged": a[0]}
                              for k, a in sweep.items()},
-              "source": f"profiles/{tag}_launches_bench.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
+              "source": f"profiles/{tag}_launches_bench.csv: ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over "
+                        f"the launches of `python bench.py --steps 1 --warmup 1` (the bench command itself, same workload)"}
         json.dump(js, open(os.path.join(out_dir, "spmv_traffic.json"), "w"), indent=1)
         print("spmv_traffic.json:", js["dram_bytes_per_sweep"] / 1e9, "GB per sweep")
 else:

@@ -1,4 +1,4 @@
-"""The Python surface on the CPU: cugraph_b200.pylibcugraph wrappers, bench.py's single-GPU arm and scripts/bench_side.py
+"""The Python surface on the CPU: cugraph_b200.pylibcugraph wrappers, bench.py's single-GPU and reference arms
 driven through the emulation build of the library (tests/emu_py.py).  Catches Python-level mistakes in the wrappers and
 the measurement scripts before they reach the GPU box; says nothing about timing or stream ordering."""
 import argparse
@@ -72,64 +72,45 @@ def test_wrappers_match_oracle(surface):
 
 
 def test_bench_single_gpu_arm(surface, monkeypatch, capsys):
-    """bench.run_single end to end at a toy scale: one JSON line with every key of the contract; the side processes
-    (which need a real GPU) fail here and must not take the main line with them."""
+    """bench.run_single end to end at a toy scale: one JSON line with every key of the contract, including the BFS / SSSP
+    numbers as flat keys of `config` (the driver keeps `config`) and the CPU port + NetworkX baselines."""
     monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    monkeypatch.setenv("CUGRAPH_B200_BENCH_SIDE_BUDGET_S", "0")   # traversal process only; variants are skipped
+    monkeypatch.setenv("CUGRAPH_B200_BENCH_BFS_SOURCES", "3")
+    monkeypatch.setenv("CUGRAPH_B200_BENCH_SSSP_SOURCES", "2")
     bench = _load(os.path.join(ROOT, "bench.py"), "bench_under_test")
-    monkeypatch.setattr(bench, "_run_side", lambda argv, timeout_s: {"error": "no GPU in this test"})
     args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="b200", scale=10, cpu_sample_scale=10)
     bench.run_single(args)
     line = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1]
     out = json.loads(line)
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline",
-                "timing", "side"):
+                "timing"):
         assert key in out, key
+    assert "RMAT-10" in out["metric"]
     assert out["value"] > 0 and out["gpu_launches"] > 0 and out["steps"] == 2
     assert out["e2e"]["value"] is not None and out["e2e"]["value"] > 0, out["e2e"]
     assert out["e2e"]["h2d_bytes_per_step"] == 2 * 4 * (16 << 10)
     assert out["roofline"]["bound"] == "hbm" and out["roofline"]["achieved"] > 0 and 0 < out["roofline"]["frac"]
-    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["value"] > 0
-    assert out["cpu_baseline"]["networkx"]["value"] > 0 and out["cpu_baseline"]["networkx"]["cores"] == 1
-    assert out["side"]["traversal"] == {"error": "no GPU in this test"}
-    assert all("skipped" in v for v in out["side"]["variants"])
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["value"] > 0 and out["cpu_baseline"]["cores"] >= 1
+    assert out["cpu_baseline"]["networkx_mteps"] > 0 and out["config"]["networkx_mteps"] == out["cpu_baseline"]["networkx_mteps"]
+    cfg = out["config"]
+    assert "traversal_error" not in cfg, cfg.get("traversal_error")
+    assert cfg["traversal_checks_ok"] is True
+    assert cfg["bfs_sources"] == 3 and cfg["sssp_sources"] == 2
+    for k in ("bfs_harmonic_mteps", "bfs_mean_mteps", "bfs_ms_per_source", "sssp_harmonic_mteps", "sssp_mean_mteps", "sssp_ms_per_source"):
+        assert cfg[k] > 0, k
 
 
-def test_bench_side_subprocess_failure_is_contained(monkeypatch):
-    """_run_side with a script that cannot succeed here (no GPU): an error record, not an exception"""
-    bench = _load(os.path.join(ROOT, "bench.py"), "bench_under_test2")
-    res = bench._run_side(["no-such-mode"], 120)
-    assert "error" in res
-
-
-def _side_variants():
-    return _load(os.path.join(ROOT, "bench.py"), "bench_for_variant_list").SIDE_VARIANTS
-
-
-@pytest.mark.parametrize("cfg", _side_variants())
-def test_bench_side_variant(surface, monkeypatch, capsys, cfg):
-    """every switch set bench.py's side run will time on the GPU: parity of the configured sweep against the plain one"""
-    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    side = _load(os.path.join(ROOT, "scripts", "bench_side.py"), "bench_side_under_test")
-    for kv in cfg.split(","):
-        if "=" in kv:
-            monkeypatch.setenv(*kv.split("="))
-    side.variant(10, cfg)
-    out = json.loads(capsys.readouterr().out.splitlines()[-1])
-    assert out["config"] == cfg and out["parity_ok"], out
-    assert out["sweep_ms"] > 0 and abs(out["pagerank_mass"] - 1.0) < 1e-4
-
-
-def test_bench_side_traversal(surface, capsys):
-    side = _load(os.path.join(ROOT, "scripts", "bench_side.py"), "bench_side_under_test3")
-    side.traversal(9, 2, 1)
-    out = json.loads(capsys.readouterr().out.splitlines()[-1])
-    assert len(out["schedule_ab"]) == 4 and all(r.get("harmonic_mean_mteps", 0) > 0 for r in out["schedule_ab"]), out["schedule_ab"]
-    for name in ("bfs", "sssp"):
-        assert out[name]["harmonic_mean_mteps"] > 0
-        assert all(out[name]["check"][k] for k in ("tree_property", "source_distance_zero",
-                                                   "every_reached_vertex_but_the_source_has_a_predecessor")), out[name]
+def test_bench_reference_arm(capsys):
+    """--impl reference: the CPU port on the benchmark configuration (here a toy scale), same keys, same_config fields"""
+    bench = _load(os.path.join(ROOT, "bench.py"), "bench_ref_under_test")
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="reference", scale=10, cpu_sample_scale=10)
+    bench.run_reference(args)
+    out = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    assert out["impl"] == "reference" and out["value"] > 0 and out["dtype"] == "f32"
+    assert out["config"]["workload"] == "pagerank_rmat10_ef16_100it" and out["config"]["iterations_timed_per_step"] == 100
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["value"] == out["value"]
+    assert out["e2e"] == {"value": out["value"], "unit": "MTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
 def test_graft_entry_smoke(surface, capsys):
