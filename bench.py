@@ -170,15 +170,29 @@ def _cpu_port_pagerank(scale, budget_s, steps=1, warmup=0):
 
 
 def _cpu_baseline(sample_scale=22, target_s=12.0):
-    """cpu_baseline of the GPU arm: the same port as `--impl reference` on a bounded sample (rank 0, N = 1 only)."""
-    r = _cpu_port_pagerank(sample_scale, target_s, steps=1, warmup=0)
+    """cpu_baseline of the GPU arm: the same port as `--impl reference` on a bounded sample (rank 0, N = 1 only).  Runs in a
+    CHILD process: the OpenMP settings of the CPU arm (one bound, actively waiting thread per physical core) must not leak
+    into the process that drives the GPU — with them set here the host thread could not keep the GPU fed (PageRank measured
+    100 ms per step instead of 39)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--scale", str(sample_scale)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError(f"cpu-sample child failed ({r.returncode}): {r.stderr[-300:]}")
+    return json.loads(lines[-1])
+
+
+def run_cpu_sample(args, target_s=12.0):
+    """child of _cpu_baseline (threads already pinned by main): prints the cpu_baseline object"""
+    scale = args.scale or 22
+    r = _cpu_port_pagerank(scale, target_s, steps=1, warmup=0)
     out = {"value": r["value"], "unit": "MTEPS", "cores": r["cores"], "kind": "port",
            "sample": f"{r['iterations_per_step']} float32 PageRank iterations (oracle/bench_ref.c, OpenMP, threads bound to "
-                     f"physical cores) on RMAT scale-{sample_scale} ef-16; graph set-up ({r['setup_s']:.1f} s) not timed"}
-    nx = _networkx_baseline(16)
+                     f"physical cores) on RMAT scale-{scale} ef-16; graph set-up ({r['setup_s']:.1f} s) not timed"}
+    nx = _networkx_baseline(min(scale, 16))
     out["networkx_mteps"] = nx.get("value")
     out["networkx_sample"] = nx.get("sample") or nx.get("error")
-    return out
+    print(json.dumps(out), flush=True)
 
 
 def _networkx_baseline(scale):
@@ -475,7 +489,6 @@ def _protect_stdout():
 
 def main():
     _protect_stdout()
-    pin_host_threads()  # before numpy / torch / the oracle load an OpenMP runtime
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -484,8 +497,9 @@ def main():
     ap.add_argument("--scale", type=int, default=None, help="override RMAT scale (development only)")
     ap.add_argument("--cpu-sample-scale", type=int, default=22, help="RMAT scale of the cpu_baseline sample")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+    if args.impl in ("reference", "cpu-sample"):
+        pin_host_threads()  # before numpy / the oracle load an OpenMP runtime; ONLY in the CPU arms (see _cpu_baseline)
+        return run_reference(args) if args.impl == "reference" else run_cpu_sample(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
         return run_multi(args)  # weak scaling: scale 24 + log2(N); N = 8 is BASELINE's scale-27 configuration

@@ -136,7 +136,7 @@ def _unique_big(tensors, chunk=1 << 29):
 class Partition:
     groups: Groups
     rows: torch.Tensor        # int32, local destination slot of every local edge: c_v * maxpart + lid
-    cols: torch.Tensor        # int32, local source slot: lid * R + r_u (interleaved)
+    cols: torch.Tensor        # int32, local source slot: r_u * maxpart + lid (partition-major: the all-gather output order)
     weights: object           # tensor or None
     vertices: torch.Tensor    # external ids of the vertices this rank owns, in local-id order
     n_local: int
@@ -184,9 +184,10 @@ def partition_edges(src: torch.Tensor, dst: torch.Tensor, weights=None, groups: 
     maxpart = max(int(mx.item()), 1)
     kd = torch.searchsorted(u, dst_e)
     rows = ((ou[kd] % Cc) * maxpart + lid[kd]).to(torch.int32)
-    # columns are INTERLEAVED across the R partitions of the column group (slot = lid * R + r_u): the hot
-    # sources of every partition share the lowest column ids
-    cols = (lid[ks] * g.R + (ou[ks] // Cc)).to(torch.int32)
+    # columns are partition-major (slot = r_u * maxpart + lid): exactly the layout all_gather_into_tensor produces, so the
+    # gathered x is consumed in place (an interleaved order put all hot sources into the first column block but cost a
+    # strided 4 * n_cols-byte transpose copy per iteration; every partition's hot sources still lead ITS column range)
+    cols = ((ou[ks] // Cc) * maxpart + lid[ks]).to(torch.int32)
     return Partition(g, rows, cols, w_e, mine, n_local, maxpart, int(tot.item()))
 
 
@@ -246,8 +247,7 @@ class MGGraph:
         # out-weight sums of the owned vertices: partial per column slot, reduce-scattered in the column group
         ones = p.weights.to(torch.float64) if p.weights is not None else torch.ones(p.cols.numel(), dtype=torch.float64, device=src.device)
         partial = torch.zeros(self.n_cols, dtype=torch.float64, device=src.device)
-        partial.index_add_(0, p.cols.long(), ones)
-        partial = partial.view(p.maxpart, g.R).t().contiguous().view(-1)   # interleaved -> partition-major
+        partial.index_add_(0, p.cols.long(), ones)                          # partition-major already
         ow = torch.empty(p.maxpart, dtype=torch.float64, device=src.device)
         reduce_scatter_into(ow, partial, g.col_group)
         self.out_w = ow.to(self.dtype)
@@ -276,7 +276,6 @@ class MGGraph:
         pr[:p.n_local] = 1.0 / p.n_global
         x_local = torch.zeros(mp, dtype=dt, device=dev)
         xg = torch.zeros(self.x_elems, dtype=dt, device=dev)
-        xseg = torch.zeros(self.n_cols, dtype=dt, device=dev)
         ypart = torch.zeros(self.span, dtype=dt, device=dev)
         yred = torch.zeros(mp, dtype=dt, device=dev)
         tot = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -284,24 +283,30 @@ class MGGraph:
         views = {k: _view(v) for k, v in dict(pr=pr, x=x_local, xg=xg, yp=ypart, yr=yred, ow=self.out_w).items()}
         err = C.c_void_p()
 
+        pending = [None]
+
         def vertex_step(first):
+            # the totals of the previous step are needed now: their all-reduce ran under the sweep in between
+            if pending[0] is not None:
+                pending[0].wait()
+                pending[0] = None
             part.zero_()
             code = L.cugraph_b200_pagerank_vertex_step(self.handle.ptr, views["yr"].ptr, views["pr"].ptr, views["ow"].ptr,
                                                        views["x"].ptr, p.n_local, float(alpha), float(p.n_global),
                                                        1 if first else 0, C.c_void_p(tot.data_ptr()),
                                                        C.c_void_p(part.data_ptr()), C.byref(err))
             capi.check(code, err, "cugraph_b200_pagerank_vertex_step")
-            dist.all_reduce(part)
+            pending[0] = dist.all_reduce(part, async_op=True)
 
         vertex_step(True)
         tot, part = part, tot
         iters, converged = 0, False
+        xcols = xg[:self.n_cols]
         for _ in range(int(max_iterations)):
             if g.R == 1:
-                xg[:mp].copy_(x_local)
+                xcols[:mp].copy_(x_local)
             else:
-                all_gather_into(xseg, x_local, g.col_group)              # [R, maxpart] partition-major
-                xg[:self.n_cols].view(mp, g.R).copy_(xseg.view(g.R, mp).t())  # -> interleaved column order
+                all_gather_into(xcols, x_local, g.col_group)            # partition-major = the block's column order
             code = L.cugraph_b200_block_pull_sweep(self.handle.ptr, self.block, views["xg"].ptr, views["yp"].ptr,
                                                    float(alpha), C.byref(err))
             capi.check(code, err, "cugraph_b200_block_pull_sweep")
@@ -309,8 +314,13 @@ class MGGraph:
             vertex_step(False)
             tot, part = part, tot
             iters += 1
-            if epsilon > 0.0 and float(tot[0].item()) < epsilon:   # host sync only when a tolerance is requested
-                break
+            if epsilon > 0.0:   # host sync only when a tolerance is requested
+                pending[0].wait()
+                pending[0] = None
+                if float(tot[0].item()) < epsilon:
+                    break
+        if pending[0] is not None:
+            pending[0].wait()
         converged = iters < max_iterations
         for v in views.values():
             v.free()
@@ -327,7 +337,6 @@ def _pagerank_split(self, alpha=0.85, epsilon=1e-5, max_iterations=100):
     pr[:p.n_local] = 1.0 / p.n_global
     x_local = torch.zeros(mp, dtype=dt, device=dev)
     xg = torch.zeros(self.x_elems, dtype=dt, device=dev)
-    xseg = torch.zeros(self.n_cols, dtype=dt, device=dev)
     ybufs = [torch.zeros(sp, dtype=dt, device=dev) for sp in self.spans]
     ymine = ybufs[g.c][:mp]                      # the reduction for this rank's vertices lands here
     tot = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -352,8 +361,7 @@ def _pagerank_split(self, alpha=0.85, epsilon=1e-5, max_iterations=100):
         if g.R == 1:
             xg[:mp].copy_(x_local)
         else:
-            all_gather_into(xseg, x_local, g.col_group)
-            xg[:self.n_cols].view(mp, g.R).copy_(xseg.view(g.R, mp).t())
+            all_gather_into(xg[:self.n_cols], x_local, g.col_group)
         works = []
         for j in range(g.C):
             code = L.cugraph_b200_block_pull_sweep(self.handle.ptr, self.blocks[j], views["xg"].ptr, yviews[j].ptr,

@@ -52,7 +52,7 @@ def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, m
     r_of, c_of = owner // Cc, owner % Cc
     handle = C.c_void_p(L.cugraph_b200_create_resource_handle_on_stream(None))
     n_rows, n_cols = Cc * mp, R * mp
-    # rank (r, c): edges u -> v with r = r_of[v], c = c_of[u]; row = c_of[v] * mp + lid[v]; column = lid[u] * R + r_of[u]
+    # rank (r, c): edges u -> v with r = r_of[v], c = c_of[u]; row = c_of[v] * mp + lid[v]; column = r_of[u] * mp + lid[u]
     blocks, spans = {}, {}
     keep = []
 
@@ -68,7 +68,7 @@ def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, m
         for c in range(Cc):
             m = (r_of[d] == r) & (c_of[s] == c)
             rows = (c_of[d[m]] * mp + lid[d[m]]).astype(np.int32)
-            cols = (lid[s[m]] * R + r_of[s[m]]).astype(np.int32)
+            cols = (r_of[s[m]] * mp + lid[s[m]]).astype(np.int32)
             ww = w[m].copy() if weighted else None
             if not split:
                 blocks[(r, c)] = [make_block(rows, cols, ww, n_rows)]
@@ -110,9 +110,9 @@ def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, m
         ypart = {}
         for r in range(R):
             for c in range(Cc):
-                xg = np.zeros(x_elems, np.float32)                     # all-gather inside the column group, interleaved
+                xg = np.zeros(x_elems, np.float32)                     # all-gather inside the column group, partition-major
                 for rr in range(R):
-                    xg[np.arange(mp) * R + rr] = x_loc[rr * Cc + c]
+                    xg[rr * mp:(rr + 1) * mp] = x_loc[rr * Cc + c]
                 yp = np.zeros(max(span, n_rows), np.float32)
                 for j, blk in enumerate(blocks[(r, c)]):
                     yj = np.zeros(span, np.float32)

@@ -46,11 +46,11 @@ def _worker(rank, world, port, V, E, weighted, out_q):
     # ---- every edge landed on the right GPU, with slots that decode back to its external endpoints
     verts = [None] * world
     dist.all_gather_object(verts, part.vertices.numpy())
-    r_u = (part.cols.long() % g.R).numpy()
+    r_u = (part.cols.long() // part.maxpart).numpy()
     c_v = (part.rows.long() // mp_).numpy()
     src_owner = r_u * g.C + g.c
     dst_owner = g.r * g.C + c_v
-    dec_src = np.array([verts[o][l] for o, l in zip(src_owner, (part.cols.long() // g.R).numpy())], dtype=np.int64)
+    dec_src = np.array([verts[o][l] for o, l in zip(src_owner, (part.cols.long() % part.maxpart).numpy())], dtype=np.int64)
     dec_dst = np.array([verts[o][l] for o, l in zip(dst_owner, (part.rows.long() % mp_).numpy())], dtype=np.int64)
     blocks = [None] * world
     dist.all_gather_object(blocks, (dec_src, dec_dst, None if w is None else part.weights.numpy()))
@@ -58,7 +58,6 @@ def _worker(rank, world, port, V, E, weighted, out_q):
     alpha, iters = 0.85, 25
     ones = part.weights.double() if weighted else torch.ones(part.cols.numel(), dtype=torch.float64)
     partial = torch.zeros(g.R * mp_, dtype=torch.float64).index_add_(0, part.cols.long(), ones)
-    partial = partial.view(mp_, g.R).t().contiguous().view(-1)
     out_w = torch.empty(mp_, dtype=torch.float64)
     mg.reduce_scatter_into(out_w, partial, g.col_group)
     pr = torch.zeros(mp_, dtype=torch.float64)
@@ -81,7 +80,7 @@ def _worker(rank, world, port, V, E, weighted, out_q):
     for _ in range(iters):
         xseg = torch.zeros(g.R * mp_, dtype=torch.float64)
         mg.all_gather_into(xseg, x, g.col_group)
-        xg = xseg.view(g.R, mp_).t().contiguous().view(-1)
+        xg = xseg   # partition-major columns: the all-gather output is the block's column order
         ypart = torch.zeros(g.C * mp_, dtype=torch.float64).index_add_(0, part.rows.long(), alpha * xg[part.cols.long()] * ones)
         mg.reduce_scatter_into(yred, ypart, g.row_group)
         x, dang = step(False, dang)
