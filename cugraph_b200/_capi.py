@@ -101,9 +101,6 @@ def lib():
     _sig(L.cugraph_b200_version, C.c_char_p, [])
     _sig(L.cugraph_b200_handle_stream, vp, [vp])
     _sig(L.cugraph_b200_handle_launch_count, sz, [vp])
-    _sig(L.cugraph_b200_get_nccl_unique_id, i32, [vp, pvp])
-    _sig(L.cugraph_b200_comm_create, i32, [vp, i32, i32, pvp, pvp])
-    _sig(L.cugraph_b200_comm_free, None, [vp])
     _sig(L.cugraph_b200_time_pull_spmv, i32, [vp, vp, sz, C.POINTER(dbl), C.POINTER(dbl), pvp])
     _sig(L.cugraph_b200_create_resource_handle_on_stream, vp, [vp])
     _sig(L.cugraph_b200_padded_elems, sz, [sz, sz])

@@ -49,7 +49,7 @@ void cugraph_error_free(cugraph_error_t* error)
 }
 
 // ------------------------------------------------------------------- resource_handle.h:25-31
-// NULL -> single-GPU handle on the current device.  Non-NULL -> a cugraph_b200_comm_t* (b200_ext.h).
+// NULL -> single-GPU handle on the current device.  Non-NULL (a raft handle in the reference) is refused (mg.cu: attach_comm).
 cugraph_resource_handle_t* cugraph_create_resource_handle(void* raft_handle)
 {
   try {

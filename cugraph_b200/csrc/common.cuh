@@ -99,7 +99,7 @@ struct comm_impl;
 struct tuning_t {
   long long sweep_min_edges{1ll << 22};  // CUGRAPH_B200_SWEEP_MIN_EDGES: graphs below it use the plain sweep (tests: 0)
   bool sweep_bank_order{true};           // CUGRAPH_B200_SWEEP_BANK_ORDER
-  double bfs_alpha{14.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer's switch points)
+  double bfs_alpha{40.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer switch points; alpha 14 -> 40: -7 % per source on RMAT-24, r02_notes)
   bool sssp_adaptive{true};                // CUGRAPH_B200_SSSP_ADAPTIVE
   double sssp_delta_scale{1.0};            // CUGRAPH_B200_SSSP_DELTA_SCALE
   double sssp_start_div{64.0};             // CUGRAPH_B200_SSSP_START_DIV: the controller starts with delta / this

@@ -1132,10 +1132,8 @@ bool plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, sweep_p
 // so that the k-th shared-memory gathers of the 32 lanes in every step (one LDS of the sweep kernel) fall into different
 // banks.  Any assignment of a piece's entries to its (step, position) places is a valid layout (the sweep adds all of them
 // into one sum per piece); padding may point at any of the kHotZeroPad zero columns, i.e. at any bank.  Greedy, place by
-// place: the lanes that still hold entries take turns and pick an entry on a bank nobody took at this place; a lane without
-// such an entry waits for a later place while it has spare places left, else takes a bank used once, else any; all padding
-// of a place shares one zero column on a free bank.  Measured (emulated staging, r01_notes.md): 3.1 -> 1.5 wavefronts per
-// LDS on RMAT-20; ncu r02 on RMAT-24: 2.46 -> ~1.7 for the F kinds.
+// place (bank_order_place below); a lane without a free bank waits for a later place while it has spare places left; all
+// padding of a place shares one zero column on a free bank.  Sweep on RMAT-24: 0.373 ms without, 0.331 ms with this order.
 // State per lane: bank_bits[b] = the piece's entries (bit e = entry e, <= 64 per piece) on bank b, `rem` = not placed yet,
 // `have` = banks with an entry left.
 struct bank_piece_t {
@@ -1145,44 +1143,59 @@ struct bank_piece_t {
   unsigned have2;  // banks with at least two entries left: used first, which keeps the number of distinct banks up
 };
 
-// one place of all 32 lanes: returns this lane's entry index (>= 0) or -1 - pad_bank for padding
+// one place of all 32 lanes: returns this lane's entry index (>= 0) or -1 - pad_bank for padding.
+// PARALLEL greedy: every lane that still holds entries proposes a bank nobody has taken at this place (preferring banks of
+// which its piece still holds several entries, search start rotated by lane and place); of the lanes proposing the same
+// bank the one that comes first in an order rotating with the place wins, the others propose again — three rounds, then
+// lanes that must place an entry now (no spare places left) take any bank.  (A version in which the 32 lanes took turns
+// one after the other reached 1.5 wavefronts per load on RMAT-20 but cost 42 ms of staging at RMAT-24.)
+constexpr int kBankRounds = 8;
 __device__ __forceinline__ int bank_order_place(bank_piece_t& P, int places_left, int lane)
 {
   unsigned taken = 0, taken2 = 0;  // banks used once / twice at this place (the same in every lane)
   int mine       = -1;
-  const unsigned active = __ballot_sync(0xffffffffu, P.rem != 0ull);
-  const int t0          = (11 * places_left) & 31;  // the lane that chooses first changes from place to place
-  unsigned turns        = t0 ? ((active >> t0) | (active << (32 - t0))) : active;
-  while (turns) {
-    const int l = (__ffs(turns) - 1 + t0) & 31;
-    turns &= turns - 1;
-    int bank = -1;
-    if (lane == l) {
-      const int spare = places_left - __popcll(P.rem);  // places beyond the ones the remaining entries need
-      unsigned pick   = P.have2 & ~taken;
+  const int spare = places_left - __popcll(P.rem);  // places beyond the ones the remaining entries need
+  const int prio  = (lane + 11 * places_left) & 31;  // who wins a contested bank changes from place to place
+  const int r0    = (lane + 5 * places_left) & 31;
+#pragma unroll 1
+  for (int round = 0; round < kBankRounds; ++round) {
+    int want = -1;
+    if (mine < 0 && P.rem != 0ull) {
+      unsigned pick = P.have2 & ~taken;
       if (!pick) pick = P.have & ~taken;
-      if (!pick && spare <= 0) {
+      if (!pick && round >= kBankRounds - 2 && spare <= 0) {  // must place now: accept a conflict, on a bank used once if any
         pick = P.have & ~taken2;
-        if (!pick) pick = P.have;
+        if (!pick && round == kBankRounds - 1) pick = P.have;
       }
       if (pick) {
-        // start the search at a bank that depends on lane and place: always taking the lowest bank would use up every
-        // piece's low banks first and leave the late places with what nobody could use
-        const int r0       = (lane + 5 * places_left) & 31;
         const unsigned rot = r0 ? ((pick >> r0) | (pick << (32 - r0))) : pick;
-        bank               = (__ffs(rot) - 1 + r0) & 31;
-        mine = __ffsll((long long)(P.bank_bits[bank] & P.rem)) - 1;
-        P.rem &= ~(1ull << mine);
-        const int left = __popcll(P.bank_bits[bank] & P.rem);
-        if (left < 2) P.have2 &= ~(1u << bank);
-        if (left < 1) P.have &= ~(1u << bank);
+        want               = (__ffs(rot) - 1 + r0) & 31;
       }
     }
-    bank = __shfl_sync(0xffffffffu, bank, l);
-    if (bank >= 0) {
-      taken2 |= taken & (1u << bank);
-      taken |= 1u << bank;
+    // lanes with the same proposal: the smallest rotated priority wins (in the last round everybody proposing wins)
+    const unsigned same = __match_any_sync(0xffffffffu, want);
+    bool win            = want >= 0;
+    if (win && round < kBankRounds - 1) {
+      // winner = the lane of `same` whose prio is smallest: compare by scanning the (few) competitors
+      unsigned others = same & ~(1u << lane);
+      while (others) {
+        const int o = __ffs(others) - 1;
+        others &= others - 1;
+        const int po = (o + 11 * places_left) & 31;
+        if (po < prio) win = false;
+      }
     }
+    if (win) {
+      mine = __ffsll((long long)(P.bank_bits[want] & P.rem)) - 1;
+      P.rem &= ~(1ull << mine);
+      const int left = __popcll(P.bank_bits[want] & P.rem);
+      if (left < 2) P.have2 &= ~(1u << want);
+      if (left < 1) P.have &= ~(1u << want);
+    }
+    const unsigned won = __reduce_or_sync(0xffffffffu, win ? (1u << want) : 0u);
+    taken2 |= taken & won;
+    taken |= won;
+    if (!__any_sync(0xffffffffu, mine < 0 && P.rem != 0ull)) break;
   }
   if (mine >= 0) return mine;
   const int pad_bank = (~taken) ? __ffs(~taken) - 1 : 0;

@@ -227,17 +227,7 @@ cugraph_error_code_t cugraph_b200_pagerank_vertex_step(const cugraph_resource_ha
   });
 }
 
-// the reference's MG constructors take raft comms; see cugraph_b200/mg.py for the torch.distributed path
-cugraph_error_code_t cugraph_b200_get_nccl_unique_id(byte_t*, cugraph_error_t** error)
-{
-  return guarded(error, [&] { throw capi_exception(CUGRAPH_NOT_IMPLEMENTED, "communicators are owned by torch.distributed"); });
-}
-cugraph_error_code_t cugraph_b200_comm_create(const byte_t*, int, int, cugraph_b200_comm_t**, cugraph_error_t** error)
-{
-  return guarded(error, [&] { throw capi_exception(CUGRAPH_NOT_IMPLEMENTED, "communicators are owned by torch.distributed"); });
-}
-void cugraph_b200_comm_free(cugraph_b200_comm_t*) {}
-
+// the reference's MG constructors take raft comms (not part of this build): see cugraph_b200/mg.py for the torch.distributed path
 cugraph_error_code_t cugraph_graph_create_mg(cugraph_resource_handle_t const*, cugraph_graph_properties_t const*,
   cugraph_type_erased_device_array_view_t const* const*, cugraph_type_erased_device_array_view_t const* const*,
   cugraph_type_erased_device_array_view_t const* const*, cugraph_type_erased_device_array_view_t const* const*,

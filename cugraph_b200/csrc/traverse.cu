@@ -579,11 +579,37 @@ __global__ void k_min_beyond(DA dist, int n, T hi, T unreached, T* out_min)
   if ((threadIdx.x & 31) == 0 && m < (T)INFINITY) atomic_min_nonneg(out_min, m);
 }
 
+// the window state lives on the device: the next window's bounds are computed from the result of pass 1 by a one-thread
+// kernel, pass 2 reads them — one host synchronisation per window change instead of two
+template <typename T>
+struct sssp_window_t {
+  T lo, hi;
+  int any;  // 0: nothing is pending beyond the old bound (the traversal is complete)
+};
+template <typename T>
+__global__ void k_next_window(T const* __restrict__ pending_min, T delta, sssp_window_t<T>* __restrict__ win)
+{
+  const T hmin = *pending_min, hi = win->hi;
+  const T inf  = (T)INFINITY;
+  if (!(hmin < inf)) {
+    win->any = 0;
+    return;
+  }
+  const T steps = floor((hmin - hi) / delta);
+  T nhi         = hi + (steps > (T)0 ? steps : (T)0) * delta + delta;
+  if (!(nhi > hmin)) nhi = nextafter(hmin, inf);  // rounding must not produce a window without its smallest entry
+  win->lo  = hi;
+  win->hi  = nhi;
+  win->any = 1;
+}
+
 // dense pass 2: the vertices of the window [lo, hi) form the next near queue
 template <typename O, typename T, typename DA>
-__global__ void k_select_window(O const* __restrict__ off, DA dist, int n, T lo, T hi, int32_t* stamp,
+__global__ void k_select_window(O const* __restrict__ off, DA dist, int n, sssp_window_t<T> const* __restrict__ win, int32_t* stamp,
                                 int round, int32_t* near_out, int32_t* near_deg_out, frontier_counters_t* cnt)
 {
+  if (!win->any) return;
+  const T lo = win->lo, hi = win->hi;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     const T d = dist.get(v);
     if (d >= lo && d < hi) {
@@ -750,6 +776,8 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
   B200_LAUNCH(h, (k_sssp_seed<O, DA>), 1, 1, 0, dist, stamp.as<int32_t>(), qa.as<int32_t>(), la.as<int32_t>(), off, source);
   frontier_counters_t* hc = reinterpret_cast<frontier_counters_t*>(h.pinned);
   T* hmin_pinned          = reinterpret_cast<T*>(reinterpret_cast<char*>(h.pinned) + 256);
+  auto* hwin              = reinterpret_cast<sssp_window_t<T>*>(reinterpret_cast<char*>(h.pinned) + 320);
+  dbuf dwin               = make_dbuf<sssp_window_t<T>>(1, h.stream);
   int32_t *near = qa.as<int32_t>(), *next_near = qb.as<int32_t>();
   int32_t *near_deg = la.as<int32_t>(), *next_near_deg = lb.as<int32_t>();  // degrees of the queue entries
   int n_near = 1, round = 1, window = 1;
@@ -816,27 +844,26 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
       if (window_rounds <= 2) { if (delta < std::numeric_limits<T>::max() / (T)4) delta = delta * (T)2; }
       else if (window_rounds >= 6 && delta > delta_floor) delta = delta / (T)2;
     }
-    // advance the window to the smallest pending distance (dense pass 1), then select its vertices (dense pass 2)
+    // advance the window to the smallest pending distance (dense pass 1), then select its vertices (dense pass 2); the
+    // bounds are computed on the device in between, the host reads them back together with the new queue's size
     const T inf = (T)INFINITY;
+    hwin->lo = lo; hwin->hi = hi; hwin->any = 1;
     *hmin_pinned = inf;
+    CUDA_TRY(cudaMemcpyAsync(dwin.data(), hwin, sizeof(sssp_window_t<T>), cudaMemcpyHostToDevice, h.stream));
     CUDA_TRY(cudaMemcpyAsync(dmin.data(), hmin_pinned, sizeof(T), cudaMemcpyHostToDevice, h.stream));
     B200_LAUNCH(h, (k_min_beyond<T, DA>), std::min(grid_for(nv), h.sm_count * 64), kBlock, 0, dist, nv, hi, unreached, dmin.as<T>());
-    CUDA_TRY(cudaMemcpyAsync(hmin_pinned, dmin.data(), sizeof(T), cudaMemcpyDeviceToHost, h.stream));
-    sync(h);
-    const T hmin = *hmin_pinned;
-    if (!(hmin < inf)) break;  // nothing pending: done
-    lo      = hi;
-    T steps = std::floor((hmin - hi) / delta);
-    T nhi   = hi + (steps > (T)0 ? steps : (T)0) * delta + delta;
-    if (!(nhi > hmin)) nhi = std::nextafter(hmin, inf);  // rounding must not produce a window without its smallest entry
-    hi      = nhi;
+    B200_LAUNCH(h, (k_next_window<T>), 1, 1, 0, dmin.as<T>(), delta, dwin.as<sssp_window_t<T>>());
     ++round;
     ++window;
     CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
-    B200_LAUNCH(h, (k_select_window<O, T, DA>), grid_for(nv), kBlock, 0, off, dist, nv, lo, hi,
+    B200_LAUNCH(h, (k_select_window<O, T, DA>), grid_for(nv), kBlock, 0, off, dist, nv, dwin.as<sssp_window_t<T>>(),
                 stamp.as<int32_t>(), round, near, near_deg, dc);
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
+    CUDA_TRY(cudaMemcpyAsync(hwin, dwin.data(), sizeof(sssp_window_t<T>), cudaMemcpyDeviceToHost, h.stream));
     sync(h);
+    if (!hwin->any) break;  // nothing pending: done
+    lo = hwin->lo;
+    hi = hwin->hi;
     n_near     = hc->n_small;
     near_edges = hc->m_f;
   }

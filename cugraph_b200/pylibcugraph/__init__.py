@@ -5,9 +5,8 @@ cupy, numba) and come back as torch CUDA tensors (cupy is not a dependency here)
 from cugraph_b200.pylibcugraph.exceptions import FailedToConvergeError
 from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
 from cugraph_b200.pylibcugraph.graph_properties import GraphProperties
-from cugraph_b200.pylibcugraph.graphs import SGGraph, MGGraph
+from cugraph_b200.pylibcugraph.graphs import SGGraph
 from cugraph_b200.pylibcugraph.algorithms import pagerank, personalized_pagerank, bfs, sssp
-from cugraph_b200.pylibcugraph import comms
 
-__all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph", "MGGraph",
-           "pagerank", "personalized_pagerank", "bfs", "sssp", "comms"]
+__all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph",
+           "pagerank", "personalized_pagerank", "bfs", "sssp"]

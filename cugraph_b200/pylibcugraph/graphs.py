@@ -79,45 +79,3 @@ class SGGraph(_GPUGraph):
         _capi.check(code, err, where)
         self._ptr = g.value
         self._handle = resource_handle
-
-
-class MGGraph(_GPUGraph):
-    """Multi-GPU graph: every rank passes its share of the edge list
-    (graphs.pyx MGGraph -> cugraph_graph_create_with_times_mg)."""
-
-    def __init__(self, resource_handle, graph_properties, src_array, dst_array, weight_array=None,
-                 store_transposed=False, do_expensive_check=False, edge_id_array=None, edge_type_array=None,
-                 edge_start_time_array=None, edge_end_time_array=None, vertices_array=None, num_arrays=1,
-                 drop_self_loops=False, drop_multi_edges=False, symmetrize=False):
-        super().__init__()
-
-        def as_list(a):
-            if a is None:
-                return None
-            return list(a) if isinstance(a, (list, tuple)) else [a]
-
-        lists = [as_list(a) for a in (vertices_array, src_array, dst_array, weight_array, edge_id_array,
-                                      edge_type_array, edge_start_time_array, edge_end_time_array)]
-        n = len(lists[1])
-        keep = []
-        arrs = []
-        for lst in lists:
-            if lst is None:
-                arrs.append(None)
-                continue
-            vs = [View(a) for a in lst]
-            keep.extend(vs)
-            arr = (C.c_void_p * len(vs))(*[x.ptr for x in vs])
-            arrs.append(arr)
-        g = C.c_void_p()
-        err = C.c_void_p()
-        pp = [C.cast(a, C.POINTER(C.c_void_p)) if a is not None else None for a in arrs]
-        code = self._lib.cugraph_graph_create_with_times_mg(
-            resource_handle.ptr, C.byref(graph_properties.c), pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], pp[7],
-            int(store_transposed), n, int(drop_self_loops), int(drop_multi_edges), int(symmetrize),
-            int(do_expensive_check), C.byref(g), C.byref(err))
-        for x in keep:
-            x.free()
-        _capi.check(code, err, "cugraph_graph_create_with_times_mg()")
-        self._ptr = g.value
-        self._handle = resource_handle

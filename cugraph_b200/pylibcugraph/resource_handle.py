@@ -3,8 +3,8 @@ from cugraph_b200 import _capi
 
 
 class ResourceHandle:
-    """Owns a cugraph_resource_handle_t.  `handle_ptr` None -> single-GPU handle on the current
-    device; otherwise the integer address of a cugraph_b200_comm_t (see comms.py)."""
+    """Owns a cugraph_resource_handle_t.  `handle_ptr` must be None (single-GPU handle on the current device): the
+    reference passes a raft handle with NCCL comms here, which this build has no counterpart for (multi-GPU: cugraph_b200.mg)."""
 
     def __init__(self, handle_ptr=None, stream=None):
         self._lib = _capi.lib()

@@ -307,6 +307,25 @@ inline int __all_sync(unsigned m, int p)
   return 1;
 }
 inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+template <typename T> inline unsigned __match_any_sync(unsigned m, T v)
+{
+  unsigned long long out[32];
+  const unsigned pm = emu::warp_collect(m, emu_bits(v), out);
+  const unsigned long long mine = emu_bits(v);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i)
+    if (((pm >> i) & 1u) && out[i] == mine) r |= 1u << i;
+  return r;
+}
+inline unsigned __reduce_or_sync(unsigned m, unsigned v)
+{
+  unsigned long long out[32];
+  const unsigned pm = emu::warp_collect(m, (unsigned long long)v, out);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i)
+    if ((pm >> i) & 1u) r |= (unsigned)out[i];
+  return r;
+}
 template <typename T> inline T __reduce_add_sync(unsigned m, T v)
 {
   unsigned long long out[32];

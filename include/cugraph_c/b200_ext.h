@@ -1,11 +1,12 @@
 /*
  * Extensions that have no counterpart in the reference ABI (prefixed cugraph_b200_).
  *
- *  - comm bootstrap: the reference receives NCCL communicators inside a raft::handle_t built by
- *    raft-dask / MPI (python/pylibcugraph/pylibcugraph/comms/comms_wrapper.pyx:10-32,
- *    cpp/tests/utilities/mg_utilities.cpp:37-55).  Here one process per GPU calls
- *    cugraph_b200_comm_create() with an ncclUniqueId obtained from rank 0
- *    (cugraph_b200_get_nccl_unique_id) and distributed by the launcher (torch.distributed).
+ *  - multi-GPU: the reference receives NCCL communicators inside a raft::handle_t built by raft-dask / MPI
+ *    (python/pylibcugraph/pylibcugraph/comms/comms_wrapper.pyx:10-32, cpp/tests/utilities/mg_utilities.cpp:37-55) and keeps
+ *    the 2D-partitioned blocks inside graph_t.  raft is not part of this build: cugraph_graph_create_mg and the multi-GPU
+ *    algorithm entry points return CUGRAPH_NOT_IMPLEMENTED; multi-GPU PageRank is driven by the launcher
+ *    (cugraph_b200/mg.py, one process per GPU over torch.distributed / NCCL) on top of the cugraph_b200_block_* device
+ *    pieces declared below.
  *  - profiling hooks used by bench.py to time the dominant kernel on the handle's stream.
  */
 #pragma once
@@ -13,17 +14,6 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-
-typedef struct { int32_t align_; } cugraph_b200_comm_t;
-
-#define CUGRAPH_B200_NCCL_UNIQUE_ID_BYTES 128
-
-CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_get_nccl_unique_id(byte_t* id_out /* 128 bytes */,
-                                                                    cugraph_error_t** error);
-CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_comm_create(const byte_t* nccl_unique_id, int rank,
-                                                             int size, cugraph_b200_comm_t** comm,
-                                                             cugraph_error_t** error);
-CUGRAPH_EXPORT void cugraph_b200_comm_free(cugraph_b200_comm_t* comm);
 
 /* Library version string and the CUDA stream of a handle (as an integer, for event timing). */
 CUGRAPH_EXPORT const char* cugraph_b200_version(void);

@@ -3,8 +3,9 @@
  *
  * The reference's argument is a raft::handle_t* (cpp/src/c_api/resource_handle.hpp:12-25).  raft is
  * not part of this build: NULL creates a single-GPU handle on the current device (its own stream
- * and stream-ordered memory pool); a non-NULL argument must be a cugraph_b200_comm_t* made by
- * cugraph_b200_comm_create() (cugraph_c/b200_ext.h) and yields a multi-GPU handle.
+ * and stream-ordered memory pool); a non-NULL argument (the reference's raft handle with NCCL comms) is refused: handle
+ * creation fails and returns NULL.  get_rank / get_comm_size therefore always report 0 / 1; multi-GPU runs are driven by
+ * cugraph_b200/mg.py over the cugraph_b200_block_* entry points (cugraph_c/b200_ext.h).
  */
 #pragma once
 #include <cugraph_c/error.h>
