@@ -54,7 +54,7 @@ if os.path.exists(lpath):
     print(f"{'kernel':34s} {'n':>5s} {'total us':>10s} {'avg us':>9s} {'share':>6s} {'DRAM MB/launch':>15s}")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:34s} {a[0]:5d} {a[1]:10.1f} {a[1] / a[0]:9.1f} {100 * a[1] / total:5.1f}% {a[2] / a[0] / 1e6:15.1f}")
-    sweep = {k: a for k, a in agg.items() if k.startswith("k_sweep")}
+    sweep = {k: a for k, a in agg.items() if k in ("k_sweep", "k_sweep_finish")}
     if sweep:
         js = {"dram_bytes_per_sweep": sum(a[2] / a[0] for a in sweep.values()),  # k_sweep + k_sweep_finish, per launch
               "per_kernel": {k: {"dram_bytes": a[2] / a[0], "time_us_under_ncu": a[1] / a[0], "launches_averaged": a[0]}
