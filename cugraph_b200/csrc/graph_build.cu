@@ -1136,13 +1136,8 @@ bool plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, sweep_p
 // padding of a place shares one zero column on a free bank.  Sweep on RMAT-24: 0.373 ms without, 0.331 ms with this order.
 // State per lane: bank_bits[b] = the piece's entries (bit e = entry e, <= 64 per piece) on bank b, `rem` = not placed yet,
 // `have` = banks with an entry left.
-constexpr int kFillWarps = 6;  // = the largest kind_chunk_groups()
-struct bank_bits_ref {  // the 32 bank words of one thread, in shared memory (bank-major: word b of thread t at [b][t])
-  unsigned long long* base;
-  __device__ __forceinline__ unsigned long long& operator[](int b) const { return base[b * (kFillWarps * 32)]; }
-};
 struct bank_piece_t {
-  bank_bits_ref bank_bits;  // dynamically indexed: in registers / local memory it cost 35 GB of DRAM traffic per staging
+  unsigned long long bank_bits[32];
   unsigned long long rem;
   unsigned have;
   unsigned have2;  // banks with at least two entries left: used first, which keeps the number of distinct banks up
@@ -1207,6 +1202,8 @@ __device__ __forceinline__ int bank_order_place(bank_piece_t& P, int places_left
   return -1 - pad_bank;
 }
 
+constexpr int kFillWarps = 6;  // = the largest kind_chunk_groups()
+
 // one CTA per chunk, one warp per group
 template <typename T, bool BANK>
 __global__ void __launch_bounds__(kFillWarps * 32)
@@ -1252,13 +1249,7 @@ k_sweep_fill(sweep_chunk_t const* __restrict__ chunks, sweep_fill_t const* __res
     row         = piece_row[p];
   }
   rows_out[(size_t)(unsigned)ch.row_begin + (size_t)g * 32 + lane] = row;
-#ifndef B200_HOST_EMU
-  __shared__ unsigned long long s_bank_bits[BANK ? 32 * kFillWarps * 32 : 1];
-#else
-  static thread_local unsigned long long s_bank_bits[32 * kFillWarps * 32];  // fibers of one OS thread: same layout
-#endif
   bank_piece_t bp;  // only used by the BANK instantiation
-  bp.bank_bits.base = s_bank_bits + (BANK ? threadIdx.x : 0);
   if (BANK) {       // the whole warp takes part (lanes without a piece hold padding only)
     for (int b = 0; b < 32; ++b) bp.bank_bits[b] = 0ull;
     bp.have = bp.have2 = 0u;
