@@ -3,7 +3,9 @@
 #include "graph.cuh"
 
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <unordered_set>
 
 namespace b200 {
@@ -14,7 +16,79 @@ std::unordered_set<cudaStream_t>& live_streams()
   static auto* s = new std::unordered_set<cudaStream_t>();  // leaked on purpose: used during exit
   return *s;
 }
+// Freed blocks per stream (see block_alloc in common.cuh).  Leaked on purpose like the stream set.
+struct block_cache_t {
+  std::multimap<size_t, void*> blocks;  // capacity -> block
+  size_t total{0};
+};
+std::unordered_map<cudaStream_t, block_cache_t>& block_caches()
+{
+  static auto* c = new std::unordered_map<cudaStream_t, block_cache_t>();
+  return *c;
+}
+constexpr size_t kBlockCacheCap = 32ull << 30;  // bytes kept per stream; beyond it the cache of that stream is returned to the pool
+
+// caller holds g_stream_mutex
+void flush_cache_locked(cudaStream_t s, block_cache_t& c, bool stream_alive)
+{
+  for (auto& b : c.blocks) {
+    if (stream_alive) cudaFreeAsync(b.second, s);
+    else cudaFree(b.second);
+  }
+  c.blocks.clear();
+  c.total = 0;
+}
 }  // namespace
+
+void* block_alloc(size_t bytes, cudaStream_t s, size_t* capacity)
+{
+  {
+    std::lock_guard<std::mutex> lk(g_stream_mutex);
+    auto it = block_caches().find(s);
+    if (it != block_caches().end()) {
+      auto b = it->second.blocks.lower_bound(bytes);
+      if (b != it->second.blocks.end() && b->first <= bytes + bytes / 8 + 512) {
+        void* p   = b->second;
+        *capacity = b->first;
+        it->second.total -= b->first;
+        it->second.blocks.erase(b);
+        return p;
+      }
+    }
+  }
+  void* p       = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, bytes, s);
+  if (e != cudaSuccess) {  // give everything cached back and try once more
+    (void)cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(g_stream_mutex);
+      for (auto& kv : block_caches()) flush_cache_locked(kv.first, kv.second, live_streams().count(kv.first) != 0);
+    }
+    cudaDeviceSynchronize();
+    e = cudaMallocAsync(&p, bytes, s);
+  }
+  CUDA_TRY(e);
+  *capacity = bytes;
+  return p;
+}
+
+void block_free(void* p, size_t capacity, cudaStream_t s)
+{
+  std::lock_guard<std::mutex> lk(g_stream_mutex);
+  if (live_streams().count(s) == 0) {
+    cudaFree(p);
+    return;
+  }
+  block_cache_t& c = block_caches()[s];
+  if (c.total + capacity > kBlockCacheCap) flush_cache_locked(s, c, true);
+  if (capacity > kBlockCacheCap) {
+    cudaFreeAsync(p, s);
+    return;
+  }
+  c.blocks.emplace(capacity, p);
+  c.total += capacity;
+}
+
 bool stream_is_live(cudaStream_t s)
 {
   std::lock_guard<std::mutex> lk(g_stream_mutex);
@@ -28,6 +102,11 @@ void register_stream(cudaStream_t s)
 void unregister_stream(cudaStream_t s)
 {
   std::lock_guard<std::mutex> lk(g_stream_mutex);
+  auto it = block_caches().find(s);
+  if (it != block_caches().end()) {  // the caller synchronised the stream: the cached blocks are idle
+    flush_cache_locked(s, it->second, true);
+    block_caches().erase(it);
+  }
   live_streams().erase(s);
 }
 }  // namespace b200

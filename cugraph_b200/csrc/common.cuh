@@ -157,6 +157,14 @@ bool stream_is_live(cudaStream_t s);
 void register_stream(cudaStream_t s);
 void unregister_stream(cudaStream_t s);
 
+// Blocks behind dbuf (capi_basic.cu).  A freed block stays with its stream and serves the next request of (about) its
+// size on that stream — stream order makes that safe exactly like cudaFreeAsync / cudaMallocAsync — so that a repeated
+// workload (graph after graph of the same shape) makes no allocator calls at all: with the driver's pool alone identical
+// staging steps took between 20 ms and 1.8 s depending on what the pool had to map (profiles/r02_notes.md §5).  The cache of
+// a stream is bounded (32 GiB, then handed back to the pool) and is released when the stream's handle is destroyed.
+void* block_alloc(size_t bytes, cudaStream_t s, size_t* capacity);
+void block_free(void* p, size_t capacity, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------
 // stream-ordered owning device buffer (the rmm::device_buffer role)
 // ---------------------------------------------------------------------------------------------
@@ -165,7 +173,7 @@ class dbuf {
   dbuf() = default;
   dbuf(size_t bytes, cudaStream_t s) : bytes_(bytes), stream_(s)
   {
-    if (bytes_ > 0) { CUDA_TRY(cudaMallocAsync(&p_, bytes_, s)); }
+    if (bytes_ > 0) p_ = block_alloc(bytes_, s, &cap_);
   }
   dbuf(dbuf const&)            = delete;
   dbuf& operator=(dbuf const&) = delete;
@@ -181,19 +189,9 @@ class dbuf {
   ~dbuf() { release(); }
   void release()
   {
-    if (p_) {
-      if (stream_is_live(stream_)) cudaFreeAsync(p_, stream_);
-      else cudaFree(p_);
-    }
+    if (p_) block_free(p_, cap_, stream_);
     p_     = nullptr;
-    bytes_ = 0;
-  }
-  void* detach()
-  {
-    void* p = p_;
-    p_      = nullptr;
-    bytes_  = 0;
-    return p;
+    bytes_ = cap_ = 0;
   }
   void* data() const { return p_; }
   template <typename T>
@@ -209,10 +207,12 @@ class dbuf {
   {
     std::swap(p_, o.p_);
     std::swap(bytes_, o.bytes_);
+    std::swap(cap_, o.cap_);
     std::swap(stream_, o.stream_);
   }
   void* p_{nullptr};
   size_t bytes_{0};
+  size_t cap_{0};  // what the block really holds (a reused block may be a little larger than asked for)
   cudaStream_t stream_{nullptr};
 };
 

@@ -620,15 +620,16 @@ __global__ void k_select_window(O const* __restrict__ off, DA dist, int n, sssp_
   }
 }
 
-// Predecessors from the distance fixpoint.  A tree parent u of v has dist[v] == fl(dist[u] + w(u,v)); with dist[u] <
-// dist[v] any such u is valid and the parent pointers cannot form a cycle (distances strictly decrease along them).  Tight edges
-// between vertices at the SAME distance (zero-weight edges, or a weight absorbed by float rounding) are tight in both
-// directions: taking any of them could pair two vertices as each other's parents.  Inside such a plateau pass 1 only accepts
-// a parent with a smaller vertex id ((distance, id) decreases along every parent pointer: still no cycle); vertices that are
-// left without a parent (their only tight edges come from larger ids) are attached in extra passes, each to a tight
-// neighbour that already has a parent (or is the source), with a compare-and-swap from "none" — a vertex only ever gets a
-// parent that was attached before it, so the result is a tree (the reference records the predecessor at the relaxation that
-// set the distance, sssp_impl.cuh:43-73: also a tree).
+// Predecessors from the distance fixpoint (double weights, and float without the packed word).  A tree parent u of v has
+// dist[v] == fl(dist[u] + w(u,v)); with dist[u] < dist[v] any such u is valid and the parent pointers cannot form a cycle
+// (distances strictly decrease along them).  Tight edges between vertices at the SAME distance (zero-weight edges, or a
+// weight absorbed by rounding) are tight in both directions on a symmetric graph: pass 1 therefore only accepts strictly
+// closer parents.  Vertices left without a parent (their distance arrived over a same-distance edge) are attached in extra
+// passes, each to a tight same-distance neighbour that ALREADY has a parent (or is the source), with a compare-and-swap
+// from "none": a parent pointer is written once, so a vertex only ever points at a vertex attached before it, and a cycle —
+// which could only consist of same-distance edges — would need one that points at a later one.  (An id-ordered acceptance
+// inside a plateau in pass 1 looked like a shortcut and is wrong: x takes the smaller-id v in pass 1, the orphan v then finds
+// the "attached" x.)  The reference records the predecessor at the relaxation that set the distance, sssp_impl.cuh:43-73.
 template <typename O, typename T>
 __global__ void k_sssp_pred(O const* __restrict__ off, int32_t const* __restrict__ idx, T const* __restrict__ w,
                             T const* __restrict__ dist, int32_t n_vertices, int32_t source, T unreached,
@@ -642,7 +643,7 @@ __global__ void k_sssp_pred(O const* __restrict__ off, int32_t const* __restrict
     for (long long e = (long long)off[u] + lane; e < (long long)off[u + 1]; e += 32) {
       const int v = idx[e];
       const T dv  = dist[v];
-      if (v != source && v != (int)u && (du < dv || (du == dv && (int)u < v)) && du + w[e] == dv) pred[v] = (int32_t)u;
+      if (v != source && v != (int)u && du < dv && du + w[e] == dv) pred[v] = (int32_t)u;
     }
   }
 }
@@ -657,7 +658,7 @@ struct sssp_pred_op {
   __device__ __forceinline__ void edge(int src, long long e, int nbr) const
   {
     const T du = dist[src], dv = dist[nbr];
-    if (du != unreached && nbr != source && nbr != src && (du < dv || (du == dv && src < nbr)) && du + w[e] == dv) pred[nbr] = src;
+    if (du != unreached && nbr != source && nbr != src && du < dv && du + w[e] == dv) pred[nbr] = src;
   }
 };
 

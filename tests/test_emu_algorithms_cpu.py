@@ -145,7 +145,7 @@ def symmetric_edges(V, E, seed):
 
 def create_sym_graph(L, s, d, w):
     views = [L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, t) if a is not None else None
-             for a, t in ((s, INT32), (d, INT32), (w, FLOAT32))]
+             for a, t in ((s, INT32), (d, INT32), (w, 9 if (w is not None and w.dtype == np.float64) else FLOAT32))]  # 9 = FLOAT64
     g, err = C.c_void_p(), C.c_void_p()
     code = L.cugraph_graph_create_with_times_sg(
         C.c_void_p(L.handle), C.byref(Props(1, 1)), None, C.c_void_p(views[0]), C.c_void_p(views[1]),
@@ -231,9 +231,11 @@ def follow_to_source(verts, dist, pred, source, unreached):
             assert steps <= len(verts), f"predecessor cycle reached from vertex {int(v)}"
 
 
-def test_sssp_zero_weight_predecessors_emulated(emu):  # noqa: F811
+@pytest.mark.parametrize("wdtype", [np.float32, np.float64])
+def test_sssp_zero_weight_predecessors_emulated(emu, wdtype):  # noqa: F811
     """symmetric zero-weight edges and zero-weight cycles: the distance fixpoint alone cannot orient them (both directions of
-    the edge are tight), the predecessors must still form a tree rooted at the source"""
+    the edge are tight), the predecessors must still form a tree rooted at the source (float32: packed word at the relaxation,
+    float64: strict pass + tie passes)"""
     r = np.random.default_rng(3)
     V = 400
     half_s = r.integers(0, V, 1600).astype(np.int32)
@@ -244,16 +246,19 @@ def test_sssp_zero_weight_predecessors_emulated(emu):  # noqa: F811
     half_s = np.concatenate([half_s, np.array([e[0] for e in extra], np.int32)])
     half_d = np.concatenate([half_d, np.array([e[1] for e in extra], np.int32)])
     wh = np.concatenate([wh, np.array([e[2] for e in extra], np.float32)])
+    if wdtype == np.float64:
+        wh = wh.astype(np.float64)
+        wh[wh == 1e8] = 1e16
     s, d, w = np.concatenate([half_s, half_d]), np.concatenate([half_d, half_s]), np.concatenate([wh, wh])
     g = create_sym_graph(emu, s, d, w)
     ids, ss, dd = dense_ids(s, d)
     for source in (int(ids[0]), int(ids[7])):
         verts, dist, pred = _sssp_dist(emu, g, source)
-        ref_d, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=True)
-        got = np.zeros(ids.size, dtype=np.float32)
+        ref_d, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=(wdtype == np.float32))
+        got = np.zeros(ids.size, dtype=wdtype)
         got[np.searchsorted(ids, verts)] = dist
-        assert (got == ref_d.astype(np.float32)).all()
-        follow_to_source(verts, dist, pred, source, np.finfo(np.float32).max)
+        assert (got == ref_d.astype(wdtype)).all()
+        follow_to_source(verts, dist, pred, source, np.finfo(wdtype).max)
         assert oracle.check_sssp_predecessors(ss, dd, w, ids.size, ref_d, _scatter(ids, verts, pred), int(np.searchsorted(ids, source)))
     emu.cugraph_graph_free(g)
 

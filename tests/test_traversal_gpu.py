@@ -178,9 +178,11 @@ def test_sssp_random_vs_oracle(V, E, use_float):
     assert oracle.check_sssp_predecessors(s, d, w, V, got_d, by_vertex(verts, pred, V), 1)
 
 
-def test_sssp_zero_weight_predecessors_form_a_tree():
+@pytest.mark.parametrize("wdtype", [np.float32, np.float64])
+def test_sssp_zero_weight_predecessors_form_a_tree(wdtype):
     """symmetric zero-weight edges, a zero-weight cycle and a weight absorbed by float rounding: both directions of such
-    an edge are tight, the predecessors must still lead every reached vertex back to the source"""
+    an edge are tight, the predecessors must still lead every reached vertex back to the source.  float32 records the
+    predecessor at the relaxation (packed word), float64 derives it from the distance fixpoint (strict pass + tie passes)."""
     r = np.random.default_rng(3)
     V = 4000
     hs = r.integers(0, V, 16000).astype(np.int32)
@@ -190,15 +192,18 @@ def test_sssp_zero_weight_predecessors_form_a_tree():
     hs = np.concatenate([hs, np.array([e[0] for e in extra], np.int32)])
     hd = np.concatenate([hd, np.array([e[1] for e in extra], np.int32)])
     hw = np.concatenate([hw, np.array([e[2] for e in extra], np.float32)])
+    if wdtype == np.float64:  # 1e16 + 1 == 1e16 in double
+        hw = hw.astype(np.float64)
+        hw[hw == 1e8] = 1e16
     s, d, w = np.concatenate([hs, hd]), np.concatenate([hd, hs]), np.concatenate([hw, hw])
-    h, g = make_graph(s, d, w, symmetric=True, vertices=np.arange(V, dtype=np.int32))
+    h, g = make_graph(s, d, w, symmetric=True, vertices=np.arange(V, dtype=np.int32), weight_dtype=wdtype)
     for source in (0, 7):
         verts, dist, pred = _sssp(h, g, source)
-        ref_d, _ = oracle.sssp(s, d, w, V, source, use_float=True)
+        ref_d, _ = oracle.sssp(s, d, w, V, source, use_float=(wdtype == np.float32))
         got_d, got_p = by_vertex(verts, dist, V), by_vertex(verts, pred, V)
         assert np.array_equal(got_d.astype(np.float64), ref_d)
         assert oracle.check_sssp_predecessors(s, d, w, V, got_d.astype(np.float64), got_p, source)
-        unreached = np.finfo(np.float32).max
+        unreached = np.finfo(wdtype).max
         for v in range(V):
             if got_d[v] == unreached:
                 assert got_p[v] == -1
