@@ -99,6 +99,10 @@ struct comm_impl;
 struct tuning_t {
   long long sweep_min_edges{1ll << 22};  // CUGRAPH_B200_SWEEP_MIN_EDGES: graphs below it use the plain sweep (tests: 0)
   bool sweep_bank_order{true};           // CUGRAPH_B200_SWEEP_BANK_ORDER
+  // row-aligned groups of the piece stream (graph_build.cu, "window policy"): cost of a scattered piece, of a 16-bit id
+  // slot and of an aligned 32-row group, in 1/100 load/store-unit cycles; CUGRAPH_B200_SWEEP_ALIGN=0 switches them off
+  bool sweep_align{false};  // measured: +13 % sweep time with the policy on (profiles/r02_align_ab.log): the padding costs the load path more than the sectors save
+  int sweep_cost_scat{160}, sweep_cost_slot{10}, sweep_cost_group{800}, sweep_cost_lane{25};
   double bfs_alpha{40.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer switch points; alpha 14 -> 40: -7 % per source on RMAT-24, r02_notes)
   bool sssp_adaptive{true};                // CUGRAPH_B200_SSSP_ADAPTIVE
   double sssp_delta_scale{1.0};            // CUGRAPH_B200_SSSP_DELTA_SCALE
@@ -112,6 +116,11 @@ struct tuning_t {
     auto get = [](const char* k) { return std::getenv(k); };
     if (auto e = get("CUGRAPH_B200_SWEEP_MIN_EDGES")) t.sweep_min_edges = std::atoll(e);
     if (auto e = get("CUGRAPH_B200_SWEEP_BANK_ORDER")) t.sweep_bank_order = std::atoi(e) != 0;
+    if (auto e = get("CUGRAPH_B200_SWEEP_ALIGN")) t.sweep_align = std::atoi(e) != 0;
+    if (auto e = get("CUGRAPH_B200_SWEEP_COST_SCAT")) t.sweep_cost_scat = std::max(1, std::atoi(e));
+    if (auto e = get("CUGRAPH_B200_SWEEP_COST_SLOT")) t.sweep_cost_slot = std::max(0, std::atoi(e));
+    if (auto e = get("CUGRAPH_B200_SWEEP_COST_GROUP")) t.sweep_cost_group = std::max(0, std::atoi(e));
+    if (auto e = get("CUGRAPH_B200_SWEEP_COST_LANE")) t.sweep_cost_lane = std::max(0, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_BFS_ALPHA")) t.bfs_alpha = std::atof(e);
     if (auto e = get("CUGRAPH_B200_BFS_BETA")) t.bfs_beta = std::atof(e);
     if (auto e = get("CUGRAPH_B200_SSSP_ADAPTIVE")) t.sssp_adaptive = std::atoi(e) != 0;
