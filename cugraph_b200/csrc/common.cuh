@@ -102,11 +102,13 @@ struct tuning_t {
   // row-aligned groups of the piece stream (graph_build.cu, "window policy"): cost of a scattered piece, of a 16-bit id
   // slot and of an aligned 32-row group, in 1/100 load/store-unit cycles; CUGRAPH_B200_SWEEP_ALIGN=0 switches them off
   bool sweep_align{false};  // measured: +13 % sweep time with the policy on (profiles/r02_align_ab.log): the padding costs the load path more than the sectors save
+  int sweep_finish_steps{8};  // CUGRAPH_B200_SWEEP_FINISH_STEPS: 2, 4 or 8 (64-row steps per warp of the finish kernel)
   int sweep_cost_scat{160}, sweep_cost_slot{10}, sweep_cost_group{800}, sweep_cost_lane{25};
   double bfs_alpha{40.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer switch points; alpha 14 -> 40: -7 % per source on RMAT-24, r02_notes)
   bool sssp_adaptive{true};                // CUGRAPH_B200_SSSP_ADAPTIVE
   double sssp_delta_scale{1.0};            // CUGRAPH_B200_SSSP_DELTA_SCALE
   double sssp_start_div{64.0};             // CUGRAPH_B200_SSSP_START_DIV: the controller starts with delta / this
+  bool sssp_small_rounds{true};            // CUGRAPH_B200_SSSP_SMALL_ROUNDS: small near queues are relaxed round after round by one CTA
   int sssp_split_rounds{1};                // CUGRAPH_B200_SSSP_SPLIT_ROUNDS
   unsigned long long sssp_split_min_edges{1ull << 20};  // CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES
   bool bfs_trace{false}, sssp_trace{false}, build_trace{false};  // CUGRAPH_B200_{BFS,SSSP,BUILD}_TRACE
@@ -117,6 +119,7 @@ struct tuning_t {
     if (auto e = get("CUGRAPH_B200_SWEEP_MIN_EDGES")) t.sweep_min_edges = std::atoll(e);
     if (auto e = get("CUGRAPH_B200_SWEEP_BANK_ORDER")) t.sweep_bank_order = std::atoi(e) != 0;
     if (auto e = get("CUGRAPH_B200_SWEEP_ALIGN")) t.sweep_align = std::atoi(e) != 0;
+    if (auto e = get("CUGRAPH_B200_SWEEP_FINISH_STEPS")) { const int v = std::atoi(e); t.sweep_finish_steps = (v == 2 || v == 4) ? v : 8; }
     if (auto e = get("CUGRAPH_B200_SWEEP_COST_SCAT")) t.sweep_cost_scat = std::max(1, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_SWEEP_COST_SLOT")) t.sweep_cost_slot = std::max(0, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_SWEEP_COST_GROUP")) t.sweep_cost_group = std::max(0, std::atoi(e));
@@ -126,6 +129,7 @@ struct tuning_t {
     if (auto e = get("CUGRAPH_B200_SSSP_ADAPTIVE")) t.sssp_adaptive = std::atoi(e) != 0;
     if (auto e = get("CUGRAPH_B200_SSSP_DELTA_SCALE")) t.sssp_delta_scale = std::atof(e);
     if (auto e = get("CUGRAPH_B200_SSSP_START_DIV")) t.sssp_start_div = std::max(1.0, std::atof(e));
+    if (auto e = get("CUGRAPH_B200_SSSP_SMALL_ROUNDS")) t.sssp_small_rounds = std::atoi(e) != 0;
     if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_ROUNDS")) t.sssp_split_rounds = std::max(1, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) t.sssp_split_min_edges = std::strtoull(e, nullptr, 10);
     t.bfs_trace   = get("CUGRAPH_B200_BFS_TRACE") != nullptr;

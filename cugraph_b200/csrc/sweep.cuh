@@ -547,8 +547,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_sweep(sweep_args_t<T> a)
 // accumulators and one 256-byte store of y per warp (lane = two rows), all four loads issued before the first use.
 // (Eight CONSECUTIVE rows per thread looked the same on paper and ran at 2.3 TB/s: every warp-wide 128-bit access then
 // touched sixteen 128-byte lines for a quarter of their bytes.)
-constexpr int kFinishSteps = 4;
-template <typename T>
+template <typename T, int kFinishSteps>
 __global__ void __launch_bounds__(256)
 k_sweep_finish(double* __restrict__ acc, int n_cov, int n_rows, T* __restrict__ y, int32_t const* __restrict__ row_vertex,
                double alpha, int* __restrict__ cursor, int n_phases, pr_state_t const* __restrict__ st)
@@ -607,9 +606,18 @@ void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L,
   a.W         = L.W;
   if (weighted) B200_LAUNCH(h, (k_sweep<T, true>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
   else B200_LAUNCH(h, (k_sweep<T, false>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
-  const int n = std::max((c.n_rows + 2 * kFinishSteps - 1) / (2 * kFinishSteps), L.n_phases);  // threads: 8 rows each
-  B200_LAUNCH(h, (k_sweep_finish<T>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
-              L.cursor.as<int>(), L.n_phases, st);
+  // 64-row steps per warp: 8 measured 0.335 ms per sweep, 4: 0.340, 2: 0.354 (profiles/r02_fullchunk_ab.log)
+  const int fs = h.tune.sweep_finish_steps;
+  const int n  = std::max((c.n_rows + 2 * fs - 1) / (2 * fs), L.n_phases);  // threads: 2 * fs rows each
+  if (fs == 2)
+    B200_LAUNCH(h, (k_sweep_finish<T, 2>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
+                L.cursor.as<int>(), L.n_phases, st);
+  else if (fs == 4)
+    B200_LAUNCH(h, (k_sweep_finish<T, 4>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
+                L.cursor.as<int>(), L.n_phases, st);
+  else
+    B200_LAUNCH(h, (k_sweep_finish<T, 8>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
+                L.cursor.as<int>(), L.n_phases, st);
 }
 
 // dispatch: the piece stream when it exists for this graph, else the plain edge-balanced sweep

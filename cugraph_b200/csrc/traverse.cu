@@ -40,6 +40,7 @@ struct frontier_counters_t {
   int n_far;                // unused (kept for the layout)
   int n_conv;               // bitmap -> queue conversion cursor
   unsigned long long m_f;   // sum of degrees of the vertices appended (direction-optimising heuristic)
+  unsigned long long packed;  // SSSP with 32-bit offsets: (sum of degrees << 32) | entries appended — ONE atomic per append
 };
 
 // ------------------------------------------------------------------------------------------
@@ -243,6 +244,41 @@ __device__ __forceinline__ unsigned enqueue_with_degree(O const* off, int v, int
   q[pos]           = v;
   q_deg[pos]       = (int32_t)d;
   return d;
+}
+
+// SSSP flavour: count and degree sum advance with one warp-aggregated 64-bit atomic (every append of a round hits the same
+// address; two atomics per append were two serialised streams at the L2).  With 64-bit offsets the degree sum of a round may
+// pass 2^32: the two separate counters are kept there.
+template <typename O>
+__device__ __forceinline__ void enqueue_counted(O const* off, int v, int32_t* q, int32_t* q_deg, frontier_counters_t* cnt)
+{
+  if (sizeof(O) == 8) {
+    const unsigned d = enqueue_with_degree(off, v, q, q_deg, cnt);
+    warp_add_u64(&cnt->m_f, d);
+    return;
+  }
+  const unsigned d    = (unsigned)((long long)off[v + 1] - (long long)off[v]);
+  const unsigned mask = __activemask();
+  const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+  const unsigned sum = __reduce_add_sync(mask, d);
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(&cnt->packed, ((unsigned long long)sum << 32) | (unsigned)__popc(mask));
+  base          = __shfl_sync(mask, base, leader);
+  const int pos = (int)(unsigned)(base & 0xffffffffull) + __popc(mask & ((1u << lane) - 1u));
+  q[pos]        = v;
+  q_deg[pos]    = (int32_t)d;
+}
+// what the host reads back after a round (pinned copy of the counters)
+template <typename O>
+inline void read_counters(frontier_counters_t const* hc, int& n, unsigned long long& edges)
+{
+  if (sizeof(O) == 8) {
+    n     = hc->n_small;
+    edges = hc->m_f;
+  } else {
+    n     = (int)(unsigned)(hc->packed & 0xffffffffull);
+    edges = hc->packed >> 32;
+  }
 }
 
 template <typename O>
@@ -483,6 +519,7 @@ template <typename T>
 struct dist_plain {
   T* d;
   __device__ __forceinline__ T get(int v) const { return d[v]; }
+  __device__ __forceinline__ T get_fresh(int v) const { return *reinterpret_cast<volatile T const*>(d + v); }  // not through a stale L1 line
   __device__ __forceinline__ bool improve(int v, T nd, int) const { return nd < atomic_min_nonneg(d + v, nd); }
   __device__ __forceinline__ void set_source(int v) const { d[v] = (T)0; }
 };
@@ -493,6 +530,10 @@ struct dist_packed {
     return ((unsigned long long)dist_bits << 32) | (unsigned)pred;
   }
   __device__ __forceinline__ float get(int v) const { return __uint_as_float((unsigned)(p[v] >> 32)); }
+  __device__ __forceinline__ float get_fresh(int v) const
+  {
+    return __uint_as_float((unsigned)(*reinterpret_cast<volatile unsigned long long const*>(p + v) >> 32));
+  }
   // STRICT improvement only (compare-and-swap loop): with a plain 64-bit atomicMin a relaxation at an EQUAL distance and a
   // smaller source id would replace the predecessor; the pre-check that should prevent it reads through L1, which is not
   // coherent with the other SMs' atomics, and on hardware that produced predecessor cycles inside zero-weight cycles.
@@ -538,13 +579,118 @@ struct sssp_relax_op {
     if (!(nd < dist.get(nbr)) || !(nd < cutoff)) return;
     if (!dist.improve(nbr, nd, src)) return;
     if (nd < threshold) {
-      if (atomicExch(stamp + nbr, round) != round) {
-        const unsigned d = enqueue_with_degree(off, nbr, next_near, next_near_deg, cnt);
-        warp_add_u64(&cnt->m_f, d);
-      }
+      if (atomicExch(stamp + nbr, round) != round) enqueue_counted(off, nbr, next_near, next_near_deg, cnt);
     }
   }
 };
+
+// ---- rounds with a SMALL near queue run inside ONE CTA, round after round, without the host: on RMAT-24 two thirds of the
+// ~208 rounds of a traversal relax fewer than 16 K edges, and each cost ~45 us of launches (scan, tile owners, advance) plus a
+// read-back.  The CTA scans the degrees of the queue (<= kSmallVerts entries) in shared memory, strides over the edges
+// (owner by binary search in the scan), relaxes them exactly like sssp_relax_op and appends to the other queue through a
+// shared-memory counter; it stops when the window's queue is empty, outgrows the limits or max_rounds is reached, and leaves
+// the state for the host.  Distances are read with volatile loads: within one kernel the L1 may hold the value from before
+// another thread's atomic improved it — relaxing from a stale (larger) distance would lose the improvement for good.
+constexpr int kSmallVerts   = 2048;
+constexpr int kSmallEdges   = 16384;
+constexpr int kSmallThreads = 1024;
+struct sssp_small_state_t {
+  int n;                     // entries of the queue that is current on exit
+  int round;                 // last round number used
+  int rounds_done;
+  int cur;                   // 0: the current queue is the one passed as `qa`, 1: `qb`
+  unsigned long long edges;  // degree sum of the current queue
+  unsigned long long relaxed;  // edges relaxed by this call (trace)
+};
+
+template <typename O, typename T, typename DA>
+__global__ void __launch_bounds__(kSmallThreads)
+k_sssp_small_rounds(O const* __restrict__ off, int32_t const* __restrict__ idx, T const* __restrict__ w, DA dist, int32_t* stamp,
+                    int32_t* qa, int32_t* la, int32_t* qb, int32_t* lb, int n0, int round0, T threshold, T cutoff, int max_rounds,
+                    sssp_small_state_t* __restrict__ out)
+{
+  __shared__ int s_scan[kSmallVerts + 1];
+  __shared__ int s_warp[kSmallThreads / 32];
+  __shared__ unsigned long long s_next;  // (degree sum << 32) | entries of the next queue
+  constexpr int kPer = kSmallVerts / kSmallThreads;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t *q = qa, *l = la, *nq = qb, *nl = lb;
+  int n = n0, round = round0, done = 0, cur = 0;
+  unsigned long long edges = 0, relaxed = 0;
+  while (true) {
+    // exclusive scan of the queue's degrees
+    int d[kPer], mine = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = threadIdx.x * kPer + j;
+      d[j]        = i < n ? l[i] : 0;
+      mine += d[j];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    if (threadIdx.x == 0) s_next = 0ull;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < kSmallThreads / 32; ++k) {
+      const int c = s_warp[k];
+      if (k < wid) before += c;
+      total += c;
+    }
+    int run = before + incl - mine;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = threadIdx.x * kPer + j;
+      if (i <= n) s_scan[i] = run;
+      run += d[j];
+    }
+    if (threadIdx.x == 0) s_scan[n] = total;  // n <= kSmallVerts: the slot exists
+    __syncthreads();
+    ++round;
+    relaxed += (unsigned long long)total;
+    for (int e = threadIdx.x; e < total; e += kSmallThreads) {
+      int lo = 0, hi = n;  // last k with s_scan[k] <= e
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_scan[mid] <= e) lo = mid; else hi = mid;
+      }
+      const int v         = q[lo];
+      const long long pos = (long long)off[v] + (e - s_scan[lo]);
+      const int nbr       = idx[pos];
+      const T nd          = dist.get_fresh(v) + w[pos];
+      if (!(nd < dist.get_fresh(nbr)) || !(nd < cutoff)) continue;
+      if (!dist.improve(nbr, nd, v)) continue;
+      if (nd < threshold && atomicExch(stamp + nbr, round) != round) {
+        const unsigned dg = (unsigned)((long long)off[nbr + 1] - (long long)off[nbr]);
+        const int p       = (int)(unsigned)(atomicAdd(&s_next, ((unsigned long long)dg << 32) | 1ull) & 0xffffffffull);
+        nq[p]             = nbr;
+        nl[p]             = (int32_t)dg;
+      }
+    }
+    __syncthreads();
+    const unsigned long long nx = s_next;
+    n     = (int)(unsigned)(nx & 0xffffffffull);
+    edges = nx >> 32;
+    ++done;
+    cur ^= 1;
+    int32_t* t = q; q = nq; nq = t;
+    t = l; l = nl; nl = t;
+    __syncthreads();  // everybody has read s_next before thread 0 clears it
+    if (n == 0 || n > kSmallVerts || edges > (unsigned long long)kSmallEdges || done >= max_rounds) break;
+  }
+  if (threadIdx.x == 0) {
+    out->n           = n;
+    out->round       = round;
+    out->rounds_done = done;
+    out->cur         = cur;
+    out->edges       = edges;
+    out->relaxed     = relaxed;
+  }
+}
 
 // mid-window split: keep the queue entries below the new bound (the others are found again by the window selection)
 template <typename O, typename T, typename DA>
@@ -556,9 +702,8 @@ __global__ void k_split_near(O const* __restrict__ off, int32_t const* __restric
   if (i >= n) return;
   const int v = q_in[i];
   if (dist.get(v) < hi) {
-    stamp[v]         = round;
-    const unsigned d = enqueue_with_degree(off, v, near_out, near_deg_out, cnt);
-    warp_add_u64(&cnt->m_f, d);
+    stamp[v] = round;
+    enqueue_counted(off, v, near_out, near_deg_out, cnt);
   }
 }
 
@@ -603,20 +748,92 @@ __global__ void k_next_window(T const* __restrict__ pending_min, T delta, sssp_w
   win->any = 1;
 }
 
-// dense pass 2: the vertices of the window [lo, hi) form the next near queue
+// dense pass 2: the vertices of the window [lo, hi) form the next near queue.  Block-level compaction: a CTA looks at 2048
+// consecutive vertices per step and reserves queue space with ONE atomic (the per-warp appends of the first version were
+// up to 275 K atomics on one address per window: 139 us per pass, 9.5 ms of a 31 ms traversal on RMAT-24).
+constexpr int kSelectPer = 8;  // vertices per thread and step
 template <typename O, typename T, typename DA>
-__global__ void k_select_window(O const* __restrict__ off, DA dist, int n, sssp_window_t<T> const* __restrict__ win, int32_t* stamp,
-                                int round, int32_t* near_out, int32_t* near_deg_out, frontier_counters_t* cnt)
+__global__ void __launch_bounds__(kBlock)
+k_select_window(O const* __restrict__ off, DA dist, int n, sssp_window_t<T> const* __restrict__ win, int32_t* stamp,
+                int round, int32_t* near_out, int32_t* near_deg_out, frontier_counters_t* cnt)
 {
   if (!win->any) return;
+  __shared__ int s_warp[kBlock / 32];
+  __shared__ long long s_base;
   const T lo = win->lo, hi = win->hi;
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
-    const T d = dist.get(v);
-    if (d >= lo && d < hi) {
-      stamp[v]          = round;
-      const unsigned dg = enqueue_with_degree(off, v, near_out, near_deg_out, cnt);
-      warp_add_u64(&cnt->m_f, dg);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (long long base = (long long)blockIdx.x * (kBlock * kSelectPer); base < n; base += (long long)gridDim.x * (kBlock * kSelectPer)) {
+    unsigned sel = 0;
+    int mine     = 0;
+#pragma unroll
+    for (int k = 0; k < kSelectPer; ++k) {
+      const long long v = base + k * kBlock + threadIdx.x;
+      if (v < n) {
+        const T d = dist.get((int)v);
+        if (d >= lo && d < hi) {
+          sel |= 1u << k;
+          ++mine;
+        }
+      }
     }
+    int incl = mine;  // inclusive scan over the CTA
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) {
+      const int c = s_warp[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    if (total > 0) {  // CTA-uniform
+      unsigned long long dsum = 0;
+      // degrees first: the reservation carries their sum
+      int32_t dg[kSelectPer];
+#pragma unroll
+      for (int k = 0; k < kSelectPer; ++k) {
+        dg[k] = 0;
+        if (sel & (1u << k)) {
+          const long long v = base + k * kBlock + threadIdx.x;
+          dg[k]             = (int32_t)((long long)off[v + 1] - (long long)off[v]);
+          dsum += (unsigned)dg[k];
+        }
+      }
+      unsigned long long wsum = dsum;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+      __shared__ unsigned long long s_deg[kBlock / 32];
+      if (lane == 0) s_deg[wid] = wsum;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long ds = 0;
+        for (int w = 0; w < kBlock / 32; ++w) ds += s_deg[w];
+        if (sizeof(O) == 8) {
+          s_base = atomicAdd(&cnt->n_small, total);
+          atomicAdd(&cnt->m_f, ds);
+        } else {
+          s_base = (long long)(atomicAdd(&cnt->packed, (ds << 32) | (unsigned)total) & 0xffffffffull);
+        }
+      }
+      __syncthreads();
+      int pos = (int)s_base + before + incl - mine;
+#pragma unroll
+      for (int k = 0; k < kSelectPer; ++k) {
+        if (sel & (1u << k)) {
+          const int v       = (int)(base + k * kBlock + threadIdx.x);
+          stamp[v]          = round;
+          near_out[pos]     = v;
+          near_deg_out[pos] = dg[k];
+          ++pos;
+        }
+      }
+    }
+    __syncthreads();  // s_warp / s_base are reused by the next step
   }
 }
 
@@ -779,6 +996,10 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
   T* hmin_pinned          = reinterpret_cast<T*>(reinterpret_cast<char*>(h.pinned) + 256);
   auto* hwin              = reinterpret_cast<sssp_window_t<T>*>(reinterpret_cast<char*>(h.pinned) + 320);
   dbuf dwin               = make_dbuf<sssp_window_t<T>>(1, h.stream);
+  auto* hsmall            = reinterpret_cast<sssp_small_state_t*>(reinterpret_cast<char*>(h.pinned) + 384);
+  dbuf dsmall             = make_dbuf<sssp_small_state_t>(1, h.stream);
+  const bool small_rounds = h.tune.sssp_small_rounds;
+  int tr_small            = 0;
   int32_t *near = qa.as<int32_t>(), *next_near = qb.as<int32_t>();
   int32_t *near_deg = la.as<int32_t>(), *next_near_deg = lb.as<int32_t>();  // degrees of the queue entries
   int n_near = 1, round = 1, window = 1;
@@ -800,6 +1021,25 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
   while (true) {
     int window_rounds = 0;
     while (n_near > 0) {
+      if (small_rounds && sizeof(O) == 4 && n_near <= kSmallVerts && near_edges <= (unsigned long long)kSmallEdges) {
+        // the tail of the window: rounds on the device until the queue is empty or grows past one CTA's reach
+        B200_LAUNCH(h, (k_sssp_small_rounds<O, T, DA>), 1, kSmallThreads, 0, off, idx, w, dist, stamp.as<int32_t>(), near, near_deg,
+                    next_near, next_near_deg, n_near, round, hi, cutoff, 256, dsmall.as<sssp_small_state_t>());
+        CUDA_TRY(cudaMemcpyAsync(hsmall, dsmall.data(), sizeof(sssp_small_state_t), cudaMemcpyDeviceToHost, h.stream));
+        sync(h);
+        n_near     = hsmall->n;
+        near_edges = hsmall->edges;
+        round      = hsmall->round;
+        window_rounds += hsmall->rounds_done;
+        tr_rounds += hsmall->rounds_done;
+        tr_edges += hsmall->relaxed;
+        ++tr_small;
+        if (hsmall->cur) {
+          std::swap(near, next_near);
+          std::swap(near_deg, next_near_deg);
+        }
+        continue;
+      }
       ++round;
       ++tr_rounds;
       ++window_rounds;
@@ -809,8 +1049,7 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
       advance<O>(h, adv, off, idx, near, n_near, near_edges, op, near_deg);
       CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
       sync(h);
-      n_near     = hc->n_small;
-      near_edges = hc->m_f;
+      read_counters<O>(hc, n_near, near_edges);
       std::swap(near, next_near);
       std::swap(near_deg, next_near_deg);
       // A window that is still busy after `split_rounds` rounds is too wide for this stretch of the graph (the hub core
@@ -827,8 +1066,7 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
                       round, next_near, next_near_deg, dc);
           CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
           sync(h);
-          n_near     = hc->n_small;
-          near_edges = hc->m_f;
+          read_counters<O>(hc, n_near, near_edges);
           std::swap(near, next_near);
           std::swap(near_deg, next_near_deg);
           hi = nhi;
@@ -839,8 +1077,8 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
       }
     }
     if (trace)
-      std::fprintf(stderr, "sssp window %d hi=%g width %g: %d rounds, rounds so far %d, edges relaxed so far %llu, splits so far %d\n",
-                   window, (double)hi, (double)delta, window_rounds, tr_rounds, tr_edges, tr_splits);
+      std::fprintf(stderr, "sssp window %d hi=%g width %g: %d rounds, rounds so far %d (single-CTA calls %d), edges relaxed so far %llu, splits so far %d\n",
+                   window, (double)hi, (double)delta, window_rounds, tr_rounds, tr_small, tr_edges, tr_splits);
     if (adaptive) {
       if (window_rounds <= 2) { if (delta < std::numeric_limits<T>::max() / (T)4) delta = delta * (T)2; }
       else if (window_rounds >= 6 && delta > delta_floor) delta = delta / (T)2;
@@ -857,7 +1095,7 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
     ++round;
     ++window;
     CUDA_TRY(cudaMemsetAsync(cnt.data(), 0, sizeof(frontier_counters_t), h.stream));
-    B200_LAUNCH(h, (k_select_window<O, T, DA>), grid_for(nv), kBlock, 0, off, dist, nv, dwin.as<sssp_window_t<T>>(),
+    B200_LAUNCH(h, (k_select_window<O, T, DA>), std::min(grid_for((nv + kSelectPer - 1) / kSelectPer), h.sm_count * 8), kBlock, 0, off, dist, nv, dwin.as<sssp_window_t<T>>(),
                 stamp.as<int32_t>(), round, near, near_deg, dc);
     CUDA_TRY(cudaMemcpyAsync(hc, cnt.data(), sizeof(frontier_counters_t), cudaMemcpyDeviceToHost, h.stream));
     CUDA_TRY(cudaMemcpyAsync(hwin, dwin.data(), sizeof(sssp_window_t<T>), cudaMemcpyDeviceToHost, h.stream));
@@ -865,8 +1103,7 @@ void sssp_windows(handle_impl const& h, csx_t const& c, int32_t nv, int32_t sour
     if (!hwin->any) break;  // nothing pending: done
     lo = hwin->lo;
     hi = hwin->hi;
-    n_near     = hc->n_small;
-    near_edges = hc->m_f;
+    read_counters<O>(hc, n_near, near_edges);
   }
   check_last("sssp");
 }

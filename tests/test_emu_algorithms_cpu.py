@@ -309,6 +309,37 @@ def test_sssp_window_control_emulated(emu, monkeypatch, capfd, weights):  # noqa
     emu.cugraph_graph_free(g)
 
 
+def test_sssp_single_cta_rounds_emulated(emu, monkeypatch, capfd):  # noqa: F811
+    """small near queues are relaxed round after round inside one CTA (k_sssp_small_rounds): same distances, valid predecessors,
+    and the path is really taken"""
+    s, d = symmetric_edges(6_000, 40_000, seed=11)
+    r = np.random.default_rng(2)
+    wh = r.random(s.size // 2).astype(np.float32)
+    w = np.concatenate([wh, wh])
+    g = create_sym_graph(emu, s, d, w)
+    ids, ss, dd = dense_ids(s, d)
+    source = int(ids[1])
+    ref_d, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=True)
+    calls = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CUGRAPH_B200_SSSP_SMALL_ROUNDS", mode)
+        monkeypatch.setenv("CUGRAPH_B200_SSSP_TRACE", "1")
+        emu.emu_reload_tuning(C.c_void_p(emu.handle))
+        capfd.readouterr()
+        verts, dist, pred = _sssp_dist(emu, g, source)
+        trace = capfd.readouterr().err
+        got = np.zeros(ids.size, dtype=np.float32)
+        got[np.searchsorted(ids, verts)] = dist
+        assert (got == ref_d.astype(np.float32)).all(), mode
+        last = [ln for ln in trace.splitlines() if ln.startswith("sssp window")][-1]
+        calls[mode] = int(last.split("single-CTA calls")[1].split(")")[0])
+    assert calls["1"] > 0 and calls["0"] == 0, calls
+    monkeypatch.delenv("CUGRAPH_B200_SSSP_SMALL_ROUNDS")
+    monkeypatch.delenv("CUGRAPH_B200_SSSP_TRACE")
+    emu.emu_reload_tuning(C.c_void_p(emu.handle))
+    emu.cugraph_graph_free(g)
+
+
 def test_smoke_equivalent_emulated(emu):  # noqa: F811
     """the sequence of __graft_entry__.smoke() (RMAT-12, vertices_array with isolated vertices, PageRank + BFS + SSSP)"""
     from oracle.rmat import rmat_edgelist
