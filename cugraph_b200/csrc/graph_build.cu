@@ -1247,6 +1247,46 @@ k_window_emit(int32_t const* __restrict__ run_start, int32_t n_runs, int32_t con
   }
 }
 
+// ---- without the window policy (the default): one thread per segment, no window sort
+template <typename O>
+__global__ void k_seg_count_plain(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz, O const* __restrict__ off,
+                                  int32_t n_cov, int32_t* __restrict__ seg_row, int32_t* __restrict__ seg_pieces)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_segs) return;
+  if (k == n_segs) {
+    seg_pieces[k] = 0;
+    return;
+  }
+  const long long start = head_pos[k];
+  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz;
+  int lo = 0, hi = n_cov;  // last row r with off[r] <= start
+  while (hi - lo > 1) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((long long)off[mid] <= start) lo = mid; else hi = mid;
+  }
+  seg_row[k]    = lo;
+  seg_pieces[k] = (int)((end - start + kHotPieceEntries - 1) / kHotPieceEntries);
+}
+
+__global__ void k_seg_emit_plain(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz, int32_t const* __restrict__ idx,
+                                 int W, int32_t const* __restrict__ seg_row, int32_t const* __restrict__ piece_off,
+                                 uint32_t* __restrict__ piece_key, int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
+                                 int32_t* __restrict__ piece_row)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_segs) return;
+  const long long start = head_pos[k];
+  const long long end   = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz;
+  const int b           = idx[start] / W;
+  const int row         = seg_row[k];
+  int p                 = piece_off[k];
+  for (long long s = start; s < end; s += kHotPieceEntries, ++p) {
+    const int len = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
+    put_piece(piece_key, piece_start, piece_len, piece_row, p, b, piece_kind(len), true, (int)s, len, row);
+  }
+}
+
 __global__ void k_hot_class_starts(uint32_t const* __restrict__ sorted_key, int32_t n_pieces, int n_keys,
                                    int32_t* __restrict__ class_start)
 {
@@ -1537,12 +1577,29 @@ std::unique_ptr<sweep_layout_t> build_sweep_layout(handle_impl const& h, csx_t c
   const int32_t n_segs = (int32_t)n_segs64;
   tr.mark("sweep layout: segment heads");
 
+  dbuf seg_row = make_dbuf<int32_t>(n_segs, h.stream);
+  dbuf piece_key, piece_key2, piece_start, piece_len, piece_row;
+  int32_t n_pieces = 0;
+  int32_t n_runs   = 0;
+  if (!h.tune.sweep_align) {
+    // 2+3 (default). every piece on its own: one thread per segment
+    dbuf seg_pieces = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream), piece_off = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
+    B200_LAUNCH(h, (k_seg_count_plain<O>), grid_for((int64_t)n_segs + 1), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz,
+                c.offsets.as<O>(), n_cov, seg_row.as<int32_t>(), seg_pieces.as<int32_t>());
+    exclusive_scan_i32(h, seg_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_segs + 1);
+    CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_segs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    piece_key = make_dbuf<uint32_t>(n_pieces, h.stream); piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
+    piece_start = make_dbuf<int32_t>(n_pieces, h.stream); piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
+    piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
+    B200_LAUNCH(h, k_seg_emit_plain, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W,
+                seg_row.as<int32_t>(), piece_off.as<int32_t>(), piece_key.as<uint32_t>(), piece_start.as<int32_t>(),
+                piece_len.as<int32_t>(), piece_row.as<int32_t>());
+  } else {
   // 2. runs = the segments of one (block, 32-row window), found by sorting the segments by their window key
   const long long n_win = ((long long)n_cov + 31) / 32;
-  dbuf seg_row = make_dbuf<int32_t>(n_segs, h.stream);
   dbuf seg_perm2 = make_dbuf<uint32_t>(n_segs, h.stream);
   dbuf run_start;
-  int32_t n_runs = 0;
   {
     dbuf seg_key = make_dbuf<uint64_t>(n_segs, h.stream), seg_key2 = make_dbuf<uint64_t>(n_segs, h.stream);
     dbuf seg_perm = make_dbuf<uint32_t>(n_segs, h.stream);
@@ -1579,22 +1636,19 @@ std::unique_ptr<sweep_layout_t> build_sweep_layout(handle_impl const& h, csx_t c
     if (tot >= (1ll << 31) - 64) return nullptr;  // 32-bit piece numbers
   }
   exclusive_scan_i32(h, run_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_runs + 1);
-  int32_t n_pieces = 0;
   CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_runs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
   sync(h);
   run_pieces.release();
-  L->n_pieces = n_pieces;
-  dbuf piece_key = make_dbuf<uint32_t>(n_pieces, h.stream), piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
-  dbuf piece_start = make_dbuf<int32_t>(n_pieces, h.stream), piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
-  dbuf piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
+  piece_key = make_dbuf<uint32_t>(n_pieces, h.stream); piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
+  piece_start = make_dbuf<int32_t>(n_pieces, h.stream); piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
+  piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
   B200_LAUNCH(h, k_window_emit, run_grid, 256, 0, run_start.as<int32_t>(), n_runs, seg_perm2.as<int32_t>(), head_pos.as<int32_t>(),
               seg_row.as<int32_t>(), n_segs, (long long)nnz, idx, W, pol, piece_off.as<int32_t>(), piece_key.as<uint32_t>(),
               piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>());
+  }
+  L->n_pieces = n_pieces;
   head_pos.release();
   seg_row.release();
-  seg_perm2.release();
-  run_start.release();
-  piece_off.release();
   tr.mark("sweep layout: pieces");
 
   const int n_keys = B * kNumKinds;
