@@ -27,6 +27,11 @@ def _sig(fn, res, args):
     fn.argtypes = args
 
 
+def emulated():
+    """True when the CPU emulation build of the library is loaded (tests/emu_py.py): test infrastructure only"""
+    return os.path.basename(LIB_PATH).startswith("libcugraph_c_emu")
+
+
 def lib():
     """Load libcugraph_c.so (fails loudly: there is no CPU fallback)."""
     global _lib
@@ -108,6 +113,7 @@ def lib():
     _sig(L.cugraph_b200_block_free, None, [vp])
     _sig(L.cugraph_b200_block_span, sz, [vp])
     _sig(L.cugraph_b200_block_pull_sweep, i32, [vp, vp, vp, vp, dbl, pvp])
+    _sig(L.cugraph_b200_block_bfs_pull, i32, [vp, vp, vp, vp, sz, i32, i32, vp, pvp])
     _sig(L.cugraph_b200_pagerank_vertex_step, i32, [vp, vp, vp, vp, vp, sz, dbl, dbl, i32, vp, vp, pvp])
     _lib = L
     return L

@@ -67,6 +67,80 @@ k_mg_vertex_step(T const* __restrict__ y, T* __restrict__ pr, T const* __restric
   }
 }
 
+
+// ---- one level of multi-GPU BFS on this GPU's edge block, pull direction (the MG form of k_bfs_bottomup, traverse.cu;
+// reference: the bottom-up step of bfs_impl.cuh:593-869 on an edge partition, with the frontier arriving through
+// fill_edge_dst_property-style broadcasts, fill_edge_src_dst_property.cuh:1368).  The block stores its edges by destination
+// slot (rows) with the source slots as neighbours (columns, ascending).  frontier[col] / visited[row] are byte flags over
+// the block's column / row slots (the launcher all-gathers them inside the column / row group); every unvisited row scans
+// its sources until it meets one in the frontier and reports it as cand[row] = GLOBAL code of that source
+// ((owner rank) * maxpart + local id, owner rank = (col / maxpart) * grid_cols + grid_c), else -1.  Rows of degree >= 32
+// (the prefix of the degree-ordered physical rows) take a warp each with a ballot early exit, the others a thread each.
+template <typename O>
+__global__ void __launch_bounds__(256)
+k_block_bfs_pull_hi(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ row_vertex, int32_t n_hi,
+                    uint8_t const* __restrict__ frontier, uint8_t const* __restrict__ visited, long long maxpart, int grid_cols,
+                    int grid_c, long long* __restrict__ cand)
+{
+  const int lane = threadIdx.x & 31;
+  for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < n_hi; r += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int slot = row_vertex ? row_vertex[r] : (int)r;
+    if (visited[slot]) continue;
+    const long long e1 = (long long)off[r + 1];
+    int found          = -1;
+    for (long long e = (long long)off[r] + lane; __any_sync(0xffffffffu, e < e1); e += 32) {
+      const int col = e < e1 ? idx[e] : -1;
+      const bool hit = col >= 0 && frontier[col] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        found = __shfl_sync(0xffffffffu, col, __ffs((int)m) - 1);
+        break;
+      }
+    }
+    if (lane == 0 && found >= 0) cand[slot] = ((long long)(found / maxpart) * grid_cols + grid_c) * maxpart + (found % maxpart);
+  }
+}
+
+template <typename O>
+__global__ void __launch_bounds__(256)
+k_block_bfs_pull_low(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t const* __restrict__ row_vertex, int32_t r0,
+                     int32_t r1, uint8_t const* __restrict__ frontier, uint8_t const* __restrict__ visited, long long maxpart,
+                     int grid_cols, int grid_c, long long* __restrict__ cand)
+{
+  for (long long r = r0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; r < r1; r += (long long)gridDim.x * blockDim.x) {
+    const int slot = row_vertex ? row_vertex[r] : (int)r;
+    if (visited[slot]) continue;
+    const long long e1 = (long long)off[r + 1];
+    for (long long e = (long long)off[r]; e < e1; ++e) {
+      const int col = idx[e];
+      if (frontier[col]) {
+        cand[slot] = ((long long)(col / maxpart) * grid_cols + grid_c) * maxpart + (col % maxpart);
+        break;
+      }
+    }
+  }
+}
+
+__global__ void k_fill_i64(long long* __restrict__ a, long long n, long long v)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = v;
+}
+
+template <typename O>
+void block_bfs_pull(handle_impl const& h, csx_t const& c, uint8_t const* frontier, uint8_t const* visited, long long maxpart,
+                    int grid_cols, int grid_c, long long* cand, int32_t n_row_slots)
+{
+  B200_LAUNCH(h, k_fill_i64, std::min((n_row_slots + 255) / 256 + 1, h.sm_count * 8), 256, 0, cand, (long long)n_row_slots, -1ll);
+  const int32_t n_hi = c.degree_sorted ? c.seg[0] : 0;
+  const int32_t n_ne = c.degree_sorted ? c.seg[kNumSeg - 2] : c.n_rows;  // rows with at least one edge
+  if (n_hi > 0)
+    B200_LAUNCH(h, (k_block_bfs_pull_hi<O>), std::min((n_hi + 7) / 8, h.sm_count * 16), 256, 0, c.offsets.as<O>(),
+                c.indices.as<int32_t>(), c.row_vertex.as<int32_t>(), n_hi, frontier, visited, maxpart, grid_cols, grid_c, cand);
+  if (n_ne > n_hi)
+    B200_LAUNCH(h, (k_block_bfs_pull_low<O>), std::min((n_ne - n_hi + 255) / 256, h.sm_count * 16), 256, 0, c.offsets.as<O>(),
+                c.indices.as<int32_t>(), c.row_vertex.as<int32_t>(), n_hi, n_ne, frontier, visited, maxpart, grid_cols, grid_c, cand);
+}
+
 }  // namespace
 
 void attach_comm(handle_impl*, void*)
@@ -224,6 +298,36 @@ cugraph_error_code_t cugraph_b200_pagerank_vertex_step(const cugraph_resource_ha
                   (double const*)ov->data, (double*)xv->data, (int32_t)n_local, alpha, n_vertices_global,
                   first == TRUE ? 1 : 0, totals_prev_device, partial_out_device);
     check_last("pagerank_vertex_step");
+  });
+}
+
+// cand[row slot] = global code of a frontier source adjacent to that (unvisited) row, or -1.  Asynchronous.
+cugraph_error_code_t cugraph_b200_block_bfs_pull(const cugraph_resource_handle_t* handle, cugraph_b200_block_t* block,
+                                                 const cugraph_type_erased_device_array_view_t* frontier_cols,
+                                                 const cugraph_type_erased_device_array_view_t* visited_rows, size_t maxpart,
+                                                 int grid_cols, int grid_c, cugraph_type_erased_device_array_view_t* cand,
+                                                 cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(block && frontier_cols && visited_rows && cand, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto* b        = reinterpret_cast<block_impl*>(block);
+    auto const* fv = V(frontier_cols);
+    auto const* vv = V(visited_rows);
+    auto const* cv = V(cand);
+    B200_EXPECTS(dtype_size(fv->type) == 1 && dtype_size(vv->type) == 1, CUGRAPH_INVALID_INPUT, "frontier / visited are byte flags");
+    B200_EXPECTS(cv->type == INT64, CUGRAPH_INVALID_INPUT, "cand must be INT64");
+    B200_EXPECTS(fv->size >= (size_t)b->n_cols && vv->size >= (size_t)b->n_rows && cv->size >= (size_t)b->n_rows,
+                 CUGRAPH_INVALID_INPUT, "flag / candidate arrays shorter than the block's slots");
+    B200_EXPECTS(maxpart > 0 && grid_cols > 0 && grid_c >= 0 && grid_c < grid_cols, CUGRAPH_INVALID_INPUT, "bad grid position");
+    csx_t const& c = *b->csx;
+    if (c.offs64)
+      block_bfs_pull<int64_t>(h, c, (uint8_t const*)fv->data, (uint8_t const*)vv->data, (long long)maxpart, grid_cols, grid_c,
+                              (long long*)cv->data, b->n_rows);
+    else
+      block_bfs_pull<int32_t>(h, c, (uint8_t const*)fv->data, (uint8_t const*)vv->data, (long long)maxpart, grid_cols, grid_c,
+                              (long long*)cv->data, b->n_rows);
+    check_last("block_bfs_pull");
   });
 }
 

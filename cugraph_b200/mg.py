@@ -1,4 +1,4 @@
-"""Multi-GPU PageRank: 2D edge partition over one process per GPU (torch.distributed, NCCL on NVLink 5).
+"""Multi-GPU PageRank and BFS: 2D edge partition over one process per GPU (torch.distributed, NCCL on NVLink 5).
 
 What the reference does: P = R x C GPUs, vertex -> GPU by hash
 (cpp/include/cugraph/utilities/graph_partition_utils.cuh:30-43, 101-128), every GPU holds the edge
@@ -108,12 +108,13 @@ def all_gather_into(out: torch.Tensor, inp: torch.Tensor, group):
         out.copy_(torch.cat(parts))
 
 
-def reduce_scatter_into(out: torch.Tensor, inp: torch.Tensor, group):
+def reduce_scatter_into(out: torch.Tensor, inp: torch.Tensor, group, op=None):
+    op = op or dist.ReduceOp.SUM
     if _is_nccl(group):
-        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+        dist.reduce_scatter_tensor(out, inp, op=op, group=group)
     else:
         tmp = inp.clone()
-        dist.all_reduce(tmp, group=group)
+        dist.all_reduce(tmp, op=op, group=group)
         k = dist.get_rank(group)
         out.copy_(tmp[k * out.numel():(k + 1) * out.numel()])
 
@@ -205,7 +206,7 @@ class MGGraph:
     def __init__(self, src, dst, weights=None, groups: Groups | None = None, dtype=torch.float32):
         from cugraph_b200 import _capi
         from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
-        assert src.is_cuda, "MGGraph needs CUDA tensors"
+        assert src.is_cuda or _capi.emulated(), "MGGraph needs CUDA tensors"
         self.lib = _capi.lib()
         self._capi = _capi
         self.dtype = dtype if weights is None else weights.dtype
@@ -252,6 +253,7 @@ class MGGraph:
         reduce_scatter_into(ow, partial, g.col_group)
         self.out_w = ow.to(self.dtype)
         self.num_edges_local = int(p.rows.numel())
+        self.device = src.device
         p.rows = p.cols = p.weights = None  # the block owns its own copy
         torch.cuda.synchronize()
 
@@ -326,6 +328,95 @@ class MGGraph:
             v.free()
         return p.vertices, pr[:p.n_local].clone(), iters, converged
 
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU BFS.  The reference's MG BFS (bfs_impl.cuh:446-869) moves the frontier through the edge partitions with
+    # fill_edge_dst_property broadcasts (fill_edge_src_dst_property.cuh:1368) and an all-to-all-v of the discovered
+    # (vertex, predecessor) pairs over the row communicator (transform_reduce_if_v_frontier_outgoing_e_by_dst.cuh:981-1074).
+    # Here one level is: all-gather of the owners' frontier flags inside the column group (-> flags over the block's
+    # source slots), all-gather of the visited flags inside the row group (-> flags over its destination slots), the
+    # block's pull step on the device (cugraph_b200_block_bfs_pull: every unvisited destination looks for a source in the
+    # frontier), ONE max-reduce-scatter of the candidate predecessors inside the row group, and the owners' update.
+    # Distances are the BFS levels (bit-exact vs single-GPU); a predecessor is any frontier neighbour, as in the reference.
+    # ------------------------------------------------------------------------------------------
+    def bfs(self, source, depth_limit=-1, compute_predecessors=True):
+        """source: external vertex id (the same value on every rank).  Returns (vertices, distances, predecessors) of the
+        vertices this rank owns: int32 distances (INT32_MAX = unreachable), predecessors as external ids (-1 = none)."""
+        assert self.block is not None, "bfs needs the unsplit block"
+        p, g, L, capi = self.part, self.part.groups, self.lib, self._capi
+        dev, mp = self.device, p.maxpart
+        imax = torch.iinfo(torch.int32).max
+        dist_own = torch.full((mp,), imax, dtype=torch.int32, device=dev)
+        pred_code = torch.full((mp,), -1, dtype=torch.int64, device=dev)
+        visited = torch.zeros(mp, dtype=torch.uint8, device=dev)
+        visited[p.n_local:] = 1                                  # padding slots never take part
+        frontier = torch.zeros(mp, dtype=torch.uint8, device=dev)
+        owner = int(vertex_owner(torch.tensor([int(source)], dtype=torch.int64), g.world)[0])
+        found = torch.zeros(1, dtype=torch.int64, device=dev)
+        if owner == g.rank:
+            hit = (p.vertices == int(source)).nonzero()
+            if hit.numel():
+                lid = int(hit[0, 0])
+                dist_own[lid] = 0
+                visited[lid] = 1
+                frontier[lid] = 1
+                found += 1
+        dist.all_reduce(found)
+        if int(found.item()) == 0:
+            raise ValueError(f"bfs source {source} is not a vertex of the graph")
+        f_cols = torch.zeros(self.n_cols, dtype=torch.uint8, device=dev)
+        v_rows = torch.zeros(self.n_rows, dtype=torch.uint8, device=dev)
+        cand = torch.full((self.n_rows,), -1, dtype=torch.int64, device=dev)
+        cand_own = torch.full((mp,), -1, dtype=torch.int64, device=dev)
+        views = {k: _view(v) for k, v in dict(f=f_cols, v=v_rows, c=cand).items()}
+        err = C.c_void_p()
+        level = 0
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        while depth_limit < 0 or level < depth_limit:
+            if g.R == 1:
+                f_cols.copy_(frontier)
+            else:
+                all_gather_into(f_cols, frontier, g.col_group)
+            if g.C == 1:
+                v_rows.copy_(visited)
+            else:
+                all_gather_into(v_rows, visited, g.row_group)
+            code = L.cugraph_b200_block_bfs_pull(self.handle.ptr, self.block, views["f"].ptr, views["v"].ptr, mp, g.C, g.c,
+                                                 views["c"].ptr, C.byref(err))
+            capi.check(code, err, "cugraph_b200_block_bfs_pull")
+            if g.C == 1:
+                cand_own.copy_(cand)
+            else:
+                reduce_scatter_into(cand_own, cand, g.row_group, op=dist.ReduceOp.MAX)
+            new = (visited == 0) & (cand_own >= 0)
+            level += 1
+            dist_own[new] = level
+            pred_code[new] = cand_own[new]
+            visited |= new.to(torch.uint8)
+            frontier = new.to(torch.uint8)
+            count.fill_(int(new.sum().item()))
+            dist.all_reduce(count)
+            if int(count.item()) == 0:
+                break
+        for v in views.values():
+            v.free()
+        verts = p.vertices
+        d_out = dist_own[:p.n_local].clone()
+        if not compute_predecessors:
+            return verts, d_out, None
+        # predecessor codes (owner rank * maxpart + local id) -> external ids, answered by the owners
+        codes = pred_code[:p.n_local]
+        has = codes >= 0
+        ask = codes[has]
+        (req,), order, sc, rc = exchange([ask % mp], torch.div(ask, mp, rounding_mode="floor"), g.world)
+        ans = verts[req]
+        back = torch.empty(sum(sc), dtype=ans.dtype, device=dev)
+        dist.all_to_all_single(back, ans.contiguous(), output_split_sizes=sc, input_split_sizes=rc)
+        got = torch.empty_like(back)
+        got[order] = back
+        pred = torch.full((p.n_local,), -1, dtype=verts.dtype, device=dev)
+        pred[has] = got
+        return verts, d_out, pred
+
 
 # EXPERIMENTAL: same iteration, but the block is split by destination partition: sweep j, then an asynchronous
 # reduce of its partial sums to member j of the row group while sweep j+1 runs (the reference's per-block
@@ -382,6 +473,11 @@ def _pagerank_split(self, alpha=0.85, epsilon=1e-5, max_iterations=100):
 
 
 MGGraph.pagerank_split = _pagerank_split
+
+
+def bfs(graph: MGGraph, source, depth_limit=-1, compute_predecessors=True):
+    """(vertices, distances, predecessors) of the vertices owned by this rank (the MG contract of pylibcugraph.bfs)."""
+    return graph.bfs(source, depth_limit, compute_predecessors)
 
 
 def pagerank(graph: MGGraph, alpha=0.85, epsilon=1e-5, max_iterations=100):

@@ -21,8 +21,18 @@ def mg_parity(groups, alpha, scale=16, iters=30):
     src, dst = rmat_edgelist(scale, E_local, seed=77 + rank)
     G = mg.MGGraph(src, dst, None, groups)
     verts, pr, _, _ = G.pagerank(alpha, 0.0, iters)
+    # multi-GPU BFS from the first source of rank 0's edge list (distances must equal the single-GPU ones bit for bit); a
+    # failure is reported in the line, it does not cost the PageRank measurement
+    first = [int(src[0].item()) if rank == 0 else None]
+    dist.broadcast_object_list(first, src=0)
+    bfs_err, bv, bd = None, None, None
+    try:
+        bv, bd, _ = G.bfs(first[0], compute_predecessors=False)
+        bv, bd = bv.cpu(), bd.cpu()
+    except Exception as e:  # noqa: BLE001
+        bfs_err = f"{type(e).__name__}: {e}"[:200]
     parts = [None] * world
-    dist.all_gather_object(parts, (src.cpu(), dst.cpu(), verts.cpu(), pr.cpu()))
+    dist.all_gather_object(parts, (src.cpu(), dst.cpu(), verts.cpu(), pr.cpu(), bv, bd, bfs_err))
     del G
     if rank != 0:
         return None
@@ -41,7 +51,25 @@ def mg_parity(groups, alpha, scale=16, iters=30):
     b[v1.cpu().long()] = p1.cpu().double()
     same_set = bool(((a > 0) == (b > 0)).all())
     rel = ((a - b).abs() / b.clamp_min(1e-300))[b > 0].max().item() if bool((b > 0).any()) else 0.0
-    return {"max_rel": rel, "ok": bool(same_set and rel < 1e-6), "vertices": int((b > 0).sum()), "scale": scale, "iterations": iters}
+    out = {"max_rel": rel, "ok": bool(same_set and rel < 1e-6), "vertices": int((b > 0).sum()), "scale": scale, "iterations": iters}
+    errs = [p[6] for p in parts if p[6]]
+    if errs:
+        out["bfs"] = {"ok": False, "error": errs[0]}
+    else:
+        try:
+            g2 = plc.SGGraph(h, plc.GraphProperties(is_multigraph=True), s_all, d_all, store_transposed=False, renumber=True)
+            srcs = torch.tensor([int(parts[0][0][0])], dtype=s_all.dtype, device="cuda")
+            d1, _, v1b = plc.bfs(h, g2, srcs, True, -1, False, False)
+            imax = torch.iinfo(torch.int32).max
+            da = torch.full((n,), imax, dtype=torch.int64)
+            db = torch.full((n,), imax, dtype=torch.int64)
+            da[torch.cat([p[4] for p in parts]).long()] = torch.cat([p[5] for p in parts]).long()
+            db[v1b.cpu().long()] = d1.cpu().long()
+            reached = int((db < imax).sum())
+            out["bfs"] = {"ok": bool((da == db).all()), "reached": reached, "levels": int(db[db < imax].max()) if reached else 0}
+        except Exception as e:  # noqa: BLE001
+            out["bfs"] = {"ok": False, "error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 def run_mg_pagerank(args, metric_name, alpha, iters, ClockSampler, peaks):
@@ -103,6 +131,31 @@ def run_mg_pagerank(args, metric_name, alpha, iters, ClockSampler, peaks):
     mass = pr.double().sum().reshape(1)
     dist.all_reduce(mass)
 
+    # multi-GPU BFS on the bench graph (pull steps on every block, frontier / visited flags all-gathered per level): a few
+    # sources, time per traversal as the max over ranks; never fatal for the PageRank line
+    mg_bfs = None
+    try:
+        from cugraph_b200.mg import vertex_owner  # noqa: F401
+        srcs = [None] * 4
+        if rank == 0:
+            pick = torch.randperm(h_src.numel() if h_src is not None else 1, generator=torch.Generator().manual_seed(5))[:4]
+            srcs = [int(h_src[i]) for i in pick] if h_src is not None else srcs
+        dist.broadcast_object_list(srcs, src=0)
+        if srcs[0] is not None:
+            G.bfs(srcs[0], compute_predecessors=False)  # warm-up
+            times, reached = [], []
+            for sv in srcs:
+                tb, (bv, bd, _) = timed(lambda: G.bfs(sv, compute_predecessors=False), 1)
+                r = (bd < torch.iinfo(torch.int32).max).sum().reshape(1).to(torch.int64)
+                dist.all_reduce(r)
+                times.append(tb)
+                reached.append(int(r.item()))
+            hm = len(times) / sum(t / E_total for t in times) / 1e6   # harmonic-mean MTEPS over the sources (Graph500 style)
+            mg_bfs = {"sources": len(times), "ms_mean": 1e3 * sum(times) / len(times), "mteps_harmonic": hm,
+                      "reached_mean": sum(reached) / len(reached), "direction": "pull on every level (flags all-gathered)"}
+    except Exception as e:  # noqa: BLE001
+        mg_bfs = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # roofline of the local sweep (no communication): CUDA events on the stream the kernels run on
     import ctypes as C
     from cugraph_b200.pylibcugraph.utils import View
@@ -156,6 +209,7 @@ def run_mg_pagerank(args, metric_name, alpha, iters, ClockSampler, peaks):
                           "mass": float(mass.item()),
                           "mg_parity_ok": parity["ok"], "mg_parity_max_rel": parity["max_rel"],
                           "mg_parity_sample": f"RMAT-{parity['scale']} ef-16, {parity['iterations']} iterations, MG on {world} GPUs vs the single-GPU C-ABI on rank 0, {parity['vertices']} vertices",
+                          "mg_bfs_parity": parity.get("bfs"), "mg_bfs": mg_bfs,
                           "mg_split": os.environ.get("CUGRAPH_B200_MG_SPLIT", "0") == "1",
                           "l2": "inputs per sweep exceed the 126 MB L2; no explicit flush"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None}

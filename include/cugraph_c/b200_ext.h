@@ -60,6 +60,16 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_pagerank_vertex_step(
   cugraph_type_erased_device_array_view_t* x, size_t n_local, double alpha, double n_vertices_global, bool_t first,
   const double* totals_prev_device, double* partial_out_device, cugraph_error_t** error);
 
+/* One level of multi-GPU BFS on this GPU's edge block (pull direction; the role of the bottom-up step of
+ * cpp/src/traversal/bfs_impl.cuh:593-869 on one edge partition).  frontier_cols / visited_rows: byte flags over the block's
+ * column (source) / row (destination) slots, gathered by the launcher inside the column / row group.  cand (INT64, one per row
+ * slot) receives, for every unvisited row with a source in the frontier, that source's global code
+ * ((col / maxpart) * grid_cols + grid_c) * maxpart + col % maxpart  (= owner rank * maxpart + local id), else -1. */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_block_bfs_pull(
+  const cugraph_resource_handle_t* handle, cugraph_b200_block_t* block,
+  const cugraph_type_erased_device_array_view_t* frontier_cols, const cugraph_type_erased_device_array_view_t* visited_rows,
+  size_t maxpart, int grid_cols, int grid_c, cugraph_type_erased_device_array_view_t* cand, cugraph_error_t** error);
+
 /* Debug hook: one sweep as PageRank would run it on this graph (the shared-memory piece stream when the graph has one)
  * against the plain sweep (an independent implementation) on the same pseudo-random x.  out[0..3] = degree >= 32 rows
  * {max relative difference, its row, that row's degree, rows above 1e-5}; out[4..7] = the same for the degree < 32 rows. */

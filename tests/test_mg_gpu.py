@@ -1,4 +1,4 @@
-"""2-GPU NCCL run of the multi-GPU PageRank (skipped when fewer than 2 GPUs are visible): MG result ==
+"""2- and 4-GPU NCCL run of the multi-GPU PageRank and BFS (skipped when fewer than 2 GPUs are visible): MG result ==
 oracle on the gathered graph, as the reference's mg_pagerank_test.cpp:158-248 compares MG with SG."""
 import os
 import socket
@@ -40,8 +40,11 @@ def _worker(rank, world, port, scale, weighted, q):
     dist.all_gather_object(res, (verts.cpu().numpy(), pr.cpu().numpy()))
     # converging run: iteration count must agree on all ranks and with the scalar exchange
     v2, p2, it2, c2 = G.pagerank(0.85, 1e-6, 500)
+    bv, bd, bp = G.bfs(int(s[0]))
+    bres = [None] * world
+    dist.all_gather_object(bres, (bv.cpu().numpy(), bd.cpu().numpy(), bp.cpu().numpy()))
     if rank == 0:
-        q.put((res, it2, c2))
+        q.put((res, it2, c2, bres))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,7 +65,7 @@ def test_mg_pagerank_multi_gpu(weighted, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, scale, weighted, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res, it2, c2 = q.get(timeout=300)
+    res, it2, c2, bres = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -83,3 +86,20 @@ def test_mg_pagerank_multi_gpu(weighted, world):
     _, it_ref, conv_ref = oracle.pagerank(remap[s], remap[d], present.size, w_all if weighted else None, alpha=0.85,
                                           epsilon=1e-6, max_iterations=500)
     assert c2 == conv_ref and abs(it2 - it_ref) <= 1
+    # multi-GPU BFS: distances bit-exact vs the oracle, predecessors by the reference's predicate (bfs_test.cpp:213-233)
+    ref_d, _ = oracle.bfs(remap[s].astype(np.int32), remap[d].astype(np.int32), present.size,
+                          np.array([remap[s[0]]], dtype=np.int32))
+    imax = np.iinfo(np.int32).max
+    ref_d = np.asarray(ref_d, dtype=np.int64)
+    ref_d = np.where((ref_d < 0) | (ref_d >= imax), imax, ref_d)
+    got_d = np.full(present.size, -5, dtype=np.int64)
+    got_p = np.full(present.size, -5, dtype=np.int64)
+    for bv, bd, bp in bres:
+        got_d[remap[bv]] = bd
+        got_p[remap[bv]] = np.where(bp >= 0, remap[np.maximum(bp, 0)], -1)
+    assert np.array_equal(got_d, ref_d)
+    edges = set(zip(remap[s].tolist(), remap[d].tolist()))
+    for v in np.flatnonzero((ref_d < imax) & (ref_d > 0))[:20000]:
+        pv = int(got_p[v])
+        assert pv >= 0 and ref_d[pv] == ref_d[v] - 1 and (pv, int(v)) in edges
+    assert got_p[remap[s[0]]] == -1 and (got_p[ref_d == imax] == -1).all()
