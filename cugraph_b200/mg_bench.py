@@ -59,7 +59,7 @@ def mg_parity(groups, alpha, scale=16, iters=30):
         try:
             g2 = plc.SGGraph(h, plc.GraphProperties(is_multigraph=True), s_all, d_all, store_transposed=False, renumber=True)
             srcs = torch.tensor([int(parts[0][0][0])], dtype=s_all.dtype, device="cuda")
-            d1, _, v1b = plc.bfs(h, g2, srcs, True, -1, False, False)
+            d1, _, v1b = plc.bfs(h, g2, srcs, False, -1, False, False)  # the graph is directed: no direction optimisation
             imax = torch.iinfo(torch.int32).max
             da = torch.full((n,), imax, dtype=torch.int64)
             db = torch.full((n,), imax, dtype=torch.int64)

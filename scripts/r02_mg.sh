@@ -1,18 +1,20 @@
 #!/bin/bash
-# multi-GPU check: NCCL tests + the N-GPU bench line     gpurun --gpus N -- 'bash scripts/r02_mg.sh N'
-N=${1:-2}
+# 2-GPU check of the NCCL path: gpurun --gpus 2 --timeout 900 -- 'bash scripts/r02_mg.sh'
 mkdir -p gpurun_out
 make -s -C oracle
-timeout 600 python -m pytest tests/test_mg_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 3 --warmup 2 > gpurun_out/r02_bench_mg$N.json 2> gpurun_out/r02_bench_mg$N.err
-python - <<PY
+nvidia-smi -L | head -4
+timeout 400 python -m pytest tests/test_mg_gpu.py -x -q 2>&1 | tail -4
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+  bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r02_bench_mg2.json 2> gpurun_out/r02_bench_mg2.err
+tail -2 gpurun_out/r02_bench_mg2.err
+python - <<'PY'
 import json
 try:
-    d=json.loads([l for l in open('gpurun_out/r02_bench_mg$N.json') if l.startswith('{')][-1])
-    print('value',d['value'],'ms/step',d['ms_per_step'],'roofline',d['roofline']['frac'],d['roofline']['ms_per_sweep'])
-    print({k:v for k,v in d['config'].items() if k.startswith(('mg_','mass','workload'))})
+    d=json.loads([l for l in open('gpurun_out/r02_bench_mg2.json') if l.startswith('{')][-1])
+    c=d['config']
+    print('value',d['value'],'ms',d['ms_per_step'],'sweep frac',d['roofline']['frac'],'ms_sweep',d['roofline']['ms_per_sweep'])
+    print('parity',c['mg_parity_ok'],c['mg_parity_max_rel'],'bfs parity',c.get('mg_bfs_parity'),'bfs',c.get('mg_bfs'))
     print('e2e',d['e2e'])
 except Exception as e:
-    print('no bench line',e)
+    print('no line',e)
 PY
-tail -5 gpurun_out/r02_bench_mg$N.err
