@@ -60,6 +60,15 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_pagerank_vertex_step(
   cugraph_type_erased_device_array_view_t* x, size_t n_local, double alpha, double n_vertices_global, bool_t first,
   const double* totals_prev_device, double* partial_out_device, cugraph_error_t** error);
 
+/* RMAT edge list written into caller-allocated INT32 arrays (the role of cugraph_generate_rmat_edgelist,
+ * cpp/include/cugraph_c/graph_generators.h, without its rng_state / coo objects): the reference's sampling rule, clip-and-flip
+ * and id scramble (generate_rmat_edgelist.cuh:66-108, scramble.cuh:44-67) over a counter-based uniform stream, so that
+ * the same (scale, seed) gives the same edges on any grid size — restated in numpy by oracle/rmat.py for the parity test. */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_generate_rmat_edgelist(
+  const cugraph_resource_handle_t* handle, size_t scale, size_t num_edges, double a, double b, double c, uint64_t seed,
+  bool_t clip_and_flip, bool_t scramble_vertex_ids, cugraph_type_erased_device_array_view_t* src,
+  cugraph_type_erased_device_array_view_t* dst, cugraph_error_t** error);
+
 /* One level of multi-GPU BFS on this GPU's edge block (pull direction; the role of the bottom-up step of
  * cpp/src/traversal/bfs_impl.cuh:593-869 on one edge partition).  frontier_cols / visited_rows: byte flags over the block's
  * column (source) / row (destination) slots, gathered by the launcher inside the column / row group.  cand (INT64, one per row

@@ -72,3 +72,43 @@ def rmat_edgelist(scale: int, num_edges: int, a: float = 0.57, b: float = 0.19, 
         dst[done:done + n] = d
         done += n
     return src, dst
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def rmat_edgelist_counter(scale: int, num_edges: int, a: float = 0.57, b: float = 0.19, c: float = 0.19, seed: int = 0,
+                          clip_and_flip: bool = False, scramble: bool = True):
+    """numpy twin of the DEVICE generator (cugraph_b200/csrc/generators.cu: cugraph_b200_generate_rmat_edgelist) — the
+    same sampling rule as rmat_edgelist above over the device's counter-based uniform stream: for edge e and bit k,
+    r = mix64(seed ^ (64 e + k)), r0 = (r >> 40) / 2^24, r1 = ((r >> 8) & 0xffffff) / 2^24.  Bit-exact with the device."""
+    assert 1 <= scale <= 31
+    ab = np.float32(a + b)
+    a_norm = np.float32(a / (a + b) if (a + b) > 0 else 0.0)
+    c_norm = np.float32(c / (1.0 - (a + b)) if (1.0 - (a + b)) > 0 else 0.0)
+    e = np.arange(num_edges, dtype=np.uint64)
+    s = np.zeros(num_edges, dtype=np.uint32)
+    d = np.zeros(num_edges, dtype=np.uint32)
+    inv = np.float32(1.0 / 16777216.0)
+    for bit in range(scale - 1, -1, -1):
+        with np.errstate(over="ignore"):
+            r = _mix64(np.uint64(seed) ^ (e * np.uint64(64) + np.uint64(bit)))
+        r0 = (r >> np.uint64(40)).astype(np.float32) * inv
+        r1 = ((r >> np.uint64(8)) & np.uint64(0xFFFFFF)).astype(np.float32) * inv
+        sb = r0 > ab
+        db = r1 > np.where(sb, c_norm, a_norm)
+        if clip_and_flip:
+            flip = (s == d) & (~sb) & db
+            sb = sb | flip
+            db = db & ~flip
+        s |= sb.astype(np.uint32) << np.uint32(bit)
+        d |= db.astype(np.uint32) << np.uint32(bit)
+    if scramble:
+        s = scramble32(s, scale).astype(np.uint32)
+        d = scramble32(d, scale).astype(np.uint32)
+    return s.astype(np.int32), d.astype(np.int32)
