@@ -102,6 +102,10 @@ def lib():
     _sig(L.cugraph_paths_result_free, None, [vp])
     _sig(L.cugraph_bfs, i32, [vp, vp, vp, i32, sz, i32, i32, pvp, pvp])
     _sig(L.cugraph_sssp, i32, [vp, vp, sz, dbl, i32, i32, pvp, pvp])
+    _sig(L.cugraph_extract_paths, i32, [vp, vp, vp, vp, vp, pvp, pvp])
+    _sig(L.cugraph_extract_paths_result_get_max_path_length, sz, [vp])
+    _sig(L.cugraph_extract_paths_result_get_paths, vp, [vp])
+    _sig(L.cugraph_extract_paths_result_free, None, [vp])
     # extensions (b200_ext.h)
     _sig(L.cugraph_b200_version, C.c_char_p, [])
     _sig(L.cugraph_b200_handle_stream, vp, [vp])

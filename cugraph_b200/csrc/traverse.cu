@@ -1181,6 +1181,56 @@ device_array_impl* finish_predecessors(handle_impl const& h, graph_impl const& g
 
 using namespace b200;
 
+namespace b200 {
+namespace {
+
+// ---- extract_paths (reference cpp/src/traversal/extract_bfs_paths_impl.cuh:129-238, cpp/src/c_api/extract_paths.cpp): walk the
+// predecessor chain of every destination back to its source.  Row i of the result holds the path source ... destination_i in
+// columns 0 .. distance(destination_i), the rest is the invalid vertex (-1); the row length is 1 + the largest distance of
+// a destination that has a predecessor.  One thread per destination (paths are as short as the BFS is deep); the
+// reference does one gather round per path position over all destinations.
+template <typename D>
+__global__ void k_scatter_to_internal(int32_t const* __restrict__ int_of_pos, D const* __restrict__ dist_pos,
+                                      int32_t const* __restrict__ pred_int_pos, int32_t n, long long* __restrict__ dist_int,
+                                      int32_t* __restrict__ pred_int)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int v = int_of_pos[p];
+  if (v < 0) return;
+  dist_int[v] = (long long)dist_pos[p];
+  pred_int[v] = pred_int_pos[p];
+}
+
+__global__ void k_paths_max_len(int32_t const* __restrict__ dest, int32_t n_dest, long long const* __restrict__ dist,
+                                int32_t const* __restrict__ pred, int32_t nv, long long unreachable, long long* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dest) return;
+  const int v = dest[i];
+  if (v < 0 || v >= nv || pred[v] < 0 || dist[v] >= unreachable) return;
+  atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)dist[v]);
+}
+
+__global__ void k_paths_walk(int32_t const* __restrict__ dest, int32_t n_dest, long long const* __restrict__ dist,
+                             int32_t const* __restrict__ pred, int32_t nv, long long unreachable, long long len,
+                             int32_t* __restrict__ paths)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dest) return;
+  int v = dest[i];
+  if (v < 0 || v >= nv) return;
+  long long d = dist[v];
+  if (d >= unreachable || d >= len) return;  // not reached: the row stays invalid
+  for (; d >= 0 && v >= 0; --d) {
+    paths[(long long)i * len + d] = v;
+    v = pred[v];
+  }
+}
+
+}  // namespace
+}  // namespace b200
+
 extern "C" {
 
 cugraph_type_erased_device_array_view_t* cugraph_paths_result_get_vertices(cugraph_paths_result_t* r)
@@ -1307,6 +1357,98 @@ cugraph_error_code_t cugraph_sssp(const cugraph_resource_handle_t* handle, cugra
     sync(h);
     *result = reinterpret_cast<cugraph_paths_result_t*>(res.release());
   });
+}
+
+
+struct extract_paths_result_impl {
+  size_t max_path_length{0};
+  device_array_impl* paths{nullptr};
+};
+
+cugraph_error_code_t cugraph_extract_paths(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph,
+                                           const cugraph_type_erased_device_array_view_t* sources,
+                                           const cugraph_paths_result_t* paths_result,
+                                           const cugraph_type_erased_device_array_view_t* destinations,
+                                           cugraph_extract_paths_result_t** result, cugraph_error_t** error)
+{
+  (void)sources;  // the reference takes them and does not read them either (c_api/extract_paths.cpp:60-130)
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    auto* g       = G(graph);
+    B200_EXPECTS(result != nullptr, CUGRAPH_INVALID_INPUT, "result out-pointer is NULL");
+    *result = nullptr;
+    B200_EXPECTS(paths_result != nullptr && destinations != nullptr, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto const* pr = reinterpret_cast<paths_result_impl const*>(paths_result);
+    auto const* dv = V(destinations);
+    B200_EXPECTS(dv->type == g->vertex_type, CUGRAPH_INVALID_INPUT, "vertex type of graph and destinations must match");
+    B200_EXPECTS(pr->distances && pr->vertices, CUGRAPH_INVALID_INPUT, "Invalid input argument: distances cannot be null");
+    B200_EXPECTS(pr->predecessors && pr->predecessors->size == pr->vertices->size, CUGRAPH_INVALID_INPUT,
+                 "Invalid input argument: predecessors cannot be null");
+    B200_EXPECTS(pr->distances->type == INT32 || pr->distances->type == INT64, CUGRAPH_INVALID_INPUT,
+                 "extract_paths expects the integer distances of a BFS result");
+    const int32_t nv = g->n_vertices;
+    B200_EXPECTS((size_t)nv == pr->vertices->size, CUGRAPH_INVALID_INPUT, "the paths result does not belong to this graph");
+    const size_t nd = dv->size;
+    // result positions -> internal ids; distances / predecessors re-indexed by internal id
+    dbuf int_of_pos = make_dbuf<int32_t>(std::max(nv, 1), h.stream), pred_pos = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+    ext_to_int(h, *g, pr->vertices->buf.data(), (size_t)nv, int_of_pos.as<int32_t>());
+    ext_to_int(h, *g, pr->predecessors->buf.data(), (size_t)nv, pred_pos.as<int32_t>());
+    dbuf dist_int = make_dbuf<long long>(std::max(nv, 1), h.stream), pred_int = make_dbuf<int32_t>(std::max(nv, 1), h.stream);
+    const long long unreachable = pr->distances->type == INT64 ? (long long)INT64_MAX : (long long)INT32_MAX;
+    if (nv > 0) {
+      if (pr->distances->type == INT64)
+        B200_LAUNCH(h, (k_scatter_to_internal<int64_t>), grid_for(nv), kBlock, 0, int_of_pos.as<int32_t>(),
+                    pr->distances->buf.as<int64_t>(), pred_pos.as<int32_t>(), nv, dist_int.as<long long>(), pred_int.as<int32_t>());
+      else
+        B200_LAUNCH(h, (k_scatter_to_internal<int32_t>), grid_for(nv), kBlock, 0, int_of_pos.as<int32_t>(),
+                    pr->distances->buf.as<int32_t>(), pred_pos.as<int32_t>(), nv, dist_int.as<long long>(), pred_int.as<int32_t>());
+    }
+    dbuf dest_int = make_dbuf<int32_t>(std::max<size_t>(nd, 1), h.stream);
+    ext_to_int(h, *g, dv->data, nd, dest_int.as<int32_t>());
+    dbuf d_max = make_dbuf<long long>(1, h.stream);
+    CUDA_TRY(cudaMemsetAsync(d_max.data(), 0, sizeof(long long), h.stream));
+    if (nd > 0)
+      B200_LAUNCH(h, k_paths_max_len, grid_for((int64_t)nd), kBlock, 0, dest_int.as<int32_t>(), (int32_t)nd, dist_int.as<long long>(),
+                  pred_int.as<int32_t>(), nv, unreachable, d_max.as<long long>());
+    long long hmax = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hmax, d_max.data(), sizeof(long long), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    const long long len = hmax + 1;
+    const size_t total  = nd * (size_t)len;
+    dbuf paths_int      = make_dbuf<int32_t>(std::max<size_t>(total, 1), h.stream);
+    if (total > 0) {
+      CUDA_TRY(cudaMemsetAsync(paths_int.data(), 0xff, sizeof(int32_t) * total, h.stream));  // -1 = invalid vertex
+      B200_LAUNCH(h, k_paths_walk, grid_for((int64_t)nd), kBlock, 0, dest_int.as<int32_t>(), (int32_t)nd, dist_int.as<long long>(),
+                  pred_int.as<int32_t>(), nv, unreachable, len, paths_int.as<int32_t>());
+    }
+    dbuf paths_ext(std::max<size_t>(total, 1) * dtype_size(g->vertex_type), h.stream);
+    int_to_ext(h, *g, paths_int.as<int32_t>(), total, paths_ext.data());
+    check_last("extract_paths");
+    auto res             = std::make_unique<extract_paths_result_impl>();
+    res->max_path_length = (size_t)len;
+    res->paths           = make_array(std::move(paths_ext), total, g->vertex_type);
+    sync(h);
+    *result = reinterpret_cast<cugraph_extract_paths_result_t*>(res.release());
+  });
+}
+
+size_t cugraph_extract_paths_result_get_max_path_length(cugraph_extract_paths_result_t* result)
+{
+  return result ? reinterpret_cast<extract_paths_result_impl*>(result)->max_path_length : 0;
+}
+
+cugraph_type_erased_device_array_view_t* cugraph_extract_paths_result_get_paths(cugraph_extract_paths_result_t* result)
+{
+  if (!result) return nullptr;
+  return reinterpret_cast<cugraph_type_erased_device_array_view_t*>(reinterpret_cast<extract_paths_result_impl*>(result)->paths->new_view());
+}
+
+void cugraph_extract_paths_result_free(cugraph_extract_paths_result_t* result)
+{
+  if (!result) return;
+  auto* r = reinterpret_cast<extract_paths_result_impl*>(result);
+  delete r->paths;
+  delete r;
 }
 
 }  // extern "C"

@@ -39,6 +39,21 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_sssp(
   bool_t compute_predecessors, bool_t do_expensive_check, cugraph_paths_result_t** result,
   cugraph_error_t** error);
 
+/* Paths of a BFS (or SSSP) result: cpp/include/cugraph_c/traversal_algorithms.h:141-201, cpp/src/c_api/extract_paths.cpp,
+ * cpp/src/traversal/extract_bfs_paths_impl.cuh:129-238.  Row i of the row-major matrix holds the path
+ * source ... destinations[i] in columns 0 .. distance(destinations[i]); unused cells and the rows of destinations that were
+ * not reached hold the invalid vertex (-1).  max_path_length = 1 + the largest distance of a destination with a predecessor. */
+typedef struct { int32_t align_; } cugraph_extract_paths_result_t;
+
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_extract_paths(
+  const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, const cugraph_type_erased_device_array_view_t* sources,
+  const cugraph_paths_result_t* paths_result, const cugraph_type_erased_device_array_view_t* destinations,
+  cugraph_extract_paths_result_t** result, cugraph_error_t** error);
+CUGRAPH_EXPORT size_t cugraph_extract_paths_result_get_max_path_length(cugraph_extract_paths_result_t* result);
+CUGRAPH_EXPORT cugraph_type_erased_device_array_view_t* cugraph_extract_paths_result_get_paths(
+  cugraph_extract_paths_result_t* result);
+CUGRAPH_EXPORT void cugraph_extract_paths_result_free(cugraph_extract_paths_result_t* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,6 +309,59 @@ def test_sssp_window_control_emulated(emu, monkeypatch, capfd, weights):  # noqa
     emu.cugraph_graph_free(g)
 
 
+def test_extract_paths_emulated(emu):  # noqa: F811
+    """cugraph_extract_paths on a BFS result: every row is the path source ... destination (consecutive vertices are
+    edges, length = distance + 1), -1 behind it; unreachable destinations give an all -1 row; the source gives a row of one.
+    (The reference's own extract_paths_test.c runs against the library in tests/test_reference_c_tests_*.py.)"""
+    L = emu
+    s, d = symmetric_edges(5_000, 9_000, seed=77)                  # sparse: several components, deep BFS
+    g = create_sym_graph(L, s, d, None)
+    ids, ss, dd = dense_ids(s, d)
+    source = int(ids[np.bincount(ss).argmax()])
+    srcs = np.array([source], dtype=np.int32)
+    sv = L.cugraph_type_erased_device_array_view_create(srcs.ctypes.data, 1, INT32)
+    res, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_bfs(C.c_void_p(L.handle), g, C.c_void_p(sv), 0, C.c_size_t(2**31 - 2), 1, 0, C.byref(res), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    for f in ("cugraph_paths_result_get_vertices", "cugraph_paths_result_get_distances"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    verts = _view_to_np(L, L.cugraph_paths_result_get_vertices(res))
+    dist = _view_to_np(L, L.cugraph_paths_result_get_distances(res))
+    dist_of = dict(zip(verts.tolist(), dist.tolist()))
+    imax = np.iinfo(np.int32).max
+    unreached = [v for v in verts.tolist() if dist_of[v] == imax]
+    assert unreached, "the test graph should have several components"
+    r = np.random.default_rng(1)
+    dests = np.concatenate([r.choice(verts, 200), np.array(unreached[:5] + [source])]).astype(np.int32)
+    dv = L.cugraph_type_erased_device_array_view_create(dests.ctypes.data, dests.size, INT32)
+    L.cugraph_extract_paths.argtypes = [C.c_void_p] * 7
+    L.cugraph_extract_paths_result_get_max_path_length.restype = C.c_size_t
+    L.cugraph_extract_paths_result_get_max_path_length.argtypes = [C.c_void_p]
+    L.cugraph_extract_paths_result_get_paths.restype = C.c_void_p
+    L.cugraph_extract_paths_result_get_paths.argtypes = [C.c_void_p]
+    L.cugraph_extract_paths_result_free.argtypes = [C.c_void_p]
+    out = C.c_void_p()
+    code = L.cugraph_extract_paths(C.c_void_p(L.handle), g, C.c_void_p(sv), res, C.c_void_p(dv), C.byref(out), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    length = int(L.cugraph_extract_paths_result_get_max_path_length(out))
+    paths = _view_to_np(L, L.cugraph_extract_paths_result_get_paths(out)).reshape(dests.size, length)
+    reached_d = [dist_of[int(t)] for t in dests if dist_of[int(t)] != imax]
+    assert length == 1 + max(reached_d)
+    edges = set(zip(s.tolist(), d.tolist()))
+    for row, t in zip(paths, dests.tolist()):
+        dt = dist_of[t]
+        if dt == imax:
+            assert (row == -1).all()
+            continue
+        assert row[0] == source and row[dt] == t and (row[dt + 1:] == -1).all()
+        assert all((int(a), int(b)) in edges for a, b in zip(row[:dt], row[1:dt + 1]))
+        assert [dist_of[int(x)] for x in row[:dt + 1]] == list(range(dt + 1))
+    L.cugraph_extract_paths_result_free(out)
+    L.cugraph_paths_result_free(res)
+    L.cugraph_graph_free(g)
+
+
 def test_sssp_single_cta_rounds_emulated(emu, monkeypatch, capfd):  # noqa: F811
     """small near queues are relaxed round after round inside one CTA (k_sssp_small_rounds): same distances, valid predecessors,
     and the path is really taken"""
