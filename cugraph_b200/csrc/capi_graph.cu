@@ -121,6 +121,9 @@ void create_sg_common(const cugraph_resource_handle_t* handle, const cugraph_gra
                "Invalid input arguments: src size != edge end time size");
   B200_EXPECTS(!(symmetrize && (eid || ety)), CUGRAPH_INVALID_INPUT,
                "symmetrize with edge ids / edge types is not supported");
+  // graph_sg.cpp:737-742
+  B200_EXPECTS(symmetrize != TRUE || properties->is_symmetric == TRUE, CUGRAPH_INVALID_INPUT,
+               "Invalid input arguments: The graph property must be symmetric if 'symmetrize' is set to True.");
 
   auto g              = std::make_unique<graph_impl>();
   g->vertex_type      = s->type;

@@ -111,6 +111,7 @@ struct tuning_t {
   bool sssp_small_rounds{true};            // CUGRAPH_B200_SSSP_SMALL_ROUNDS: small near queues are relaxed round after round by one CTA
   int sssp_split_rounds{1};                // CUGRAPH_B200_SSSP_SPLIT_ROUNDS
   unsigned long long sssp_split_min_edges{1ull << 20};  // CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES
+  unsigned long long advance_split_edges{1ull << 31};  // CUGRAPH_B200_ADVANCE_SPLIT_EDGES: frontiers with this many edges are advanced in halves (tests lower it)
   bool bfs_trace{false}, sssp_trace{false}, build_trace{false};  // CUGRAPH_B200_{BFS,SSSP,BUILD}_TRACE
   static tuning_t from_env()
   {
@@ -132,6 +133,7 @@ struct tuning_t {
     if (auto e = get("CUGRAPH_B200_SSSP_SMALL_ROUNDS")) t.sssp_small_rounds = std::atoi(e) != 0;
     if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_ROUNDS")) t.sssp_split_rounds = std::max(1, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_SSSP_SPLIT_MIN_EDGES")) t.sssp_split_min_edges = std::strtoull(e, nullptr, 10);
+    if (auto e = get("CUGRAPH_B200_ADVANCE_SPLIT_EDGES")) t.advance_split_edges = std::min<unsigned long long>(std::max<unsigned long long>(std::strtoull(e, nullptr, 10), 2ull), 1ull << 31);
     t.bfs_trace   = get("CUGRAPH_B200_BFS_TRACE") != nullptr;
     t.sssp_trace  = get("CUGRAPH_B200_SSSP_TRACE") != nullptr;
     t.build_trace = get("CUGRAPH_B200_BUILD_TRACE") != nullptr;

@@ -833,25 +833,29 @@ void stage_graph_typed(handle_impl const& h, graph_impl& g, device_array_view_im
   g.n_vertices = nv;
   g.renumbered = renumber;
 
+  // the reference removes multi-edges FIRST (keeping the minimum weight when the graph is declared symmetric) and symmetrizes
+  // what is left (c_api/graph_sg.cpp:203-247): (u,v,1), (u,v,2), (v,u,5) -> (u,v,1), (v,u,5) -> one undirected edge of weight 3
+  if (drop_multi_edges && n > 0) {
+    csx_t tmp;
+    int32_t const* mj = g.store_transposed ? ranks.dst_rank.as<int32_t>() : ranks.src_rank.as<int32_t>();
+    int32_t const* mn = g.store_transposed ? ranks.src_rank.as<int32_t>() : ranks.dst_rank.as<int32_t>();
+    build_csx(h, tmp, mj, mn, g.weighted ? w.data() : nullptr, g.weight_type, n, nv, nullptr, nullptr, true, g.is_symmetric);
+    dbuf maj_d = expand_majors(h, tmp);
+    n          = tmp.nnz;
+    if (g.store_transposed) {
+      ranks.dst_rank = std::move(maj_d);
+      ranks.src_rank = std::move(tmp.indices);
+    } else {
+      ranks.src_rank = std::move(maj_d);
+      ranks.dst_rank = std::move(tmp.indices);
+    }
+    if (g.weighted) w = std::move(tmp.weights);
+  }
   if (symmetrize && n > 0) symmetrize_ranks(h, ranks.src_rank, ranks.dst_rank, w, g.weight_type, n, nv);
 
   int32_t const* major = g.store_transposed ? ranks.dst_rank.as<int32_t>() : ranks.src_rank.as<int32_t>();
   int32_t const* minor = g.store_transposed ? ranks.src_rank.as<int32_t>() : ranks.dst_rank.as<int32_t>();
-
-  // optional multi-edge removal has to happen before degrees are counted
-  csx_t tmp;
-  dbuf maj_d, min_d;
-  if (drop_multi_edges && n > 0) {
-    build_csx(h, tmp, major, minor, g.weighted ? w.data() : nullptr, g.weight_type, n, nv, nullptr, nullptr, true,
-              g.is_symmetric);
-    maj_d = expand_majors(h, tmp);
-    major = maj_d.as<int32_t>();
-    minor = tmp.indices.as<int32_t>();
-    n     = tmp.nnz;
-    ranks.src_rank.release();
-    ranks.dst_rank.release();
-  }
-  void const* wptr = g.weighted ? (drop_multi_edges && tmp.nnz > 0 ? tmp.weights.data() : w.data()) : nullptr;
+  void const* wptr     = g.weighted ? w.data() : nullptr;
 
   // degree-descending internal order (ties: ascending rank) — renumber_edgelist_impl.cuh:732-738
   dbuf deg = make_dbuf<int32_t>(std::max(nv, 1), h.stream);

@@ -101,10 +101,14 @@ __global__ void k_tile_owners(int32_t const* __restrict__ scan, int n_frontier, 
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  const int total = scan[n_frontier];
-  const int e0    = t * kTileEdges;
-  const int e1    = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
-  tile_k[t]       = make_int2(upper_bound_minus1(scan, n_frontier, e0), upper_bound_minus1(scan, n_frontier, e1 - 1));
+  const long long total = scan[n_frontier];  // < 2^31 (advance() splits larger queues); the tile bounds are computed in 64 bits
+  const long long e0    = (long long)t * kTileEdges;
+  const long long e1    = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
+  if (e0 >= total) {
+    tile_k[t] = make_int2(0, -1);
+    return;
+  }
+  tile_k[t] = make_int2(upper_bound_minus1(scan, n_frontier, (int)e0), upper_bound_minus1(scan, n_frontier, (int)(e1 - 1)));
 }
 
 // IDENT: the queue is the identity (vertex k is queue entry k) and `scan` are the row offsets themselves
@@ -121,8 +125,8 @@ k_advance(O const* __restrict__ off, int32_t const* __restrict__ idx, int32_t co
   const int total    = scan[n_frontier];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int tile = blockIdx.x; tile < n_tiles && (long long)tile * kTileEdges < total; tile += gridDim.x) {
-    const int e0  = tile * kTileEdges;
-    const int e1  = (e0 + kTileEdges < total) ? e0 + kTileEdges : total;
+    const int e0  = tile * kTileEdges;  // < total < 2^31 by the loop condition
+    const int e1  = ((long long)e0 + kTileEdges < (long long)total) ? e0 + kTileEdges : total;
     const int2 kk = tile_k[tile];
     const int k0 = kk.x, k1 = kk.y;
     const int nv = k1 - k0 + 1;
@@ -192,12 +196,40 @@ struct advance_scratch_t {
 // total_edges = sum of the degrees of the queue entries (known on the host from the previous level)
 // ready_deg: degrees of the queue entries if the producer of the queue already wrote them (n + 1 readable elements; the
 // exclusive scan never uses the last one), else nullptr
+// degree sum of queue entries [0, n)
+template <typename O>
+__global__ void k_queue_degree_sum(O const* __restrict__ off, int32_t const* __restrict__ q, int32_t const* __restrict__ ready_deg,
+                                   int n, unsigned long long* __restrict__ out)
+{
+  unsigned long long t = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    t += ready_deg ? (unsigned long long)(unsigned)ready_deg[i] : (unsigned long long)((long long)off[q[i] + 1] - (long long)off[q[i]]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0 && t) atomicAdd(out, t);
+}
+
 template <typename O, typename Op>
 void advance(handle_impl const& h, advance_scratch_t& sc, O const* off, int32_t const* idx, int32_t const* queue, int n,
              unsigned long long total_edges, Op op, int32_t const* ready_deg = nullptr)
 {
   if (n <= 0) return;
-  B200_EXPECTS(total_edges < (1ull << 31), CUGRAPH_UNKNOWN_ERROR, "frontier too large for one advance");
+  B200_EXPECTS(total_edges < (1ull << 31) || n > 1, CUGRAPH_UNKNOWN_ERROR, "a single vertex with 2^31 or more edges");
+  if (total_edges >= h.tune.advance_split_edges && n > 1) {
+    // the tile numbering is 32-bit: a queue whose degrees sum to 2^31 or more (graphs with 64-bit offsets) is advanced in
+    // halves, each with its own degree sum (one small reduction + read-back per split; only such graphs ever get here)
+    const int n1 = n / 2;
+    dbuf d_sum   = make_dbuf<unsigned long long>(1, h.stream);
+    CUDA_TRY(cudaMemsetAsync(d_sum.data(), 0, sizeof(unsigned long long), h.stream));
+    B200_LAUNCH(h, (k_queue_degree_sum<O>), std::min((n1 + kBlock - 1) / kBlock, h.sm_count * 8), kBlock, 0, off, queue, ready_deg, n1,
+                d_sum.as<unsigned long long>());
+    unsigned long long e1 = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e1, d_sum.data(), sizeof(e1), cudaMemcpyDeviceToHost, h.stream));
+    sync(h);
+    advance<O, Op>(h, sc, off, idx, queue, n1, e1, op, ready_deg);
+    advance<O, Op>(h, sc, off, idx, queue + n1, n - n1, total_edges - e1, op, ready_deg ? ready_deg + n1 : nullptr);
+    return;
+  }
   if (!ready_deg) {
     B200_LAUNCH(h, (k_queue_degrees<O>), (n + 1 + kBlock - 1) / kBlock, kBlock, 0, off, queue, n, sc.deg.as<int32_t>());
     ready_deg = sc.deg.as<int32_t>();

@@ -20,6 +20,7 @@ def make_graph(src, dst, weights=None, store_transposed=False, renumber=True, sy
     d = torch.as_tensor(np.asarray(dst, dtype=vertex_dtype)).cuda()
     w = None if weights is None else torch.as_tensor(np.asarray(weights, dtype=weight_dtype)).cuda()
     v = None if vertices is None else torch.as_tensor(np.asarray(vertices, dtype=vertex_dtype)).cuda()
+    symmetric = symmetric or bool(kw.get("symmetrize"))   # the reference rejects symmetrize without the property (graph_sg.cpp:737-742)
     g = plc.SGGraph(h, plc.GraphProperties(is_symmetric=symmetric, is_multigraph=True), s, d, weight_array=w,
                     store_transposed=store_transposed, renumber=renumber, vertices_array=v, **kw)
     return h, g

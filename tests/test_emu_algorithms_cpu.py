@@ -309,6 +309,41 @@ def test_sssp_window_control_emulated(emu, monkeypatch, capfd, weights):  # noqa
     emu.cugraph_graph_free(g)
 
 
+def test_advance_in_halves_emulated(emu, monkeypatch):  # noqa: F811
+    """a frontier whose degree sum reaches the 32-bit tile numbering's limit is advanced in halves (graphs with 64-bit
+    offsets); the limit is lowered to 500 edges here so that BFS and SSSP take that path at every level"""
+    monkeypatch.setenv("CUGRAPH_B200_ADVANCE_SPLIT_EDGES", "500")
+    emu.emu_reload_tuning(C.c_void_p(emu.handle))
+    try:
+        s, d = symmetric_edges(4_000, 30_000, seed=13)
+        w = np.random.default_rng(4).random(s.size // 2).astype(np.float32)
+        w = np.concatenate([w, w])
+        g = create_sym_graph(emu, s, d, w)
+        ids, ss, dd = dense_ids(s, d)
+        source = int(ids[5])
+        srcs = np.array([source], dtype=np.int32)
+        sv = emu.cugraph_type_erased_device_array_view_create(srcs.ctypes.data, 1, INT32)
+        res, err = C.c_void_p(), C.c_void_p()
+        code = emu.cugraph_bfs(C.c_void_p(emu.handle), g, C.c_void_p(sv), 0, C.c_size_t(2**31 - 2), 1, 0, C.byref(res), C.byref(err))
+        assert code == 0, emu.cugraph_error_message(err)
+        verts, dist, _ = _paths(emu, res)
+        ref_d, _ = oracle.bfs(ss, dd, ids.size, [int(np.searchsorted(ids, source))])
+        got = np.zeros(ids.size, dtype=np.int64)
+        got[np.searchsorted(ids, verts)] = dist
+        ref = np.asarray(ref_d, dtype=np.int64)
+        reached = (ref >= 0) & (ref < np.iinfo(np.int32).max)
+        assert (got[reached] == ref[reached]).all() and (got[~reached] == np.iinfo(np.int32).max).all()
+        verts, sd, _ = _sssp_dist(emu, g, source)
+        ref_s, _ = oracle.sssp(ss, dd, w, ids.size, int(np.searchsorted(ids, source)), use_float=True)
+        gs = np.zeros(ids.size, dtype=np.float32)
+        gs[np.searchsorted(ids, verts)] = sd
+        assert (gs == ref_s.astype(np.float32)).all()
+        emu.cugraph_graph_free(g)
+    finally:
+        monkeypatch.delenv("CUGRAPH_B200_ADVANCE_SPLIT_EDGES")
+        emu.emu_reload_tuning(C.c_void_p(emu.handle))
+
+
 def test_extract_paths_emulated(emu):  # noqa: F811
     """cugraph_extract_paths on a BFS result: every row is the path source ... destination (consecutive vertices are
     edges, length = distance + 1), -1 behind it; unreachable destinations give an all -1 row; the source gives a row of one.

@@ -187,6 +187,20 @@ def test_symmetrize_and_drop_flags_match_oracle_bfs(emu):  # noqa: F811
     assert np.array_equal(by_vertex(verts, dist, V), rd)
 
 
+def test_multi_edges_are_removed_before_symmetrize(emu):  # noqa: F811
+    """the reference's order (c_api/graph_sg.cpp:203-247): remove_multi_edges (minimum weight: the graph is declared
+    symmetric) THEN symmetrize (reciprocal pairs are averaged): (0,1,1), (0,1,2), (1,0,5) -> (0,1,1), (1,0,5) -> weight 3;
+    and symmetrize without the symmetric property is rejected (graph_sg.cpp:737-742)"""
+    s = np.array([0, 0, 1, 1], np.int32)
+    d = np.array([1, 1, 0, 2], np.int32)
+    w = np.array([1.0, 2.0, 5.0, 4.0], np.float32)
+    g = G(emu, s, d, w, vertices=np.arange(3), symmetric=True, renumber=True, drop_multi_edges=1, symmetrize=1)
+    verts, dist, _ = g.sssp(2)
+    assert by_vertex(verts, dist, 3).tolist() == [7.0, 4.0, 0.0]       # 2 -(4)- 1 -(3)- 0
+    code, msg = _create_checked(emu, s, d, symmetric=False, multigraph=True, symmetrize=1)
+    assert code != 0 and "must be symmetric if 'symmetrize'" in msg
+
+
 def test_csr_input(emu):  # noqa: F811
     rng = np.random.default_rng(3)
     V, E = 200, 1500
