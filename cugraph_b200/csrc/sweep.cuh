@@ -73,6 +73,59 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p)
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// the same with an L2 eviction policy (createpolicy): the 0.8 GB stream is read once — marked evict-first it leaves the L2 to
+// the 59 MB of accumulators (ncu r02: 57 % of the RED sectors missed the L2 and fetched their line from DRAM first)
+__device__ __forceinline__ unsigned long long make_l2_policy(bool evict_first)
+{
+  unsigned long long pol;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p, unsigned long long pol)
+{
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const void* p, unsigned long long pol)
+{
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+// fp64 accumulation with an L2 eviction policy on the accumulator line (acc_pol == 0: plain RED)
+#ifndef B200_ACC_POLICY
+// 2: every RED carries an evict-last policy for its accumulator line (0: plain RED, 1: chosen at run time).  Measured on
+// RMAT-24 with the stream evict-first (profiles/r02_evict_ab3.log): 0 -> 0.3191-0.3196 ms per sweep, 2 -> 0.3141-0.3143,
+// 1 (policy off) -> 0.3274-0.3288: the per-RED branch of the run-time choice costs what the policy gains.
+#define B200_ACC_POLICY 2
+#endif
+__device__ __forceinline__ void red_acc(double* p, double v, unsigned long long acc_pol)
+{
+#if B200_ACC_POLICY == 0
+  atomicAdd(p, v);
+#elif B200_ACC_POLICY == 2
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(acc_pol) : "memory");
+#else
+  if (acc_pol) asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(acc_pol) : "memory");
+  else atomicAdd(p, v);
+#endif
+}
+__device__ __forceinline__ unsigned long long make_l2_policy_evict_last()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int ld_stream_i32(const int* p, unsigned long long pol)
+{
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ uint2 ld_stream_v2(const void* p)
 {
   uint2 v;
@@ -105,6 +158,12 @@ inline uint2 ld_stream_v2(const void* p)
   return v;
 }
 inline int ld_volatile(const int* p) { return *p; }
+inline unsigned long long make_l2_policy(bool) { return 0ull; }
+inline uint4 ld_stream_v4(const void* p, unsigned long long) { return ld_stream_v4(p); }
+inline uint2 ld_stream_v2(const void* p, unsigned long long) { return ld_stream_v2(p); }
+inline int ld_stream_i32(const int* p, unsigned long long) { return *p; }
+inline void red_acc(double* p, double v, unsigned long long) { *p += v; }
+inline unsigned long long make_l2_policy_evict_last() { return 0ull; }
 #define B200_DYN_SMEM(name) extern unsigned char name[] /* one CTA at a time: emu/emu_debug.cpp defines b200::smem_raw */
 #endif
 
@@ -144,12 +203,12 @@ __device__ __forceinline__ void load_w8(T (&wv)[8], T const* __restrict__ w, siz
 
 // end of an F8 group (full 64-entry pieces): consecutive lanes may hold pieces of the same (hub) row — suffix-sum inside
 // the runs first, run heads emit
-__device__ __forceinline__ void emit_runs(double acc, int row, double* __restrict__ acc_out, int lane)
+__device__ __forceinline__ void emit_runs(double acc, int row, double* __restrict__ acc_out, int lane, unsigned long long acc_pol)
 {
   const int r0 = __shfl_sync(0xffffffffu, row, 0);
   if (__all_sync(0xffffffffu, row == r0)) {  // 32 pieces of one hub row
     acc = warp_sum(acc);
-    if (lane == 0 && r0 >= 0) atomicAdd(acc_out + r0, acc);
+    if (lane == 0 && r0 >= 0) red_acc(acc_out + r0, acc, acc_pol);
     return;
   }
   const int left = __shfl_up_sync(0xffffffffu, row, 1);
@@ -160,7 +219,7 @@ __device__ __forceinline__ void emit_runs(double acc, int row, double* __restric
     if (lane + o < 32 && rn == row) acc += nb;
   }
   if (lane > 0 && left == row) row = -1;  // not the head of its run
-  if (row >= 0) atomicAdd(acc_out + row, acc);
+  if (row >= 0) red_acc(acc_out + row, acc, acc_pol);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -183,6 +242,8 @@ struct sweep_ptrs_t {
   int32_t const* __restrict__ rows;
   void const* __restrict__ w;
   double* __restrict__ acc;
+  unsigned long long pol;      // L2 eviction policy of the stream loads
+  unsigned long long acc_pol;  // of the accumulator REDs (0: none)
 };
 
 template <int C, int G>
@@ -194,8 +255,8 @@ __device__ __forceinline__ void load_F(chunk_regs_t& b, sweep_chunk_t const& ch,
   for (int g = 0; g < G; ++g) {
     if (g < ch.n_groups) {
 #pragma unroll
-      for (int j = 0; j < C; ++j) b.q[g * C + j] = ld_stream_v4(ip + ((g * C + j) << 5));
-      const int r = ld_stream(rp + (g << 5));
+      for (int j = 0; j < C; ++j) b.q[g * C + j] = ld_stream_v4(ip + ((g * C + j) << 5), p.pol);
+      const int r = ld_stream_i32(rp + (g << 5), p.pol);
       if (C >= 4) {
         if (g == 0) b.r0 = r; else b.r1 = r;
       } else if (C == 1) {
@@ -226,8 +287,8 @@ __device__ __forceinline__ void process_F(chunk_regs_t const& b, sweep_chunk_t c
       if (C >= 4) row = g == 0 ? b.r0 : b.r1;
       else if (C == 1) row = (int)(g < 4 ? comp(b.q[6], g) : comp(b.q[7], g - 4));
       else row = (int)comp(b.q[6], g);
-      if (C == 8) emit_runs(s, row, p.acc, lane);
-      else if (row >= 0) atomicAdd(p.acc + row, s);
+      if (C == 8) emit_runs(s, row, p.acc, lane, p.acc_pol);
+      else if (row >= 0) red_acc(p.acc + row, s, p.acc_pol);
     }
   }
 }
@@ -241,17 +302,17 @@ __device__ __forceinline__ void load_N(chunk_regs_t& b, sweep_chunk_t const& ch,
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     if (g < ch.n_groups) {
-      const uint4 ids = ld_stream_v4(ip + (g << 5));
+      const uint4 ids = ld_stream_v4(ip + (g << 5), p.pol);
       if (ROWS == 8) {
         b.q[3 * g]     = ids;
-        b.q[3 * g + 1] = ld_stream_v4(rp + g * 256);
-        b.q[3 * g + 2] = ld_stream_v4(rp + g * 256 + 4);
+        b.q[3 * g + 1] = ld_stream_v4(rp + g * 256, p.pol);
+        b.q[3 * g + 2] = ld_stream_v4(rp + g * 256 + 4, p.pol);
       } else if (ROWS == 4) {
         b.q[2 * g]     = ids;
-        b.q[2 * g + 1] = ld_stream_v4(rp + g * 128);
+        b.q[2 * g + 1] = ld_stream_v4(rp + g * 128, p.pol);
       } else {
         b.q[g]        = ids;
-        const uint2 r = ld_stream_v2(rp + g * 64);
+        const uint2 r = ld_stream_v2(rp + g * 64, p.pol);
         uint4& dst    = b.q[4 + (g >> 1)];
         if (g & 1) {
           dst.z = r.x;
@@ -282,7 +343,7 @@ __device__ __forceinline__ void process_N(chunk_regs_t const& b, sweep_chunk_t c
           T v                 = sx[(k & 1) ? hi16(word) : lo16(word)];
           if (WEIGHTED) v *= wv[k];
           const int row = (int)comp(b.q[3 * g + 1 + (k >> 2)], k & 3);
-          if (row >= 0) atomicAdd(p.acc + row, (double)v);
+          if (row >= 0) red_acc(p.acc + row, (double)v, p.acc_pol);
         }
       } else if (ROWS == 4) {
         const uint4 ids = b.q[2 * g];
@@ -290,7 +351,7 @@ __device__ __forceinline__ void process_N(chunk_regs_t const& b, sweep_chunk_t c
         for (int k = 0; k < 4; ++k) {
           const T v     = pair_sum<T, WEIGHTED>(comp(ids, k), sx, wv + 2 * k);
           const int row = (int)comp(b.q[2 * g + 1], k);
-          if (row >= 0) atomicAdd(p.acc + row, (double)v);
+          if (row >= 0) red_acc(p.acc + row, (double)v, p.acc_pol);
         }
       } else {
         const uint4 ids = b.q[g];
@@ -298,8 +359,8 @@ __device__ __forceinline__ void process_N(chunk_regs_t const& b, sweep_chunk_t c
         const T v0      = pair_sum<T, WEIGHTED>(ids.x, sx, wv) + pair_sum<T, WEIGHTED>(ids.y, sx, wv + 2);
         const T v1      = pair_sum<T, WEIGHTED>(ids.z, sx, wv + 4) + pair_sum<T, WEIGHTED>(ids.w, sx, wv + 6);
         const int row0 = (int)((g & 1) ? rr.z : rr.x), row1 = (int)((g & 1) ? rr.w : rr.y);
-        if (row0 >= 0) atomicAdd(p.acc + row0, (double)v0);
-        if (row1 >= 0) atomicAdd(p.acc + row1, (double)v1);
+        if (row0 >= 0) red_acc(p.acc + row0, (double)v0, p.acc_pol);
+        if (row1 >= 0) red_acc(p.acc + row1, (double)v1, p.acc_pol);
       }
     }
   }
@@ -358,6 +419,8 @@ struct sweep_args_t {
   pr_state_t const* __restrict__ st;
   int n_phases;
   int W;
+  int stream_evict_first;
+  int acc_evict_last;
 };
 
 // ---- chunk supply of a warp.  Chunks are drawn from the phase's cursor in BATCHES of consecutive chunks (lane j holds
@@ -462,6 +525,12 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_sweep(sweep_args_t<T> a)
   __shared__ int s_best;
   __shared__ uint4 s_ring[kSweepWarps][2 * kDrawMax];
   if (a.st->done) return;
+  a.p.pol        = make_l2_policy(a.stream_evict_first != 0);
+#if B200_ACC_POLICY == 2
+  a.p.acc_pol    = make_l2_policy_evict_last();
+#else
+  a.p.acc_pol    = a.acc_evict_last ? make_l2_policy_evict_last() : 0ull;
+#endif
   const int lane = threadIdx.x & 31;
   const int me   = (int)blockIdx.x;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -604,6 +673,10 @@ void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L,
   a.st        = st;
   a.n_phases  = L.n_phases;
   a.W         = L.W;
+  a.p.pol     = 0;
+  a.p.acc_pol = 0;
+  a.stream_evict_first = h.tune.sweep_stream_evict_first ? 1 : 0;
+  a.acc_evict_last     = h.tune.sweep_acc_evict_last ? 1 : 0;
   if (weighted) B200_LAUNCH(h, (k_sweep<T, true>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
   else B200_LAUNCH(h, (k_sweep<T, false>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
   // 64-row steps per warp: 8 measured 0.335 ms per sweep, 4: 0.340, 2: 0.354 (profiles/r02_fullchunk_ab.log)

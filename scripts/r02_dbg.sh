@@ -1,10 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-out=gpurun_out/r02_sssp_ab.log
+out=gpurun_out/r02_evict_ab3.log
 : > $out
-run() { echo "== $*" >> $out; env "$@" timeout 200 ./cugraph_b200/lib/cbench 24 trav 4 2>&1 | grep -E "^\{|window" | tail -4 >> $out; }
-run CUGRAPH_B200_SSSP_SMALL_ROUNDS=0 CUGRAPH_B200_SSSP_TRACE=1
-run CUGRAPH_B200_SSSP_SMALL_ROUNDS=1 CUGRAPH_B200_SSSP_TRACE=1
-run A=1
-cat $out
-timeout 600 python -m pytest tests/test_traversal_gpu.py -x -q 2>&1 | tail -3
+for rep in 1 2; do
+for v in lib_a lib lib_c; do
+  echo "== $v (a: plain RED, lib: run-time choice off, c: always evict-last) sweep" >> $out
+  timeout 120 ./cugraph_b200/$v/cbench 24 sweep >> $out 2>&1
+done
+done
+for v in lib_a lib_c; do
+  echo "== $v pagerank" >> $out
+  timeout 120 ./cugraph_b200/$v/cbench 24 pagerank >> $out 2>&1
+done
+grep -E "^==|sweep_ms|pagerank100|rror" $out | sed 's/"max_rel.*//'
