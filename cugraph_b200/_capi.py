@@ -106,6 +106,17 @@ def lib():
     _sig(L.cugraph_extract_paths_result_get_max_path_length, sz, [vp])
     _sig(L.cugraph_extract_paths_result_get_paths, vp, [vp])
     _sig(L.cugraph_extract_paths_result_free, None, [vp])
+    _sig(L.cugraph_katz_centrality, i32, [vp, vp, vp, dbl, dbl, dbl, sz, i32, pvp, pvp])
+    _sig(L.cugraph_hits, i32, [vp, vp, dbl, sz, vp, vp, i32, i32, pvp, pvp])
+    for f in ("vertices", "hubs", "authorities"):
+        _sig(getattr(L, f"cugraph_hits_result_get_{f}"), vp, [vp])
+    _sig(L.cugraph_hits_result_get_hub_score_differences, dbl, [vp])
+    _sig(L.cugraph_hits_result_get_number_of_iterations, sz, [vp])
+    _sig(L.cugraph_hits_result_free, None, [vp])
+    _sig(L.cugraph_weakly_connected_components, i32, [vp, vp, i32, pvp, pvp])
+    _sig(L.cugraph_labeling_result_get_vertices, vp, [vp])
+    _sig(L.cugraph_labeling_result_get_labels, vp, [vp])
+    _sig(L.cugraph_labeling_result_free, None, [vp])
     # extensions (b200_ext.h)
     _sig(L.cugraph_b200_version, C.c_char_p, [])
     _sig(L.cugraph_b200_handle_stream, vp, [vp])

@@ -139,6 +139,7 @@ struct graph_impl {
   std::unique_ptr<csx_t> primary;    // orientation requested at creation (degree-sorted, identity rows)
   std::unique_ptr<csx_t> pull_alt;   // lazily built CSC with re-sorted rows (PageRank on a CSR graph)
   std::unique_ptr<csx_t> push_alt;   // lazily built CSR in vertex order (BFS/SSSP on a CSC graph)
+  std::unique_ptr<csx_t> out_alt;    // lazily built CSR with rows re-sorted by out-degree (HITS' hub sweep on a CSC graph)
 
   // multi-GPU (mg.cu): this rank's blocks of the 2D partition
   void* mg{nullptr};
@@ -155,6 +156,7 @@ csx_t const& pull_view(handle_impl const& h, graph_impl& g);  // rows = destinat
 // piece stream for elements of `elem_size` bytes, or nullptr when the graph is too small for it
 sweep_layout_t const* sweep_layout(handle_impl const& h, csx_t const& c, int32_t n_vertices, size_t elem_size);
 csx_t const& push_view(handle_impl const& h, graph_impl& g);  // rows = sources, vertex-indexed offsets
+csx_t const& out_sweep_view(handle_impl const& h, graph_impl& g);  // rows = sources, binned for the sweep kernels (HITS)
 
 // external <-> internal id helpers (graph_build.cu)
 // out[i] = internal id of ext[i], or -1 if ext[i] is not a vertex.

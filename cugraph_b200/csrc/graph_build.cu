@@ -941,6 +941,20 @@ csx_t const& pull_view(handle_impl const& h, graph_impl& g)
   return *g.pull_alt;
 }
 
+// rows = sources, indices = destinations, in a layout the sweep kernels accept (degree-descending physical rows): the
+// primary orientation of a CSR graph, a re-sorted transpose of a CSC graph (the mirror image of pull_view)
+csx_t const& out_sweep_view(handle_impl const& h, graph_impl& g)
+{
+  if (!g.store_transposed || g.is_symmetric) return *g.primary;
+  if (!g.out_alt) {
+    csx_t const& p = *g.primary;  // CSC: rows = destinations, indices = sources
+    dbuf maj       = expand_majors(h, p);
+    g.out_alt      = build_binned_rows(h, p.indices.as<int32_t>(), maj.as<int32_t>(), g.weighted ? p.weights.data() : nullptr,
+                                       g.weight_type, p.nnz, g.n_vertices);
+  }
+  return *g.out_alt;
+}
+
 csx_t const& push_view(handle_impl const& h, graph_impl& g)
 {
   if (!g.store_transposed || g.is_symmetric) return *g.primary;

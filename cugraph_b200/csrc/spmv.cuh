@@ -226,11 +226,11 @@ inline low_bins_t make_low_bins(csx_t const& c)
 
 template <typename O, typename T>
 void launch_pull_sweep(handle_impl const& h, csx_t const& c, T const* x, T* y, double* acc_hi, double alpha,
-                       pr_state_t const* st)
+                       pr_state_t const* st, bool use_weights = true)
 {
   O const* off        = c.offsets.as<O>();
   int32_t const* idx  = c.indices.as<int32_t>();
-  T const* w          = c.weights.as<T>();
+  T const* w          = use_weights ? c.weights.as<T>() : nullptr;  // HITS sums plain neighbour values on a weighted graph too
   int32_t const* rv   = c.row_vertex.as<int32_t>();
   const bool weighted = (w != nullptr);
   if (c.n_chunks > 0) {

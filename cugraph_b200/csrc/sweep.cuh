@@ -654,10 +654,10 @@ k_sweep_finish(double* __restrict__ acc, int n_cov, int n_rows, T* __restrict__ 
 // x must hold padded_x_elems() elements, zero behind n_vertices (slices are copied whole)
 template <typename T>
 void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L, T const* x, T* y, double* acc, double alpha,
-                  pr_state_t const* st)
+                  pr_state_t const* st, bool use_weights = true)
 {
   // the attribute is per device and cheap to set: no process-wide "done" flag (a second device would miss it)
-  const bool weighted = L.w.data() != nullptr;
+  const bool weighted = use_weights && L.w.data() != nullptr;
   if (weighted) CUDA_TRY(cudaFuncSetAttribute(k_sweep<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepDynSmem));
   else CUDA_TRY(cudaFuncSetAttribute(k_sweep<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSweepDynSmem));
   sweep_args_t<T> a;
@@ -696,11 +696,11 @@ void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L,
 // dispatch: the piece stream when it exists for this graph, else the plain edge-balanced sweep
 template <typename O, typename T>
 void launch_pull_sweep_auto(handle_impl const& h, csx_t const& c, int32_t n_vertices, T const* x, T* y, double* acc,
-                            double alpha, pr_state_t const* st)
+                            double alpha, pr_state_t const* st, bool use_weights = true)
 {
   sweep_layout_t const* L = sweep_layout(h, c, n_vertices, sizeof(T));
-  if (!L) launch_pull_sweep<O, T>(h, c, x, y, acc, alpha, st);
-  else launch_sweep<T>(h, c, *L, x, y, acc, alpha, st);
+  if (!L) launch_pull_sweep<O, T>(h, c, x, y, acc, alpha, st, use_weights);
+  else launch_sweep<T>(h, c, *L, x, y, acc, alpha, st, use_weights);
 }
 
 // elements an x buffer needs: whole slices are TMA-copied and everything behind n_vertices must read 0.

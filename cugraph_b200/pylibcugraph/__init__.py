@@ -6,7 +6,8 @@ from cugraph_b200.pylibcugraph.exceptions import FailedToConvergeError
 from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
 from cugraph_b200.pylibcugraph.graph_properties import GraphProperties
 from cugraph_b200.pylibcugraph.graphs import SGGraph
-from cugraph_b200.pylibcugraph.algorithms import pagerank, personalized_pagerank, bfs, sssp
+from cugraph_b200.pylibcugraph.algorithms import (pagerank, personalized_pagerank, bfs, sssp, katz_centrality, hits,
+                                                  weakly_connected_components)
 
 __all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph",
-           "pagerank", "personalized_pagerank", "bfs", "sssp"]
+           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "hits", "weakly_connected_components"]

@@ -112,3 +112,56 @@ def sssp(resource_handle, graph, source, cutoff, compute_predecessors, do_expens
     _capi.check(code, err, "cugraph_sssp")
     verts, dist, pred = _paths_result(resource_handle, res)
     return (verts, dist, pred)
+
+
+def katz_centrality(resource_handle, graph, betas, alpha, beta, epsilon, max_iterations, do_expensive_check):
+    """Returns (vertices, values) — katz_centrality.pyx:47-145.  `betas` is accepted and, as in the reference's C entry
+    point (c_api/katz.cpp:151-152), not used: every vertex gets `beta`."""
+    assert_CAI_type(betas, "betas", allow_none=True)
+    bv = View(betas)
+    res, err = C.c_void_p(), C.c_void_p()
+    resource_handle.order_after_caller()
+    code = _capi.lib().cugraph_katz_centrality(resource_handle.ptr, graph.ptr, bv.ptr, float(alpha), float(beta), float(epsilon),
+                                               int(max_iterations), int(bool(do_expensive_check)), C.byref(res), C.byref(err))
+    bv.free()
+    _capi.check(code, err, "cugraph_katz_centrality")
+    verts, vals, _, _ = _centrality_result(resource_handle, res)
+    return (verts, vals)
+
+
+def hits(resource_handle, graph, tol, max_iter, initial_hubs_guess_vertices, initial_hubs_guess_values, normalized,
+         do_expensive_check):
+    """Returns (vertices, hubs, authorities) — hits.pyx:49-184."""
+    assert_CAI_type(initial_hubs_guess_vertices, "initial_hubs_guess_vertices", allow_none=True)
+    assert_CAI_type(initial_hubs_guess_values, "initial_hubs_guess_values", allow_none=True)
+    gv, gx = View(initial_hubs_guess_vertices), View(initial_hubs_guess_values)
+    res, err = C.c_void_p(), C.c_void_p()
+    resource_handle.order_after_caller()
+    L = _capi.lib()
+    code = L.cugraph_hits(resource_handle.ptr, graph.ptr, float(tol), int(max_iter), gv.ptr, gx.ptr, int(bool(normalized)),
+                          int(bool(do_expensive_check)), C.byref(res), C.byref(err))
+    gv.free()
+    gx.free()
+    _capi.check(code, err, "cugraph_hits")
+    verts = copy_to_torch(resource_handle, L.cugraph_hits_result_get_vertices(res))
+    hubs = copy_to_torch(resource_handle, L.cugraph_hits_result_get_hubs(res))
+    auth = copy_to_torch(resource_handle, L.cugraph_hits_result_get_authorities(res))
+    L.cugraph_hits_result_free(res)
+    return (verts, hubs, auth)
+
+
+def weakly_connected_components(resource_handle, graph, offsets, indices, weights, labels, do_expensive_check):
+    """Returns (vertices, labels) — weakly_connected_components.pyx:107-271 (the graph form; the legacy CSR-array form
+    `graph=None, offsets=..., indices=...` of the reference is not supported)."""
+    if graph is None:
+        raise NotImplementedError("weakly_connected_components needs a graph (the legacy offsets / indices form is not supported)")
+    res, err = C.c_void_p(), C.c_void_p()
+    resource_handle.order_after_caller()
+    L = _capi.lib()
+    code = L.cugraph_weakly_connected_components(resource_handle.ptr, graph.ptr, int(bool(do_expensive_check)), C.byref(res),
+                                                 C.byref(err))
+    _capi.check(code, err, "cugraph_weakly_connected_components")
+    verts = copy_to_torch(resource_handle, L.cugraph_labeling_result_get_vertices(res))
+    labs = copy_to_torch(resource_handle, L.cugraph_labeling_result_get_labels(res))
+    L.cugraph_labeling_result_free(res)
+    return (verts, labs)

@@ -69,6 +69,29 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_personalized_pagerank_allow_nonconve
   double alpha, double epsilon, size_t max_iterations, bool_t do_expensive_check,
   cugraph_centrality_result_t** result, cugraph_error_t** error);
 
+/* ---- sibling algorithms on the same primitive ----
+ * Katz centrality: cpp/include/cugraph_c/centrality_algorithms.h:328-364, cpp/src/c_api/katz.cpp,
+ * cpp/src/centrality/katz_centrality_impl.cuh:34-196.  x <- alpha * A^T x + beta until sum |x_new - x_old| < epsilon, then
+ * divided by its L2 norm; `betas` is accepted and — as in the reference's C entry point — not used. */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_katz_centrality(
+  const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, const cugraph_type_erased_device_array_view_t* betas,
+  double alpha, double beta, double epsilon, size_t max_iterations, bool_t do_expensive_check,
+  cugraph_centrality_result_t** result, cugraph_error_t** error);
+
+/* HITS: centrality_algorithms.h:488-591, cpp/src/c_api/hits.cpp, cpp/src/link_analysis/hits_impl.cuh:29-206. */
+typedef struct { int32_t align_; } cugraph_hits_result_t;
+CUGRAPH_EXPORT cugraph_type_erased_device_array_view_t* cugraph_hits_result_get_vertices(cugraph_hits_result_t* result);
+CUGRAPH_EXPORT cugraph_type_erased_device_array_view_t* cugraph_hits_result_get_hubs(cugraph_hits_result_t* result);
+CUGRAPH_EXPORT cugraph_type_erased_device_array_view_t* cugraph_hits_result_get_authorities(cugraph_hits_result_t* result);
+CUGRAPH_EXPORT double cugraph_hits_result_get_hub_score_differences(cugraph_hits_result_t* result);
+CUGRAPH_EXPORT size_t cugraph_hits_result_get_number_of_iterations(cugraph_hits_result_t* result);
+CUGRAPH_EXPORT void cugraph_hits_result_free(cugraph_hits_result_t* result);
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_hits(
+  const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, double epsilon, size_t max_iterations,
+  const cugraph_type_erased_device_array_view_t* initial_hubs_guess_vertices,
+  const cugraph_type_erased_device_array_view_t* initial_hubs_guess_values, bool_t normalize, bool_t do_expensive_check,
+  cugraph_hits_result_t** result, cugraph_error_t** error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -236,3 +236,80 @@ def check_sssp_predecessors(src, dst, weights, num_vertices, dist, pred, source,
     good = sel & (np.abs(dist[src] + w - dist[dst]) <= tol)
     ok[dst[good]] = True
     return bool(np.all(ok))
+
+
+# ---------------------------------------------------------------------------------------------
+# sibling algorithms: numpy restatements of the reference tests' own CPU references
+# ---------------------------------------------------------------------------------------------
+def katz(src, dst, num_vertices, weights=None, alpha=0.01, beta=1.0, epsilon=1e-6, max_iterations=500, normalize=True,
+         dtype=np.float64):
+    """katz_centrality_reference (cpp/tests/centrality/katz_centrality_test.cpp:37-103) with the update of
+    katz_centrality_impl.cuh:104-196: x <- alpha * A^T x + beta from x = 0, until sum |x_new - x_old| < epsilon;
+    then x / ||x||_2.  Arithmetic in `dtype` (the device computes in the graph's weight type).  Returns (x, iterations)."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    w = np.ones(src.size, dtype=np.float64) if weights is None else np.asarray(weights, dtype=np.float64)
+    x = np.zeros(num_vertices, dtype=np.float64)
+    it = 0
+    while True:
+        new = np.bincount(dst, weights=alpha * x[src] * w, minlength=num_vertices) + beta
+        new = new.astype(dtype).astype(np.float64)
+        diff = np.abs(new - x).sum()
+        x = new
+        it += 1
+        if dtype(diff) < dtype(epsilon):
+            break
+        if it >= max_iterations:
+            raise RuntimeError("Katz Centrality failed to converge.")
+    if normalize:
+        x = x / np.sqrt((x * x).sum())
+    return x, it
+
+
+def hits(src, dst, num_vertices, epsilon=1e-5, max_iterations=500, initial_hubs=None, normalize=True):
+    """hits_reference (cpp/tests/link_analysis/hits_test.cpp:40-120) / hits_impl.cuh:49-191: authorities = sum of the
+    in-neighbours' hubs, hubs = sum of the out-neighbours' authorities, both divided by their maximum; until
+    sum |hubs - previous hubs| < V * epsilon; finally both divided by their sum if `normalize`.  fp64.
+    Returns (hubs, authorities, iterations, last difference)."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    V = num_vertices
+    if initial_hubs is None:
+        prev = np.full(V, 1.0 / V)
+    else:
+        prev = np.asarray(initial_hubs, dtype=np.float64) / np.sum(initial_hubs)
+    it = 0
+    while True:
+        auth = np.bincount(dst, weights=prev[src], minlength=V)
+        curr = np.bincount(src, weights=auth[dst], minlength=V)
+        curr = curr / curr.max()
+        auth = auth / auth.max()
+        diff = np.abs(curr - prev).sum()
+        prev = curr
+        it += 1
+        if diff < V * epsilon:
+            break
+        if it >= max_iterations:
+            raise RuntimeError("HITS failed to converge.")
+    if normalize:
+        prev = prev / prev.sum()
+        auth = auth / auth.sum()
+    return prev, auth, it, diff
+
+
+def wcc(src, dst, num_vertices):
+    """component index per vertex of the undirected graph — the role of weakly_connected_components_reference
+    (cpp/tests/components/weakly_connected_components_test.cpp:36-77: BFS from every unvisited vertex): plain union-find."""
+    parent = np.arange(num_vertices, dtype=np.int64)
+
+    def find(v):
+        while parent[v] != v:
+            parent[v] = parent[parent[v]]
+            v = parent[v]
+        return v
+
+    for u, v in zip(np.asarray(src).tolist(), np.asarray(dst).tolist()):
+        ru, rv = find(u), find(v)
+        if ru != rv:
+            parent[max(ru, rv)] = min(ru, rv)
+    return np.array([find(v) for v in range(num_vertices)], dtype=np.int64)

@@ -67,8 +67,8 @@ def create_graph(L, src, dst, w, **flags):
     code = L.cugraph_graph_create_with_times_sg(
         C.c_void_p(L.handle), C.byref(Props(0, 1)), None, C.c_void_p(views[0]), C.c_void_p(views[1]),
         C.c_void_p(views[2]) if views[2] else None, None, None, None, None,
-        1, 1, int(flags.get("drop_self_loops", 0)), int(flags.get("drop_multi_edges", 0)), int(flags.get("symmetrize", 0)), 0,
-        C.byref(g), C.byref(err))
+        int(flags.get("store_transposed", 1)), 1, int(flags.get("drop_self_loops", 0)), int(flags.get("drop_multi_edges", 0)),
+        int(flags.get("symmetrize", 0)), 0, C.byref(g), C.byref(err))
     assert code == 0, L.cugraph_error_message(err)
     for v in views:
         if v:
