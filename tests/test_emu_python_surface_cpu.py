@@ -118,3 +118,59 @@ def test_graft_entry_smoke(surface, capsys):
     entry = _load(os.path.join(ROOT, "__graft_entry__.py"), "graft_entry_under_test")
     entry.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def test_user_level_api(surface):
+    """cugraph_b200.api (the shape of the reference's `cugraph` package: Graph.from_pandas_edgelist + functions returning one row
+    per vertex) against the oracle: directed PageRank / Katz / HITS, undirected BFS / SSSP / components"""
+    import pandas as pd
+    from cugraph_b200 import api
+    r = np.random.default_rng(5)
+    V, E = 400, 3000
+    s = (r.integers(0, V, E) * r.random(E) ** 1.5).astype(np.int64)
+    d = r.integers(0, V, E).astype(np.int64)
+    w = (r.random(E) + 0.25).astype(np.float32)
+    pdf = pd.DataFrame({"src": s, "dst": d, "wgt": w})
+    ids, inv = np.unique(np.concatenate([s, d]), return_inverse=True)
+    si, di = inv[:E], inv[E:]
+
+    def by_id(df, col):
+        out = np.zeros(ids.size)
+        out[np.searchsorted(ids, df["vertex"].to_numpy())] = df[col].to_numpy()
+        return out
+
+    G = api.Graph(directed=True).from_pandas_edgelist(pdf, source="src", destination="dst")
+    df = api.pagerank(G, alpha=0.85, max_iter=200, tol=1e-7)
+    ref, _, _ = oracle.pagerank(si, di, ids.size, None, alpha=0.85, epsilon=1e-7, max_iterations=200)
+    np.testing.assert_allclose(by_id(df, "pagerank"), ref, rtol=2e-5)
+    df, conv = api.pagerank(G, max_iter=3, tol=1e-12, fail_on_nonconvergence=False)
+    assert conv is False and list(df.columns) == ["vertex", "pagerank"]
+    alpha = 0.5 / np.bincount(di).max()
+    dk = api.katz_centrality(G, alpha=alpha, beta=1.0, max_iter=300, tol=1e-5)
+    rk, _ = oracle.katz(si, di, ids.size, None, alpha=alpha, beta=1.0, epsilon=1e-5, dtype=np.float32)
+    np.testing.assert_allclose(by_id(dk, "katz_centrality"), rk, rtol=5e-5)
+    dh = api.hits(G, max_iter=500, tol=1e-7)
+    rh, ra, _, _ = oracle.hits(si, di, ids.size, epsilon=1e-7)
+    np.testing.assert_allclose(by_id(dh, "hubs"), rh, rtol=5e-3, atol=1e-8)
+    np.testing.assert_allclose(by_id(dh, "authorities"), ra, rtol=5e-3, atol=1e-8)
+
+    # undirected: symmetrised (and de-duplicated, minimum weight) at creation
+    GU = api.Graph(directed=False).from_pandas_edgelist(pdf, source="src", destination="dst", edge_attr="wgt")
+    keep = si != di
+    a, b = np.minimum(si, di)[keep], np.maximum(si, di)[keep]
+    start = int(ids[np.bincount(np.concatenate([a, b])).argmax()])
+    db = api.bfs(GU, start=start)
+    us, ud = np.concatenate([a, b, si[~keep]]), np.concatenate([b, a, di[~keep]])
+    rd, _ = oracle.bfs(us.astype(np.int32), ud.astype(np.int32), ids.size, [int(np.searchsorted(ids, start))])
+    rd = np.asarray(rd, dtype=np.int64)
+    imax = np.iinfo(np.int32).max
+    got = by_id(db, "distance").astype(np.int64)
+    assert np.array_equal(got[rd < imax], rd[rd < imax]) and set(db.columns) == {"vertex", "distance", "predecessor"}
+    dc = api.weakly_connected_components(GU)
+    comp = oracle.wcc(us, ud, ids.size)
+    pairs = set(zip(comp.tolist(), by_id(dc, "labels").astype(np.int64).tolist()))
+    assert len(pairs) == len(set(comp.tolist()))
+    ds = api.sssp(GU, source=start)
+    assert set(ds.columns) == {"vertex", "distance", "predecessor"} and float(by_id(ds, "distance")[np.searchsorted(ids, start)]) == 0.0
+    with pytest.raises(RuntimeError):
+        api.sssp(api.Graph(directed=False).from_pandas_edgelist(pdf, source="src", destination="dst"), source=start)
