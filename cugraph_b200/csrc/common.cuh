@@ -100,16 +100,6 @@ struct comm_impl;
 struct tuning_t {
   long long sweep_min_edges{1ll << 22};  // CUGRAPH_B200_SWEEP_MIN_EDGES: graphs below it use the plain sweep (tests: 0)
   bool sweep_bank_order{true};           // CUGRAPH_B200_SWEEP_BANK_ORDER
-  // row-aligned groups of the piece stream (graph_build.cu, "window policy"): cost of a scattered piece, of a 16-bit id
-  // slot and of an aligned 32-row group, in 1/100 load/store-unit cycles; CUGRAPH_B200_SWEEP_ALIGN=0 switches them off
-  bool sweep_align{false};  // measured: +13 % sweep time with the policy on (profiles/r02_align_ab.log): the padding costs the load path more than the sectors save
-  // L2 policies of the sweep: the id / row stream is read once (evict-first: 0.331 -> 0.322 ms per sweep on RMAT-24,
-  // profiles/r02_evict_ab.log); the accumulators are hit by every RED (evict-last, compiled in: B200_ACC_POLICY in sweep.cuh;
-  // together 0.314 ms, profiles/r02_evict_ab3.log)
-  bool sweep_stream_evict_first{true};  // CUGRAPH_B200_SWEEP_EVICT_FIRST
-  bool sweep_acc_evict_last{false};     // CUGRAPH_B200_SWEEP_ACC_EVICT_LAST (only read by B200_ACC_POLICY == 1 builds)
-  int sweep_finish_steps{8};  // CUGRAPH_B200_SWEEP_FINISH_STEPS: 2, 4 or 8 (64-row steps per warp of the finish kernel)
-  int sweep_cost_scat{160}, sweep_cost_slot{10}, sweep_cost_group{800}, sweep_cost_lane{25};
   double bfs_alpha{40.0}, bfs_beta{24.0};  // CUGRAPH_B200_BFS_ALPHA / _BETA (Beamer switch points; alpha 14 -> 40: -7 % per source on RMAT-24, r02_notes)
   bool sssp_adaptive{true};                // CUGRAPH_B200_SSSP_ADAPTIVE
   double sssp_delta_scale{1.0};            // CUGRAPH_B200_SSSP_DELTA_SCALE
@@ -125,14 +115,6 @@ struct tuning_t {
     auto get = [](const char* k) { return std::getenv(k); };
     if (auto e = get("CUGRAPH_B200_SWEEP_MIN_EDGES")) t.sweep_min_edges = std::atoll(e);
     if (auto e = get("CUGRAPH_B200_SWEEP_BANK_ORDER")) t.sweep_bank_order = std::atoi(e) != 0;
-    if (auto e = get("CUGRAPH_B200_SWEEP_ALIGN")) t.sweep_align = std::atoi(e) != 0;
-    if (auto e = get("CUGRAPH_B200_SWEEP_EVICT_FIRST")) t.sweep_stream_evict_first = std::atoi(e) != 0;
-    if (auto e = get("CUGRAPH_B200_SWEEP_ACC_EVICT_LAST")) t.sweep_acc_evict_last = std::atoi(e) != 0;
-    if (auto e = get("CUGRAPH_B200_SWEEP_FINISH_STEPS")) { const int v = std::atoi(e); t.sweep_finish_steps = (v == 2 || v == 4) ? v : 8; }
-    if (auto e = get("CUGRAPH_B200_SWEEP_COST_SCAT")) t.sweep_cost_scat = std::max(1, std::atoi(e));
-    if (auto e = get("CUGRAPH_B200_SWEEP_COST_SLOT")) t.sweep_cost_slot = std::max(0, std::atoi(e));
-    if (auto e = get("CUGRAPH_B200_SWEEP_COST_GROUP")) t.sweep_cost_group = std::max(0, std::atoi(e));
-    if (auto e = get("CUGRAPH_B200_SWEEP_COST_LANE")) t.sweep_cost_lane = std::max(0, std::atoi(e));
     if (auto e = get("CUGRAPH_B200_BFS_ALPHA")) t.bfs_alpha = std::atof(e);
     if (auto e = get("CUGRAPH_B200_BFS_BETA")) t.bfs_beta = std::atof(e);
     if (auto e = get("CUGRAPH_B200_SSSP_ADAPTIVE")) t.sssp_adaptive = std::atoi(e) != 0;

@@ -1004,271 +1004,11 @@ __global__ void k_hot_heads(int32_t const* __restrict__ idx, long long nnz, int 
 constexpr int kHotPieceSlots   = 8;                          // slots per piece (= steps per group) at most
 constexpr int kHotPieceEntries = kHotPieceSlots * kHotSlot;  // 64
 
-// per segment: its row (binary search in the offsets) and its WINDOW key = block * n_win + row / 32
+// per segment: its row (binary search in the offsets) and how many pieces it yields
 template <typename O>
-__global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t n_segs, int32_t const* __restrict__ idx, int W,
-                                   O const* __restrict__ off, int32_t n_cov, long long n_win, int32_t* __restrict__ seg_row,
-                                   uint64_t* __restrict__ seg_key)
-{
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_segs) return;
-  const long long start = head_pos[k];
-  int lo = 0, hi = n_cov;  // last row r with off[r] <= start
-  while (hi - lo > 1) {
-    const int mid = lo + ((hi - lo) >> 1);
-    if ((long long)off[mid] <= start) lo = mid; else hi = mid;
-  }
-  seg_row[k] = lo;
-  seg_key[k] = (uint64_t)(idx[start] / W) * (uint64_t)n_win + (uint64_t)(lo >> 5);
-}
-
-__host__ __device__ __forceinline__ int piece_kind(int len)
-{
-  return len == 1 ? kKindS : (len == 2 ? kKindQ : (len <= 4 ? kKindH : kKindF1 + (len + kHotSlot - 1) / kHotSlot - 1));
-}
-__host__ __device__ __forceinline__ int kind_capacity(int kind) { return kind == kKindS ? 1 : (kind == kKindQ ? 2 : (kind == kKindH ? 4 : (kind - 2) * kHotSlot)); }
-
-__global__ void k_sum_i32(int32_t const* __restrict__ v, int64_t n, long long* __restrict__ out)
-{
-  long long t = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) t += v[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  if ((threadIdx.x & 31) == 0 && t) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)t);
-}
-
-__global__ void k_hot_run_heads(uint64_t const* __restrict__ sorted_key, int32_t n_segs, uint8_t* __restrict__ flag)
-{
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n_segs) flag[k] = (k == 0 || sorted_key[k] != sorted_key[k - 1]) ? 1 : 0;
-}
-
-// ---- the window policy.  A RUN = the segments of one 32-row window in one block (<= 32, one per row, ascending rows).
-// The sweep adds one partial sum per piece into acc[row] with a RED; the L2 executes those per 32-byte SECTOR (4 rows)
-// at ~170 G sectors/s chip-wide whatever the lanes (scripts/red_probe.cu, profiles/r02_red_probe.log: scattered 51
-// cycles per warp, 32 consecutive rows 16, half of them 12).  Pieces of one (block, kind) come in ascending row order, but a
-// kind holds only a fraction of the rows, so nearly every RED of the old layout had a sector to itself.  An ALIGNED group
-// is a group whose lane l holds the piece of row 32 * window + l (a hole — no entries, row -1 — where that row has none,
-// shorter pieces padded up to the group's kind): its REDs hit 8 sectors instead of up to 32, at the price of padding.
-// Per run the cheapest of these layouts is chosen (costs in 1/100 cycles, tuning_t): every piece on its own; or the
-// remainder pieces (the last, partly filled piece of every segment) split at a kind K1 into a lower and an upper class,
-// each either one aligned group (of kind K1 / of the largest kind present) or left unaligned.  Full 64-entry pieces
-// (ordinals 0 .. n_full-1 of long segments) form aligned F8 groups for the ordinals that at least kAlignFullMin rows have.
-// Aligned pieces sort in front of the unaligned ones of their (block, kind) and always come in multiples of 32, so the
-// k-th RED of a step covers exactly one window (fill: piece k * 32 + lane of a group).
-struct window_policy_t {
-  int c_scat, c_slot, c_group, c_lane;
-  int enabled;
-};
-constexpr int kAlignFullMin = 28;
-
-struct window_choice_t {
-  int K1;      // remainder pieces of kind <= K1 form the lower class
-  int lower;   // 1: the lower class is one aligned group of kind K1
-  int upper;   // 1: the upper class is one aligned group of kind kU
-  int kU;      // largest kind present
-  int J;       // aligned F8 groups (ordinals 0 .. J-1 of the full pieces)
-};
-
-// warp-uniform: every lane passes its segment (valid, kind of its remainder piece, number of full pieces)
-__device__ __forceinline__ window_choice_t window_choose(window_policy_t const& P, bool valid, int kind, int n_full, int lane)
-{
-  window_choice_t ch{-1, 0, 0, 0, 0};
-  if (!P.enabled) return ch;
-  int cnt[kNumKinds];
-  int kmax = 0, total = 0, total_slots = 0;
-#pragma unroll
-  for (int k = 0; k < kNumKinds; ++k) {
-    cnt[k] = __popc(__ballot_sync(0xffffffffu, valid && kind == k));
-    if (cnt[k]) kmax = k;
-    total += cnt[k];
-    total_slots += cnt[k] * kind_capacity(k);
-  }
-  ch.kU = kmax;
-  const int base = total * P.c_scat + total_slots * P.c_slot;  // every piece on its own
-  // candidate of this lane: K1 = lane / 3, variant = lane % 3 (0: lower aligned; 1: both aligned; 2: upper aligned)
-  const int K1 = lane / 3, variant = lane % 3;
-  int nL = 0, sL = 0;
-#pragma unroll
-  for (int k = 0; k < kNumKinds; ++k)
-    if (k <= K1) {
-      nL += cnt[k];
-      sL += cnt[k] * kind_capacity(k);
-    }
-  const int nU = total - nL, sU = total_slots - sL;
-  const int lower_al = P.c_group + P.c_lane * nL + 32 * kind_capacity(K1 < kNumKinds ? K1 : 0) * P.c_slot;
-  const int upper_al = P.c_group + P.c_lane * nU + 32 * kind_capacity(kmax) * P.c_slot;
-  const int lower_un = nL * P.c_scat + sL * P.c_slot, upper_un = nU * P.c_scat + sU * P.c_slot;
-  int cost = 0x3fffffff;
-  if (K1 < kNumKinds) {
-    if (variant == 0 && nL > 0) cost = lower_al + upper_un;
-    if (variant == 1 && nL > 0 && nU > 0) cost = lower_al + upper_al;
-    if (variant == 2 && nL > 0 && nU > 0) cost = lower_un + upper_al;
-  }
-  int best = cost < base ? ((cost << 5) | lane) : 0x7fffffff;  // ties: the smallest lane
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const int t = __shfl_xor_sync(0xffffffffu, best, o);
-    best        = t < best ? t : best;
-  }
-  if (best != 0x7fffffff) {
-    const int win = best & 31;
-    ch.K1         = win / 3;
-    ch.lower      = (win % 3) != 2;
-    ch.upper      = (win % 3) != 0;
-  }
-  // full pieces: J = the kAlignFullMin-th largest n_full of the run
-  if (__any_sync(0xffffffffu, valid && n_full > 0)) {
-    const int v = valid ? n_full : 0;
-    int rank    = 0;
-    for (int j = 0; j < 32; ++j) {
-      const int vj = __shfl_sync(0xffffffffu, v, j);
-      rank += (vj > v || (vj == v && j < lane)) ? 1 : 0;
-    }
-    const unsigned who = __ballot_sync(0xffffffffu, rank == kAlignFullMin - 1);
-    ch.J               = __shfl_sync(0xffffffffu, v, __ffs((int)who) - 1);
-  }
-  return ch;
-}
-
-struct window_seg_t {
-  bool valid;
-  int start, len, row, block;
-  int n_full, rem, kind;
-};
-__device__ __forceinline__ window_seg_t window_load(int32_t const* __restrict__ run_start, int run, int32_t const* __restrict__ seg_perm,
-                                                    int32_t const* __restrict__ head_pos, int32_t const* __restrict__ seg_row,
-                                                    int32_t n_segs, long long nnz, int32_t const* __restrict__ idx, int W, int lane)
-{
-  window_seg_t s{};
-  const int r0 = run_start[run], r1 = run_start[run + 1];
-  s.valid      = lane < r1 - r0;
-  if (s.valid) {
-    const int k         = seg_perm[r0 + lane];
-    const long long st  = head_pos[k];
-    const long long end = (k + 1 < n_segs) ? (long long)head_pos[k + 1] : nnz;
-    s.start             = (int)st;
-    s.len               = (int)(end - st);
-    s.row               = seg_row[k];
-    s.n_full            = (s.len - 1) / kHotPieceEntries;
-    s.rem               = s.len - s.n_full * kHotPieceEntries;
-    s.kind              = piece_kind(s.rem);
-  }
-  s.block = idx[head_pos[seg_perm[r0]]] / W;  // the same for the whole run
-  return s;
-}
-
-// pass 1: pieces a run emits.  One warp per run.
-__global__ void __launch_bounds__(256)
-k_window_count(int32_t const* __restrict__ run_start, int32_t n_runs, int32_t const* __restrict__ seg_perm,
-               int32_t const* __restrict__ head_pos, int32_t const* __restrict__ seg_row, int32_t n_segs, long long nnz,
-               int32_t const* __restrict__ idx, int W, window_policy_t P, int32_t* __restrict__ run_pieces)
-{
-  const int lane = threadIdx.x & 31;
-  const int run  = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  if (run > n_runs) return;
-  if (run == n_runs) {
-    if (lane == 0) run_pieces[run] = 0;
-    return;
-  }
-  const window_seg_t s     = window_load(run_start, run, seg_perm, head_pos, seg_row, n_segs, nnz, idx, W, lane);
-  const window_choice_t ch = window_choose(P, s.valid, s.kind, s.n_full, lane);
-  int mine = 0;
-  if (s.valid) {
-    const bool in_lower = s.kind <= ch.K1;
-    const bool rem_al   = in_lower ? ch.lower != 0 : ch.upper != 0;
-    mine                = (rem_al ? 0 : 1) + (s.n_full > ch.J ? s.n_full - ch.J : 0);
-  }
-  mine = __reduce_add_sync(0xffffffffu, mine);
-  const bool any_lower = __any_sync(0xffffffffu, s.valid && s.kind <= ch.K1);
-  const bool any_upper = __any_sync(0xffffffffu, s.valid && s.kind > ch.K1);
-  const int groups     = ((ch.lower && any_lower) ? 1 : 0) + ((ch.upper && any_upper) ? 1 : 0) + ch.J;
-  if (lane == 0) run_pieces[run] = mine + 32 * groups;
-}
-
-__device__ __forceinline__ void put_piece(uint32_t* piece_key, int32_t* piece_start, int32_t* piece_len, int32_t* piece_row, int p,
-                                          int block, int kind, bool unaligned, int start, int len, int row)
-{
-  piece_key[p]   = (uint32_t)(((block * kNumKinds + kind) << 1) | (unaligned ? 1 : 0));
-  piece_start[p] = start;
-  piece_len[p]   = len;
-  piece_row[p]   = row;
-}
-
-// pass 2: the pieces (start edge, entries, row) and their key = ((block * kNumKinds + kind) << 1) | unaligned
-__global__ void __launch_bounds__(256)
-k_window_emit(int32_t const* __restrict__ run_start, int32_t n_runs, int32_t const* __restrict__ seg_perm,
-              int32_t const* __restrict__ head_pos, int32_t const* __restrict__ seg_row, int32_t n_segs, long long nnz,
-              int32_t const* __restrict__ idx, int W, window_policy_t P, int32_t const* __restrict__ piece_off,
-              uint32_t* __restrict__ piece_key, int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
-              int32_t* __restrict__ piece_row)
-{
-  const int lane = threadIdx.x & 31;
-  const int run  = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  if (run >= n_runs) return;
-  const window_seg_t s     = window_load(run_start, run, seg_perm, head_pos, seg_row, n_segs, nnz, idx, W, lane);
-  const window_choice_t ch = window_choose(P, s.valid, s.kind, s.n_full, lane);
-  int out                  = piece_off[run];
-  // which segment (lane) owns window position `lane`: rows of a run are distinct
-  unsigned eq = __ballot_sync(0xffffffffu, s.valid);
-#pragma unroll
-  for (int bit = 0; bit < 5; ++bit) {
-    const unsigned b = __ballot_sync(0xffffffffu, s.valid && ((s.row >> bit) & 1));
-    eq &= ((lane >> bit) & 1) ? b : ~b;
-  }
-  const int owner   = eq ? __ffs((int)eq) - 1 : -1;
-  const int src     = owner < 0 ? 0 : owner;
-  const int o_start = __shfl_sync(0xffffffffu, s.start, src), o_row = __shfl_sync(0xffffffffu, s.row, src);
-  const int o_full = __shfl_sync(0xffffffffu, s.n_full, src), o_rem = __shfl_sync(0xffffffffu, s.rem, src);
-  const int o_kind = __shfl_sync(0xffffffffu, s.kind, src);
-  const bool any_lower = __any_sync(0xffffffffu, s.valid && s.kind <= ch.K1);
-  const bool any_upper = __any_sync(0xffffffffu, s.valid && s.kind > ch.K1);
-  if (ch.lower && any_lower) {
-    const bool have = owner >= 0 && o_kind <= ch.K1;
-    put_piece(piece_key, piece_start, piece_len, piece_row, out + lane, s.block, ch.K1, false,
-              have ? o_start + o_full * kHotPieceEntries : 0, have ? o_rem : 0, have ? o_row : -1);
-    out += 32;
-  }
-  if (ch.upper && any_upper) {
-    const bool have = owner >= 0 && o_kind > ch.K1;
-    put_piece(piece_key, piece_start, piece_len, piece_row, out + lane, s.block, ch.kU, false,
-              have ? o_start + o_full * kHotPieceEntries : 0, have ? o_rem : 0, have ? o_row : -1);
-    out += 32;
-  }
-  for (int j = 0; j < ch.J; ++j) {
-    const bool have = owner >= 0 && o_full > j;
-    put_piece(piece_key, piece_start, piece_len, piece_row, out + lane, s.block, kNumKinds - 1, false,
-              have ? o_start + j * kHotPieceEntries : 0, have ? kHotPieceEntries : 0, have ? o_row : -1);
-    out += 32;
-  }
-  // the unaligned pieces of this lane's segment
-  bool rem_un = false;
-  int mine    = 0;
-  if (s.valid) {
-    rem_un = !((s.kind <= ch.K1) ? ch.lower != 0 : ch.upper != 0);
-    mine   = (rem_un ? 1 : 0) + (s.n_full > ch.J ? s.n_full - ch.J : 0);
-  }
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  int p = out + incl - mine;
-  if (s.valid) {
-    for (int j = ch.J; j < s.n_full; ++j, ++p)
-      put_piece(piece_key, piece_start, piece_len, piece_row, p, s.block, kNumKinds - 1, true, s.start + j * kHotPieceEntries,
-                kHotPieceEntries, s.row);
-    if (rem_un)
-      put_piece(piece_key, piece_start, piece_len, piece_row, p, s.block, s.kind, true, s.start + s.n_full * kHotPieceEntries, s.rem,
-                s.row);
-  }
-}
-
-// ---- without the window policy (the default): one thread per segment, no window sort
-template <typename O>
-__global__ void k_seg_count_plain(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz, O const* __restrict__ off,
-                                  int32_t n_cov, int32_t* __restrict__ seg_row, int32_t* __restrict__ seg_pieces)
+__global__ void k_hot_segment_info(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz,
+                                   O const* __restrict__ off, int32_t n_cov, int32_t* __restrict__ seg_row,
+                                   int32_t* __restrict__ seg_pieces)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n_segs) return;
@@ -1287,10 +1027,17 @@ __global__ void k_seg_count_plain(int32_t const* __restrict__ head_pos, int32_t 
   seg_pieces[k] = (int)((end - start + kHotPieceEntries - 1) / kHotPieceEntries);
 }
 
-__global__ void k_seg_emit_plain(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz, int32_t const* __restrict__ idx,
-                                 int W, int32_t const* __restrict__ seg_row, int32_t const* __restrict__ piece_off,
-                                 uint32_t* __restrict__ piece_key, int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
-                                 int32_t* __restrict__ piece_row)
+__host__ __device__ __forceinline__ int piece_kind(int len)
+{
+  return len == 1 ? kKindS : (len == 2 ? kKindQ : (len <= 4 ? kKindH : kKindF1 + (len + kHotSlot - 1) / kHotSlot - 1));
+}
+
+// per segment: write its pieces (start edge, entries, row) and their key = block * kNumKinds + kind
+__global__ void k_hot_emit_pieces(int32_t const* __restrict__ head_pos, int32_t n_segs, long long nnz,
+                                  int32_t const* __restrict__ idx, int W, int32_t const* __restrict__ seg_row,
+                                  int32_t const* __restrict__ piece_off, uint32_t* __restrict__ piece_key,
+                                  int32_t* __restrict__ piece_start, int32_t* __restrict__ piece_len,
+                                  int32_t* __restrict__ piece_row)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_segs) return;
@@ -1300,8 +1047,11 @@ __global__ void k_seg_emit_plain(int32_t const* __restrict__ head_pos, int32_t n
   const int row         = seg_row[k];
   int p                 = piece_off[k];
   for (long long s = start; s < end; s += kHotPieceEntries, ++p) {
-    const int len = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
-    put_piece(piece_key, piece_start, piece_len, piece_row, p, b, piece_kind(len), true, (int)s, len, row);
+    const int len  = (int)((end - s < kHotPieceEntries) ? end - s : kHotPieceEntries);
+    piece_key[p]   = (uint32_t)(b * kNumKinds + piece_kind(len));
+    piece_start[p] = (int32_t)s;
+    piece_len[p]   = len;
+    piece_row[p]   = row;
   }
 }
 
@@ -1339,20 +1089,17 @@ struct sweep_plan_t {
   int n_cta{1};
 };
 
-inline double sweep_group_cost(int kind, double aligned_fraction = 0.0)
+inline double sweep_group_cost(int kind)
 {
   // Load/store-unit cycles.  The atomics dominate: a scattered 64-bit RED costs about one cycle PER LANE whatever its
   // sectors (measured, profiles/r02_notes.md: no atomics -0.106 ms, plain stores or one sector per warp: no change), i.e.
   // ~1.2 cycles per piece; a step-row costs 4 lines of ids + 8 gathers at ~1.5 wavefronts.  The F8 pieces of hub rows are
   // summed by shuffles first (one RED per 32 pieces).
-  // Row-aligned pieces (window policy above) share sectors: ~0.45 cycles per piece slot.
-  const double per_piece = (kind == kNumKinds - 1 ? 0.1 : 1.2) * (1.0 - aligned_fraction) + 0.45 * aligned_fraction;
-  return kind_steps(kind) * 14.0 + kind_pieces(kind) * per_piece + 4.0;
+  return kind_steps(kind) * 14.0 + kind_pieces(kind) * (kind == kNumKinds - 1 ? 0.1 : 1.2) + 4.0;
 }
 constexpr double kPhaseCost = 2500.0;  // barrier + 192 KiB slice fill, in the same unit
 
-bool plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, sweep_plan_t& P,
-                std::vector<int32_t> const* c_aligned = nullptr)
+bool plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, sweep_plan_t& P)
 {
   std::vector<double> cost;  // per chunk, the phase overhead on the first chunk of every block
   for (int b = 0; b < B; ++b) {
@@ -1368,12 +1115,7 @@ bool plan_sweep(std::vector<int32_t> const& cstart, int B, int sm_count, sweep_p
           return false;  // 32-bit step-row / row-slot numbers
         P.chunks.push_back({(int32_t)P.n_steprows, (int32_t)P.n_rowslots, groups, kind});
         P.fills.push_back({p, pe, b, 0});
-        double al = 0.0;  // fraction of this chunk's pieces that are row-aligned (the aligned ones lead their class)
-        if (c_aligned) {
-          const int64_t a_end = (int64_t)cstart[key] + (*c_aligned)[key], c_end = (int64_t)p + (int64_t)groups * ppg;
-          al = a_end <= p ? 0.0 : (double)(std::min(a_end, c_end) - p) / (double)(groups * ppg);
-        }
-        cost.push_back(groups * sweep_group_cost(kind, al) + (first ? kPhaseCost : 0.0));
+        cost.push_back(groups * sweep_group_cost(kind) + (first ? kPhaseCost : 0.0));
         first = false;
         P.n_steprows += (int64_t)groups * steps;
         P.n_rowslots += (int64_t)groups * ppg;
@@ -1595,117 +1337,55 @@ std::unique_ptr<sweep_layout_t> build_sweep_layout(handle_impl const& h, csx_t c
   const int32_t n_segs = (int32_t)n_segs64;
   tr.mark("sweep layout: segment heads");
 
-  dbuf seg_row = make_dbuf<int32_t>(n_segs, h.stream);
-  dbuf piece_key, piece_key2, piece_start, piece_len, piece_row;
+  // 2. pieces
+  dbuf seg_row = make_dbuf<int32_t>(n_segs, h.stream), seg_pieces = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
+  dbuf piece_off = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
+  B200_LAUNCH(h, (k_hot_segment_info<O>), grid_for((int64_t)n_segs + 1), kBlock, 0, head_pos.as<int32_t>(), n_segs,
+              (long long)nnz, c.offsets.as<O>(), n_cov, seg_row.as<int32_t>(), seg_pieces.as<int32_t>());
+  exclusive_scan_i32(h, seg_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_segs + 1);
   int32_t n_pieces = 0;
-  int32_t n_runs   = 0;
-  if (!h.tune.sweep_align) {
-    // 2+3 (default). every piece on its own: one thread per segment
-    dbuf seg_pieces = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream), piece_off = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
-    B200_LAUNCH(h, (k_seg_count_plain<O>), grid_for((int64_t)n_segs + 1), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz,
-                c.offsets.as<O>(), n_cov, seg_row.as<int32_t>(), seg_pieces.as<int32_t>());
-    exclusive_scan_i32(h, seg_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_segs + 1);
-    CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_segs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
-    sync(h);
-    piece_key = make_dbuf<uint32_t>(n_pieces, h.stream); piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
-    piece_start = make_dbuf<int32_t>(n_pieces, h.stream); piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
-    piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
-    B200_LAUNCH(h, k_seg_emit_plain, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W,
-                seg_row.as<int32_t>(), piece_off.as<int32_t>(), piece_key.as<uint32_t>(), piece_start.as<int32_t>(),
-                piece_len.as<int32_t>(), piece_row.as<int32_t>());
-  } else {
-  // 2. runs = the segments of one (block, 32-row window), found by sorting the segments by their window key
-  const long long n_win = ((long long)n_cov + 31) / 32;
-  dbuf seg_perm2 = make_dbuf<uint32_t>(n_segs, h.stream);
-  dbuf run_start;
-  {
-    dbuf seg_key = make_dbuf<uint64_t>(n_segs, h.stream), seg_key2 = make_dbuf<uint64_t>(n_segs, h.stream);
-    dbuf seg_perm = make_dbuf<uint32_t>(n_segs, h.stream);
-    B200_LAUNCH(h, (k_hot_segment_info<O>), grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, idx, W, c.offsets.as<O>(),
-                n_cov, n_win, seg_row.as<int32_t>(), seg_key.as<uint64_t>());
-    B200_LAUNCH(h, k_iota64, grid_for(n_segs, 4), kBlock, 0, (int64_t)n_segs, seg_perm.as<uint32_t>());
-    sort_pairs<uint64_t, uint32_t>(h, seg_key.as<uint64_t>(), seg_key2.as<uint64_t>(), seg_perm.as<uint32_t>(),
-                                   seg_perm2.as<uint32_t>(), n_segs, 0, bits_for((int64_t)B * n_win + 1));
-    dbuf rflag = make_dbuf<uint8_t>(n_segs, h.stream);
-    B200_LAUNCH(h, k_hot_run_heads, grid_for(n_segs), kBlock, 0, seg_key2.as<uint64_t>(), n_segs, rflag.as<uint8_t>());
-    B200_LAUNCH(h, k_iota64, grid_for(n_segs, 4), kBlock, 0, (int64_t)n_segs, seg_perm.as<uint32_t>());  // positions 0 .. n_segs-1
-    run_start = make_dbuf<int32_t>((size_t)n_segs + 1, h.stream);
-    n_runs    = (int32_t)select_flagged<int32_t>(h, seg_perm.as<int32_t>(), rflag.as<uint8_t>(), run_start.as<int32_t>(), n_segs);
-    CUDA_TRY(cudaMemcpyAsync(run_start.as<int32_t>() + n_runs, &n_segs, sizeof(int32_t), cudaMemcpyHostToDevice, h.stream));
-    sync(h);  // n_segs is a stack variable
-  }
-  tr.mark("sweep layout: window runs");
-
-  // 3. the window policy decides per run which pieces form row-aligned groups; pieces ordered by (block, kind, aligned first)
-  window_policy_t pol{h.tune.sweep_cost_scat, h.tune.sweep_cost_slot, h.tune.sweep_cost_group, h.tune.sweep_cost_lane,
-                      h.tune.sweep_align ? 1 : 0};
-  dbuf run_pieces = make_dbuf<int32_t>((size_t)n_runs + 1, h.stream), piece_off = make_dbuf<int32_t>((size_t)n_runs + 1, h.stream);
-  const int run_grid = (int)(((int64_t)n_runs + 1 + 7) / 8);  // 8 warps per CTA, one warp per run
-  B200_LAUNCH(h, k_window_count, run_grid, 256, 0, run_start.as<int32_t>(), n_runs, seg_perm2.as<int32_t>(), head_pos.as<int32_t>(),
-              seg_row.as<int32_t>(), n_segs, (long long)nnz, idx, W, pol, run_pieces.as<int32_t>());
-  {  // 64-bit total: aligned groups add up to 32 piece slots per run
-    dbuf d_tot = make_dbuf<long long>(1, h.stream);
-    CUDA_TRY(cudaMemsetAsync(d_tot.data(), 0, sizeof(long long), h.stream));
-    B200_LAUNCH(h, k_sum_i32, std::min(grid_for((int64_t)n_runs + 1), 148 * 8), kBlock, 0, run_pieces.as<int32_t>(), (int64_t)n_runs + 1,
-                d_tot.as<long long>());
-    long long tot = 0;
-    CUDA_TRY(cudaMemcpyAsync(&tot, d_tot.data(), sizeof(long long), cudaMemcpyDeviceToHost, h.stream));
-    sync(h);
-    if (tot >= (1ll << 31) - 64) return nullptr;  // 32-bit piece numbers
-  }
-  exclusive_scan_i32(h, run_pieces.as<int32_t>(), piece_off.as<int32_t>(), (int64_t)n_runs + 1);
-  CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_runs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
+  CUDA_TRY(cudaMemcpyAsync(&n_pieces, piece_off.as<int32_t>() + n_segs, sizeof(int32_t), cudaMemcpyDeviceToHost, h.stream));
   sync(h);
-  run_pieces.release();
-  piece_key = make_dbuf<uint32_t>(n_pieces, h.stream); piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
-  piece_start = make_dbuf<int32_t>(n_pieces, h.stream); piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
-  piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
-  B200_LAUNCH(h, k_window_emit, run_grid, 256, 0, run_start.as<int32_t>(), n_runs, seg_perm2.as<int32_t>(), head_pos.as<int32_t>(),
-              seg_row.as<int32_t>(), n_segs, (long long)nnz, idx, W, pol, piece_off.as<int32_t>(), piece_key.as<uint32_t>(),
-              piece_start.as<int32_t>(), piece_len.as<int32_t>(), piece_row.as<int32_t>());
-  }
+  seg_pieces.release();
   L->n_pieces = n_pieces;
+  dbuf piece_key = make_dbuf<uint32_t>(n_pieces, h.stream), piece_key2 = make_dbuf<uint32_t>(n_pieces, h.stream);
+  dbuf piece_start = make_dbuf<int32_t>(n_pieces, h.stream), piece_len = make_dbuf<int32_t>(n_pieces, h.stream);
+  dbuf piece_row = make_dbuf<int32_t>(n_pieces, h.stream);
+  B200_LAUNCH(h, k_hot_emit_pieces, grid_for(n_segs), kBlock, 0, head_pos.as<int32_t>(), n_segs, (long long)nnz, idx, W,
+              seg_row.as<int32_t>(), piece_off.as<int32_t>(), piece_key.as<uint32_t>(), piece_start.as<int32_t>(),
+              piece_len.as<int32_t>(), piece_row.as<int32_t>());
   head_pos.release();
   seg_row.release();
+  piece_off.release();
   tr.mark("sweep layout: pieces");
 
+  // 3. order pieces by (block, kind)
   const int n_keys = B * kNumKinds;
   dbuf perm = make_dbuf<uint32_t>(n_pieces, h.stream), perm2 = make_dbuf<uint32_t>(n_pieces, h.stream);
   B200_LAUNCH(h, k_iota64, grid_for(n_pieces, 4), kBlock, 0, (int64_t)n_pieces, perm.as<uint32_t>());
   sort_pairs<uint32_t, uint32_t>(h, piece_key.as<uint32_t>(), piece_key2.as<uint32_t>(), perm.as<uint32_t>(),
-                                 perm2.as<uint32_t>(), n_pieces, 0, bits_for(2 * (int64_t)n_keys + 1));
-  dbuf class_start = make_dbuf<int32_t>((size_t)2 * n_keys + 1, h.stream);
-  B200_LAUNCH(h, k_hot_class_starts, grid_for(2 * n_keys + 1), kBlock, 0, piece_key2.as<uint32_t>(), n_pieces, 2 * n_keys,
+                                 perm2.as<uint32_t>(), n_pieces, 0, bits_for(n_keys + 1));
+  dbuf class_start = make_dbuf<int32_t>((size_t)n_keys + 1, h.stream);
+  B200_LAUNCH(h, k_hot_class_starts, grid_for(n_keys + 1), kBlock, 0, piece_key2.as<uint32_t>(), n_pieces, n_keys,
               class_start.as<int32_t>());
-  std::vector<int32_t> cstart2((size_t)2 * n_keys + 1);
-  CUDA_TRY(cudaMemcpyAsync(cstart2.data(), class_start.data(), sizeof(int32_t) * cstart2.size(), cudaMemcpyDeviceToHost, h.stream));
+  std::vector<int32_t> cstart((size_t)n_keys + 1);
+  CUDA_TRY(cudaMemcpyAsync(cstart.data(), class_start.data(), sizeof(int32_t) * cstart.size(), cudaMemcpyDeviceToHost, h.stream));
   sync(h);
-  // per (block, kind): first piece, and how many of its pieces are aligned (they come first)
-  std::vector<int32_t> cstart((size_t)n_keys + 1), c_aligned((size_t)n_keys);
-  for (int k = 0; k < n_keys; ++k) {
-    cstart[k]    = cstart2[2 * k];
-    c_aligned[k] = cstart2[2 * k + 1] - cstart2[2 * k];
-  }
-  cstart[n_keys] = cstart2[2 * n_keys];
   piece_key.release();
   piece_key2.release();
   perm.release();
   tr.mark("sweep layout: kind sort");
   if (tr.on) {  // layout statistics: pieces by kind, per range of blocks
     int edges[] = {0, 1, 4, 16, 64, 160, B};
-    std::fprintf(stderr, "[sweep] B=%d W=%d rows=%d nnz=%lld segments=%d runs=%d piece slots=%d\n", B, W, n_cov, (long long)nnz, n_segs,
-                 n_runs, n_pieces);
+    std::fprintf(stderr, "[sweep] B=%d W=%d rows=%d nnz=%lld segments=%d pieces=%d\n", B, W, n_cov, (long long)nnz, n_segs, n_pieces);
     for (int k = 0; k + 1 < 7; ++k) {
       const int b0 = std::min(edges[k], B), b1 = std::min(edges[k + 1], B);
       if (b1 <= b0) continue;
-      std::fprintf(stderr, "[sweep] blocks [%d,%d) unaligned pieces / aligned 32-row groups by kind S Q H F1..F8:", b0, b1);
+      std::fprintf(stderr, "[sweep] blocks [%d,%d) pieces by kind S Q H F1..F8:", b0, b1);
       for (int kind = 0; kind < kNumKinds; ++kind) {
-        long long np = 0, na = 0;
-        for (int b = b0; b < b1; ++b) {
-          na += c_aligned[b * kNumKinds + kind];
-          np += cstart[b * kNumKinds + kind + 1] - cstart[b * kNumKinds + kind] - c_aligned[b * kNumKinds + kind];
-        }
-        std::fprintf(stderr, " %lld/%lld", np, na / 32);
+        long long np = 0;
+        for (int b = b0; b < b1; ++b) np += cstart[b * kNumKinds + kind + 1] - cstart[b * kNumKinds + kind];
+        std::fprintf(stderr, " %lld", np);
       }
       std::fprintf(stderr, "\n");
     }
@@ -1713,7 +1393,7 @@ std::unique_ptr<sweep_layout_t> build_sweep_layout(handle_impl const& h, csx_t c
 
   // 4. chunks, CTA ranges, phases
   sweep_plan_t plan;
-  if (!plan_sweep(cstart, B, h.sm_count, plan, &c_aligned)) return nullptr;  // step-row numbers overflow 31 bits
+  if (!plan_sweep(cstart, B, h.sm_count, plan)) return nullptr;  // step-row numbers overflow 31 bits
   L->n_steprows = plan.n_steprows;
   L->n_rowslots = plan.n_rowslots;
   L->n_chunks   = (int32_t)plan.chunks.size();

@@ -73,13 +73,14 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p)
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-// the same with an L2 eviction policy (createpolicy): the 0.8 GB stream is read once — marked evict-first it leaves the L2 to
-// the 59 MB of accumulators (ncu r02: 57 % of the RED sectors missed the L2 and fetched their line from DRAM first)
-__device__ __forceinline__ unsigned long long make_l2_policy(bool evict_first)
+// L2 eviction policies (createpolicy).  The 0.8 GB id / row stream is read once: marked evict-FIRST it leaves the L2 to the
+// 59 MB of accumulators, whose REDs carry an evict-LAST policy (ncu r02: 57 % of the RED sectors missed the L2 and fetched
+// their line from DRAM first).  RMAT-24: 0.331 -> 0.314 ms per sweep (profiles/r02_evict_ab*.log; a run-time choice per RED
+// cost as much as the policy gains, so both are unconditional).
+__device__ __forceinline__ unsigned long long make_l2_policy_evict_first()
 {
   unsigned long long pol;
-  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p, unsigned long long pol)
@@ -96,23 +97,10 @@ __device__ __forceinline__ uint2 ld_stream_v2(const void* p, unsigned long long 
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
   return v;
 }
-// fp64 accumulation with an L2 eviction policy on the accumulator line (acc_pol == 0: plain RED)
-#ifndef B200_ACC_POLICY
-// 2: every RED carries an evict-last policy for its accumulator line (0: plain RED, 1: chosen at run time).  Measured on
-// RMAT-24 with the stream evict-first (profiles/r02_evict_ab3.log): 0 -> 0.3191-0.3196 ms per sweep, 2 -> 0.3141-0.3143,
-// 1 (policy off) -> 0.3274-0.3288: the per-RED branch of the run-time choice costs what the policy gains.
-#define B200_ACC_POLICY 2
-#endif
+// fp64 accumulation with an L2 eviction policy on the accumulator line
 __device__ __forceinline__ void red_acc(double* p, double v, unsigned long long acc_pol)
 {
-#if B200_ACC_POLICY == 0
-  atomicAdd(p, v);
-#elif B200_ACC_POLICY == 2
   asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(acc_pol) : "memory");
-#else
-  if (acc_pol) asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(acc_pol) : "memory");
-  else atomicAdd(p, v);
-#endif
 }
 __device__ __forceinline__ unsigned long long make_l2_policy_evict_last()
 {
@@ -158,7 +146,7 @@ inline uint2 ld_stream_v2(const void* p)
   return v;
 }
 inline int ld_volatile(const int* p) { return *p; }
-inline unsigned long long make_l2_policy(bool) { return 0ull; }
+inline unsigned long long make_l2_policy_evict_first() { return 0ull; }
 inline uint4 ld_stream_v4(const void* p, unsigned long long) { return ld_stream_v4(p); }
 inline uint2 ld_stream_v2(const void* p, unsigned long long) { return ld_stream_v2(p); }
 inline int ld_stream_i32(const int* p, unsigned long long) { return *p; }
@@ -243,7 +231,7 @@ struct sweep_ptrs_t {
   void const* __restrict__ w;
   double* __restrict__ acc;
   unsigned long long pol;      // L2 eviction policy of the stream loads
-  unsigned long long acc_pol;  // of the accumulator REDs (0: none)
+  unsigned long long acc_pol;  // of the accumulator REDs
 };
 
 template <int C, int G>
@@ -419,8 +407,6 @@ struct sweep_args_t {
   pr_state_t const* __restrict__ st;
   int n_phases;
   int W;
-  int stream_evict_first;
-  int acc_evict_last;
 };
 
 // ---- chunk supply of a warp.  Chunks are drawn from the phase's cursor in BATCHES of consecutive chunks (lane j holds
@@ -525,12 +511,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) k_sweep(sweep_args_t<T> a)
   __shared__ int s_best;
   __shared__ uint4 s_ring[kSweepWarps][2 * kDrawMax];
   if (a.st->done) return;
-  a.p.pol        = make_l2_policy(a.stream_evict_first != 0);
-#if B200_ACC_POLICY == 2
+  a.p.pol        = make_l2_policy_evict_first();
   a.p.acc_pol    = make_l2_policy_evict_last();
-#else
-  a.p.acc_pol    = a.acc_evict_last ? make_l2_policy_evict_last() : 0ull;
-#endif
   const int lane = threadIdx.x & 31;
   const int me   = (int)blockIdx.x;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -675,22 +657,13 @@ void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L,
   a.W         = L.W;
   a.p.pol     = 0;
   a.p.acc_pol = 0;
-  a.stream_evict_first = h.tune.sweep_stream_evict_first ? 1 : 0;
-  a.acc_evict_last     = h.tune.sweep_acc_evict_last ? 1 : 0;
   if (weighted) B200_LAUNCH(h, (k_sweep<T, true>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
   else B200_LAUNCH(h, (k_sweep<T, false>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
-  // 64-row steps per warp: 8 measured 0.335 ms per sweep, 4: 0.340, 2: 0.354 (profiles/r02_fullchunk_ab.log)
-  const int fs = h.tune.sweep_finish_steps;
-  const int n  = std::max((c.n_rows + 2 * fs - 1) / (2 * fs), L.n_phases);  // threads: 2 * fs rows each
-  if (fs == 2)
-    B200_LAUNCH(h, (k_sweep_finish<T, 2>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
-                L.cursor.as<int>(), L.n_phases, st);
-  else if (fs == 4)
-    B200_LAUNCH(h, (k_sweep_finish<T, 4>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
-                L.cursor.as<int>(), L.n_phases, st);
-  else
-    B200_LAUNCH(h, (k_sweep_finish<T, 8>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
-                L.cursor.as<int>(), L.n_phases, st);
+  // 8 steps of 64 rows per warp: 0.335 ms per sweep against 0.340 with 4 and 0.354 with 2 (profiles/r02_fullchunk_ab.log)
+  constexpr int kFinishSteps = 8;
+  const int n = std::max((c.n_rows + 2 * kFinishSteps - 1) / (2 * kFinishSteps), L.n_phases);  // threads: 16 rows each
+  B200_LAUNCH(h, (k_sweep_finish<T, kFinishSteps>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
+              L.cursor.as<int>(), L.n_phases, st);
 }
 
 // dispatch: the piece stream when it exists for this graph, else the plain edge-balanced sweep

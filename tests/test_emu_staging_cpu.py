@@ -145,7 +145,7 @@ def red_units(rr, stats):
             stats["aligned_lanes"] = stats.get("aligned_lanes", 0) + int(live.size)
 
 
-def sweep_pieces(L, g, P, stats=None, tight=False):
+def sweep_pieces(L, g, P, stats=None):
     """(row, col[, w]) triples reconstructed from the piece stream + structural checks.
     stats: dict that receives the LDS count and the wavefront count of the F kinds (bank order)."""
     ints = (C.c_int64 * 12)()
@@ -200,9 +200,7 @@ def sweep_pieces(L, g, P, stats=None, tight=False):
                 real = sl < W
                 assert not real[:, rr < 0, :].any()
                 per_piece = real.sum((0, 2))
-                assert (per_piece[rr >= 0] >= 1).all() and (per_piece[rr >= 0] <= steps * 8).all()   # the kind fits
-                if tight:           # without row-aligned groups a piece is never padded up to a larger kind
-                    assert (per_piece[rr >= 0] > (steps - 1) * 8).all()
+                assert (per_piece[rr >= 0] > (steps - 1) * 8).all() and (per_piece[rr >= 0] <= steps * 8).all()   # the kind fits
                 if not bank:
                     flat = real.transpose(1, 0, 2).reshape(32, -1)
                     assert (flat[:, :-1] >= flat[:, 1:]).all()
@@ -218,17 +216,15 @@ def sweep_pieces(L, g, P, stats=None, tight=False):
                     ww = sw[sr0 + q * steps: sr0 + (q + 1) * steps]
                     assert (ww[~real] == 0).all()
                     out_w.append(ww[real])
-    assert n_real_pieces <= n_pieces     # piece slots: the holes of row-aligned groups count
-    if tight:
-        assert n_real_pieces == n_pieces
+    assert n_real_pieces == n_pieces
     r = np.concatenate(out_r) if out_r else np.zeros(0, np.int64)
     c = np.concatenate(out_c) if out_c else np.zeros(0, np.int64)
     w = np.concatenate(out_w) if out_w else None
     return dict(r=r, c=c, w=w, W=W, B=B, chunks=chunks, phases=phases, bank=bank)
 
 
-def check_sweep_layout(L, g, P, stats=None, tight=False):
-    H = sweep_pieces(L, g, P, stats, tight)
+def check_sweep_layout(L, g, P, stats=None):
+    H = sweep_pieces(L, g, P, stats)
     n_cov, nnz = P["seg"][5], P["nnz"]
     rows = np.repeat(np.arange(n_cov), np.diff(P["off"][:n_cov + 1]))
     cols = P["idx"][:nnz].astype(np.int64)
@@ -253,26 +249,6 @@ def test_staging_and_piece_stream(emu, monkeypatch, weighted):
     H = check_sweep_layout(emu, g, P)
     assert H["B"] >= 2 and all((H["chunks"][:, 3] == k).any() for k in (0, 1, 2, 3, 10))   # S, Q, H, F1 and F8 pieces exist
     emu.cugraph_graph_free(g)
-
-
-def test_row_aligned_groups(emu, monkeypatch):
-    """window policy: the lanes of a warp-wide accumulation hold consecutive rows where a 32-row window is dense enough in a
-    block, so the accumulations touch fewer 32-byte sectors; same (row, source) multiset with and without"""
-    monkeypatch.setenv("CUGRAPH_B200_SWEEP_MIN_EDGES", "0")
-    src, dst, w = make_edges(120_000, 900_000, seed=5, weighted=False, id_offset=1)
-    res = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("CUGRAPH_B200_SWEEP_ALIGN", mode)
-        g = create_graph(emu, src, dst, w)
-        P = primary(emu, g)
-        st = {}
-        check_sweep_layout(emu, g, P, stats=st, tight=(mode == "0"))
-        res[mode] = st
-        emu.cugraph_graph_free(g)
-    print({m: {k: res[m].get(k, 0) for k in ("red_units", "red_lanes", "red_sectors", "aligned_units", "aligned_lanes")} for m in res})
-    assert res["0"]["red_lanes"] == res["1"]["red_lanes"]                 # the same pieces, holes are idle lanes
-    assert res["1"].get("aligned_lanes", 0) > 0.3 * res["1"]["red_lanes"]
-    assert res["1"]["red_sectors"] < 0.8 * res["0"]["red_sectors"]
 
 
 @pytest.mark.parametrize("weighted", [False, True])
