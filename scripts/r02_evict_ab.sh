@@ -1,4 +1,6 @@
 #!/bin/bash
+# A/B of the L2 eviction-policy builds of the sweep (profiles/r02_evict_ab3.log); earlier contents of this scratch script produced
+# r02_tma_ab / r02_fullchunk_ab / r02_sssp_ab / r02_evict_ab{,2}.log
 mkdir -p gpurun_out
 out=gpurun_out/r02_evict_ab3.log
 : > $out

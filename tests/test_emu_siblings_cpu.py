@@ -128,3 +128,102 @@ def test_wcc_emulated(emu):  # noqa: F811
     code = L.cugraph_weakly_connected_components(C.c_void_p(L.handle), g2, 0, C.byref(res), C.byref(err))
     assert code != 0 and b"should be symmetric" in L.cugraph_error_message(err)
     L.cugraph_graph_free(g2)
+
+
+def test_int64_ids_double_weights_and_empty_graph(emu):  # noqa: F811
+    """64-bit external ids, fp64 weights (results come back in the graph's types), renumber = FALSE reporting order, and an
+    edgeless graph, through Katz / HITS / components / extract_paths"""
+    from tests.test_emu_edge_cases_cpu import G, _view
+    L = emu
+    r = np.random.default_rng(8)
+    V, E = 300, 2500
+    big = 5_000_000_000
+    a, b = r.integers(0, V, E), r.integers(0, V, E)
+    s = np.concatenate([a, b]) * 7 + big
+    d = np.concatenate([b, a]) * 7 + big
+    w = np.concatenate([r.random(E) + 0.5] * 2)
+    g = G(L, s, d, w, symmetric=True, store_transposed=False, idt=np.int64)
+    ids, inv = np.unique(np.concatenate([s, d]), return_inverse=True)
+    si, di = inv[:s.size], inv[s.size:]
+    # Katz in fp64
+    L.cugraph_katz_centrality.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_size_t, C.c_int,
+                                          C.c_void_p, C.c_void_p]
+    alpha = 0.4 / (np.bincount(di).max() * float(w.max()))
+    res, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_katz_centrality(C.c_void_p(L.handle), g.g, None, alpha, 1.0, 1e-10, 500, 0, C.byref(res), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    verts, x = _centrality(L, res)
+    assert verts.dtype == np.int64 and x.dtype == np.float64
+    ref, _ = oracle.katz(si, di, ids.size, w, alpha=alpha, beta=1.0, epsilon=1e-10)
+    got = np.zeros(ids.size)
+    got[np.searchsorted(ids, verts)] = x
+    np.testing.assert_allclose(got, ref, rtol=1e-9)
+    # components with 64-bit labels
+    L.cugraph_weakly_connected_components.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    for f in ("cugraph_labeling_result_get_vertices", "cugraph_labeling_result_get_labels"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.cugraph_labeling_result_free.argtypes = [C.c_void_p]
+    code = L.cugraph_weakly_connected_components(C.c_void_p(L.handle), g.g, 0, C.byref(res), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    lv = _view_to_np(L, L.cugraph_labeling_result_get_vertices(res))
+    ll = _view_to_np(L, L.cugraph_labeling_result_get_labels(res))
+    L.cugraph_labeling_result_free(res)
+    assert lv.dtype == np.int64 and ll.dtype == np.int64 and set(ll.tolist()) <= set(ids.tolist())
+    comp = oracle.wcc(si, di, ids.size)
+    gl = np.zeros(ids.size, dtype=np.int64)
+    gl[np.searchsorted(ids, lv)] = ll
+    assert len(set(zip(comp.tolist(), gl.tolist()))) == len(set(comp.tolist())) == len(set(gl.tolist()))
+    # BFS + extract_paths with 64-bit ids
+    src_v = int(ids[np.bincount(si).argmax()])
+    verts, dist, pred = None, None, None
+    sv = np.array([src_v], dtype=np.int64)
+    bres = C.c_void_p()
+    code = L.cugraph_bfs(C.c_void_p(L.handle), g.g, _view(L, sv), 0, C.c_size_t(2**31 - 2), 1, 0, C.byref(bres), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    for f in ("cugraph_paths_result_get_vertices", "cugraph_paths_result_get_distances"):
+        getattr(L, f).restype = C.c_void_p
+        getattr(L, f).argtypes = [C.c_void_p]
+    bv = _view_to_np(L, L.cugraph_paths_result_get_vertices(bres))
+    bd = _view_to_np(L, L.cugraph_paths_result_get_distances(bres))
+    dist_of = dict(zip(bv.tolist(), bd.tolist()))
+    dests = ids[r.integers(0, ids.size, 40)].astype(np.int64)
+    L.cugraph_extract_paths.argtypes = [C.c_void_p] * 7
+    L.cugraph_extract_paths_result_get_max_path_length.restype = C.c_size_t
+    L.cugraph_extract_paths_result_get_max_path_length.argtypes = [C.c_void_p]
+    L.cugraph_extract_paths_result_get_paths.restype = C.c_void_p
+    L.cugraph_extract_paths_result_get_paths.argtypes = [C.c_void_p]
+    L.cugraph_extract_paths_result_free.argtypes = [C.c_void_p]
+    out = C.c_void_p()
+    code = L.cugraph_extract_paths(C.c_void_p(L.handle), g.g, _view(L, sv), bres, _view(L, dests), C.byref(out), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    length = int(L.cugraph_extract_paths_result_get_max_path_length(out))
+    paths = _view_to_np(L, L.cugraph_extract_paths_result_get_paths(out)).reshape(dests.size, length)
+    assert paths.dtype == np.int64
+    i64max = np.iinfo(np.int64).max
+    edges = set(zip(s.tolist(), d.tolist()))
+    for row, t in zip(paths, dests.tolist()):
+        dt = dist_of[t]
+        if dt == i64max:
+            assert (row == -1).all()
+        else:
+            assert row[0] == src_v and row[dt] == t and all((int(p), int(q)) in edges for p, q in zip(row[:dt], row[1:dt + 1]))
+    L.cugraph_extract_paths_result_free(out)
+    L.cugraph_paths_result_free(bres)
+    L.cugraph_graph_free(g.g)
+    # a graph with vertices and no edges: Katz gives beta / ||.||, components one label per vertex, HITS reports a zero norm
+    g0 = G(L, np.zeros(0, np.int32), np.zeros(0, np.int32), vertices=np.arange(6), symmetric=True, store_transposed=True)
+    code = L.cugraph_katz_centrality(C.c_void_p(L.handle), g0.g, None, 0.1, 1.0, 1e-6, 10, 0, C.byref(res), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    _, x0 = _centrality(L, res)
+    np.testing.assert_allclose(x0, np.full(6, 1.0 / np.sqrt(6.0)), rtol=1e-6)
+    code = L.cugraph_weakly_connected_components(C.c_void_p(L.handle), g0.g, 0, C.byref(res), C.byref(err))
+    assert code == 0
+    l0 = _view_to_np(L, L.cugraph_labeling_result_get_labels(res))
+    L.cugraph_labeling_result_free(res)
+    assert sorted(l0.tolist()) == list(range(6))
+    L.cugraph_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                               C.c_void_p]
+    code = L.cugraph_hits(C.c_void_p(L.handle), g0.g, 1e-6, 10, None, None, 1, 0, C.byref(res), C.byref(err))
+    assert code != 0 and b"positive" in L.cugraph_error_message(err)      # "Norm is required to be a positive value."
+    L.cugraph_graph_free(g0.g)
