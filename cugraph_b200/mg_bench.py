@@ -138,8 +138,9 @@ def run_mg_pagerank(args, metric_name, alpha, iters, ClockSampler, peaks):
         from cugraph_b200.mg import vertex_owner  # noqa: F401
         srcs = [None] * 4
         if rank == 0:
-            pick = torch.randperm(h_src.numel() if h_src is not None else 1, generator=torch.Generator().manual_seed(5))[:4]
-            srcs = [int(h_src[i]) for i in pick] if h_src is not None else srcs
+            if h_src is not None:
+                pick = torch.randint(0, h_src.numel(), (4,), generator=torch.Generator().manual_seed(5))
+                srcs = [int(h_src[int(i)]) for i in pick]
         dist.broadcast_object_list(srcs, src=0)
         if srcs[0] is not None:
             G.bfs(srcs[0], compute_predecessors=False)  # warm-up
