@@ -30,12 +30,20 @@ import torch.distributed as dist
 # process grid (reference: cpp/tests/utilities/mg_utilities.cpp:49-53, partition_manager.hpp:106-114)
 # ----------------------------------------------------------------------------------------------
 def grid_shape(world: int):
-    """(R, C): R = largest divisor <= sqrt(world) = size of the all-gather (column) group,
-    C = world / R = size of the reduce (row) group.  2 -> 1x2, 4 -> 2x2, 8 -> 2x4."""
+    """(R, C) of the P = R x C process grid: R = size of the all-gather (column) group, C = size of the reduce (row) group.
+    The two factors are the reference's (largest divisor <= sqrt(P) and its cofactor, mg_utilities.cpp:49-53); the LARGER one
+    is R here: 2 -> 2x1, 4 -> 2x2, 8 -> 4x2.  A GPU's block has C * maxpart destination rows and R * maxpart source columns.
+    The number of pieces (= accumulations) of a block does not depend on the orientation (numpy count on RMAT, scale 20 per
+    GPU: 1x2 5.12 M pieces / 2x1 5.20 M; 2x4 6.88 M / 4x2 6.98 M) but its rows do: with R >= C the accumulator array and
+    the finish pass are half (N = 2, 8) the size — 70 MB instead of 141 MB of accumulators at RMAT-25 on 2 GPUs, i.e. inside
+    the L2 again.  CUGRAPH_B200_MG_GRID=wide restores the reference's orientation (R <= C)."""
     r = int(math.isqrt(world))
     while world % r:
         r -= 1
-    return r, world // r
+    small, large = r, world // r
+    if os.environ.get("CUGRAPH_B200_MG_GRID", "tall") == "wide":
+        return small, large
+    return large, small
 
 
 def vertex_owner(ext: torch.Tensor, world: int) -> torch.Tensor:
@@ -312,7 +320,10 @@ class MGGraph:
             code = L.cugraph_b200_block_pull_sweep(self.handle.ptr, self.block, views["xg"].ptr, views["yp"].ptr,
                                                    float(alpha), C.byref(err))
             capi.check(code, err, "cugraph_b200_block_pull_sweep")
-            reduce_scatter_into(yred, ypart[:self.n_rows], g.row_group)
+            if g.C == 1:
+                yred.copy_(ypart[:mp])
+            else:
+                reduce_scatter_into(yred, ypart[:self.n_rows], g.row_group)
             vertex_step(False)
             tot, part = part, tot
             iters += 1

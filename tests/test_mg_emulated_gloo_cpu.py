@@ -67,7 +67,7 @@ def _worker(rank, world, port, V, E, min_edges, out_q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,min_edges", [(2, "0"), (4, "1000000000")])
+@pytest.mark.parametrize("world,min_edges", [(2, "0"), (4, "1000000000"), (8, "0")])   # grids 2x1, 2x2, 4x2
 def test_mg_pagerank_and_bfs_emulated_gloo(world, min_edges):
     import oracle
     V, E = 1500, 12000

@@ -127,14 +127,17 @@ def test_partition_and_pagerank_gloo(world, weighted):
         assert got_pr[int(ids[v])] == pytest.approx(ref[k], rel=1e-9)
 
 
-def test_grid_shape_matches_reference():
+def test_grid_shape_matches_reference(monkeypatch):
     from cugraph_b200 import mg
-    # cpp/tests/utilities/mg_utilities.cpp:49-53: row comm size = largest divisor <= sqrt(P)
+    # cpp/tests/utilities/mg_utilities.cpp:49-53: the two factors are the largest divisor <= sqrt(P) and its cofactor; the
+    # larger one is the all-gather group here (fewer destination rows per block), the reference's orientation is selectable
     assert mg.grid_shape(1) == (1, 1)
-    assert mg.grid_shape(2) == (1, 2)
+    assert mg.grid_shape(2) == (2, 1)
     assert mg.grid_shape(4) == (2, 2)
-    assert mg.grid_shape(8) == (2, 4)
-    assert mg.grid_shape(6) == (2, 3)
+    assert mg.grid_shape(8) == (4, 2)
+    assert mg.grid_shape(6) == (3, 2)
+    monkeypatch.setenv("CUGRAPH_B200_MG_GRID", "wide")
+    assert mg.grid_shape(2) == (1, 2) and mg.grid_shape(8) == (2, 4) and mg.grid_shape(6) == (2, 3)
 
 
 def test_vertex_owner_balanced():
