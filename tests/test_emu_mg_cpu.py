@@ -30,7 +30,7 @@ def view(L, a):
     return C.c_void_p(L.cugraph_type_erased_device_array_view_create(a.ctypes.data, a.size, FLOAT32 if a.dtype == np.float32 else INT32))
 
 
-@pytest.mark.parametrize("R,Cc,weighted,min_edges,split", [(1, 2, False, "0", False), (2, 2, False, "0", False), (2, 4, True, "0", False),
+@pytest.mark.parametrize("R,Cc,weighted,min_edges,split", [(1, 2, False, "0", False), (2, 1, False, "0", False), (2, 2, False, "0", False), (2, 4, True, "0", False), (4, 2, True, "0", False),
                                                             (2, 2, False, "1000000000", False), (2, 4, False, "0", True)])
 def test_2d_partitioned_pagerank_on_one_cpu(emu, monkeypatch, R, Cc, weighted, min_edges, split):  # noqa: F811
     """split: one block per destination partition of the row group (the structure of mg.py's CUGRAPH_B200_MG_SPLIT path)"""
