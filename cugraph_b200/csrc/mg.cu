@@ -19,6 +19,9 @@ struct block_impl {
   cugraph_data_type_id_t wtype{FLOAT32};
   dbuf acc_hi;
   dbuf state;  // pr_state_t with init = 0, done = 0
+  // the y array whose rows WITHOUT edges this block has already written (0): later sweeps into the same array only finish the
+  // rows that have edges — in a 2D block more than half of the row slots are empty (the caller must not write them either)
+  void const* y_complete{nullptr};
 };
 
 namespace {
@@ -257,13 +260,15 @@ cugraph_error_code_t cugraph_b200_block_pull_sweep(const cugraph_resource_handle
     B200_EXPECTS(yv->size >= (size_t)b->n_span, CUGRAPH_INVALID_INPUT, "y must hold `span` elements");
     csx_t const& c = *b->csx;
     auto* st       = b->state.as<pr_state_t>();
+    const bool covered_only = b->y_complete == yv->data;  // the empty rows of this y hold their zeros from an earlier sweep
     if (f32) {
       if (c.offs64) launch_pull_sweep<int64_t, float>(h, c, (float const*)xv->data, (float*)yv->data, b->acc_hi.as<double>(), alpha, st);
-      else launch_pull_sweep_auto<int32_t, float>(h, c, b->n_span, (float const*)xv->data, (float*)yv->data, b->acc_hi.as<double>(), alpha, st);
+      else launch_pull_sweep_auto<int32_t, float>(h, c, b->n_span, (float const*)xv->data, (float*)yv->data, b->acc_hi.as<double>(), alpha, st, true, covered_only);
     } else {
       if (c.offs64) launch_pull_sweep<int64_t, double>(h, c, (double const*)xv->data, (double*)yv->data, b->acc_hi.as<double>(), alpha, st);
-      else launch_pull_sweep_auto<int32_t, double>(h, c, b->n_span, (double const*)xv->data, (double*)yv->data, b->acc_hi.as<double>(), alpha, st);
+      else launch_pull_sweep_auto<int32_t, double>(h, c, b->n_span, (double const*)xv->data, (double*)yv->data, b->acc_hi.as<double>(), alpha, st, true, covered_only);
     }
+    b->y_complete = yv->data;
     check_last("block_pull_sweep");
   });
 }

@@ -636,7 +636,7 @@ k_sweep_finish(double* __restrict__ acc, int n_cov, int n_rows, T* __restrict__ 
 // x must hold padded_x_elems() elements, zero behind n_vertices (slices are copied whole)
 template <typename T>
 void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L, T const* x, T* y, double* acc, double alpha,
-                  pr_state_t const* st, bool use_weights = true)
+                  pr_state_t const* st, bool use_weights = true, bool covered_rows_only = false)
 {
   // the attribute is per device and cheap to set: no process-wide "done" flag (a second device would miss it)
   const bool weighted = use_weights && L.w.data() != nullptr;
@@ -661,19 +661,22 @@ void launch_sweep(handle_impl const& h, csx_t const& c, sweep_layout_t const& L,
   else B200_LAUNCH(h, (k_sweep<T, false>), L.n_cta, kSweepThreads, kSweepDynSmem, a);
   // 8 steps of 64 rows per warp: 0.335 ms per sweep against 0.340 with 4 and 0.354 with 2 (profiles/r02_fullchunk_ab.log)
   constexpr int kFinishSteps = 8;
-  const int n = std::max((c.n_rows + 2 * kFinishSteps - 1) / (2 * kFinishSteps), L.n_phases);  // threads: 16 rows each
-  B200_LAUNCH(h, (k_sweep_finish<T, kFinishSteps>), (n + 255) / 256, 256, 0, acc, L.n_cov, c.n_rows, y, c.row_vertex.as<int32_t>(), alpha,
+  // covered_rows_only: y of the rows without edges already holds their (unvarying) value — multi-GPU blocks, where more than
+  // half of the row slots are empty and the unvarying term is 0 (mg.cu)
+  const int32_t finish_rows = covered_rows_only ? L.n_cov : c.n_rows;
+  const int n = std::max((finish_rows + 2 * kFinishSteps - 1) / (2 * kFinishSteps), L.n_phases);  // threads: 16 rows each
+  B200_LAUNCH(h, (k_sweep_finish<T, kFinishSteps>), (n + 255) / 256, 256, 0, acc, L.n_cov, finish_rows, y, c.row_vertex.as<int32_t>(), alpha,
               L.cursor.as<int>(), L.n_phases, st);
 }
 
 // dispatch: the piece stream when it exists for this graph, else the plain edge-balanced sweep
 template <typename O, typename T>
 void launch_pull_sweep_auto(handle_impl const& h, csx_t const& c, int32_t n_vertices, T const* x, T* y, double* acc,
-                            double alpha, pr_state_t const* st, bool use_weights = true)
+                            double alpha, pr_state_t const* st, bool use_weights = true, bool covered_rows_only = false)
 {
   sweep_layout_t const* L = sweep_layout(h, c, n_vertices, sizeof(T));
-  if (!L) launch_pull_sweep<O, T>(h, c, x, y, acc, alpha, st, use_weights);
-  else launch_sweep<T>(h, c, *L, x, y, acc, alpha, st, use_weights);
+  if (!L) launch_pull_sweep<O, T>(h, c, x, y, acc, alpha, st, use_weights);  // the plain sweep writes every row
+  else launch_sweep<T>(h, c, *L, x, y, acc, alpha, st, use_weights, covered_rows_only);
 }
 
 // elements an x buffer needs: whole slices are TMA-copied and everything behind n_vertices must read 0.
