@@ -150,11 +150,46 @@ def hits(resource_handle, graph, tol, max_iter, initial_hubs_guess_vertices, ini
     return (verts, hubs, auth)
 
 
+def _ensure_wcc_args(graph, offsets, indices, weights, labels):
+    """argument rules of weakly_connected_components.pyx:49-104"""
+    if graph is not None:
+        bad = [p for p in (offsets, indices, weights) if p is not None]
+        kind = "graph"
+    else:
+        bad = [p for p in (offsets, indices) if p is None]
+        kind = "csr_arrays"
+    if bad:
+        raise TypeError("Invalid input combination: Must set either 'graph' or "
+                        "a combination of 'offsets', 'indices' and 'weights', not both")
+    if kind == "csr_arrays":
+        assert_CAI_type(offsets, "offsets")
+        assert_CAI_type(indices, "indices")
+        assert_CAI_type(weights, "weights", True)
+    if labels is not None:
+        assert_CAI_type(labels, "labels")
+        if kind == "csr_arrays":
+            import numpy as np
+            odt, idt, ldt = (np.dtype(a.__cuda_array_interface__["typestr"]) for a in (offsets, indices, labels))
+            if odt != idt:
+                raise TypeError(f"offsets dtype must match indices dtype (got offsets.dtype={odt!r}, indices.dtype={idt!r})")
+            if ldt != idt:
+                raise TypeError(f"labels dtype must match indices dtype (got labels.dtype={ldt!r}, indices.dtype={idt!r})")
+    return kind
+
+
 def weakly_connected_components(resource_handle, graph, offsets, indices, weights, labels, do_expensive_check):
-    """Returns (vertices, labels) — weakly_connected_components.pyx:107-271 (the graph form; the legacy CSR-array form
-    `graph=None, offsets=..., indices=...` of the reference is not supported)."""
-    if graph is None:
-        raise NotImplementedError("weakly_connected_components needs a graph (the legacy offsets / indices form is not supported)")
+    """weakly_connected_components.pyx:107-290.  Either `graph`, or the CSR arrays `offsets` / `indices` [/ `weights`] of a
+    symmetric graph (the legacy form: a graph is built from them with renumber=False).  Returns (vertices, labels); with a
+    `labels` array the labels are written into it (vertex order) and None is returned."""
+    from cugraph_b200.pylibcugraph.graph_properties import GraphProperties
+    from cugraph_b200.pylibcugraph.graphs import SGGraph
+    from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
+    kind = _ensure_wcc_args(graph, offsets, indices, weights, labels)
+    if kind == "csr_arrays":
+        if resource_handle is None:
+            resource_handle = ResourceHandle()
+        graph = SGGraph(resource_handle, GraphProperties(is_symmetric=True, is_multigraph=False), offsets, indices, weights,
+                        store_transposed=False, renumber=False, do_expensive_check=True, input_array_format="CSR")
     res, err = C.c_void_p(), C.c_void_p()
     resource_handle.order_after_caller()
     L = _capi.lib()
@@ -164,4 +199,16 @@ def weakly_connected_components(resource_handle, graph, offsets, indices, weight
     verts = copy_to_torch(resource_handle, L.cugraph_labeling_result_get_vertices(res))
     labs = copy_to_torch(resource_handle, L.cugraph_labeling_result_get_labels(res))
     L.cugraph_labeling_result_free(res)
+    if labels is not None:
+        import torch
+        out = torch.as_tensor(labels, device=labs.device) if not isinstance(labels, torch.Tensor) else labels
+        out.copy_(labs)   # renumber=False: the result rows are in vertex order
+        return None
     return (verts, labs)
+
+
+def strongly_connected_components(resource_handle, graph, offsets, indices, weights, labels, do_expensive_check):
+    """Not part of this build (outside the hot path and its "next" rows); the argument rules are the
+    reference's, so that its input-validation tests behave the same."""
+    _ensure_wcc_args(graph, offsets, indices, weights, labels)
+    raise NotImplementedError("strongly_connected_components is not part of the B200 hot-path build")

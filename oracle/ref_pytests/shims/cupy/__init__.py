@@ -22,3 +22,10 @@ float32, float64, int32, int64 = _np.float32, _np.float64, _np.int32, _np.int64
 # cupy arrays answer .get() with a numpy copy; results of the mirror are torch tensors (test infrastructure only)
 if not hasattr(_torch.Tensor, "get"):
     _torch.Tensor.get = lambda self: self.detach().cpu().numpy()
+
+
+def zeros(shape, dtype=float):
+    return _torch.as_tensor(_np.zeros(shape, dtype=dtype)).to(_device())
+
+
+ndarray = _torch.Tensor
