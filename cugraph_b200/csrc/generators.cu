@@ -66,10 +66,51 @@ __global__ void k_rmat_edges(int scale, long long n, unsigned long long seed, fl
   }
 }
 
+// counter-based uniforms for edge weights / edge types: value i = lo + u_i * (hi - lo) with u_i = the top 24 (float) or 53
+// (double) bits of mix64(seed ^ i) as a fraction; integers: lo + mix64(seed ^ i) % (hi - lo)
+template <typename T>
+__global__ void k_uniform_real(T* __restrict__ out, long long n, unsigned long long seed, double lo, double hi)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long r = rmat_mix64(seed ^ (unsigned long long)i);
+    const double u = sizeof(T) == 4 ? (double)(r >> 40) * (1.0 / 16777216.0) : (double)(r >> 11) * (1.0 / 9007199254740992.0);
+    out[i]         = (T)(lo + u * (hi - lo));
+  }
+}
+__global__ void k_uniform_int(int32_t* __restrict__ out, long long n, unsigned long long seed, long long lo, long long hi)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (int32_t)(lo + (long long)(rmat_mix64(seed ^ (unsigned long long)i) % (unsigned long long)(hi - lo)));
+}
+
 }  // namespace
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" cugraph_error_code_t cugraph_b200_generate_uniform(const cugraph_resource_handle_t* handle, uint64_t seed, double lo,
+                                                              double hi, cugraph_type_erased_device_array_view_t* out,
+                                                              cugraph_error_t** error)
+{
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    B200_EXPECTS(out != nullptr, CUGRAPH_INVALID_INPUT, "NULL argument");
+    auto const* ov = V(out);
+    B200_EXPECTS(ov->type == FLOAT32 || ov->type == FLOAT64 || ov->type == INT32, CUGRAPH_INVALID_INPUT,
+                 "generate_uniform writes FLOAT32, FLOAT64 or INT32 arrays");
+    B200_EXPECTS(hi > lo, CUGRAPH_INVALID_INPUT, "Invalid input argument: the range [lo, hi) is empty");
+    if (ov->size == 0) return;
+    const int grid = (int)std::min<size_t>((ov->size + 255) / 256, (size_t)h.sm_count * 16);
+    if (ov->type == FLOAT32)
+      B200_LAUNCH(h, (k_uniform_real<float>), grid, 256, 0, (float*)ov->data, (long long)ov->size, (unsigned long long)seed, lo, hi);
+    else if (ov->type == FLOAT64)
+      B200_LAUNCH(h, (k_uniform_real<double>), grid, 256, 0, (double*)ov->data, (long long)ov->size, (unsigned long long)seed, lo, hi);
+    else
+      B200_LAUNCH(h, k_uniform_int, grid, 256, 0, (int32_t*)ov->data, (long long)ov->size, (unsigned long long)seed, (long long)lo,
+                  (long long)hi);
+    check_last("generate_uniform");
+  });
+}
 
 extern "C" cugraph_error_code_t cugraph_b200_generate_rmat_edgelist(const cugraph_resource_handle_t* handle, size_t scale,
                                                                     size_t num_edges, double a, double b, double c,

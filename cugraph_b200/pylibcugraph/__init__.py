@@ -7,7 +7,8 @@ from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
 from cugraph_b200.pylibcugraph.graph_properties import GraphProperties
 from cugraph_b200.pylibcugraph.graphs import SGGraph
 from cugraph_b200.pylibcugraph.algorithms import (pagerank, personalized_pagerank, bfs, sssp, katz_centrality, hits,
-                                                  weakly_connected_components, strongly_connected_components)
+                                                  weakly_connected_components, strongly_connected_components,
+                                                  generate_rmat_edgelist)
 
 __all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph",
-           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "hits", "weakly_connected_components", "strongly_connected_components"]
+           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "hits", "weakly_connected_components", "strongly_connected_components", "generate_rmat_edgelist"]

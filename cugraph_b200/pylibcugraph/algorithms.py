@@ -212,3 +212,48 @@ def strongly_connected_components(resource_handle, graph, offsets, indices, weig
     reference's, so that its input-validation tests behave the same."""
     _ensure_wcc_args(graph, offsets, indices, weights, labels)
     raise NotImplementedError("strongly_connected_components is not part of the B200 hot-path build")
+
+
+def generate_rmat_edgelist(resource_handle, random_state, scale, num_edges, a, b, c, clip_and_flip, scramble_vertex_ids,
+                           include_edge_weights, minimum_weight, maximum_weight, dtype, include_edge_ids, include_edge_types,
+                           min_edge_type_value, max_edge_type_value, multi_gpu):
+    """generate_rmat_edgelist.pyx: returns (sources, destinations, weights | None, edge ids | None, edge types | None).
+    The edges come from the library's device generator (the reference's sampling rule over a counter-based stream seeded with
+    `random_state`), weights / types from its uniform generator; ids are 0 .. num_edges-1 (as the reference numbers them)."""
+    import numpy as np
+    import torch
+    if multi_gpu:
+        raise NotImplementedError("generate_rmat_edgelist: multi_gpu=True is not part of this build")
+    L = _capi.lib()
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    seed = int(random_state) if random_state is not None else 0
+    src = torch.empty(num_edges, dtype=torch.int32, device=dev)
+    dst = torch.empty(num_edges, dtype=torch.int32, device=dev)
+    vs, vd, err = View(src), View(dst), C.c_void_p()
+    resource_handle.order_after_caller()
+    code = L.cugraph_b200_generate_rmat_edgelist(resource_handle.ptr, int(scale), int(num_edges), float(a), float(b), float(c), seed,
+                                                 int(bool(clip_and_flip)), int(bool(scramble_vertex_ids)), vs.ptr, vd.ptr, C.byref(err))
+    vs.free()
+    vd.free()
+    _capi.check(code, err, "cugraph_b200_generate_rmat_edgelist")
+
+    def uniform(tdtype, lo, hi, salt):
+        out = torch.empty(num_edges, dtype=tdtype, device=dev)
+        vo, e2 = View(out), C.c_void_p()
+        c2 = L.cugraph_b200_generate_uniform(resource_handle.ptr, seed + salt, float(lo), float(hi), vo.ptr, C.byref(e2))
+        vo.free()
+        _capi.check(c2, e2, "cugraph_b200_generate_uniform")
+        return out
+
+    weights = ids = types = None
+    if include_edge_weights:
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        weights = uniform(tdt, minimum_weight, maximum_weight, 0x9E37)
+    if include_edge_ids:
+        ids = torch.arange(num_edges, dtype=torch.int32, device=dev)
+    if include_edge_types:
+        types = uniform(torch.int32, min_edge_type_value, max_edge_type_value + 1, 0x79B9)
+    import torch as _t
+    if _t.cuda.is_available():
+        _t.cuda.synchronize()
+    return (src, dst, weights, ids, types)

@@ -72,6 +72,12 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_generate_rmat_edgelist(
   bool_t clip_and_flip, bool_t scramble_vertex_ids, cugraph_type_erased_device_array_view_t* src,
   cugraph_type_erased_device_array_view_t* dst, cugraph_error_t** error);
 
+/* Uniform values for synthetic edge weights / types (what cugraph_generate_edge_weights / _edge_types draw from raft's RNG):
+ * out[i] = lo + u_i * (hi - lo), u_i from a 64-bit mix of (seed, i); INT32 arrays get integers in [lo, hi). */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_b200_generate_uniform(const cugraph_resource_handle_t* handle, uint64_t seed, double lo,
+                                                                  double hi, cugraph_type_erased_device_array_view_t* out,
+                                                                  cugraph_error_t** error);
+
 /* One level of multi-GPU BFS on this GPU's edge block (pull direction; the role of the bottom-up step of
  * cpp/src/traversal/bfs_impl.cuh:593-869 on one edge partition).  frontier_cols / visited_rows: byte flags over the block's
  * column (source) / row (destination) slots, gathered by the launcher inside the column / row group.  cand (INT64, one per row

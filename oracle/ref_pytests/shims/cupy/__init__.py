@@ -29,3 +29,7 @@ def zeros(shape, dtype=float):
 
 
 ndarray = _torch.Tensor
+
+
+def union1d(a, b):
+    return _torch.unique(_torch.cat([a.reshape(-1), b.reshape(-1)]))

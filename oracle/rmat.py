@@ -112,3 +112,17 @@ def rmat_edgelist_counter(scale: int, num_edges: int, a: float = 0.57, b: float 
         s = scramble32(s, scale).astype(np.uint32)
         d = scramble32(d, scale).astype(np.uint32)
     return s.astype(np.int32), d.astype(np.int32)
+
+
+def uniform_counter(n: int, seed: int, lo: float, hi: float, dtype=np.float32):
+    """numpy twin of cugraph_b200_generate_uniform (csrc/generators.cu): value i = lo + u_i (hi - lo) with u_i the top 24
+    (float32) / 53 (float64) bits of mix64(seed ^ i) as a fraction; int32: lo + mix64(seed ^ i) % (hi - lo)."""
+    with np.errstate(over="ignore"):
+        r = _mix64(np.uint64(seed) ^ np.arange(n, dtype=np.uint64))
+    if np.dtype(dtype) == np.int32:
+        return (np.int64(lo) + (r % np.uint64(int(hi) - int(lo))).astype(np.int64)).astype(np.int32)
+    if np.dtype(dtype) == np.float32:
+        u = (r >> np.uint64(40)).astype(np.float64) * (1.0 / 16777216.0)
+    else:
+        u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lo + u * (hi - lo)).astype(dtype)

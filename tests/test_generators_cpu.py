@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from oracle.rmat import rmat_edgelist_counter
+from oracle.rmat import rmat_edgelist_counter, uniform_counter
 from tests.test_emu_staging_cpu import INT32, emu  # noqa: F401
 
 
@@ -48,4 +48,21 @@ def test_device_rmat_quadrants_and_errors(emu):  # noqa: F811
     code, *_ = _generate(emu, 8, 10, 0.6, 0.3, 0.3, 5, False, False)     # a + b + c > 1
     assert code != 0
     code, *_ = _generate(emu, 32, 10, 0.57, 0.19, 0.19, 5, False, False)  # ids would not fit 32 bits
+    assert code != 0
+
+
+@pytest.mark.parametrize("dtype,tid,lo,hi", [(np.float32, 8, 0.0, 1.0), (np.float64, 9, -2.5, 7.25), (np.int32, 2, 2, 6)])
+def test_device_uniform_matches_numpy_twin(emu, dtype, tid, lo, hi):  # noqa: F811
+    L = emu
+    L.cugraph_b200_generate_uniform.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    n = 10000
+    out = np.zeros(n, dtype=dtype)
+    v = C.c_void_p(L.cugraph_type_erased_device_array_view_create(out.ctypes.data, n, tid))   # 8 FLOAT32, 9 FLOAT64, 2 INT32
+    err = C.c_void_p()
+    code = L.cugraph_b200_generate_uniform(C.c_void_p(L.handle), 4242, lo, hi, v, C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    ref = uniform_counter(n, 4242, lo, hi, dtype)
+    assert np.array_equal(out, ref)
+    assert out.min() >= lo and out.max() < hi
+    code = L.cugraph_b200_generate_uniform(C.c_void_p(L.handle), 1, 3.0, 3.0, v, C.byref(err))   # empty range
     assert code != 0
