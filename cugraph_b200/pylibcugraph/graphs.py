@@ -30,6 +30,34 @@ def _check_flag(v, name):
         raise TypeError(f"expected int or bool for {name}, got {type(v)}")
 
 
+def _cai_dtype(a):
+    import numpy as np
+    return np.dtype(a.__cuda_array_interface__["typestr"])
+
+
+def _widen(a):
+    import torch
+    if a is None:
+        return None
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(a)
+    return t.to(torch.int64).contiguous()
+
+
+def _ensure_valid_dtypes(src, dst, vertices, edge_ids, t_start, t_end):
+    import warnings
+    vertex_args = [src, dst, vertices, edge_ids]
+    if len({_cai_dtype(a) for a in vertex_args if a is not None}) > 1:
+        warnings.warn("The graph requires 'src_or_offset_array', 'dst_or_index_array' "
+                      "'vertices_array' and 'edge_id_array' to match. "
+                      "Those will be widened to 64-bit.", UserWarning)
+        src, dst, vertices, edge_ids = (_widen(a) for a in vertex_args)
+    if len({_cai_dtype(a) for a in (t_start, t_end) if a is not None}) > 1:
+        warnings.warn("The graph requires 'edge_start_time_array' and 'edge_end_time_array' "
+                      "to match. Those will be widened to 64-bit.", UserWarning)
+        t_start, t_end = _widen(t_start), _widen(t_end)
+    return src, dst, vertices, edge_ids, t_start, t_end
+
+
 class SGGraph(_GPUGraph):
     """Single-GPU graph; argument list of graphs.pyx:150-168 (COO via
     cugraph_graph_create_with_times_sg, CSR via cugraph_graph_create_sg_from_csr)."""
@@ -53,6 +81,11 @@ class SGGraph(_GPUGraph):
                       (edge_id_array, "edge_id_array"), (edge_type_array, "edge_type_array"),
                       (edge_start_time_array, "edge_start_time_array"), (edge_end_time_array, "edge_end_time_array")):
             assert_CAI_type(a, nm, True)
+        # unequal id widths: warn and widen to 64 bits, as the reference does (utilities/api_tools.py:328-364 warns, the C layer
+        # casts: c_api/graph_sg.cpp cast_vertex_t)
+        (src_or_offset_array, dst_or_index_array, vertices_array, edge_id_array, edge_start_time_array,
+         edge_end_time_array) = _ensure_valid_dtypes(src_or_offset_array, dst_or_index_array, vertices_array, edge_id_array,
+                                                     edge_start_time_array, edge_end_time_array)
         views = [View(a) for a in (vertices_array, src_or_offset_array, dst_or_index_array, weight_array,
                                    edge_id_array, edge_type_array, edge_start_time_array, edge_end_time_array)]
         v, s, d, w, eid, ety, t0, t1 = [x.ptr for x in views]

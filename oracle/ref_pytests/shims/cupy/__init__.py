@@ -33,3 +33,11 @@ ndarray = _torch.Tensor
 
 def union1d(a, b):
     return _torch.unique(_torch.cat([a.reshape(-1), b.reshape(-1)]))
+
+
+def _astype(self, dtype=None, **kw):
+    return self.to(getattr(_torch, _np.dtype(dtype).name))
+
+
+if not hasattr(_torch.Tensor, "astype"):
+    _torch.Tensor.astype = _astype
