@@ -10,5 +10,10 @@ from cugraph_b200.pylibcugraph.algorithms import (pagerank, personalized_pageran
                                                   weakly_connected_components, strongly_connected_components,
                                                   generate_rmat_edgelist)
 
+from cugraph_b200.pylibcugraph import utilities  # noqa: F401
+
+__version__ = "26.10.00+b200"   # the reference version this surface mirrors (rapidsai/cugraph 26.10) + the build tag
+__git_commit__ = ""             # only non-empty in a built distribution, as in the reference
+
 __all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph",
            "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "hits", "weakly_connected_components", "strongly_connected_components", "generate_rmat_edgelist"]
