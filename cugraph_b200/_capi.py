@@ -107,6 +107,7 @@ def lib():
     _sig(L.cugraph_extract_paths_result_get_paths, vp, [vp])
     _sig(L.cugraph_extract_paths_result_free, None, [vp])
     _sig(L.cugraph_katz_centrality, i32, [vp, vp, vp, dbl, dbl, dbl, sz, i32, pvp, pvp])
+    _sig(L.cugraph_eigenvector_centrality, i32, [vp, vp, dbl, sz, i32, pvp, pvp])
     _sig(L.cugraph_hits, i32, [vp, vp, dbl, sz, vp, vp, i32, i32, pvp, pvp])
     for f in ("vertices", "hubs", "authorities"):
         _sig(getattr(L, f"cugraph_hits_result_get_{f}"), vp, [vp])

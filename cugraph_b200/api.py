@@ -152,6 +152,14 @@ def katz_centrality(G: Graph, alpha=None, beta=1.0, max_iter=100, tol=1.0e-6, ns
     return _frame(vertex=_host(verts), katz_centrality=_host(vals))
 
 
+def eigenvector_centrality(G: Graph, max_iter=100, tol=1.0e-6):
+    """cugraph.eigenvector_centrality (centrality/eigenvector_centrality.py): 'vertex', 'eigenvector_centrality'"""
+    plc = _plc()
+    h, g = G._plc_graph(True)
+    verts, vals = plc.eigenvector_centrality(h, g, tol, max_iter, False)
+    return _frame(vertex=_host(verts), eigenvector_centrality=_host(vals))
+
+
 def hits(G: Graph, max_iter=100, tol=1.0e-5, nstart=None, normalized=True):
     """cugraph.hits (link_analysis/hits.py): 'vertex', 'hubs', 'authorities'"""
     plc = _plc()

@@ -171,6 +171,45 @@ void katz_typed(handle_impl const& h, graph_impl& g, double alpha, double beta, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Eigenvector centrality (eigenvector_centrality_impl.cuh:34-150): x <- (A^T x + x) / ||A^T x + x||_2 from x = 1 / V, until
+// sum |x_new - x_old| < V * epsilon
+// ------------------------------------------------------------------------------------------
+template <typename T>
+void eigenvector_typed(handle_impl const& h, graph_impl& g, double epsilon, size_t max_iterations, centrality_result_impl& res)
+{
+  const int32_t nv = g.n_vertices;
+  csx_t const& c   = pull_view(h, g);
+  const size_t px  = padded_x_elems(nv, sizeof(T));
+  dbuf x = make_dbuf<T>(px, h.stream), y = make_dbuf<T>(std::max(nv, 1), h.stream);
+  CUDA_TRY(cudaMemsetAsync(x.data(), 0, px * sizeof(T), h.stream));
+  if (nv > 0) B200_LAUNCH(h, (k_fill_vec<T>), cgrid(h, nv), kCBlock, 0, x.as<T>(), (int64_t)nv, (T)(1.0 / (double)nv));
+  sweep_scratch_t sc;
+  sc.init(h, acc_rows(c));
+  dbuf d2     = make_dbuf<double>(2, h.stream);
+  size_t iter = 0;
+  while (nv > 0) {
+    sweep<T>(h, c, nv, x.as<T>(), y.as<T>(), sc, 1.0, true);
+    B200_LAUNCH(h, (k_add_vec<T>), cgrid(h, nv), kCBlock, 0, y.as<T>(), x.as<T>(), nv);
+    CUDA_TRY(cudaMemsetAsync(d2.data(), 0, 2 * sizeof(double), h.stream));
+    B200_LAUNCH(h, (k_norm<T>), cgrid(h, nv), kCBlock, 0, y.as<T>(), nv, 0, d2.as<double>());
+    const double hyp = std::sqrt(read_scalar(h, d2.as<double>()));
+    B200_LAUNCH(h, (k_scale<T>), cgrid(h, nv), kCBlock, 0, y.as<T>(), nv, 1.0 / hyp);
+    CUDA_TRY(cudaMemsetAsync(d2.data(), 0, sizeof(double), h.stream));
+    B200_LAUNCH(h, (k_abs_diff<T>), cgrid(h, nv), kCBlock, 0, y.as<T>(), x.as<T>(), nv, 1, d2.as<double>());
+    const double diff = read_scalar(h, d2.as<double>());
+    ++iter;
+    if ((T)diff < (T)nv * (T)epsilon) break;
+    B200_EXPECTS(iter < max_iterations, CUGRAPH_UNKNOWN_ERROR, "Eigenvector Centrality failed to converge.");
+  }
+  res.vertices   = new device_array_impl{reported_vertices(h, g), (size_t)nv, g.vertex_type};
+  res.values     = new device_array_impl{to_reported_order(h, g, x.data(), sizeof(T)), (size_t)nv, g.weight_type};
+  res.iterations = iter;
+  res.converged  = true;
+  check_last("eigenvector_centrality");
+  sync(h);
+}
+
+// ------------------------------------------------------------------------------------------
 // HITS (hits_impl.cuh:49-191): authorities = sum over in-edges of the hubs, hubs = sum over out-edges of the
 // authorities, both divided by their maximum; until sum |hubs - previous hubs| < V * epsilon; edge weights are not used
 // ------------------------------------------------------------------------------------------
@@ -285,6 +324,25 @@ cugraph_error_code_t cugraph_katz_centrality(const cugraph_resource_handle_t* ha
     auto res = std::make_unique<centrality_result_impl>();
     if (g->weight_type == FLOAT32) katz_typed<float>(h, *g, alpha, beta, epsilon, max_iterations, *res);
     else katz_typed<double>(h, *g, alpha, beta, epsilon, max_iterations, *res);
+    *result = reinterpret_cast<cugraph_centrality_result_t*>(res.release());
+  });
+}
+
+cugraph_error_code_t cugraph_eigenvector_centrality(const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, double epsilon,
+                                                    size_t max_iterations, bool_t do_expensive_check,
+                                                    cugraph_centrality_result_t** result, cugraph_error_t** error)
+{
+  (void)do_expensive_check;
+  return guarded(error, [&] {
+    auto const& h = H(handle);
+    auto* g       = G(graph);
+    B200_EXPECTS(result != nullptr, CUGRAPH_INVALID_INPUT, "result out-pointer is NULL");
+    *result = nullptr;
+    B200_EXPECTS(g->mg == nullptr, CUGRAPH_NOT_IMPLEMENTED, "multi-GPU eigenvector centrality is not implemented");
+    B200_EXPECTS(epsilon >= 0.0, CUGRAPH_INVALID_INPUT, "Invalid input argument: epsilon should be non-negative.");
+    auto res = std::make_unique<centrality_result_impl>();
+    if (g->weight_type == FLOAT32) eigenvector_typed<float>(h, *g, epsilon, max_iterations, *res);
+    else eigenvector_typed<double>(h, *g, epsilon, max_iterations, *res);
     *result = reinterpret_cast<cugraph_centrality_result_t*>(res.release());
   });
 }

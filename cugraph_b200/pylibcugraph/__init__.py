@@ -6,7 +6,7 @@ from cugraph_b200.pylibcugraph.exceptions import FailedToConvergeError
 from cugraph_b200.pylibcugraph.resource_handle import ResourceHandle
 from cugraph_b200.pylibcugraph.graph_properties import GraphProperties
 from cugraph_b200.pylibcugraph.graphs import SGGraph
-from cugraph_b200.pylibcugraph.algorithms import (pagerank, personalized_pagerank, bfs, sssp, katz_centrality, hits,
+from cugraph_b200.pylibcugraph.algorithms import (pagerank, personalized_pagerank, bfs, sssp, katz_centrality, eigenvector_centrality, hits,
                                                   weakly_connected_components, strongly_connected_components,
                                                   generate_rmat_edgelist)
 
@@ -16,4 +16,4 @@ __version__ = "26.10.00+b200"   # the reference version this surface mirrors (ra
 __git_commit__ = ""             # only non-empty in a built distribution, as in the reference
 
 __all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph",
-           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "hits", "weakly_connected_components", "strongly_connected_components", "generate_rmat_edgelist"]
+           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "eigenvector_centrality", "hits", "weakly_connected_components", "strongly_connected_components", "generate_rmat_edgelist"]

@@ -129,6 +129,17 @@ def katz_centrality(resource_handle, graph, betas, alpha, beta, epsilon, max_ite
     return (verts, vals)
 
 
+def eigenvector_centrality(resource_handle, graph, epsilon, max_iterations, do_expensive_check):
+    """Returns (vertices, values) — eigenvector_centrality.pyx."""
+    res, err = C.c_void_p(), C.c_void_p()
+    resource_handle.order_after_caller()
+    code = _capi.lib().cugraph_eigenvector_centrality(resource_handle.ptr, graph.ptr, float(epsilon), int(max_iterations),
+                                                      int(bool(do_expensive_check)), C.byref(res), C.byref(err))
+    _capi.check(code, err, "cugraph_eigenvector_centrality")
+    verts, vals, _, _ = _centrality_result(resource_handle, res)
+    return (verts, vals)
+
+
 def hits(resource_handle, graph, tol, max_iter, initial_hubs_guess_vertices, initial_hubs_guess_values, normalized,
          do_expensive_check):
     """Returns (vertices, hubs, authorities) — hits.pyx:49-184."""

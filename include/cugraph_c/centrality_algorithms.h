@@ -78,6 +78,12 @@ CUGRAPH_EXPORT cugraph_error_code_t cugraph_katz_centrality(
   double alpha, double beta, double epsilon, size_t max_iterations, bool_t do_expensive_check,
   cugraph_centrality_result_t** result, cugraph_error_t** error);
 
+/* Eigenvector centrality: centrality_algorithms.h:297-326, cpp/src/c_api/eigenvector_centrality.cpp,
+ * cpp/src/centrality/eigenvector_centrality_impl.cuh:34-150.  x <- (A^T x + x) / ||.||_2 until sum |x_new - x_old| < V * epsilon. */
+CUGRAPH_EXPORT cugraph_error_code_t cugraph_eigenvector_centrality(
+  const cugraph_resource_handle_t* handle, cugraph_graph_t* graph, double epsilon, size_t max_iterations,
+  bool_t do_expensive_check, cugraph_centrality_result_t** result, cugraph_error_t** error);
+
 /* HITS: centrality_algorithms.h:488-591, cpp/src/c_api/hits.cpp, cpp/src/link_analysis/hits_impl.cuh:29-206. */
 typedef struct { int32_t align_; } cugraph_hits_result_t;
 CUGRAPH_EXPORT cugraph_type_erased_device_array_view_t* cugraph_hits_result_get_vertices(cugraph_hits_result_t* result);

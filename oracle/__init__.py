@@ -313,3 +313,25 @@ def wcc(src, dst, num_vertices):
         if ru != rv:
             parent[max(ru, rv)] = min(ru, rv)
     return np.array([find(v) for v in range(num_vertices)], dtype=np.int64)
+
+
+def eigenvector(src, dst, num_vertices, weights=None, epsilon=1e-6, max_iterations=500):
+    """eigenvector_centrality_reference (cpp/tests/centrality/eigenvector_centrality_test.cpp:37-100) /
+    eigenvector_centrality_impl.cuh:34-150: x <- (A^T x + x) / ||A^T x + x||_2 from x = 1 / V, until
+    sum |x_new - x_old| < V * epsilon.  fp64.  Returns (x, iterations)."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    w = np.ones(src.size) if weights is None else np.asarray(weights, dtype=np.float64)
+    x = np.full(num_vertices, 1.0 / num_vertices)
+    it = 0
+    while True:
+        new = np.bincount(dst, weights=x[src] * w, minlength=num_vertices) + x
+        new = new / np.sqrt((new * new).sum())
+        diff = np.abs(new - x).sum()
+        x = new
+        it += 1
+        if diff < num_vertices * epsilon:
+            break
+        if it >= max_iterations:
+            raise RuntimeError("Eigenvector Centrality failed to converge.")
+    return x, it

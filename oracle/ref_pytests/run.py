@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE: run the reference's OWN pylibcugraph tests for this path —
-python/pylibcugraph/pylibcugraph/tests/{test_pagerank,test_sssp,test_graph_sg,test_katz_centrality,test_connected_components,test_rmat,test_structure,test_utils,test_version}.py with their conftest.py, unmodified, from where they lie
+python/pylibcugraph/pylibcugraph/tests/{test_pagerank,test_sssp,test_graph_sg,test_katz_centrality,test_connected_components,test_rmat,test_structure,test_utils,test_version,test_eigenvector_centrality}.py with their conftest.py, unmodified, from where they lie
 under $REF — against this repository's pylibcugraph mirror.  `import pylibcugraph` and `import cupy` resolve to the
 stand-ins in oracle/ref_pytests/shims/.  Without a GPU the library under test is the CPU emulation build
 (tests/emu_py.py); on a box with a GPU and the reference sources it is the CUDA library.
@@ -29,7 +29,7 @@ def main(argv):
         from tests.emu_py import emulated_python_surface
         cm = emulated_python_surface()
     with cm:
-        files = [a for a in argv if a.endswith(".py")] or ["test_pagerank.py", "test_sssp.py", "test_graph_sg.py", "test_katz_centrality.py", "test_connected_components.py", "test_rmat.py", "test_structure.py", "test_utils.py", "test_version.py"]
+        files = [a for a in argv if a.endswith(".py")] or ["test_pagerank.py", "test_sssp.py", "test_graph_sg.py", "test_katz_centrality.py", "test_connected_components.py", "test_rmat.py", "test_structure.py", "test_utils.py", "test_version.py", "test_eigenvector_centrality.py"]
         argv = [a for a in argv if not a.endswith(".py")]
         # test_SGGraph_create_from_cudf needs cudf (a DataFrame library outside this path; not installed); test_scc needs
         # strongly connected components (not part of this build — its argument-validation tests do run)

@@ -52,6 +52,27 @@ def test_katz_emulated(emu, monkeypatch, weighted, min_edges):  # noqa: F811
     L.emu_reload_tuning(C.c_void_p(L.handle))
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+def test_eigenvector_centrality_emulated(emu, weighted):  # noqa: F811
+    L = emu
+    src, dst, w = make_edges(2_000, 30_000, seed=29, weighted=weighted)
+    g = create_graph(L, src, dst, w)
+    ids, inv = np.unique(np.concatenate([src, dst]), return_inverse=True)
+    s, d = inv[:src.size], inv[src.size:]
+    L.cugraph_eigenvector_centrality.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    res, err = C.c_void_p(), C.c_void_p()
+    code = L.cugraph_eigenvector_centrality(C.c_void_p(L.handle), g, 1e-7, 1000, 0, C.byref(res), C.byref(err))
+    assert code == 0, L.cugraph_error_message(err)
+    verts, x = _centrality(L, res)
+    ref, _ = oracle.eigenvector(s, d, ids.size, w if weighted else None, epsilon=1e-7, max_iterations=1000)
+    got = np.zeros(ids.size)
+    got[np.searchsorted(ids, verts)] = x
+    np.testing.assert_allclose(got, ref, rtol=2e-3, atol=1e-7)
+    code = L.cugraph_eigenvector_centrality(C.c_void_p(L.handle), g, 0.0, 3, 0, C.byref(res), C.byref(err))
+    assert code != 0 and b"failed to converge" in L.cugraph_error_message(err)
+    L.cugraph_graph_free(g)
+
+
 @pytest.mark.parametrize("transposed,weighted,normalize,guess", [(False, False, True, False), (True, True, False, True)])
 def test_hits_emulated(emu, transposed, weighted, normalize, guess):  # noqa: F811
     L = emu

@@ -1,4 +1,4 @@
-"""The reference's OWN C-API tests for this path — cpp/tests/c_api/{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components}_test.c, compiled unmodified from
+"""The reference's OWN C-API tests for this path — cpp/tests/c_api/{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality}_test.c, compiled unmodified from
 where they lie under /root/reference against this repository's headers (oracle/ref_ctests/build.sh) — run here against the
 CPU emulation build of the library: every golden vector and error contract those programs check (pagerank_test.c:385-540,
 bfs_test.c:108-209, sssp_test.c:167-225) through the real C ABI.  Skipped where the reference sources are absent (the GPU
@@ -22,6 +22,7 @@ EXPECTED = {
     "hits": ["test_hits", "test_hits_with_transpose", "test_hits_with_initial", "test_hits_bigger", "test_hits_bigger_normalized",
              "test_hits_bigger_unnormalized"],
     "weakly_connected_components": ["test_weakly_connected_components", "test_weakly_connected_components_transpose"],
+    "eigenvector_centrality": ["test_eigenvector_centrality", "test_eigenvector_centrality_3971"],
 }
 
 
@@ -49,7 +50,7 @@ def binaries():
     return os.path.join(ROOT, "oracle", "_ref")
 
 
-@pytest.mark.parametrize("name", ["pagerank", "bfs", "sssp", "extract_paths", "katz", "hits", "weakly_connected_components"])
+@pytest.mark.parametrize("name", ["pagerank", "bfs", "sssp", "extract_paths", "katz", "hits", "weakly_connected_components", "eigenvector_centrality"])
 def test_reference_c_test_program(binaries, name):
     r = subprocess.run([os.path.join(binaries, f"ref_{name}_test")], capture_output=True, text=True, timeout=300)
     check_output(name, r)
