@@ -106,6 +106,11 @@ def lib():
     _sig(L.cugraph_extract_paths_result_get_max_path_length, sz, [vp])
     _sig(L.cugraph_extract_paths_result_get_paths, vp, [vp])
     _sig(L.cugraph_extract_paths_result_free, None, [vp])
+    for f in ("cugraph_in_degrees", "cugraph_out_degrees", "cugraph_degrees"):
+        _sig(getattr(L, f), i32, [vp, vp, vp, i32, pvp, pvp])
+    for f in ("vertices", "in_degrees", "out_degrees"):
+        _sig(getattr(L, f"cugraph_degrees_result_get_{f}"), vp, [vp])
+    _sig(L.cugraph_degrees_result_free, None, [vp])
     _sig(L.cugraph_katz_centrality, i32, [vp, vp, vp, dbl, dbl, dbl, sz, i32, pvp, pvp])
     _sig(L.cugraph_eigenvector_centrality, i32, [vp, vp, dbl, sz, i32, pvp, pvp])
     _sig(L.cugraph_hits, i32, [vp, vp, dbl, sz, vp, vp, i32, i32, pvp, pvp])

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cugraph_c/b200_ext.h>
+#include <cugraph_c/graph_functions.h>
 #include <cugraph_c/labeling_algorithms.h>
 #include <cuda_runtime.h>
 

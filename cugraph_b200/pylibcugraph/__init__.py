@@ -8,7 +8,7 @@ from cugraph_b200.pylibcugraph.graph_properties import GraphProperties
 from cugraph_b200.pylibcugraph.graphs import SGGraph
 from cugraph_b200.pylibcugraph.algorithms import (pagerank, personalized_pagerank, bfs, sssp, katz_centrality, eigenvector_centrality, hits,
                                                   weakly_connected_components, strongly_connected_components,
-                                                  generate_rmat_edgelist)
+                                                  generate_rmat_edgelist, in_degrees, out_degrees, degrees)
 
 from cugraph_b200.pylibcugraph import utilities  # noqa: F401
 
@@ -16,4 +16,4 @@ __version__ = "26.10.00+b200"   # the reference version this surface mirrors (ra
 __git_commit__ = ""             # only non-empty in a built distribution, as in the reference
 
 __all__ = ["FailedToConvergeError", "ResourceHandle", "GraphProperties", "SGGraph",
-           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "eigenvector_centrality", "hits", "weakly_connected_components", "strongly_connected_components", "generate_rmat_edgelist"]
+           "pagerank", "personalized_pagerank", "bfs", "sssp", "katz_centrality", "eigenvector_centrality", "hits", "weakly_connected_components", "strongly_connected_components", "generate_rmat_edgelist", "in_degrees", "out_degrees", "degrees"]

@@ -268,3 +268,37 @@ def generate_rmat_edgelist(resource_handle, random_state, scale, num_edges, a, b
     if _t.cuda.is_available():
         _t.cuda.synchronize()
     return (src, dst, weights, ids, types)
+
+
+def _degrees(fn_name, resource_handle, graph, source_vertices, do_expensive_check):
+    assert_CAI_type(source_vertices, "source_vertices", allow_none=True)
+    sv = View(source_vertices)
+    res, err = C.c_void_p(), C.c_void_p()
+    resource_handle.order_after_caller()
+    L = _capi.lib()
+    code = getattr(L, fn_name)(resource_handle.ptr, graph.ptr, sv.ptr, int(bool(do_expensive_check)), C.byref(res), C.byref(err))
+    sv.free()
+    _capi.check(code, err, fn_name)
+    verts = copy_to_torch(resource_handle, L.cugraph_degrees_result_get_vertices(res))
+    vin, vout = L.cugraph_degrees_result_get_in_degrees(res), L.cugraph_degrees_result_get_out_degrees(res)
+    ins = copy_to_torch(resource_handle, vin) if vin else None
+    outs = copy_to_torch(resource_handle, vout) if vout else None
+    L.cugraph_degrees_result_free(res)
+    return verts, ins, outs
+
+
+def in_degrees(resource_handle, graph, source_vertices, do_expensive_check):
+    """Returns (vertices, in degrees) — degrees.pyx"""
+    v, i, _ = _degrees("cugraph_in_degrees", resource_handle, graph, source_vertices, do_expensive_check)
+    return (v, i)
+
+
+def out_degrees(resource_handle, graph, source_vertices, do_expensive_check):
+    """Returns (vertices, out degrees) — degrees.pyx"""
+    v, _, o = _degrees("cugraph_out_degrees", resource_handle, graph, source_vertices, do_expensive_check)
+    return (v, o)
+
+
+def degrees(resource_handle, graph, source_vertices, do_expensive_check):
+    """Returns (vertices, in degrees, out degrees) — degrees.pyx"""
+    return _degrees("cugraph_degrees", resource_handle, graph, source_vertices, do_expensive_check)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# TEST INFRASTRUCTURE: compile the reference's OWN C-API tests for this path — cpp/tests/c_api/{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality}_test.c,
+# TEST INFRASTRUCTURE: compile the reference's OWN C-API tests for this path — cpp/tests/c_api/{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality,degrees}_test.c,
 # unmodified, from where they lie under $REF — against this repository's headers and link them with a libcugraph_c build
 # (default: the CPU emulation build, so the binaries run in the GPU-less container; pass the real library on a GPU box
 # that has the reference sources).  Outputs only into oracle/_ref/ (git-ignored).  No reference source is copied.
@@ -16,9 +16,9 @@ CUDA_INC="${CUDA_INC:-/usr/local/cuda/include}"
 [ -f "$LIB" ] || { echo "library $LIB not built"; exit 4; }
 mkdir -p "$OUT"
 LIBDIR="$(dirname "$LIB")"; LIBNAME="$(basename "$LIB")"
-for t in pagerank bfs sssp extract_paths katz hits weakly_connected_components eigenvector_centrality; do
+for t in pagerank bfs sssp extract_paths katz hits weakly_connected_components eigenvector_centrality degrees; do
   gcc -std=gnu11 -O1 -w -I "$ROOT/include" -I "$HERE/include" -I "$CUDA_INC" \
       "$REF/cpp/tests/c_api/${t}_test.c" "$HERE/support.c" -o "$OUT/ref_${t}_test${SUFFIX}" \
       -L "$LIBDIR" -l:"$LIBNAME" -Wl,-rpath,'$ORIGIN/../../cugraph_b200/lib' -Wl,-rpath,"$LIBDIR" -lm
 done
-echo "built: $OUT/ref_{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality}_test${SUFFIX} (against $LIB)"
+echo "built: $OUT/ref_{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality,degrees}_test${SUFFIX} (against $LIB)"

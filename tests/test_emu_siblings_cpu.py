@@ -248,3 +248,40 @@ def test_int64_ids_double_weights_and_empty_graph(emu):  # noqa: F811
     code = L.cugraph_hits(C.c_void_p(L.handle), g0.g, 1e-6, 10, None, None, 1, 0, C.byref(res), C.byref(err))
     assert code != 0 and b"positive" in L.cugraph_error_message(err)      # "Norm is required to be a positive value."
     L.cugraph_graph_free(g0.g)
+
+
+@pytest.mark.parametrize("store_transposed", [0, 1])
+def test_degrees_emulated(emu, store_transposed):  # noqa: F811
+    """cugraph_degrees / _in_degrees / _out_degrees on a directed multigraph, for all vertices and for a subset"""
+    L = emu
+    src, dst, _ = make_edges(1_500, 12_000, seed=41)
+    g = create_graph(L, src, dst, None, store_transposed=store_transposed)
+    ids = np.unique(np.concatenate([src, dst]))
+    indeg = dict(zip(*np.unique(dst, return_counts=True)))
+    outdeg = dict(zip(*np.unique(src, return_counts=True)))
+    for f in ("cugraph_in_degrees", "cugraph_out_degrees", "cugraph_degrees"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    for f in ("vertices", "in_degrees", "out_degrees"):
+        getattr(L, f"cugraph_degrees_result_get_{f}").restype = C.c_void_p
+        getattr(L, f"cugraph_degrees_result_get_{f}").argtypes = [C.c_void_p]
+    L.cugraph_degrees_result_free.argtypes = [C.c_void_p]
+    subset = np.ascontiguousarray(ids[::7][::-1], dtype=np.int32)
+    sub_view = C.c_void_p(L.cugraph_type_erased_device_array_view_create(subset.ctypes.data, subset.size, INT32))
+    for fn, want_in, want_out in (("cugraph_degrees", True, True), ("cugraph_in_degrees", True, False), ("cugraph_out_degrees", False, True)):
+        for sv, expect_v in ((None, None), (sub_view, subset)):
+            res, err = C.c_void_p(), C.c_void_p()
+            code = getattr(L, fn)(C.c_void_p(L.handle), g, sv, 0, C.byref(res), C.byref(err))
+            assert code == 0, L.cugraph_error_message(err)
+            v = _view_to_np(L, L.cugraph_degrees_result_get_vertices(res))
+            pin, pout = L.cugraph_degrees_result_get_in_degrees(res), L.cugraph_degrees_result_get_out_degrees(res)
+            assert bool(pin) == want_in and bool(pout) == want_out
+            if expect_v is None:
+                assert sorted(v.tolist()) == ids.tolist()
+            else:
+                assert v.tolist() == expect_v.tolist()
+            if pin:
+                assert _view_to_np(L, pin).tolist() == [int(indeg.get(x, 0)) for x in v.tolist()]
+            if pout:
+                assert _view_to_np(L, pout).tolist() == [int(outdeg.get(x, 0)) for x in v.tolist()]
+            L.cugraph_degrees_result_free(res)
+    L.cugraph_graph_free(g)

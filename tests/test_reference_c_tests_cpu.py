@@ -1,4 +1,4 @@
-"""The reference's OWN C-API tests for this path — cpp/tests/c_api/{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality}_test.c, compiled unmodified from
+"""The reference's OWN C-API tests for this path — cpp/tests/c_api/{pagerank,bfs,sssp,extract_paths,katz,hits,weakly_connected_components,eigenvector_centrality,degrees}_test.c, compiled unmodified from
 where they lie under /root/reference against this repository's headers (oracle/ref_ctests/build.sh) — run here against the
 CPU emulation build of the library: every golden vector and error contract those programs check (pagerank_test.c:385-540,
 bfs_test.c:108-209, sssp_test.c:167-225) through the real C ABI.  Skipped where the reference sources are absent (the GPU
@@ -23,6 +23,8 @@ EXPECTED = {
              "test_hits_bigger_unnormalized"],
     "weakly_connected_components": ["test_weakly_connected_components", "test_weakly_connected_components_transpose"],
     "eigenvector_centrality": ["test_eigenvector_centrality", "test_eigenvector_centrality_3971"],
+    "degrees": ["test_degrees", "test_degrees_symmetric", "test_in_degrees", "test_out_degrees", "test_degrees_subset",
+                "test_degrees_symmetric_subset", "test_in_degrees_subset", "test_out_degrees_subset"],
 }
 
 
@@ -50,7 +52,7 @@ def binaries():
     return os.path.join(ROOT, "oracle", "_ref")
 
 
-@pytest.mark.parametrize("name", ["pagerank", "bfs", "sssp", "extract_paths", "katz", "hits", "weakly_connected_components", "eigenvector_centrality"])
+@pytest.mark.parametrize("name", ["pagerank", "bfs", "sssp", "extract_paths", "katz", "hits", "weakly_connected_components", "eigenvector_centrality", "degrees"])
 def test_reference_c_test_program(binaries, name):
     r = subprocess.run([os.path.join(binaries, f"ref_{name}_test")], capture_output=True, text=True, timeout=300)
     check_output(name, r)
