@@ -174,3 +174,18 @@ def test_user_level_api(surface):
     assert set(ds.columns) == {"vertex", "distance", "predecessor"} and float(by_id(ds, "distance")[np.searchsorted(ids, start)]) == 0.0
     with pytest.raises(RuntimeError):
         api.sssp(api.Graph(directed=False).from_pandas_edgelist(pdf, source="src", destination="dst"), source=start)
+    # mirror-level extras: eigenvector centrality and the degree functions
+    import torch
+    from cugraph_b200 import pylibcugraph as plc
+    de = api.eigenvector_centrality(G, max_iter=1000, tol=1e-7)
+    re_, _ = oracle.eigenvector(si, di, ids.size, None, epsilon=1e-7, max_iterations=1000)
+    np.testing.assert_allclose(by_id(de, "eigenvector_centrality"), re_, rtol=5e-3, atol=1e-7)
+    h, g = G._plc_graph(True)
+    v, din, dout = plc.degrees(h, g, None, False)
+    vi = np.searchsorted(ids, v.numpy())
+    assert np.array_equal(din.numpy(), np.bincount(di, minlength=ids.size)[vi]) and np.array_equal(dout.numpy(), np.bincount(si, minlength=ids.size)[vi])
+    some = torch.as_tensor(ids[:5].copy())
+    v2, din2 = plc.in_degrees(h, g, some, False)
+    assert v2.numpy().tolist() == ids[:5].tolist() and din2.numpy().tolist() == np.bincount(di, minlength=ids.size)[:5].tolist()
+    v3, dout3 = plc.out_degrees(h, g, some, False)
+    assert dout3.numpy().tolist() == np.bincount(si, minlength=ids.size)[:5].tolist()
