@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: records how profiles/r02_align_ab.log was produced; the window policy and its knobs were removed from the library afterwards
+# (profiles/r02_window_policy.patch), so this script only makes sense on a tree with that patch applied.
 # A/B of the row-aligned window policy on RMAT-24 (cbench: device RMAT, sweep parity + live sweep time)
 mkdir -p gpurun_out
 out=gpurun_out/r02_align_ab.log

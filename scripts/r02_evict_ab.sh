@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: the three library variants compared here (B200_ACC_POLICY = 0 / 1 / 2) existed only for this experiment; the kept code is variant 2.
 # A/B of the L2 eviction-policy builds of the sweep (profiles/r02_evict_ab3.log); earlier contents of this scratch script produced
 # r02_tma_ab / r02_fullchunk_ab / r02_sssp_ab / r02_evict_ab{,2}.log
 mkdir -p gpurun_out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: records how profiles/r02_tma_ab.log was produced, on a tree with profiles/r02_tma_stream_attempt.patch applied (not kept).
 mkdir -p gpurun_out
 out=gpurun_out/r02_tma_ab.log
 : > $out
