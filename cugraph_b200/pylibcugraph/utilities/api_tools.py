@@ -26,22 +26,22 @@ def experimental_warning_wrapper(obj):
     msg = (f"{namespace}.{name} is experimental and will change or be removed in a future release.")
 
     if inspect.isclass(obj):
-        class WarningWrapperClass(obj):
+        class _Experimental(obj):
             def __init__(self, *args, **kwargs):
                 warnings.warn(msg, PendingDeprecationWarning)
                 super().__init__(*args, **kwargs)
 
-        WarningWrapperClass.__module__ = namespace
-        WarningWrapperClass.__qualname__ = name
-        WarningWrapperClass.__name__ = name
-        return WarningWrapperClass
+        _Experimental.__module__ = namespace
+        _Experimental.__qualname__ = name
+        _Experimental.__name__ = name
+        return _Experimental
 
     @functools.wraps(obj)
-    def warning_wrapper_function(*args, **kwargs):
+    def _experimental_call(*args, **kwargs):
         warnings.warn(msg, PendingDeprecationWarning)
         return obj(*args, **kwargs)
 
-    warning_wrapper_function.__module__ = namespace
-    warning_wrapper_function.__qualname__ = name
-    warning_wrapper_function.__name__ = name
-    return warning_wrapper_function
+    _experimental_call.__module__ = namespace
+    _experimental_call.__qualname__ = name
+    _experimental_call.__name__ = name
+    return _experimental_call
