@@ -15,4 +15,6 @@ from tests.emu_py import emulated_python_surface  # noqa: E402
 
 with emulated_python_surface():
     sys.exit(pytest.main([os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "--deselect", "tests/test_mg_gpu.py",
-                          "--deselect", "tests/test_reference_c_tests_gpu.py", "-p", "no:cacheprovider"] + sys.argv[1:]))
+                          "--deselect", "tests/test_reference_c_tests_gpu.py",
+                          "--deselect", "tests/test_zz_late_additions_gpu.py::test_reference_c_test_program_on_gpu",
+                          "-p", "no:cacheprovider"] + sys.argv[1:]))

@@ -34,16 +34,6 @@ def test_katz_gpu(weighted):
     np.testing.assert_allclose(got, ref, rtol=2e-5)
 
 
-def test_eigenvector_centrality_gpu():
-    import oracle
-    plc, h, g, ids, s, d, _ = _graph()
-    verts, vals = plc.eigenvector_centrality(h, g, 1e-7, 1000, False)
-    ref, _ = oracle.eigenvector(s, d, ids.size, None, epsilon=1e-7, max_iterations=1000)
-    got = np.zeros(ids.size)
-    got[np.searchsorted(ids, verts.cpu().numpy())] = vals.cpu().numpy()
-    np.testing.assert_allclose(got, ref, rtol=2e-3, atol=1e-8)
-
-
 @pytest.mark.parametrize("store_transposed", [True, False])
 def test_hits_gpu(store_transposed):
     import oracle
